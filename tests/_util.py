@@ -1,0 +1,42 @@
+"""Shared helpers for the test-suite (golden replay, synthetic generators)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+GOLDEN_DEEP = {
+    "fm_cfg1": ("FMAdam", dict(k=10)),
+    "fm_small_scaled": ("FMAdam", dict(k=10)),
+    "deepfm_small": ("DeepFMAdam", dict(k=10, L=3, H=16)),
+    "deepfm_raw": ("DeepFMAdam", dict(k=10, L=2, H=8)),
+    "nfm_k64": ("NFMAdam", dict(k=64, L=1, H=64)),
+    "deepfm_onn": ("DeepFMOnn", dict(k=10, L=5, H=10, batch_size=1)),
+    "nfm_onn": ("NFMOnn", dict(k=10, L=5, H=10, batch_size=1)),
+    "nfm_onn_b8": ("NFMOnn", dict(k=10, L=3, H=10, batch_size=8)),
+}
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-3))) if a.size else 0.0
+
+
+def synth(feature_sizes, n, seed, real_xv=False, zipf=False):
+    rng = np.random.RandomState(seed)
+    if zipf:
+        Xi = np.stack([np.minimum(rng.zipf(1.3, size=n) - 1, fs - 1) for fs in feature_sizes], 1)
+    else:
+        Xi = np.stack([rng.randint(0, fs, size=n) for fs in feature_sizes], 1)
+    Xv = rng.uniform(0.25, 2.0, size=Xi.shape).astype(np.float32) if real_xv else np.ones(Xi.shape, np.float32)
+    Y = (rng.uniform(size=n) < 0.3).astype(np.float32)
+    return Xi.astype(np.int64), Xv, Y
