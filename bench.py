@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py -- train samples/s (fwd + bwd + update) of the FM hot path on B200, with roofline and
+CPU-baseline evidence.  Contract: see DESIGN.md "Measurement".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg5|cfg4]
+
+A "step" is one `update_embedding` (forward_fm + BCEWithLogits + sparse backward + fresh-Adam row
+update, the reference's pre-training hot loop main_experiment.py:92-105) over one batch of 8192
+synthetic Criteo-shaped samples per GPU.  Workload cfg5 = BASELINE.json configs[4]: 39 fields,
+33 M embedding rows (1.6 GB packed, far larger than the 126 MB L2), k = 10.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CRITEO_SMALL13 = [63, 113, 126, 51, 224, 148, 100, 79, 104, 9, 32, 57, 82]
+CRITEO_TINY = CRITEO_SMALL13 + [1457, 555, 176373, 129683, 305, 19, 11887, 632, 3, 41738, 5170, 175446, 3170, 27,
+                                11356, 165602, 10, 4641, 2030, 4, 172761, 18, 15, 57903, 86, 44549]
+
+
+def feature_sizes(workload):
+    if workload == "cfg4":
+        return list(CRITEO_TINY)  # main_experiment.py:56-58, sum = 1 006 628
+    if workload == "cfg5":
+        return CRITEO_SMALL13 + [1_269_185] * 26  # 13 dense-bucket fields + 26 categorical, sum = 33 000 000 - 4
+    raise SystemExit(f"unknown workload {workload}")
+
+
+def synth_batches(sizes, B, nb, seed):
+    rng = np.random.RandomState(seed)
+    out = []
+    for _ in range(nb):
+        Xi = np.stack([rng.randint(0, fs, size=B) for fs in sizes], 1).astype(np.int64)
+        Y = (rng.uniform(size=B) < 0.3).astype(np.float32)
+        out.append((Xi, Y))
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+def cpu_port_rate(sizes, k, B, budget_s, seed=0):
+    """The oracle port (single thread, C) timed on this box's host cores on the same workload."""
+    from oracle.deep import OracleDeep
+    orc = OracleDeep("DeepFMAdam", sizes, k, 3, 400, lr=1e-4, seed=seed)
+    batches = synth_batches(sizes, B, 4, 99)
+    ones = np.ones((B, len(sizes)), np.float32)
+    orc.update_embedding(batches[0][0], ones, batches[0][1])  # warm-up
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        Xi, Y = batches[n % len(batches)]
+        orc.update_embedding(Xi, ones, Y)
+        n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 200:
+            break
+    dt = time.perf_counter() - t0
+    return n * B / dt, n, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference is pure Python/PyTorch and cannot travel to the GPU box, so this
+    arm times the CPU oracle port of the same step (oracle/fm_oracle.c) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sizes = feature_sizes(args.workload)
+    B = args.batch
+    from oracle.deep import OracleDeep
+    orc = OracleDeep("DeepFMAdam", sizes, 10, 3, 400, lr=1e-4, seed=0)
+    batches = synth_batches(sizes, B, 4, 99)
+    ones = np.ones((B, len(sizes)), np.float32)
+    for w in range(max(1, min(args.warmup, 2))):
+        orc.update_embedding(batches[0][0], ones, batches[0][1])
+    K = min(args.steps, 40)
+    t0 = time.perf_counter()
+    for i in range(K):
+        Xi, Y = batches[i % len(batches)]
+        orc.update_embedding(Xi, ones, Y)
+    dt = time.perf_counter() - t0
+    v = K * B / dt
+    line = {"impl": "reference", "metric": "train samples/sec (fwd+bwd+update)", "value": v, "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": K, "warmup": args.warmup, "ms_per_step": dt / K * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, sizes),
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": 1, "kind": "port",
+                             "sample": f"{K} update_embedding steps of B={B} (oracle/fm_oracle.c, 1 thread)"},
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, sizes):
+    return {"workload": f"{args.workload}: DeepFMAdam.update_embedding, Criteo-shaped F={len(sizes)} fields, "
+                        f"R={sum(sizes)} rows, k=10, batch {args.batch} per GPU",
+            "batch_per_gpu": args.batch, "fields": len(sizes), "rows": int(sum(sizes)), "k": 10,
+            "update": "fresh-Adam sign step (reference)", "l2": "tables larger than L2; a different batch every step"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import fm_for_online_recommendation_b200 as pkg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sizes = feature_sizes(args.workload)
+    F, k, B = len(sizes), 10, args.batch
+    K, W = args.steps, max(args.warmup, 3)
+    lib = pkg.require_cuda()
+
+    if world > 1:
+        from fm_for_online_recommendation_b200 import sharded
+        return sharded.bench_main(args, sizes, workload_config(args, sizes))
+
+    torch.manual_seed(0)
+    model = pkg.DeepFMAdam(sizes, embedding_size=k, num_hidden_layers=3, neuron_per_hidden_layer=400, n=1e-4)
+    NB = 16
+    host = synth_batches(sizes, B, NB, 1234 + rank)
+    enc = [model.encode(Xi, None, Y) for Xi, Y in host]
+    host_ids = [np.ascontiguousarray((Xi + model._offsets_np[:-1][None, :]).astype(np.int32)) for Xi, _ in host]
+    host_y = [Y for _, Y in host]
+    stream = torch.cuda.current_stream()
+    sess = model._get_session(B)
+
+    def step(i):
+        return model._fm_step(enc[i % NB], 0)
+
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+    launches0 = lib.fmb_session_launches(sess)
+    sampler = ClockSampler(local)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(K):
+        step(W + i)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.fmb_session_launches(sess) - launches0
+
+    # ---- e2e: host buffers through the C-ABI host entry point (H2D of ids/y + D2H of the loss inside)
+    loss = C.c_float()
+    tptr, bptr = C.c_void_p(model._table.data_ptr()), C.c_void_p(model.bias.data_ptr())
+
+    def host_step(i):
+        j = i % NB
+        rc = lib.fmb_session_fm_step_host(sess, host_ids[j].ctypes.data_as(C.c_void_p), None,
+                                          host_y[j].ctypes.data_as(C.c_void_p), B, tptr, bptr, model._key_bits, 0,
+                                          model._lr, 0, C.byref(loss), C.c_void_p(stream.cuda_stream))
+        assert rc == 0, lib.fmb_last_error()
+
+    for i in range(W):
+        host_step(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(K):
+        host_step(W + i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    # ---- per-phase device time (CUDA events on the launching stream) for the roofline
+    p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    N = B * F
+    S = torch.empty(B, model._kp4, device="cuda"); z = torch.empty(B, device="cuda")
+    delta = torch.empty(B, device="cuda"); lossv = torch.empty(B, device="cuda")
+    wsb = lib.fmb_sort_workspace_bytes(N); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    sk = torch.empty(N, dtype=torch.int32, device="cuda"); pm = torch.empty(N, dtype=torch.int32, device="cuda")
+    bwsb = lib.fmb_bwd_workspace_bytes(N); bws = torch.empty(bwsb, dtype=torch.uint8, device="cuda")
+    lossd = torch.empty(1, device="cuda")
+    st = C.c_void_p(stream.cuda_stream)
+    phases = {"fm_forward": 0.0, "sort": 0.0, "fm_backward_update": 0.0, "finish": 0.0}
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    reps = max(5, min(K, 50))
+    for i in range(reps + 2):
+        e = enc[i % NB]
+        evs[0].record(stream)
+        lib.fmb_fm_forward(p(e.ids), None, tptr, bptr, B, F, k, None, p(S), None, None, p(z), p(e.y), 0, p(delta),
+                           p(lossv), st)
+        evs[1].record(stream)
+        lib.fmb_sort_segment(p(e.ids), N, model._key_bits, p(ws), wsb, p(sk), p(pm), None, None, st)
+        evs[2].record(stream)
+        lib.fmb_fm_backward_update(p(sk), p(pm), N, None, tptr, F, k, p(S), p(delta), 1, None, model._lr, 0, p(bws),
+                                   bwsb, st)
+        evs[3].record(stream)
+        lib.fmb_finish_step(p(delta), p(lossv), B, bptr, model._lr, 0, p(lossd), st)
+        evs[4].record(stream)
+        torch.cuda.synchronize()
+        if i >= 2:
+            for j, name in enumerate(phases):
+                phases[name] += evs[j].elapsed_time(evs[j + 1]) / reps
+    peaks, peak_src = measured_peaks()
+    kp1 = k + 1
+    alg_bytes = {  # algorithmic bytes per launch (DESIGN.md "Kernels")
+        "fm_forward": B * (4 * F + 4 * F * kp1 + 4 * model._kp4 + 16),
+        "fm_backward_update": B * (8 * F + 8 * F * kp1 + 4 * model._kp4 + 4),
+        "sort": B * F * 8 * 2 * ((model._key_bits + 7) // 8),
+    }
+    dom = max(("fm_forward", "fm_backward_update"), key=lambda n: phases[n])
+    achieved = alg_bytes[dom] / (phases[dom] * 1e-3) / 1e9
+    step_bytes = B * (8 * F * kp1 + 8 * F + 8)
+
+    value = B * K / (ms * 1e-3)
+    line = {
+        "metric": "train samples/sec (fwd+bwd+update)", "value": value, "unit": "samples/s", "n_gpus": 1,
+        "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, sizes),
+        "clocks": clocks,
+        "e2e": {"value": B * K / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": 4 * B * F + 4 * B,
+                "d2h_bytes_per_step": 4, "api": "fmb_session_fm_step_host (host ids/y in, loss out)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes[dom],
+                     "phase_ms": phases,
+                     "whole_step_GBps": step_bytes / (ms / K * 1e-3) / 1e9},
+    }
+    if not args.no_cpu_baseline:
+        v, n, dt = cpu_port_rate(sizes, k, B, args.cpu_budget)
+        line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": 1, "kind": "port",
+                                "sample": f"{n} update_embedding steps of B={B} in {dt:.1f}s "
+                                          f"(oracle/fm_oracle.c, 1 of {os.cpu_count()} host cores)"}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg5", choices=["cfg5", "cfg4"])
+    ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

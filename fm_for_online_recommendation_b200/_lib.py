@@ -1,0 +1,91 @@
+"""ctypes loader for lib/libfmb200.so (the C-ABI boundary declared in include/fmb200.h).
+
+There is NO CPU fallback: `require_cuda()` raises if the extension is missing or no B200 is visible,
+and every wrapper raises `FmbError` on a non-zero status.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "lib", "libfmb200.so")
+
+c_i32p = C.POINTER(C.c_int32)
+c_f32p = C.POINTER(C.c_float)
+vp = C.c_void_p
+
+
+class FmbError(RuntimeError):
+    pass
+
+
+_SIGS = {
+    "fmb_version": (C.c_int, []),
+    "fmb_last_error": (C.c_char_p, []),
+    "fmb_device_count": (C.c_int, []),
+    "fmb_rowp": (C.c_int, [C.c_int]),
+    "fmb_kp4": (C.c_int, [C.c_int]),
+    "fmb_fm_forward": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp,
+                                 vp]),
+    "fmb_loss_delta": (C.c_int, [C.c_int, vp, vp, C.c_int, vp, vp, vp]),
+    "fmb_sum_aten": (C.c_int, [vp, C.c_int64, vp, vp]),
+    "fmb_update_dense": (C.c_int, [vp, vp, C.c_int64, C.c_float, C.c_int, vp]),
+    "fmb_finish_step": (C.c_int, [vp, vp, C.c_int, vp, C.c_float, C.c_int, vp, vp]),
+    "fmb_sort_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "fmb_sort_segment": (C.c_int, [vp, C.c_int64, C.c_int, vp, C.c_size_t, vp, vp, vp, vp, vp]),
+    "fmb_bwd_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "fmb_fm_backward_update": (C.c_int, [vp, vp, C.c_int64, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, C.c_float,
+                                         C.c_int, vp, C.c_size_t, vp]),
+    "fmb_mlp_numel": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    "fmb_mlp_forward": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    "fmb_mlp_bwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "fmb_mlp_backward": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
+                                   C.c_int, vp, C.c_size_t, vp]),
+    "fmb_combine_logit": (C.c_int, [C.c_int, vp, vp, vp, vp, C.c_int, vp, vp]),
+    "fmb_onn_heads": (C.c_int, [C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]),
+    "fmb_predict": (C.c_int, [vp, C.c_int, vp, vp]),
+    "fmb_hedge_head_grad": (C.c_int, [vp, vp, C.c_int, vp, vp, vp]),
+    "fmb_hedge_accumulate": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "fmb_hedge_apply": (C.c_int, [vp, vp, C.c_float, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                  C.c_float, vp]),
+    "fmb_session_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int64]),
+    "fmb_session_destroy": (None, [vp]),
+    "fmb_session_launches": (C.c_int64, [vp]),
+    "fmb_session_fm_step": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp]),
+    "fmb_session_fm_step_host": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_float, C.c_int,
+                                           C.POINTER(C.c_float), vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (works without a GPU: symbols only)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise FmbError(f"{SO_PATH} is missing: run `python -m fm_for_online_recommendation_b200.build` "
+                           "(there is no CPU fallback)")
+        lib = C.CDLL(SO_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def require_cuda():
+    lib = load()
+    if lib.fmb_device_count() < 1:
+        raise FmbError("no CUDA device visible: fm_for_online_recommendation_b200 has no CPU fallback")
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise FmbError(f"{what} failed (status {rc}): {load().fmb_last_error().decode()}")
+
+
+def ptr(t):
+    """device/host pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

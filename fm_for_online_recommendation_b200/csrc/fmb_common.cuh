@@ -1,0 +1,197 @@
+// fmb_common.cuh -- shared device helpers for the FM hot path (sm_100a).
+//
+// Parity-critical fp32 arithmetic is written with explicit round-to-nearest intrinsics
+// (__fmul_rn/__fadd_rn/__fsub_rn/__fmaf_rn/__fdiv_rn/__fsqrt_rn) so nvcc can never contract a
+// multiply-add that ATen executes as two roundings (SURVEY.md section 7 "hard parts"); the
+// library is additionally built with -fmad=false.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define FMB_API extern "C" __attribute__((visibility("default")))
+
+// ---- error plumbing (thread-local message, int status; no exceptions cross the C ABI) ----
+void fmb_set_error(const char* fmt, ...);
+#define FMB_OK 0
+#define FMB_ERR_ARG (-1)
+#define FMB_ERR_CUDA (-2)
+#define FMB_ERR_WS (-3)
+#define FMB_CHECK_ARG(cond, ...)                         \
+    do {                                                 \
+        if (!(cond)) { fmb_set_error(__VA_ARGS__); return FMB_ERR_ARG; } \
+    } while (0)
+#define FMB_CHECK_LAUNCH(name)                                                           \
+    do {                                                                                 \
+        cudaError_t e__ = cudaGetLastError();                                            \
+        if (e__ != cudaSuccess) { fmb_set_error("%s: %s", name, cudaGetErrorString(e__)); return FMB_ERR_CUDA; } \
+    } while (0)
+
+static inline int fmb_round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+namespace fmb {
+
+// ---------------------------------------------------------------------------------------------
+// fp32 transcendental functions: the SAME algorithms as oracle/oracle_math.h, restated.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float pow2i(int n) { return __int_as_float((n + 127) << 23); }
+
+__device__ __forceinline__ float expf_p(float x) {
+    if (x != x) return x;
+    if (x > 88.7228317f) return __int_as_float(0x7f800000);
+    if (x < -103.972084f) return 0.0f;
+    float fn = rintf(__fmul_rn(x, 1.44269504f));
+    float r = __fmaf_rn(fn, -0.693359375f, x);
+    r = __fmaf_rn(fn, 2.12194440e-4f, r);
+    float p = 1.9875691500e-4f;
+    p = __fmaf_rn(p, r, 1.3981999507e-3f);
+    p = __fmaf_rn(p, r, 8.3334519073e-3f);
+    p = __fmaf_rn(p, r, 4.1665795894e-2f);
+    p = __fmaf_rn(p, r, 1.6666665459e-1f);
+    p = __fmaf_rn(p, r, 5.0000001201e-1f);
+    float r2 = __fmul_rn(r, r);
+    float y = __fmaf_rn(p, r2, r);
+    y = __fadd_rn(y, 1.0f);
+    int n = (int)fn;
+    int n1 = n / 2;
+    int n2 = n - n1;
+    y = __fmul_rn(y, pow2i(n1));
+    y = __fmul_rn(y, pow2i(n2));
+    return y;
+}
+
+__device__ __forceinline__ float logf_p(float x) {
+    if (x != x) return x;
+    if (x < 0.0f) return __int_as_float(0x7fc00000);
+    if (x == 0.0f) return __int_as_float(0xff800000);
+    if (x == __int_as_float(0x7f800000)) return x;
+    int e = 0;
+    if (x < 1.17549435e-38f) { x = __fmul_rn(x, 8388608.0f); e = -23; }
+    uint32_t b = (uint32_t)__float_as_int(x);
+    e += (int)((b >> 23) & 0xffu) - 126;
+    float m = __int_as_float((int)((b & 0x807fffffu) | 0x3f000000u));
+    if (m < 0.707106781f) { e -= 1; m = __fsub_rn(__fadd_rn(m, m), 1.0f); } else { m = __fsub_rn(m, 1.0f); }
+    float z = __fmul_rn(m, m);
+    float y = 7.0376836292e-2f;
+    y = __fmaf_rn(y, m, -1.1514610310e-1f);
+    y = __fmaf_rn(y, m, 1.1676998740e-1f);
+    y = __fmaf_rn(y, m, -1.2420140846e-1f);
+    y = __fmaf_rn(y, m, 1.4249322787e-1f);
+    y = __fmaf_rn(y, m, -1.6668057665e-1f);
+    y = __fmaf_rn(y, m, 2.0000714765e-1f);
+    y = __fmaf_rn(y, m, -2.4999993993e-1f);
+    y = __fmaf_rn(y, m, 3.3333331174e-1f);
+    y = __fmul_rn(__fmul_rn(y, m), z);
+    float fe = (float)e;
+    y = __fmaf_rn(-2.12194440e-4f, fe, y);
+    y = __fmaf_rn(-0.5f, z, y);
+    float r = __fadd_rn(m, y);
+    r = __fmaf_rn(0.693359375f, fe, r);
+    return r;
+}
+
+// log(1 + u) for any u > -1 (u == -1 -> -inf)
+__device__ __forceinline__ float log1pf_p(float u) {
+    float w = __fadd_rn(1.0f, u);
+    if (w == 1.0f) return u;
+    if (w == 0.0f) return __int_as_float(0xff800000);
+    float l = logf_p(w);
+    float c = __fdiv_rn(__fsub_rn(__fsub_rn(w, 1.0f), u), w);
+    return __fsub_rn(l, c);
+}
+
+__device__ __forceinline__ float sigmoidf_p(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf_p(-x))); }
+__device__ __forceinline__ float powf_p(float b, float e) { return expf_p(__fmul_rn(e, logf_p(b))); }
+
+// ---------------------------------------------------------------------------------------------
+// update rules.  mode 0: torch.optim.Adam, first step with fresh
+// state, lr an fp32 scalar; mode 1: plain SGD p -= lr*g.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float adam1(float p, float g, float lr) {
+    const float bc2s = 0.03162277660168381f;
+    float m = __fmul_rn(0.1f, g);
+    float v = __fmul_rn(__fmul_rn(0.001f, g), g);
+    float d = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2s), 1e-8f);
+    float a = -__fdiv_rn(lr, 0.1f);
+    return __fadd_rn(p, __fdiv_rn(__fmul_rn(a, m), d));
+}
+__device__ __forceinline__ float apply_update(float p, float g, float lr, int mode) {
+    return mode == 0 ? adam1(p, g, lr) : __fsub_rn(p, __fmul_rn(lr, g));
+}
+
+// ---------------------------------------------------------------------------------------------
+// ATen's x86 (AVX2 build, 8 lanes x 4 ilp) sum order of a contiguous fp32 row, evaluated by ONE
+// thread.  Valid for n < 512 (the 16-step cascade never triggers); restates oracle orc_sum_aten.
+// ---------------------------------------------------------------------------------------------
+template <typename Load>
+__device__ __forceinline__ float aten_row_sum_small(Load ld, int n) {
+    if (n < 8) {
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+        int i = 0;
+        if (n >= 4) { p0 = __fadd_rn(p0, ld(0)); p1 = __fadd_rn(p1, ld(1)); p2 = __fadd_rn(p2, ld(2)); p3 = __fadd_rn(p3, ld(3)); i = 4; }
+        for (; i < n; ++i) p0 = __fadd_rn(p0, ld(i));
+        p0 = __fadd_rn(p0, p1); p0 = __fadd_rn(p0, p2); p0 = __fadd_rn(p0, p3);
+        return p0;
+    }
+    const int vec_size = n >> 3, size_ilp = vec_size >> 2;
+    float fin = 0.f;
+    for (int i = vec_size << 3; i < n; ++i) fin = __fadd_rn(fin, ld(i));
+#pragma unroll 1
+    for (int l = 0; l < 8; ++l) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int i = 0; i < size_ilp; ++i) {
+            a0 = __fadd_rn(a0, ld(i * 32 + l));
+            a1 = __fadd_rn(a1, ld(i * 32 + 8 + l));
+            a2 = __fadd_rn(a2, ld(i * 32 + 16 + l));
+            a3 = __fadd_rn(a3, ld(i * 32 + 24 + l));
+        }
+        for (int v = size_ilp << 2; v < vec_size; ++v) a0 = __fadd_rn(a0, ld(v * 8 + l));
+        a0 = __fadd_rn(a0, a1); a0 = __fadd_rn(a0, a2); a0 = __fadd_rn(a0, a3);
+        fin = __fadd_rn(fin, a0);
+    }
+    return fin;
+}
+
+// The same order evaluated by ONE WARP for any n (cascade included): lane a = t*8+l owns
+// accumulator (ilp t, vector lane l) and walks elements a, a+32, a+64, ...  Result in every lane.
+__device__ __forceinline__ float aten_row_sum_warp(const float* __restrict__ x, int64_t n) {
+    const int lane = threadIdx.x & 31;
+    if (n < 8) {
+        float r = 0.f;
+        if (lane == 0) r = aten_row_sum_small([&](int i) { return x[i]; }, (int)n);
+        return __shfl_sync(0xffffffffu, r, 0);
+    }
+    const int64_t vec_size = n >> 3, size_ilp = vec_size >> 2;
+    int lp = 0;
+    while (((int64_t)1 << lp) < size_ilp) ++lp;
+    lp >>= 2;
+    const int level_power = lp > 4 ? lp : 4;
+    const int64_t level_step = (int64_t)1 << level_power, level_mask = level_step - 1;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    int64_t i = 0;
+    while (i + level_step <= size_ilp) {
+        for (int64_t j = 0; j < level_step; ++j, ++i) acc0 = __fadd_rn(acc0, x[i * 32 + lane]);
+        // cascade (uniform control flow: i is warp-uniform)
+        acc1 = __fadd_rn(acc1, acc0); acc0 = 0.f;
+        if ((i & (level_mask << level_power)) == 0) {
+            acc2 = __fadd_rn(acc2, acc1); acc1 = 0.f;
+            if ((i & (level_mask << (2 * level_power))) == 0) { acc3 = __fadd_rn(acc3, acc2); acc2 = 0.f; }
+        }
+    }
+    for (; i < size_ilp; ++i) acc0 = __fadd_rn(acc0, x[i * 32 + lane]);
+    acc0 = __fadd_rn(acc0, acc1); acc0 = __fadd_rn(acc0, acc2); acc0 = __fadd_rn(acc0, acc3);
+    // left-over vectors go to ilp accumulator 0 (lanes 0..7)
+    if (lane < 8)
+        for (int64_t v = size_ilp << 2; v < vec_size; ++v) acc0 = __fadd_rn(acc0, x[v * 8 + lane]);
+    // fold ilp accumulators: ((a0 + a1) + a2) + a3 per vector lane
+    float t1 = __shfl_down_sync(0xffffffffu, acc0, 8);
+    float t2 = __shfl_down_sync(0xffffffffu, acc0, 16);
+    float t3 = __shfl_down_sync(0xffffffffu, acc0, 24);
+    float folded = __fadd_rn(__fadd_rn(__fadd_rn(acc0, t1), t2), t3);  // valid in lanes 0..7
+    float fin = 0.f;
+    for (int64_t k = vec_size << 3; k < n; ++k) fin = __fadd_rn(fin, x[k]);  // scalar tail (uniform)
+#pragma unroll
+    for (int l = 0; l < 8; ++l) fin = __fadd_rn(fin, __shfl_sync(0xffffffffu, folded, l));
+    return fin;
+}
+
+}  // namespace fmb

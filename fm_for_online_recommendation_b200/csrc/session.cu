@@ -1,0 +1,147 @@
+// session.cu -- a training session: owns every temporary of the hot path (device workspaces and
+// pinned host staging) so that one C call performs a whole `update_embedding` / `fit` step.
+//
+// This is the drop-in boundary for the FM training step: the entry points take plain pointers and
+// sizes; `*_host` variants take HOST buffers and do the H2D/D2H copies themselves (what a maintainer
+// of the reference would bind in place of fm_adam.py:56-82 / deepfm_adam.py:91-117).
+#include "fmb_common.cuh"
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+extern "C" {
+int fmb_fm_forward(const int32_t*, const float*, const float*, const float*, int, int, int, float*, float*, float*,
+                   float*, float*, const float*, int, float*, float*, cudaStream_t);
+size_t fmb_sort_workspace_bytes(int64_t);
+int fmb_sort_segment(const int32_t*, int64_t, int, void*, size_t, int32_t*, int32_t*, int32_t*, int32_t*,
+                     cudaStream_t);
+size_t fmb_bwd_workspace_bytes(int64_t);
+int fmb_fm_backward_update(const int32_t*, const int32_t*, int64_t, const float*, float*, int, int, const float*,
+                           const float*, int, const float*, float, int, void*, size_t, cudaStream_t);
+int fmb_finish_step(const float*, const float*, int, float*, float, int, float*, cudaStream_t);
+}
+
+struct fmb_session {
+    int F, k, rowp, kp4;
+    int64_t maxB;
+    // device
+    int32_t* d_ids;
+    float* d_xv;
+    float* d_y;
+    float* d_S;
+    float* d_z;
+    float* d_delta;
+    float* d_lossv;
+    float* d_loss;
+    int32_t* d_skeys;
+    int32_t* d_perm;
+    void* d_sort_ws;
+    size_t sort_ws_bytes;
+    void* d_bwd_ws;
+    size_t bwd_ws_bytes;
+    // pinned host staging
+    int32_t* h_ids;
+    float* h_xv;
+    float* h_y;
+    float* h_loss;
+    int64_t launches;  // kernels launched through this session (bench.py's gpu_launches)
+};
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) { fmb_set_error("%s: %s", #call, cudaGetErrorString(e__)); return FMB_ERR_CUDA; } \
+    } while (0)
+
+FMB_API void fmb_session_destroy(fmb_session* s) {
+    if (!s) return;
+    cudaFree(s->d_ids); cudaFree(s->d_xv); cudaFree(s->d_y); cudaFree(s->d_S); cudaFree(s->d_z);
+    cudaFree(s->d_delta); cudaFree(s->d_lossv); cudaFree(s->d_loss); cudaFree(s->d_skeys); cudaFree(s->d_perm);
+    cudaFree(s->d_sort_ws); cudaFree(s->d_bwd_ws);
+    cudaFreeHost(s->h_ids); cudaFreeHost(s->h_xv); cudaFreeHost(s->h_y); cudaFreeHost(s->h_loss);
+    delete s;
+}
+
+// F fields, embedding size k, up to max_batch samples per step.
+FMB_API int fmb_session_create(fmb_session** out, int F, int k, int64_t max_batch) {
+    FMB_CHECK_ARG(out && F > 0 && k > 0 && max_batch > 0, "fmb_session_create: bad arguments");
+    FMB_CHECK_ARG(max_batch * F < ((int64_t)1 << 31), "fmb_session_create: max_batch*F must fit int32");
+    fmb_session* s = new (std::nothrow) fmb_session();
+    FMB_CHECK_ARG(s, "fmb_session_create: out of host memory");
+    memset(s, 0, sizeof(*s));
+    s->F = F; s->k = k; s->rowp = fmb_round_up(k + 1, 4); s->kp4 = fmb_round_up(k, 4); s->maxB = max_batch;
+    const int64_t N = max_batch * F;
+    s->sort_ws_bytes = fmb_sort_workspace_bytes(N);
+    s->bwd_ws_bytes = fmb_bwd_workspace_bytes(N);
+    cudaError_t e = cudaSuccess;
+    auto dm = [&](void** p, size_t n) { if (e == cudaSuccess) e = cudaMalloc(p, n); };
+    auto hm = [&](void** p, size_t n) { if (e == cudaSuccess) e = cudaMallocHost(p, n); };
+    dm((void**)&s->d_ids, N * 4); dm((void**)&s->d_xv, N * 4); dm((void**)&s->d_y, max_batch * 4);
+    dm((void**)&s->d_S, max_batch * s->kp4 * 4); dm((void**)&s->d_z, max_batch * 4);
+    dm((void**)&s->d_delta, max_batch * 4); dm((void**)&s->d_lossv, max_batch * 4); dm((void**)&s->d_loss, 256);
+    dm((void**)&s->d_skeys, N * 4); dm((void**)&s->d_perm, N * 4);
+    dm(&s->d_sort_ws, s->sort_ws_bytes); dm(&s->d_bwd_ws, s->bwd_ws_bytes);
+    hm((void**)&s->h_ids, N * 4); hm((void**)&s->h_xv, N * 4); hm((void**)&s->h_y, max_batch * 4);
+    hm((void**)&s->h_loss, 256);
+    if (e != cudaSuccess) {
+        fmb_set_error("fmb_session_create: %s", cudaGetErrorString(e));
+        fmb_session_destroy(s);
+        return FMB_ERR_CUDA;
+    }
+    *out = s;
+    return FMB_OK;
+}
+
+FMB_API int64_t fmb_session_launches(const fmb_session* s) { return s ? s->launches : 0; }
+
+// One FM-only training step with DEVICE inputs (FMAdam.update_embedding/fit, and the
+// update_embedding of DeepFM/NFM/ONN classes whose loss is on forward_fm only).
+//   loss_kind 0: BCEWithLogits(z_fm)   (fm_adam.py:66, deepfm_adam.py:101, deepfm_onn.py:166)
+//   loss_kind 1: BCEWithLogits(sigmoid(z_fm))   (fm_adam.py:80, nfm_adam.py:100, nfm_onn.py:168)
+//   loss_dev (nullable): receives the mean loss (device scalar).
+FMB_API int fmb_session_fm_step(fmb_session* s, const int32_t* ids, const float* xv, const float* y, int B,
+                                float* table, float* bias, int key_bits, int loss_kind, float lr, int mode,
+                                float* loss_dev, cudaStream_t stream) {
+    FMB_CHECK_ARG(s && ids && y && table && bias, "fmb_session_fm_step: null pointer");
+    FMB_CHECK_ARG(B > 0 && B <= s->maxB, "fmb_session_fm_step: B=%d exceeds session max_batch", B);
+    const int64_t N = (int64_t)B * s->F;
+    int rc = fmb_fm_forward(ids, xv, table, bias, B, s->F, s->k, nullptr, s->d_S, nullptr, nullptr, s->d_z, y,
+                            loss_kind, s->d_delta, s->d_lossv, stream);
+    if (rc) return rc;
+    rc = fmb_sort_segment(ids, N, key_bits, s->d_sort_ws, s->sort_ws_bytes, s->d_skeys, s->d_perm, nullptr, nullptr,
+                          stream);
+    if (rc) return rc;
+    rc = fmb_fm_backward_update(s->d_skeys, s->d_perm, N, xv, table, s->F, s->k, s->d_S, s->d_delta, 1, nullptr, lr,
+                                mode, s->d_bwd_ws, s->bwd_ws_bytes, stream);
+    if (rc) return rc;
+    rc = fmb_finish_step(s->d_delta, s->d_lossv, B, bias, lr, mode, loss_dev ? loss_dev : s->d_loss, stream);
+    if (rc) return rc;
+    s->launches += 1 + 3 * ((key_bits + 7) / 8) + 2 + 1;
+    return FMB_OK;
+}
+
+// Same step with HOST inputs: copies ids/xv/y in (xv_host NULL = all ones, nothing copied), runs
+// the step, copies the loss back and waits for it.  Bytes moved per step: H2D 4*B*F (+4*B*F) + 4*B,
+// D2H 4.
+FMB_API int fmb_session_fm_step_host(fmb_session* s, const int32_t* ids_host, const float* xv_host,
+                                     const float* y_host, int B, float* table, float* bias, int key_bits,
+                                     int loss_kind, float lr, int mode, float* loss_host, cudaStream_t stream) {
+    FMB_CHECK_ARG(s && ids_host && y_host && table && bias, "fmb_session_fm_step_host: null pointer");
+    FMB_CHECK_ARG(B > 0 && B <= s->maxB, "fmb_session_fm_step_host: B=%d exceeds session max_batch", B);
+    const size_t N = (size_t)B * s->F;
+    memcpy(s->h_ids, ids_host, N * 4);
+    memcpy(s->h_y, y_host, (size_t)B * 4);
+    CU(cudaMemcpyAsync(s->d_ids, s->h_ids, N * 4, cudaMemcpyHostToDevice, stream));
+    CU(cudaMemcpyAsync(s->d_y, s->h_y, (size_t)B * 4, cudaMemcpyHostToDevice, stream));
+    if (xv_host) {
+        memcpy(s->h_xv, xv_host, N * 4);
+        CU(cudaMemcpyAsync(s->d_xv, s->h_xv, N * 4, cudaMemcpyHostToDevice, stream));
+    }
+    int rc = fmb_session_fm_step(s, s->d_ids, xv_host ? s->d_xv : nullptr, s->d_y, B, table, bias, key_bits,
+                                 loss_kind, lr, mode, s->d_loss, stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(s->h_loss, s->d_loss, 4, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    if (loss_host) *loss_host = s->h_loss[0];
+    return FMB_OK;
+}

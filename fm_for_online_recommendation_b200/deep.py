@@ -1,0 +1,571 @@
+"""Drop-in replacements for the reference's deep FM family (models/models_online_deep/*.py).
+
+Same class names, constructor kwargs, method names, argument meaning and return types as
+`FMAdam` (fm_adam.py), `DeepFMAdam` (deepfm_adam.py), `NFMAdam` (nfm_adam.py), `DeepFMOnn`
+(deepfm_onn.py) and `NFMOnn` (nfm_onn.py); every method body is a call sequence into
+lib/libfmb200.so (include/fmb200.h).  There is no CPU path: constructing a model without a visible
+CUDA device raises `FmbError`.
+
+Layout: one packed device table [R, rowp] (rowp = round_up(k+1, 4)) holds, per global row, the
+second-order embedding (k floats), the first-order weight and padding.
+`second_order_embeddings[f].weight` / `first_order_embeddings[f].weight` are strided Parameter
+views into it, `hidden_layers[l].weight/.bias` are views into one flat MLP buffer, so
+`parameters()`, `state_dict()`, `str()` and `pickle` keep working.
+
+Semantics follow the reference's CPU path (`use_cuda=False`): the bias IS trained (SURVEY.md
+fact 6); "Adam" is the per-call fresh-state sign step (fact 1).
+"""
+import ctypes as C
+from time import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import FmbError, check, ptr
+
+UPDATE_ADAM1, UPDATE_SGD = 0, 1
+LOSS_LOGITS, LOSS_LOGITS_OF_SIG = 0, 1
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class EncodedBatch:
+    """Device-resident inputs: ids int32 [B,F] global row ids, xv fp32 [B,F] or None
+    (all ones), y fp32 [B] or None."""
+
+    __slots__ = ("ids", "xv", "y", "B")
+
+    def __init__(self, ids, xv, y):
+        self.ids, self.xv, self.y, self.B = ids, xv, y, ids.shape[0]
+
+
+class _ViewEmbedding(nn.Embedding):
+    """nn.Embedding whose weight is a strided view into the packed table (no separate storage)."""
+
+    def __init__(self, view):
+        nn.Module.__init__(self)
+        self.num_embeddings, self.embedding_dim = view.shape
+        self.padding_idx = None
+        self.max_norm = None
+        self.norm_type = 2.0
+        self.scale_grad_by_freq = False
+        self.sparse = False
+        self.weight = nn.Parameter(view, requires_grad=True)
+
+
+class _ViewLinear(nn.Linear):
+    def __init__(self, wview, bview):
+        nn.Module.__init__(self)
+        self.out_features, self.in_features = wview.shape
+        self.weight = nn.Parameter(wview, requires_grad=True)
+        self.bias = nn.Parameter(bview, requires_grad=True)
+
+
+def _rebuild(cls, kwargs, state):
+    m = cls(**kwargs)
+    m._load_packed_state(state)
+    return m
+
+
+class _DeepBase(nn.Module):
+    _NAME = ""
+    _HAS_MLP = True
+    _IS_ONN = False
+    _IS_NFM = False
+
+    # ------------------------------------------------------------------ construction
+    def _setup(self, feature_sizes, embedding_size, num_hidden_layers, neuron_per_hidden_layer, batch_size,
+               num_classes, b, n, s, use_cuda, update_mode):
+        self._lib = _lib.require_cuda()  # raises: no CPU fallback
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.field_size = len(feature_sizes)
+        self.feature_sizes = feature_sizes
+        self.embedding_size = embedding_size
+        self.num_classes = num_classes
+        self.dtype = torch.long
+        self.update_mode = update_mode
+        F, k = self.field_size, embedding_size
+        if self._HAS_MLP:
+            self.num_hidden_layers = num_hidden_layers
+            self.neuron_per_hidden_layer = neuron_per_hidden_layer
+        self._L = num_hidden_layers if self._HAS_MLP else 0
+        self._H = neuron_per_hidden_layer if self._HAS_MLP else 0
+        if self._HAS_MLP and not (self._IS_NFM and not self._IS_ONN):
+            self.batch_size = batch_size  # NFMAdam has no batch_size attribute (nfm_adam.py:13-27)
+        self._batch_size = batch_size
+        self._rowp = self._lib.fmb_rowp(k)
+        self._kp4 = self._lib.fmb_kp4(k)
+        sizes = np.asarray(list(feature_sizes), dtype=np.int64)
+        self._offsets_np = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        self._R = int(self._offsets_np[-1])
+        if self._R >= 2 ** 31:
+            raise ValueError("total rows must fit int32")
+        self._key_bits = max(1, int(self._R - 1).bit_length())
+        self._offsets_dev = torch.from_numpy(self._offsets_np[:-1].copy()).to(self.device)
+
+        # parameters are drawn on the CPU in the reference's order so torch.manual_seed(s) gives the
+        # same initial model as the reference (fm_adam.py:26-32, deepfm_onn.py:30-53)
+        if self._IS_ONN:
+            bias0 = torch.rand(1)                       # deepfm_onn.py:30
+        else:
+            bias0 = torch.tensor(b)                     # fm_adam.py:26
+        self.bias = nn.Parameter(bias0.to(self.device))
+        if self._IS_ONN:
+            self.b = nn.Parameter(torch.tensor(b).to(self.device))
+        self.n = nn.Parameter(torch.tensor(n).to(self.device), requires_grad=False)
+        if self._IS_ONN:
+            self.s = nn.Parameter(torch.tensor(s).to(self.device), requires_grad=False)
+        self._lr = float(np.float32(n))
+        self._hb = float(np.float32(b))
+        self._hs = float(np.float32(s))
+
+        table = torch.zeros(self._R, self._rowp, dtype=torch.float32)
+        fo = [nn.Embedding(int(fs), 1) for fs in sizes]
+        so = [nn.Embedding(int(fs), k) for fs in sizes]
+        with torch.no_grad():
+            for f in range(F):
+                lo, hi = int(self._offsets_np[f]), int(self._offsets_np[f + 1])
+                table[lo:hi, :k] = so[f].weight
+                table[lo:hi, k] = fo[f].weight[:, 0]
+        del fo, so
+        self._table = table.to(self.device)
+        self._bind_embeddings()
+
+        if self._HAS_MLP:
+            lins = [nn.Linear(k, self._H)] + [nn.Linear(self._H, self._H) for _ in range(self._L - 1)]
+            flat = torch.cat([torch.cat([l.weight.detach().reshape(-1), l.bias.detach()]) for l in lins])
+            self._mlp = flat.to(self.device).contiguous()
+            self._bind_mlp()
+        else:
+            self._mlp = None
+        if self._IS_ONN:
+            self.alpha = nn.Parameter(torch.full((self._L,), 1.0 / (self._L + 1), device=self.device),
+                                      requires_grad=False)
+        self._session = None
+        self._session_cap = 0
+        self._ws = {}
+
+    def _bind_embeddings(self):
+        k = self.embedding_size
+        fo, so = [], []
+        for f in range(self.field_size):
+            lo, hi = int(self._offsets_np[f]), int(self._offsets_np[f + 1])
+            so.append(_ViewEmbedding(self._table[lo:hi, :k]))
+            fo.append(_ViewEmbedding(self._table[lo:hi, k:k + 1]))
+        self.first_order_embeddings = nn.ModuleList(fo)
+        self.second_order_embeddings = nn.ModuleList(so)
+
+    def _bind_mlp(self):
+        k, H = self.embedding_size, self._H
+        mods, o = [], 0
+        for l in range(self._L):
+            nin = k if l == 0 else H
+            w = self._mlp[o:o + H * nin].view(H, nin)
+            o += H * nin
+            c = self._mlp[o:o + H]
+            o += H
+            mods.append(_ViewLinear(w, c))
+        self.hidden_layers = nn.ModuleList(mods)
+
+    # ------------------------------------------------------------------ persistence
+    def _ctor_kwargs(self):
+        raise NotImplementedError
+
+    def _export_state(self):
+        st = {"table": self._table.detach().cpu(), "bias": self.bias.detach().cpu()}
+        if self._mlp is not None:
+            st["mlp"] = self._mlp.detach().cpu()
+        if self._IS_ONN:
+            st["alpha"] = self.alpha.detach().cpu()
+        return st
+
+    def _load_packed_state(self, st):
+        with torch.no_grad():
+            self._table.copy_(st["table"])
+            self.bias.copy_(st["bias"])
+            if self._mlp is not None:
+                self._mlp.copy_(st["mlp"])
+            if self._IS_ONN:
+                self.alpha.copy_(st["alpha"])
+
+    def __reduce__(self):  # pickle.dump(model) (main_experiment.py:160-162): one copy of the table, no handles
+        return (_rebuild, (type(self), self._ctor_kwargs(), self._export_state()))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_session", None):
+                self._lib.fmb_session_destroy(self._session)
+                self._session = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ inputs
+    def encode(self, Xi, Xv=None, Y=None):
+        """lists / ndarrays / tensors -> EncodedBatch on the device. Xi holds per-field local ids."""
+        if isinstance(Xi, EncodedBatch):
+            return Xi
+        F = self.field_size
+        if torch.is_tensor(Xi):
+            ids = (Xi.to(self.device).reshape(-1, F).to(torch.int64) + self._offsets_dev).to(torch.int32)
+        else:
+            a = np.asarray(Xi, dtype=np.int64).reshape(-1, F)
+            if a.size and (a.min() < 0 or (a >= (self._offsets_np[1:] - self._offsets_np[:-1])[None, :]).any()):
+                raise IndexError("index out of range in self")  # what nn.Embedding raises in the reference
+            ids = torch.from_numpy((a + self._offsets_np[:-1][None, :]).astype(np.int32)).to(self.device)
+        ids = ids.contiguous()
+        xv = None
+        if Xv is not None:
+            if torch.is_tensor(Xv):
+                xv = Xv.to(self.device, torch.float32).reshape(-1, F).contiguous()
+            else:
+                v = np.asarray(Xv, dtype=np.float32).reshape(-1, F)
+                if not np.all(v == 1.0):  # all-ones values (Criteo, data_preprocess.py:41) need no upload
+                    xv = torch.from_numpy(np.ascontiguousarray(v)).to(self.device)
+        y = None
+        if Y is not None:
+            if torch.is_tensor(Y):
+                y = Y.to(self.device, torch.float32).reshape(-1).contiguous()
+            else:
+                y = torch.from_numpy(np.asarray(Y, dtype=np.float32).reshape(-1)).to(self.device)
+        return EncodedBatch(ids, xv, y)
+
+    def _get_session(self, B):
+        if self._session is None or B > self._session_cap:
+            if self._session is not None:
+                torch.cuda.synchronize()
+                self._lib.fmb_session_destroy(self._session)
+            cap = max(B, 1)
+            h = C.c_void_p()
+            check(self._lib.fmb_session_create(C.byref(h), self.field_size, self.embedding_size, cap),
+                  "fmb_session_create")
+            self._session, self._session_cap = h, cap
+        return self._session
+
+    def _buf(self, name, shape, dtype=torch.float32):
+        t = self._ws.get(name)
+        n = int(np.prod(shape))
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._ws[name] = t
+        return t[:n].view(*shape)
+
+    # ------------------------------------------------------------------ forward pieces (A1-A5)
+    def _fm_forward(self, e, first=False, S=False, bi=False, sum_first=False, z=True):
+        B, F, k = e.B, self.field_size, self.embedding_size
+        out = {}
+        if first:
+            out["first"] = torch.empty(B, F, device=self.device)
+        if S:
+            out["S"] = self._buf("S", (B, self._kp4))
+        if bi:
+            out["bi"] = torch.empty(B, k, device=self.device)
+        if sum_first:
+            out["sum_first"] = self._buf("sum_first", (B,))
+        if z:
+            out["z"] = torch.empty(B, device=self.device)
+        check(self._lib.fmb_fm_forward(ptr(e.ids), ptr(e.xv), ptr(self._table), ptr(self.bias), B, F, k,
+                                       ptr(out.get("first")), ptr(out.get("S")), ptr(out.get("bi")),
+                                       ptr(out.get("sum_first")), ptr(out.get("z")), None, 0, None, None, _stream()),
+              "fmb_fm_forward")
+        return out
+
+    def first_order(self, Xi, Xv):
+        return self._fm_forward(self.encode(Xi, Xv), first=True, z=False)["first"]
+
+    def second_order(self, Xi, Xv):
+        return self._fm_forward(self.encode(Xi, Xv), bi=True, z=False)["bi"]
+
+    def forward_fm(self, Xi, Xv):
+        return self._fm_forward(self.encode(Xi, Xv))["z"]
+
+    def _mlp_forward(self, bi, B):
+        L, H, k = self._L, self._H, self.embedding_size
+        act = self._buf("act", (L, B, H))
+        head = self._buf("head", (L, B))
+        check(self._lib.fmb_mlp_forward(ptr(bi), k, ptr(self._mlp), B, k, L, H, ptr(act), ptr(head), _stream()),
+              "fmb_mlp_forward")
+        return act, head
+
+    def _full_forward(self, e, need_S=False):
+        """returns dict with z (logit, or last-head probability for ONN) and the intermediates."""
+        if not self._HAS_MLP:
+            o = self._fm_forward(e, S=need_S)
+            return o
+        o = self._fm_forward(e, S=need_S, bi=True, sum_first=True)
+        B = e.B
+        act, head = self._mlp_forward(o["bi"], B)
+        o["act"], o["head"] = act, head
+        nfm = 1 if self._IS_NFM else 0
+        if self._IS_ONN:
+            p = torch.empty(self._L, B, device=self.device)
+            check(self._lib.fmb_onn_heads(nfm, ptr(o["z"]), ptr(o["sum_first"]), ptr(self.bias), ptr(head), self._L,
+                                          B, ptr(p), _stream()), "fmb_onn_heads")
+            o["players"] = p
+            o["z_fm"], o["z"] = o["z"], p[self._L - 1]
+        else:
+            z = torch.empty(B, device=self.device)
+            check(self._lib.fmb_combine_logit(nfm, ptr(o["z"]), ptr(o["sum_first"]), ptr(self.bias),
+                                              ptr(head[self._L - 1]), B, ptr(z), _stream()), "fmb_combine_logit")
+            o["z_fm"], o["z"] = o["z"], z
+        return o
+
+    def forward(self, Xi, Xv):
+        o = self._full_forward(self.encode(Xi, Xv))
+        if self._IS_ONN:
+            return o["z"], o["players"]
+        return o["z"]
+
+    # ------------------------------------------------------------------ training steps (A6, A7)
+    def _fm_step(self, e, loss_kind):
+        if e.y is None:
+            raise ValueError("labels required")
+        s = self._get_session(e.B)
+        loss = torch.empty((), device=self.device)
+        check(self._lib.fmb_session_fm_step(s, ptr(e.ids), ptr(e.xv), ptr(e.y), e.B, ptr(self._table), ptr(self.bias),
+                                            self._key_bits, loss_kind, self._lr, self.update_mode, ptr(loss),
+                                            _stream()), "fmb_session_fm_step")
+        return loss
+
+    _UE_LOSS = LOSS_LOGITS
+    _FIT_LOSS = LOSS_LOGITS_OF_SIG
+
+    def update_embedding(self, Xi, Xv, Y):
+        """fm_adam.py:56-69 and the same method of the other four classes: loss on forward_fm only."""
+        self.train()
+        return self._fm_step(self.encode(Xi, Xv, Y), self._UE_LOSS)
+
+    def _sort(self, e):
+        N = e.B * self.field_size
+        wsb = self._lib.fmb_sort_workspace_bytes(N)
+        ws = self._buf("sort_ws", (wsb,), torch.uint8)
+        sk = self._buf("skeys", (N,), torch.int32)
+        pm = self._buf("perm", (N,), torch.int32)
+        check(self._lib.fmb_sort_segment(ptr(e.ids), N, self._key_bits, ptr(ws), wsb, ptr(sk), ptr(pm), None, None,
+                                         _stream()), "fmb_sort_segment")
+        return sk, pm
+
+    def _deep_fit(self, e):
+        """DeepFMAdam.fit / NFMAdam.fit (deepfm_adam.py:106-117, nfm_adam.py:105-116)."""
+        B, F, k, L, H = e.B, self.field_size, self.embedding_size, self._L, self._H
+        lib, st = self._lib, _stream()
+        o = self._full_forward(e, need_S=True)
+        delta = self._buf("delta", (B,))
+        check(lib.fmb_loss_delta(self._FIT_LOSS, ptr(o["z"]), ptr(e.y), B, ptr(delta), None, st), "fmb_loss_delta")
+        gmlp = self._buf("gmlp", (self._mlp.numel(),))
+        gbi = self._buf("gbi", (B, self._kp4))
+        wsb = lib.fmb_mlp_bwd_workspace_bytes(B, H)
+        ws = self._buf("mlp_ws", (wsb,), torch.uint8)
+        check(lib.fmb_mlp_backward(ptr(o["bi"]), k, ptr(self._mlp), ptr(o["act"]), ptr(delta), L - 1, B, k, L, H,
+                                   ptr(gmlp), ptr(gbi), self._kp4, ptr(ws), wsb, st), "fmb_mlp_backward")
+        sk, pm = self._sort(e)
+        N = B * F
+        bwsb = lib.fmb_bwd_workspace_bytes(N)
+        bws = self._buf("bwd_ws", (bwsb,), torch.uint8)
+        check(lib.fmb_fm_backward_update(ptr(sk), ptr(pm), N, ptr(e.xv), ptr(self._table), F, k, ptr(o["S"]),
+                                         ptr(delta), 0 if self._IS_NFM else 1, ptr(gbi), self._lr, self.update_mode,
+                                         ptr(bws), bwsb, st), "fmb_fm_backward_update")
+        check(lib.fmb_update_dense(ptr(self._mlp), ptr(gmlp), self._mlp.numel(), self._lr, self.update_mode, st),
+              "fmb_update_dense")
+        check(lib.fmb_finish_step(ptr(delta), None, B, ptr(self.bias), self._lr, self.update_mode, None, st),
+              "fmb_finish_step")
+
+    def _hedge_fit(self, e):
+        """DeepFMOnn.fit / NFMOnn.fit (deepfm_onn.py:109-154): hedge backpropagation; only the tower and
+        alpha change."""
+        B, k, L, H = e.B, self.embedding_size, self._L, self._H
+        if B != self._batch_size:
+            raise RuntimeError(f"shape '[{self._batch_size}]' is invalid for input of size {B}")  # out.view(batch_size)
+        lib, st = self._lib, _stream()
+        o = self._full_forward(e)
+        gtop = self._buf("delta", (B,))
+        lossv = self._buf("lossv", (B,))
+        loss_sum = self._buf("loss_sum", (L,))
+        gmlp = self._buf("gmlp", (self._mlp.numel(),))
+        acc = self._buf("hedge_acc", (self._mlp.numel(),))
+        wsb = lib.fmb_mlp_bwd_workspace_bytes(B, H)
+        ws = self._buf("mlp_ws", (wsb,), torch.uint8)
+        for i in range(L):
+            check(lib.fmb_hedge_head_grad(ptr(o["players"][i]), ptr(e.y), B, ptr(gtop), ptr(lossv), st),
+                  "fmb_hedge_head_grad")
+            check(lib.fmb_sum_aten(ptr(lossv), B, ptr(loss_sum[i:]), st), "fmb_sum_aten")
+            check(lib.fmb_mlp_backward(ptr(o["bi"]), k, ptr(self._mlp), ptr(o["act"]), ptr(gtop), i, B, k, L, H,
+                                       ptr(gmlp), None, 0, ptr(ws), wsb, st), "fmb_mlp_backward")
+            check(lib.fmb_hedge_accumulate(ptr(acc), ptr(gmlp), ptr(self.alpha), i, k, L, H, st),
+                  "fmb_hedge_accumulate")
+        check(lib.fmb_hedge_apply(ptr(self._mlp), ptr(acc), self._lr, ptr(self.alpha), ptr(loss_sum), B, k, L, H,
+                                  self._hb, self._hs, st), "fmb_hedge_apply")
+
+    def fit(self, Xi, Xv, Y):
+        self.train()
+        e = self.encode(Xi, Xv, Y)
+        if e.y is None:
+            raise ValueError("labels required")
+        if not self._HAS_MLP:
+            self._fm_step(e, self._FIT_LOSS)
+        elif self._IS_ONN:
+            self._hedge_fit(e)
+        else:
+            self._deep_fit(e)
+
+    # ------------------------------------------------------------------ predict / online loop (A8)
+    def _predict_dev(self, e):
+        z = self._full_forward(e)["z"].contiguous()
+        out = torch.empty(e.B, dtype=torch.uint8, device=self.device)
+        check(self._lib.fmb_predict(ptr(z), e.B, ptr(out), _stream()), "fmb_predict")
+        return out
+
+    def predict(self, Xi, Xv):
+        self.eval()
+        return self._predict_dev(self.encode(Xi, Xv)).cpu().numpy().astype(bool)
+
+    def run_experiment(self, data_Xi, data_Xv, data_Y):
+        """fm_adam.py:90-119: strictly sequential predict-then-fit per example."""
+        data_size = len(data_Y)
+        confusion_matrix = {"tp": 0, "fp": 0, "tn": 0, "fn": 0}
+        accuracy = []
+        roc = []
+        start = time()
+        enc = self.encode(data_Xi, data_Xv, data_Y)
+        labels = np.asarray(data_Y).reshape(-1)
+        preds_dev = torch.empty(data_size, dtype=torch.uint8, device=self.device)
+        for i in range(data_size):
+            e = EncodedBatch(enc.ids[i:i + 1], None if enc.xv is None else enc.xv[i:i + 1], enc.y[i:i + 1])
+            preds_dev[i:i + 1] = self._predict_dev(e)
+            self.fit(e, None, None)
+        preds = preds_dev.cpu().numpy().astype(bool)
+        for i in range(data_size):
+            pred = preds[i]
+            if pred == labels[i]:
+                if labels[i] == 1:
+                    confusion_matrix["tp"] += 1
+                else:
+                    confusion_matrix["tn"] += 1
+            else:
+                if labels[i] == 1:
+                    confusion_matrix["fn"] += 1
+                else:
+                    confusion_matrix["fp"] += 1
+            if i % 1000 == 0 or i == data_size - 1:
+                tpr = confusion_matrix['tp'] / (confusion_matrix['tp'] + confusion_matrix['fn'] + 1e-16)
+                fpr = confusion_matrix['fp'] / (confusion_matrix['fp'] + confusion_matrix['tn'] + 1e-16)
+                roc.append({'tpr': tpr, 'fpr': fpr})
+                accuracy.append(((confusion_matrix['tp'] + confusion_matrix['tn']) / (i + 1) * 100))
+        time_elapsed = time() - start
+        return time_elapsed, accuracy[-1], roc[-1], confusion_matrix
+
+
+class FMAdam(_DeepBase):
+    """fm_adam.py:12-123."""
+    _HAS_MLP = False
+
+    def __init__(self, feature_sizes, embedding_size=4, num_classes=1, b=0.99, n=0.01, use_cuda=True,
+                 update_mode=UPDATE_ADAM1):
+        super().__init__()
+        self._kw = dict(feature_sizes=feature_sizes, embedding_size=embedding_size, num_classes=num_classes, b=b,
+                        n=n, use_cuda=use_cuda, update_mode=update_mode)
+        self._setup(feature_sizes, embedding_size, 0, 0, 1, num_classes, b, n, 0.2, use_cuda, update_mode)
+
+    def _ctor_kwargs(self):
+        return self._kw
+
+    def __str__(self):
+        return f"FMAdam-Feature_Sizes{self.feature_sizes}-Embedding_Sizes{self.embedding_size}-" \
+               f"Num_Classes{self.num_classes}"
+
+
+class DeepFMAdam(_DeepBase):
+    """deepfm_adam.py:12-159."""
+
+    def __init__(self, feature_sizes, embedding_size=4, num_hidden_layers=2, neuron_per_hidden_layer=32,
+                 batch_size=1, num_classes=1, b=0.99, n=0.01, use_cuda=True, update_mode=UPDATE_ADAM1):
+        super().__init__()
+        self._kw = dict(feature_sizes=feature_sizes, embedding_size=embedding_size,
+                        num_hidden_layers=num_hidden_layers, neuron_per_hidden_layer=neuron_per_hidden_layer,
+                        batch_size=batch_size, num_classes=num_classes, b=b, n=n, use_cuda=use_cuda,
+                        update_mode=update_mode)
+        self._setup(feature_sizes, embedding_size, num_hidden_layers, neuron_per_hidden_layer, batch_size,
+                    num_classes, b, n, 0.2, use_cuda, update_mode)
+
+    def _ctor_kwargs(self):
+        return self._kw
+
+    def __str__(self):
+        return f"DeepFMAdam-Feature_Sizes{self.feature_sizes}-Embedding_Sizes{self.embedding_size}-" \
+               f"Num_Hidden_Layers{self.num_hidden_layers}-Neuron_Per_Hidden_Layer{self.neuron_per_hidden_layer}-" \
+               f"Num_Classes{self.num_classes}"
+
+
+class NFMAdam(_DeepBase):
+    """nfm_adam.py:12-158: update_embedding uses BCEWL(sigmoid(z_fm)) (:100), fit uses BCEWL(z) (:114)."""
+    _IS_NFM = True
+    _UE_LOSS = LOSS_LOGITS_OF_SIG
+    _FIT_LOSS = LOSS_LOGITS
+
+    def __init__(self, feature_sizes, embedding_size=4, num_hidden_layers=2, neuron_per_hidden_layer=32,
+                 num_classes=1, b=0.99, n=0.01, use_cuda=True, update_mode=UPDATE_ADAM1):
+        super().__init__()
+        self._kw = dict(feature_sizes=feature_sizes, embedding_size=embedding_size,
+                        num_hidden_layers=num_hidden_layers, neuron_per_hidden_layer=neuron_per_hidden_layer,
+                        num_classes=num_classes, b=b, n=n, use_cuda=use_cuda, update_mode=update_mode)
+        self._setup(feature_sizes, embedding_size, num_hidden_layers, neuron_per_hidden_layer, 1, num_classes, b, n,
+                    0.2, use_cuda, update_mode)
+
+    def _ctor_kwargs(self):
+        return self._kw
+
+    def __str__(self):
+        return f"NFMAdam-Feature_Sizes{self.feature_sizes}-Embedding_Sizes{self.embedding_size}-" \
+               f"Num_Hidden_Layers{self.num_hidden_layers}-Neuron_Per_Hidden_Layer{self.neuron_per_hidden_layer}-" \
+               f"Num_Classes{self.num_classes}"
+
+
+class DeepFMOnn(_DeepBase):
+    """deepfm_onn.py:12-210 (hedge backpropagation)."""
+    _IS_ONN = True
+
+    def __init__(self, feature_sizes, embedding_size=4, num_hidden_layers=2, neuron_per_hidden_layer=32,
+                 batch_size=1, num_classes=1, b=0.99, n=0.01, s=0.2, use_cuda=True, update_mode=UPDATE_ADAM1):
+        super().__init__()
+        self._kw = dict(feature_sizes=feature_sizes, embedding_size=embedding_size,
+                        num_hidden_layers=num_hidden_layers, neuron_per_hidden_layer=neuron_per_hidden_layer,
+                        batch_size=batch_size, num_classes=num_classes, b=b, n=n, s=s, use_cuda=use_cuda,
+                        update_mode=update_mode)
+        self._setup(feature_sizes, embedding_size, num_hidden_layers, neuron_per_hidden_layer, batch_size,
+                    num_classes, b, n, s, use_cuda, update_mode)
+
+    def _ctor_kwargs(self):
+        return self._kw
+
+    def __str__(self):
+        return f"DeepFMOnn-Feature_Sizes{self.feature_sizes}-Embedding_Sizes{self.embedding_size}-" \
+               f"Num_Hidden_Layers{self.num_hidden_layers}-Neuron_Per_Hidden_Layer{self.neuron_per_hidden_layer}-" \
+               f"Num_Classes{self.num_classes}-N{self.n}"
+
+
+class NFMOnn(_DeepBase):
+    """nfm_onn.py:13-212. Positional order is (..., num_classes, batch_size, ...) here (nfm_onn.py:14-15)."""
+    _IS_ONN = True
+    _IS_NFM = True
+    _UE_LOSS = LOSS_LOGITS_OF_SIG
+
+    def __init__(self, feature_sizes, embedding_size=4, num_hidden_layers=2, neuron_per_hidden_layer=32,
+                 num_classes=1, batch_size=1, b=0.99, n=0.01, s=0.2, use_cuda=True, update_mode=UPDATE_ADAM1):
+        super().__init__()
+        self._kw = dict(feature_sizes=feature_sizes, embedding_size=embedding_size,
+                        num_hidden_layers=num_hidden_layers, neuron_per_hidden_layer=neuron_per_hidden_layer,
+                        num_classes=num_classes, batch_size=batch_size, b=b, n=n, s=s, use_cuda=use_cuda,
+                        update_mode=update_mode)
+        self._setup(feature_sizes, embedding_size, num_hidden_layers, neuron_per_hidden_layer, batch_size,
+                    num_classes, b, n, s, use_cuda, update_mode)
+
+    def _ctor_kwargs(self):
+        return self._kw
+
+    def __str__(self):
+        return f"NFMOnn-Feature_Sizes{self.feature_sizes}-Embedding_Sizes{self.embedding_size}-" \
+               f"Num_Hidden_Layers{self.num_hidden_layers}-Neuron_Per_Hidden_Layer{self.neuron_per_hidden_layer}-" \
+               f"Num_Classes{self.num_classes}-N{self.n}"

@@ -1,0 +1,144 @@
+/*
+ * fmb200.h -- C ABI of libfmb200.so, the B200 (sm_100a) implementation of the FM-family training
+ * hot path of haan6/fm-for-online-recommendation.
+ *
+ * The reference has no FFI layer: its hot path is the Python method surface of
+ * models/models_online_deep/*.py and models/models_online/*.py.  Each entry
+ * point below names the reference code (file:line, relative to the reference root) it replaces.
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `dev` pointers are CUDA device pointers, `host` pointers are
+ *     host memory.  Buffers are caller-owned unless they belong to a session handle.
+ *   - every function that launches work takes a cudaStream_t and is asynchronous on it, except the
+ *     `*_host` entry points, which return after their result has been copied back.
+ *   - return value: 0 = ok, <0 = error (FMB_ERR_*); fmb_last_error() returns a thread-local
+ *     message.  No exceptions cross the boundary.
+ *   - packed parameter table: float[R][rowp], rowp = fmb_rowp(k) = round_up(k+1, 4); row r holds
+ *     second_order_embeddings row (k floats), then the first_order_embeddings weight, then zero
+ *     padding.  R = sum of feature_sizes; global row id = field offset + per-field id.
+ *   - S and gvec row pitch: kp4 = fmb_kp4(k) = round_up(k, 4).
+ */
+#ifndef FMB200_H
+#define FMB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* fmb_stream_t; /* == cudaStream_t */
+typedef struct fmb_session fmb_session;
+
+#define FMB_OK 0
+#define FMB_ERR_ARG (-1)
+#define FMB_ERR_CUDA (-2)
+#define FMB_ERR_WS (-3)
+
+/* update rules applied to touched rows / dense parameters */
+#define FMB_UPDATE_ADAM1 0 /* torch.optim.Adam re-created every call => first-step sign update
+                              (fm_adam.py:60,68) -- the reference behaviour */
+#define FMB_UPDATE_SGD 1   /* p -= lr * g (legacy notebooks' torch.optim.SGD) */
+
+/* loss variants */
+#define FMB_LOSS_BCE_LOGITS 0         /* F.binary_cross_entropy_with_logits(z, y) */
+#define FMB_LOSS_BCE_LOGITS_OF_SIG 1  /* F.binary_cross_entropy_with_logits(sigmoid(z), y) */
+
+/* ---- library identity / errors -------------------------------------------------------------- */
+int fmb_version(void);
+const char* fmb_last_error(void);
+int fmb_device_count(void); /* 0 when no usable GPU: callers must fail, there is no CPU path */
+int fmb_rowp(int k);
+int fmb_kp4(int k);
+
+/* ---- A1-A3: first_order / second_order / forward_fm ------------------------------------------
+ * replaces deepfm_adam.py:46-77 (= nfm_adam.py:45-76, deepfm_onn.py:55-86, nfm_onn.py:57-88,
+ * fm_adam.py:34-54).  ids [B,F] int32 global row ids; xv [B,F] or NULL (all ones); bias [1].
+ * Outputs (each nullable): first [B,F], S [B,kp4] (sum_f e_f), bi [B,k] (0.5*(S^2 - Q)),
+ * sum_first [B], z [B] = (sum_first + sum_j bi) + bias.  When y [B] is non-NULL the loss variant
+ * `loss_kind` is evaluated on z as well: delta [B] = dLoss/dz, lossv [B] = per-sample loss. */
+int fmb_fm_forward(const int32_t* ids_dev, const float* xv_dev, const float* table_dev, const float* bias_dev,
+                   int B, int F, int k, float* first_dev, float* S_dev, float* bi_dev, float* sum_first_dev,
+                   float* z_dev, const float* y_dev, int loss_kind, float* delta_dev, float* lossv_dev,
+                   fmb_stream_t stream);
+
+/* ---- A6: loss + gradient on the logit (fm_adam.py:63-67, :77-81) ------------------------------- */
+int fmb_loss_delta(int loss_kind, const float* z_dev, const float* y_dev, int B, float* delta_dev,
+                   float* lossv_dev, fmb_stream_t stream);
+/* sum in ATen's CPU order (loss.mean(), bias gradient): out[0] = sum(x[0:n]) */
+int fmb_sum_aten(const float* x_dev, int64_t n, float* out_dev, fmb_stream_t stream);
+/* optimizer.step() on dense parameters (bias, hidden_layers): fm_adam.py:68 */
+int fmb_update_dense(float* p_dev, const float* g_dev, int64_t n, float lr, int mode, fmb_stream_t stream);
+/* bias step from sum(delta) and mean loss; bias_dev / loss_out_dev nullable */
+int fmb_finish_step(const float* delta_dev, const float* lossv_dev, int B, float* bias_dev, float lr, int mode,
+                    float* loss_out_dev, fmb_stream_t stream);
+
+/* ---- deterministic sort by row id + segments (replaces the implicit ordering of torch's CPU
+ * embedding_dense_backward) -------------------------------------------------- */
+size_t fmb_sort_workspace_bytes(int64_t N);
+int fmb_sort_segment(const int32_t* keys_dev, int64_t N, int key_bits, void* ws_dev, size_t ws_bytes,
+                     int32_t* sorted_keys_dev, int32_t* perm_dev, int32_t* seg_start_dev /*[N+1], nullable*/,
+                     int32_t* nseg_dev /*[1], nullable*/, fmb_stream_t stream);
+
+/* ---- A6: sparse embedding gradient (segmented, in sample order) fused with the row update ------
+ * replaces loss.backward() + optimizer.step() for the embedding tables (fm_adam.py:67-68,
+ * deepfm_adam.py:102-103,115-116).  gs [B] = gradient on the FM logit; use_fm2 = it also flows
+ * through sum_j bi; gvec [B,kp4] (nullable) = gradient on bi from the MLP (deepfm_adam.py:81). */
+size_t fmb_bwd_workspace_bytes(int64_t N);
+int fmb_fm_backward_update(const int32_t* sorted_keys_dev, const int32_t* perm_dev, int64_t N,
+                           const float* xv_dev, float* table_dev, int F, int k, const float* S_dev,
+                           const float* gs_dev, int use_fm2, const float* gvec_dev, float lr, int mode,
+                           void* ws_dev, size_t ws_bytes, fmb_stream_t stream);
+
+/* ---- A4/A5: MLP tower on the Bi-Interaction vector (deepfm_adam.py:79-89, nfm_adam.py:78-88,
+ * deepfm_onn.py:88-102).  mlp = W0[H,k] c0[H] W1[H,H] c1[H] ... (nn.Linear layouts, concatenated);
+ * act [L,B,H] post-relu activations; head [L,B] = sum_j act[l][b][j]. fp32 SIMT, k-ascending FMA. */
+int64_t fmb_mlp_numel(int k, int L, int H);
+int fmb_mlp_forward(const float* bi_dev, int ldbi, const float* mlp_dev, int B, int k, int L, int H,
+                    float* act_dev, float* head_dev /*nullable*/, fmb_stream_t stream);
+size_t fmb_mlp_bwd_workspace_bytes(int B, int H);
+/* backward of head `top`: gtop [B] is the gradient on sum_j act[top][b][j]; writes the gradients of
+ * layers 0..top into gmlp (same layout as mlp) and, when gbi is non-NULL, d/d(bi) [B,ldgbi]. */
+int fmb_mlp_backward(const float* bi_dev, int ldbi, const float* mlp_dev, const float* act_dev,
+                     const float* gtop_dev, int top, int B, int k, int L, int H, float* gmlp_dev, float* gbi_dev,
+                     int ldgbi, void* ws_dev, size_t ws_bytes, fmb_stream_t stream);
+/* z = base + head, base = z_fm (DeepFM, deepfm_adam.py:88) or sum_first + bias (NFM, nfm_adam.py:79,87) */
+int fmb_combine_logit(int nfm, const float* z_fm_dev, const float* sum_first_dev, const float* bias_dev,
+                      const float* head_dev, int B, float* z_dev, fmb_stream_t stream);
+/* ONN heads p[l,b] = sigmoid(base[b] + head[l,b]) (deepfm_onn.py:95-99) */
+int fmb_onn_heads(int nfm, const float* z_fm_dev, const float* sum_first_dev, const float* bias_dev,
+                  const float* head_dev, int L, int B, float* p_dev, fmb_stream_t stream);
+/* predict threshold sigmoid(z) > 0.5 (fm_adam.py:84-88; deepfm_onn.py:171-175 applies it to p_last) */
+int fmb_predict(const float* z_dev, int n, uint8_t* out_dev, fmb_stream_t stream);
+
+/* ---- A7: hedge backpropagation (deepfm_onn.py:109-154, nfm_onn.py:111-156) ---------------------
+ * head_grad: BCELoss(p_l, y) per sample (lossv) and its gradient on the head's pre-sigmoid logit;
+ * accumulate: w[j] (+)= alpha[i] * grad for layers j <= i; apply: W -= n*w, then the alpha update. */
+int fmb_hedge_head_grad(const float* p_dev, const float* y_dev, int B, float* gtop_dev, float* lossv_dev,
+                        fmb_stream_t stream);
+int fmb_hedge_accumulate(float* acc_dev, const float* gmlp_dev, const float* alpha_dev, int i, int k, int L, int H,
+                         fmb_stream_t stream);
+int fmb_hedge_apply(float* mlp_dev, const float* acc_dev, float lr, float* alpha_dev, const float* loss_sum_dev,
+                    int B, int k, int L, int H, float hb, float hs, fmb_stream_t stream);
+
+/* ---- training session: one call per step -------------------------------------------------------
+ * fmb_session_fm_step      : FMAdam.update_embedding / FMAdam.fit and every class's
+ *                            update_embedding (fm_adam.py:56-82, deepfm_adam.py:91-104,
+ *                            nfm_adam.py:90-103, deepfm_onn.py:156-169, nfm_onn.py:158-171)
+ * fmb_session_fm_step_host : the same with HOST ids/xv/y; copies in, runs, copies the loss out. */
+int fmb_session_create(fmb_session** out, int F, int k, int64_t max_batch);
+void fmb_session_destroy(fmb_session* s);
+int64_t fmb_session_launches(const fmb_session* s);
+int fmb_session_fm_step(fmb_session* s, const int32_t* ids_dev, const float* xv_dev, const float* y_dev, int B,
+                        float* table_dev, float* bias_dev, int key_bits, int loss_kind, float lr, int mode,
+                        float* loss_dev, fmb_stream_t stream);
+int fmb_session_fm_step_host(fmb_session* s, const int32_t* ids_host, const float* xv_host, const float* y_host,
+                             int B, float* table_dev, float* bias_dev, int key_bits, int loss_kind, float lr,
+                             int mode, float* loss_host, fmb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FMB200_H */

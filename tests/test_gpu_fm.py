@@ -1,0 +1,197 @@
+"""GPU parity tests of the FM hot path (A1-A3, sort/segments, A6) through the C ABI.
+CUDA results are compared with the CPU oracle bit for bit (fp32 work mirrors ATen's op order)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from _util import synth
+
+pytestmark = pytest.mark.gpu
+
+CRITEO = [63, 113, 126, 51, 224, 148, 100, 79, 104, 9, 32, 57, 82, 1457, 555, 176373, 129683, 305, 19, 11887,
+          632, 3, 41738, 5170, 175446, 3170, 27, 11356, 165602, 10, 4641, 2030, 4, 172761, 18, 15, 57903, 86, 44549]
+FRAPPE = [957, 4082, 7, 7, 2, 3, 2, 9, 80, 233]
+
+
+def _pair(kind, sizes, k, L=0, H=0, lr=0.01, seed=0, scale=1.0, **kw):
+    """(product model on cuda, oracle) holding identical parameters."""
+    import fm_for_online_recommendation_b200 as pkg
+    from oracle.deep import OracleDeep
+    orc = OracleDeep(kind, sizes, k, L, H, lr=lr, seed=seed, **kw)
+    orc.w1 *= np.float32(scale)
+    orc.V *= np.float32(scale)
+    cls = getattr(pkg, kind)
+    ckw = dict(embedding_size=k, n=lr)
+    if kind != "FMAdam":
+        ckw.update(num_hidden_layers=L, neuron_per_hidden_layer=H)
+    if "batch_size" in kw:
+        ckw["batch_size"] = kw["batch_size"]
+    m = cls(sizes, **ckw)
+    push(m, orc)
+    return m, orc
+
+
+def push(m, orc):
+    k = orc.k
+    with torch.no_grad():
+        t = torch.zeros_like(m._table)
+        t[:, :k] = torch.from_numpy(orc.V)
+        t[:, k] = torch.from_numpy(orc.w1)
+        m._table.copy_(t)
+        m.bias.copy_(torch.from_numpy(orc.bias).reshape(m.bias.shape))
+        if orc.L:
+            m._mlp.copy_(torch.from_numpy(orc.mlp))
+        if hasattr(m, "alpha"):
+            m.alpha.copy_(torch.from_numpy(orc.alpha[:orc.L]))
+
+
+def pull(m):
+    k = m.embedding_size
+    t = m._table.detach().cpu().numpy()
+    out = dict(V=t[:, :k].copy(), w1=t[:, k].copy(), bias=m.bias.detach().cpu().numpy().reshape(1))
+    if m._mlp is not None:
+        out["mlp"] = m._mlp.detach().cpu().numpy()
+    if hasattr(m, "alpha"):
+        out["alpha"] = m.alpha.detach().cpu().numpy()
+    return out
+
+
+def assert_same_params(m, orc, exact=True, tol=1e-5):
+    p = pull(m)
+    for key in ("V", "w1", "bias"):
+        a, b = p[key], getattr(orc, key)
+        if exact:
+            assert np.array_equal(a, b), (key, int((a != b).sum()), a.size)
+        else:
+            np.testing.assert_allclose(a, b, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("sizes,k,B,real_xv", [([943, 1682], 10, 256, False), (FRAPPE, 64, 300, True),
+                                               (CRITEO, 10, 1000, False), ([5, 3], 4, 1, True),
+                                               ([7, 5, 11, 3, 13, 4], 3, 33, True)])
+def test_forward_bit_exact(sizes, k, B, real_xv):
+    m, orc = _pair("FMAdam", sizes, k, scale=0.3)
+    Xi, Xv, _ = synth(sizes, B, 5, real_xv=real_xv)
+    ref = orc.fm_parts(Xi, Xv)
+    assert np.array_equal(m.first_order(Xi, Xv).cpu().numpy(), ref["first"])
+    assert np.array_equal(m.second_order(Xi, Xv).cpu().numpy(), ref["bi"])
+    assert np.array_equal(m.forward_fm(Xi, Xv).cpu().numpy(), ref["z_fm"])
+    assert np.array_equal(m.forward(Xi, Xv).cpu().numpy(), ref["z_fm"])
+    assert np.array_equal(m.predict(Xi, Xv), orc.predict(Xi, Xv))
+
+
+@pytest.mark.parametrize("N,bits,dist", [(1, 5, "u"), (31, 3, "u"), (2048, 8, "u"), (2049, 20, "u"),
+                                         (100000, 25, "u"), (319488, 20, "zipf"), (70000, 1, "u"),
+                                         (50000, 17, "const")])
+def test_sort_and_segments_bit_exact(N, bits, dist):
+    import fm_for_online_recommendation_b200 as pkg
+    lib = pkg.require_cuda()
+    rng = np.random.RandomState(N)
+    if dist == "u":
+        keys = rng.randint(0, 2 ** bits, size=N).astype(np.int32)
+    elif dist == "zipf":
+        keys = np.minimum(rng.zipf(1.2, size=N), 2 ** bits - 1).astype(np.int32)
+    else:
+        keys = np.full(N, 2 ** bits - 3, np.int32)
+    d = torch.from_numpy(keys).cuda()
+    wsb = lib.fmb_sort_workspace_bytes(N)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    sk = torch.empty(N, dtype=torch.int32, device="cuda")
+    pm = torch.empty(N, dtype=torch.int32, device="cuda")
+    seg = torch.empty(N + 1, dtype=torch.int32, device="cuda")
+    nseg = torch.zeros(1, dtype=torch.int32, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    rc = lib.fmb_sort_segment(p(d), N, bits, p(ws), wsb, p(sk), p(pm), p(seg), p(nseg), None)
+    assert rc == 0, lib.fmb_last_error()
+    torch.cuda.synchronize()
+    order = np.argsort(keys, kind="stable").astype(np.int32)
+    assert np.array_equal(pm.cpu().numpy(), order)            # stable permutation, bit-exact
+    assert np.array_equal(sk.cpu().numpy(), keys[order])
+    starts = np.flatnonzero(np.concatenate([[True], keys[order][1:] != keys[order][:-1]])).astype(np.int32)
+    n = int(nseg.item())
+    assert n == len(starts)
+    assert np.array_equal(seg.cpu().numpy()[:n], starts) and int(seg[n].item()) == N
+
+
+@pytest.mark.parametrize("sizes,k,B,real_xv,zipf,lr,scale", [
+    ([943, 1682], 10, 256, False, False, 0.01, 1.0),      # cfg1 shape, raw N(0,1) init
+    ([7, 5, 11, 3, 13, 4], 10, 700, True, True, 0.001, 0.2),  # heavy duplicates: long runs (> 512 entries/row)
+    (FRAPPE, 64, 512, False, False, 0.001, 0.1),          # cfg3 shape
+    (CRITEO, 10, 2500, False, False, 1e-4, 1.0),          # main_experiment.py pre-training shape
+    ([5, 3], 4, 1, True, False, 0.01, 0.5),               # single sample
+])
+def test_update_embedding_and_fit_bit_exact(sizes, k, B, real_xv, zipf, lr, scale):
+    m, orc = _pair("FMAdam", sizes, k, lr=lr, scale=scale)
+    for step in range(4):
+        Xi, Xv, Y = synth(sizes, B, 10 + step, real_xv=real_xv, zipf=zipf)
+        if step % 2 == 0:
+            got = float(m.update_embedding(Xi, Xv, Y).cpu())
+            want = orc.update_embedding(Xi, Xv, Y)
+            assert np.float32(got) == np.float32(want)
+        else:
+            m.fit(Xi, Xv, Y)
+            orc.fit(Xi, Xv, Y)
+        assert_same_params(m, orc, exact=True)
+
+
+def test_sgd_mode_bit_exact():
+    import fm_for_online_recommendation_b200 as pkg
+    from oracle.deep import OracleDeep
+    sizes = [50, 20, 7]
+    orc = OracleDeep("FMAdam", sizes, 8, lr=0.05, update_mode=1, seed=3)
+    orc.V *= np.float32(0.3)
+    m = pkg.FMAdam(sizes, embedding_size=8, n=0.05, update_mode=1)
+    push(m, orc)
+    for step in range(3):
+        Xi, Xv, Y = synth(sizes, 128, 40 + step, real_xv=True)
+        m.update_embedding(Xi, Xv, Y)
+        orc.update_embedding(Xi, Xv, Y)
+    assert_same_params(m, orc, exact=True)
+
+
+def test_host_entry_point_matches_device_entry_point():
+    """fmb_session_fm_step_host (host buffers, copies inside) == the device-input step."""
+    import fm_for_online_recommendation_b200 as pkg
+    lib = pkg.require_cuda()
+    sizes, k, B = CRITEO, 10, 2048
+    m, orc = _pair("FMAdam", sizes, k, lr=1e-3, scale=0.2)
+    Xi, Xv, Y = synth(sizes, B, 77)
+    ids = orc.global_ids(Xi)
+    y = np.ascontiguousarray(Y, dtype=np.float32)
+    s = m._get_session(B)
+    loss = C.c_float()
+    rc = lib.fmb_session_fm_step_host(s, ids.ctypes.data_as(C.c_void_p), None, y.ctypes.data_as(C.c_void_p), B,
+                                      C.c_void_p(m._table.data_ptr()), C.c_void_p(m.bias.data_ptr()), m._key_bits, 0,
+                                      m._lr, 0, C.byref(loss), None)
+    assert rc == 0, lib.fmb_last_error()
+    want = orc.update_embedding(Xi, Xv, Y)
+    assert np.float32(loss.value) == np.float32(want)
+    assert_same_params(m, orc, exact=True)
+
+
+def test_full_size_properties_cfg4():
+    """BASELINE cfg4 size (B=8192, Criteo tables): properties that need no oracle run.
+    (1) rows not in the batch are untouched, (2) every touched row moves by <= lr per coordinate
+    (fresh-Adam sign step), (3) the step is deterministic run to run."""
+    import fm_for_online_recommendation_b200 as pkg
+    sizes, k, B, lr = CRITEO, 10, 8192, 1e-4
+    torch.manual_seed(0)
+    m = pkg.FMAdam(sizes, embedding_size=k, n=lr)
+    t0 = m._table.clone()
+    b0 = m.bias.clone()
+    Xi, Xv, Y = synth(sizes, B, 123)
+    e = m.encode(Xi, Xv, Y)
+    l1 = m.update_embedding(e, None, None).item()
+    t1 = m._table.clone()
+    touched = torch.zeros(m._R, dtype=torch.bool, device="cuda")
+    touched[e.ids.reshape(-1).long()] = True
+    assert torch.equal(t1[~touched], t0[~touched])
+    assert float((t1 - t0).abs().max()) <= lr * 1.0001
+    assert float((t1[touched][:, :k + 1] - t0[touched][:, :k + 1]).abs().max()) > 0
+    with torch.no_grad():
+        m._table.copy_(t0)
+        m.bias.copy_(b0)
+    l2 = m.update_embedding(e, None, None).item()
+    assert l1 == l2 and torch.equal(m._table, t1)
