@@ -239,7 +239,10 @@ def run_ours(args):
         lib.fmb_fm_forward(p(e.ids), None, tptr, bptr, B, F, k, None, p(S), None, None, p(z), p(e.y), 0, p(delta),
                            p(lossv), st)
         evs[1].record(stream)
-        lib.fmb_sort_segment(p(e.ids), N, model._key_bits, p(ws), wsb, p(sk), p(pm), None, None, st)
+        if B <= lib.fmb_sort_fields_max_batch():
+            lib.fmb_sort_fields(p(e.ids), B, F, p(model._field_off_dev), p(sk), p(pm), st)
+        else:
+            lib.fmb_sort_segment(p(e.ids), N, model._key_bits, p(ws), wsb, p(sk), p(pm), None, None, st)
         evs[2].record(stream)
         lib.fmb_fm_backward_update(p(sk), p(pm), N, None, tptr, F, k, p(S), p(delta), 1, None, model._lr, 0, p(bws),
                                    bwsb, st)

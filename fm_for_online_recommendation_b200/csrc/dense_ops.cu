@@ -31,19 +31,86 @@ __global__ void update_dense_kernel(float* __restrict__ p, const float* __restri
     if (i < n) p[i] = fmb::apply_update(p[i], g[i], lr, mode);
 }
 
-// warp 0: bias -= step(sum(delta));  warp 1: loss_out = sum(lossv) / B
-__global__ void __launch_bounds__(64) finish_step_kernel(const float* __restrict__ delta,
-                                                         const float* __restrict__ lossv, int B, float* bias,
-                                                         float lr, int mode, float* loss_out) {
-    const int warp = threadIdx.x >> 5;
-    if (warp == 0) {
-        if (bias) {
-            const float g = fmb::aten_row_sum_warp(delta, B);
-            if (threadIdx.x == 0) bias[0] = fmb::apply_update(bias[0], g, lr, mode);
+// ATen-order sum of x[0:n] by one warp, with the data staged through shared memory in chunks of
+// FIN_CHUNK floats by the whole CTA (coalesced, one latency per chunk) so the serial chain reads
+// shared memory instead of L2.  Chunk boundaries are multiples of 32*16, so the cascade state
+// simply carries over; bit-identical to fmb::aten_row_sum_warp.
+constexpr int FIN_CHUNK = 4096;  // 128 rows of 32: a multiple of every cascade step <= 128
+struct AtenAcc {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+};
+
+__global__ void __launch_bounds__(1024) finish_step_kernel(const float* __restrict__ delta,
+                                                           const float* __restrict__ lossv, int B, float* bias,
+                                                           float lr, int mode, float* loss_out) {
+    __shared__ float buf[2][FIN_CHUNK];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* src[2] = {bias ? delta : nullptr, (loss_out && lossv) ? lossv : nullptr};
+    const int64_t n = B;
+    const int64_t vec_size = n >> 3, size_ilp = vec_size >> 2;   // rows of 32 floats handled by the cascade
+    int lp = 0;
+    while (((int64_t)1 << lp) < size_ilp) ++lp;
+    lp >>= 2;
+    const int level_power = lp > 4 ? lp : 4;
+    const int64_t level_step = (int64_t)1 << level_power, level_mask = level_step - 1;
+    AtenAcc acc;
+    const bool small = n < 8;
+    for (int64_t base = 0; base < n; base += FIN_CHUNK) {
+        const int m = (int)min((int64_t)FIN_CHUNK, n - base);
+        for (int i = threadIdx.x; i < m; i += blockDim.x) {
+            if (src[0]) buf[0][i] = src[0][base + i];
+            if (src[1]) buf[1][i] = src[1][base + i];
         }
-    } else if (loss_out && lossv) {
-        const float s = fmb::aten_row_sum_warp(lossv, B);
-        if ((threadIdx.x & 31) == 0) loss_out[0] = __fdiv_rn(s, (float)B);
+        __syncthreads();
+        if (warp < 2 && src[warp] && !small) {
+            const float* b = buf[warp];
+            // rows [base/32, ...) that lie fully inside both the chunk and the cascade range
+            const int64_t r0 = base >> 5;
+            const int64_t r1 = min(size_ilp, (base + m) >> 5);
+            const int64_t full_limit = (size_ilp / level_step) * level_step;
+            const int64_t rf = min(r1, full_limit);
+            int64_t i = r0;
+            while (i + level_step <= rf) {  // chunk boundaries are multiples of level_step rows
+                for (int64_t j = 0; j < level_step; j += 16, i += 16) {  // level_step is a multiple of 16
+                    float v[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) v[u] = b[((i + u) << 5) - base + lane];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) acc.a0 = __fadd_rn(acc.a0, v[u]);
+                }
+                acc.a1 = __fadd_rn(acc.a1, acc.a0); acc.a0 = 0.f;
+                if ((i & (level_mask << level_power)) == 0) {
+                    acc.a2 = __fadd_rn(acc.a2, acc.a1); acc.a1 = 0.f;
+                    if ((i & (level_mask << (2 * level_power))) == 0) { acc.a3 = __fadd_rn(acc.a3, acc.a2); acc.a2 = 0.f; }
+                }
+            }
+            for (; i < r1; ++i) acc.a0 = __fadd_rn(acc.a0, b[(i << 5) - base + lane]);
+        }
+        __syncthreads();
+    }
+    if (warp < 2 && src[warp]) {
+        float total;
+        if (small) {
+            total = fmb::aten_row_sum_warp(src[warp], n);
+        } else {
+            float a = __fadd_rn(__fadd_rn(__fadd_rn(acc.a0, acc.a1), acc.a2), acc.a3);
+            const float* x = src[warp];
+            if (lane < 8)
+                for (int64_t v = size_ilp << 2; v < vec_size; ++v) a = __fadd_rn(a, x[v * 8 + lane]);
+            const float t1 = __shfl_down_sync(0xffffffffu, a, 8);
+            const float t2 = __shfl_down_sync(0xffffffffu, a, 16);
+            const float t3 = __shfl_down_sync(0xffffffffu, a, 24);
+            const float folded = __fadd_rn(__fadd_rn(__fadd_rn(a, t1), t2), t3);
+            float fin = 0.f;
+            for (int64_t q = vec_size << 3; q < n; ++q) fin = __fadd_rn(fin, x[q]);
+#pragma unroll
+            for (int l = 0; l < 8; ++l) fin = __fadd_rn(fin, __shfl_sync(0xffffffffu, folded, l));
+            total = fin;
+        }
+        if (lane == 0) {
+            if (warp == 0) bias[0] = fmb::apply_update(bias[0], total, lr, mode);
+            else loss_out[0] = __fdiv_rn(total, (float)B);
+        }
     }
 }
 
@@ -81,7 +148,7 @@ FMB_API int fmb_update_dense(float* p, const float* g, int64_t n, float lr, int 
 FMB_API int fmb_finish_step(const float* delta, const float* lossv, int B, float* bias, float lr, int mode,
                             float* loss_out, cudaStream_t stream) {
     FMB_CHECK_ARG(delta && B > 0, "fmb_finish_step: bad arguments");
-    finish_step_kernel<<<1, 64, 0, stream>>>(delta, lossv, B, bias, lr, mode, loss_out);
+    finish_step_kernel<<<1, 1024, 0, stream>>>(delta, lossv, B, bias, lr, mode, loss_out);
     FMB_CHECK_LAUNCH("finish_step_kernel");
     return FMB_OK;
 }

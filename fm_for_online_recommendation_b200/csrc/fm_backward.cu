@@ -35,43 +35,76 @@ struct BwdParams {
     int TE;
 };
 
-// contributions of one entry for the 4 components of chunk q
-__device__ __forceinline__ void entry_chunk(const BwdParams& p, int32_t key, int32_t e, int q, float4& outA,
-                                            float4& outB) {
-    const int b = e / p.F;
-    const float x = p.xv ? __ldg(p.xv + e) : 1.0f;
-    const float d = __ldg(p.gs + b);
-    const float4 v4 = *reinterpret_cast<const float4*>(p.table + (size_t)key * p.rowp + q * 4);
-    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = s4;
-    if (q * 4 < p.kp4) {
-        s4 = __ldg(reinterpret_cast<const float4*>(p.S + (size_t)b * p.kp4 + q * 4));
-        if (p.gvec) g4 = __ldg(reinterpret_cast<const float4*>(p.gvec + (size_t)b * p.kp4 + q * 4));
+// store the contributions of one (entry, chunk) item into the staging buffers
+__device__ __forceinline__ void store_contrib(const BwdParams& p, bool two, float* bufA, float* bufB, int i, int q,
+                                              float4 a, float4 c) {
+    const int rowp = p.rowp;
+    if (two) {
+        *reinterpret_cast<float4*>(bufA + (size_t)i * rowp + q * 4) = a;
+        *reinterpret_cast<float4*>(bufB + (size_t)i * rowp + q * 4) = c;
+    } else if (p.gvec) {  // NFM: second-order comps from the MLP path, first-order comp from delta
+        const int kq = p.k >> 2, kt = p.k & 3;
+        float av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
+        if (q == kq) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) if (t >= kt) cv[t] = av[t];
+        }
+        *reinterpret_cast<float4*>(bufA + (size_t)i * rowp + q * 4) =
+            (q > kq) ? a : make_float4(cv[0], cv[1], cv[2], cv[3]);
+    } else {
+        *reinterpret_cast<float4*>(bufA + (size_t)i * rowp + q * 4) = a;
     }
-    const float v[4] = {v4.x, v4.y, v4.z, v4.w}, s[4] = {s4.x, s4.y, s4.z, s4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w};
+}
+
+// everything one (entry, chunk) item needs from global memory, loaded up front so that a batch of
+// items has all of its loads in flight together
+struct ItemLoads {
+    float4 v4, s4, g4;
+    float x, d;
+};
+__device__ __forceinline__ void item_load(const BwdParams& p, int32_t key, int32_t e, int q, ItemLoads& L) {
+    const int b = e / p.F;
+    L.x = p.xv ? __ldg(p.xv + e) : 1.0f;
+    L.d = __ldg(p.gs + b);
+    L.v4 = *reinterpret_cast<const float4*>(p.table + (size_t)key * p.rowp + q * 4);
+    L.s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    L.g4 = L.s4;
+    if (q * 4 < p.kp4) {
+        L.s4 = __ldg(reinterpret_cast<const float4*>(p.S + (size_t)b * p.kp4 + q * 4));
+        if (p.gvec) L.g4 = __ldg(reinterpret_cast<const float4*>(p.gvec + (size_t)b * p.kp4 + q * 4));
+    }
+}
+__device__ __forceinline__ void item_compute(const BwdParams& p, int q, const ItemLoads& L, float4& outA,
+                                             float4& outB) {
+    const float v[4] = {L.v4.x, L.v4.y, L.v4.z, L.v4.w}, s[4] = {L.s4.x, L.s4.y, L.s4.z, L.s4.w},
+                g[4] = {L.g4.x, L.g4.y, L.g4.z, L.g4.w};
     float a[4], c[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         const int j = q * 4 + t;
         a[t] = 0.f; c[t] = 0.f;
         if (j < p.k) {
-            const float ej = __fmul_rn(v[t], x);
-            if (p.use_fm2) a[t] = __fmul_rn(__fsub_rn(__fmul_rn(d, s[t]), __fmul_rn(d, ej)), x);
-            if (p.gvec) c[t] = __fmul_rn(__fsub_rn(__fmul_rn(g[t], s[t]), __fmul_rn(g[t], ej)), x);
+            const float ej = __fmul_rn(v[t], L.x);
+            if (p.use_fm2) a[t] = __fmul_rn(__fsub_rn(__fmul_rn(L.d, s[t]), __fmul_rn(L.d, ej)), L.x);
+            if (p.gvec) c[t] = __fmul_rn(__fsub_rn(__fmul_rn(g[t], s[t]), __fmul_rn(g[t], ej)), L.x);
         } else if (j == p.k) {
-            a[t] = __fmul_rn(d, x);
+            a[t] = __fmul_rn(L.d, L.x);
         }
     }
     outA = make_float4(a[0], a[1], a[2], a[3]);
     outB = make_float4(c[0], c[1], c[2], c[3]);
 }
 
-__global__ void __launch_bounds__(256) fm_bwd_tile_kernel(BwdParams p) {
+constexpr int ITEM_BATCH = 3;
+
+__global__ void __launch_bounds__(256, 4) fm_bwd_tile_kernel(BwdParams p) {
     extern __shared__ __align__(16) float smem[];
     const int TE = p.TE, WN = 2 * TE, rowp = p.rowp, C = rowp >> 2;
     const bool two = p.use_fm2 && p.gvec;
     float* bufA = smem;                                       // [WN][rowp]
     float* bufB = bufA + (two ? (size_t)WN * rowp : 0);       // [WN][rowp] when both chains exist
-    int32_t* keys_s = reinterpret_cast<int32_t*>(bufB + (size_t)WN * rowp);  // [WN+1]
+    float* rowv = bufB + (size_t)WN * rowp;                   // [TE][rowp] old row values, per run start
+    int32_t* keys_s = reinterpret_cast<int32_t*>(rowv + (size_t)TE * rowp);  // [WN+1]
     int32_t* rs_s = keys_s + (WN + 1);                        // run starts [WN+1]
     __shared__ int warp_cnt[8];
     __shared__ int carry_s, nruns_tile_s;
@@ -81,9 +114,9 @@ __global__ void __launch_bounds__(256) fm_bwd_tile_kernel(BwdParams p) {
     const int TEe = min(TE, W);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    for (int i = threadIdx.x; i < WN; i += 256) keys_s[i + 1] = (i < W) ? p.skeys[t0 + i] : -2;
+    for (int i = threadIdx.x; i < WN; i += 256) keys_s[i + 1] = (i < W) ? __ldg(p.skeys + t0 + i) : -2;
     if (threadIdx.x == 0) {
-        keys_s[0] = t0 > 0 ? p.skeys[t0 - 1] : -1;
+        keys_s[0] = t0 > 0 ? __ldg(p.skeys + t0 - 1) : -1;
         carry_s = 0;
         nruns_tile_s = 0;
     }
@@ -127,20 +160,32 @@ __global__ void __launch_bounds__(256) fm_bwd_tile_kernel(BwdParams p) {
     }
     const int lo = rs_s[0], hi = rs_s[nruns];
 
-    // contributions, one thread per (entry, 16-byte chunk)
-    for (int it = threadIdx.x; it < (hi - lo) * C; it += 256) {
-        const int i = lo + it / C, q = it % C;
-        float4 a, c;
-        entry_chunk(p, keys_s[i + 1], __ldg(p.perm + t0 + i), q, a, c);
-        if (two) {
-            *reinterpret_cast<float4*>(bufA + (size_t)i * rowp + q * 4) = a;
-            *reinterpret_cast<float4*>(bufB + (size_t)i * rowp + q * 4) = c;
-        } else if (p.gvec) {  // NFM: second-order comps from the MLP path, first-order comp from delta
-            const int kq = p.k >> 2, kt = p.k & 3;
-            if (q == kq) { float* cc = &c.x; const float* aa = &a.x; for (int t = kt; t < 4; ++t) cc[t] = aa[t]; }
-            *reinterpret_cast<float4*>(bufA + (size_t)i * rowp + q * 4) = (q > kq) ? a : c;
-        } else {
-            *reinterpret_cast<float4*>(bufA + (size_t)i * rowp + q * 4) = a;
+    // contributions, one thread per (entry, 16-byte chunk); loads of ITEM_BATCH items are issued together
+    const int nitems = (hi - lo) * C;
+    for (int it0 = threadIdx.x; it0 < nitems; it0 += 256 * ITEM_BATCH) {
+        int32_t pe[ITEM_BATCH];
+        ItemLoads L[ITEM_BATCH];
+#pragma unroll
+        for (int u = 0; u < ITEM_BATCH; ++u) {
+            const int it = it0 + u * 256;
+            pe[u] = (it < nitems) ? __ldg(p.perm + t0 + lo + it / C) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < ITEM_BATCH; ++u) {
+            const int it = it0 + u * 256;
+            if (it < nitems) item_load(p, keys_s[lo + it / C + 1], pe[u], it % C, L[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < ITEM_BATCH; ++u) {
+            const int it = it0 + u * 256;
+            if (it < nitems) {
+                const int i = lo + it / C, q = it % C;
+                float4 a, c;
+                item_compute(p, q, L[u], a, c);
+                store_contrib(p, two, bufA, bufB, i, q, a, c);
+                if (i < TE && keys_s[i + 1] != keys_s[i])  // run start: keep the old row for the update
+                    *reinterpret_cast<float4*>(rowv + (size_t)i * rowp + q * 4) = L[u].v4;
+            }
         }
     }
     __syncthreads();
@@ -157,32 +202,36 @@ __global__ void __launch_bounds__(256) fm_bwd_tile_kernel(BwdParams p) {
             for (int i = s; i < e; ++i) accB = __fadd_rn(accB, bufB[(size_t)i * rowp + c]);
             acc = __fadd_rn(acc, accB);
         }
-        float* addr = p.table + (size_t)keys_s[s + 1] * rowp + c;
-        *addr = fmb::apply_update(*addr, acc, p.lr, p.mode);
+        p.table[(size_t)keys_s[s + 1] * rowp + c] = fmb::apply_update(rowv[(size_t)s * rowp + c], acc, p.lr, p.mode);
     }
 }
 
-// one CTA per long run
+// One CTA per long run.  Warps 1..7 produce the contributions of chunk c+1 into one half of a
+// double buffer while warp 0 walks chunk c left to right (one lane per component / chain), so the
+// serial fp32 chain -- the only part that cannot be parallelised without changing the rounding --
+// runs back to back.  Falls back to produce-then-consume when the components do not fit one warp.
 __global__ void __launch_bounds__(256) fm_bwd_long_kernel(BwdParams p) {
     extern __shared__ __align__(16) float smem[];
-    const int rowp = p.rowp, C = rowp >> 2, CH = p.TE;
+    const int rowp = p.rowp, C = rowp >> 2, CH = p.TE * 2;
     const bool two = p.use_fm2 && p.gvec;
-    float* bufA = smem;                                  // [CH][rowp]
-    float* bufB = bufA + (two ? (size_t)CH * rowp : 0);  // [CH][rowp]
+    const int kc = p.k + 1;
+    const int nacc = kc + (two ? p.k : 0);   // accumulator lanes: chain A comps, then chain B comps
+    const bool piped = nacc <= 32;
+    const size_t half = (size_t)CH * rowp * (two ? 2 : 1);
     __shared__ int64_t end_s;
+    __shared__ int first_s[8];
     const int nlong = *p.long_count;
+    const int warp = threadIdx.x >> 5;
     for (int li = blockIdx.x; li < nlong; li += gridDim.x) {
         const int64_t start = p.long_list[li];
-        const int32_t key = p.skeys[start];
-        // find the end of the run
+        const int32_t key = __ldg(p.skeys + start);
         if (threadIdx.x == 0) end_s = -1;
         __syncthreads();
         for (int64_t base = start; end_s < 0; base += 256) {
             const int64_t pos = base + threadIdx.x;
-            const bool mis = pos >= p.N || p.skeys[pos] != key;
+            const bool mis = pos >= p.N || __ldg(p.skeys + pos) != key;
             const unsigned bal = __ballot_sync(0xffffffffu, mis);
-            __shared__ int first_s[8];
-            if ((threadIdx.x & 31) == 0) first_s[threadIdx.x >> 5] = bal ? __ffs(bal) - 1 : -1;
+            if ((threadIdx.x & 31) == 0) first_s[warp] = bal ? __ffs(bal) - 1 : -1;
             __syncthreads();
             if (threadIdx.x == 0) {
                 for (int w = 0; w < 8; ++w)
@@ -191,38 +240,82 @@ __global__ void __launch_bounds__(256) fm_bwd_long_kernel(BwdParams p) {
             __syncthreads();
         }
         const int64_t end = end_s;
-        float acc = 0.f, accB = 0.f;
-        const int kc = p.k + 1;
-        for (int64_t cb = start; cb < end; cb += CH) {
+        const int nchunks = (int)((end - start + CH - 1) / CH);
+        float acc = 0.f;
+        // accumulator thread -> (buffer, component)
+        const int at = threadIdx.x;
+        const bool is_acc = at < nacc;
+        const bool accB = is_acc && at >= kc;
+        const int acomp = accB ? at - kc : at;
+
+        auto produce = [&](int c, int tid, int nthreads) {
+            const int64_t cb = start + (int64_t)c * CH;
             const int n = (int)min((int64_t)CH, end - cb);
-            for (int it = threadIdx.x; it < n * C; it += 256) {
-                const int i = it / C, q = it % C;
-                float4 a, c;
-                entry_chunk(p, key, __ldg(p.perm + cb + i), q, a, c);
-                if (two) {
-                    *reinterpret_cast<float4*>(bufA + (size_t)i * rowp + q * 4) = a;
-                    *reinterpret_cast<float4*>(bufB + (size_t)i * rowp + q * 4) = c;
-                } else if (p.gvec) {
-                    const int kq = p.k >> 2, kt = p.k & 3;
-                    if (q == kq) { float* cc = &c.x; const float* aa = &a.x; for (int t = kt; t < 4; ++t) cc[t] = aa[t]; }
-                    *reinterpret_cast<float4*>(bufA + (size_t)i * rowp + q * 4) = (q > kq) ? a : c;
-                } else {
-                    *reinterpret_cast<float4*>(bufA + (size_t)i * rowp + q * 4) = a;
+            float* bA = smem + (size_t)(c & 1) * half;
+            float* bB = bA + (two ? (size_t)CH * rowp : 0);
+            const int nitems = n * C;
+            for (int it0 = tid; it0 < nitems; it0 += nthreads * ITEM_BATCH) {
+                int32_t pe[ITEM_BATCH];
+                ItemLoads L[ITEM_BATCH];
+#pragma unroll
+                for (int u = 0; u < ITEM_BATCH; ++u) {
+                    const int it = it0 + u * nthreads;
+                    pe[u] = (it < nitems) ? __ldg(p.perm + cb + it / C) : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < ITEM_BATCH; ++u) {
+                    const int it = it0 + u * nthreads;
+                    if (it < nitems) item_load(p, key, pe[u], it % C, L[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < ITEM_BATCH; ++u) {
+                    const int it = it0 + u * nthreads;
+                    if (it < nitems) {
+                        float4 a, cc;
+                        item_compute(p, it % C, L[u], a, cc);
+                        store_contrib(p, two, bA, bB, it / C, it % C, a, cc);
+                    }
                 }
             }
-            __syncthreads();
-            if (threadIdx.x < kc) {
-                const int c = threadIdx.x;
-                for (int i = 0; i < n; ++i) acc = __fadd_rn(acc, bufA[(size_t)i * rowp + c]);
-                if (two && c < p.k)
-                    for (int i = 0; i < n; ++i) accB = __fadd_rn(accB, bufB[(size_t)i * rowp + c]);
+        };
+        auto consume = [&](int c) {
+            const int64_t cb = start + (int64_t)c * CH;
+            const int n = (int)min((int64_t)CH, end - cb);
+            const float* b = smem + (size_t)(c & 1) * half + (accB ? (size_t)CH * rowp : 0) + acomp;
+            int i = 0;
+            for (; i + 8 <= n; i += 8) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = b[(size_t)(i + u) * rowp];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, v[u]);
             }
+            for (; i < n; ++i) acc = __fadd_rn(acc, b[(size_t)i * rowp]);
+        };
+
+        if (piped) {
+            if (warp > 0) produce(0, threadIdx.x - 32, 224);
             __syncthreads();
+            for (int c = 0; c < nchunks; ++c) {
+                if (warp == 0) { if (is_acc) consume(c); }
+                else if (c + 1 < nchunks) produce(c + 1, threadIdx.x - 32, 224);
+                __syncthreads();
+            }
+        } else {
+            for (int c = 0; c < nchunks; ++c) {
+                produce(c, threadIdx.x, 256);
+                __syncthreads();
+                if (is_acc) consume(c);
+                __syncthreads();
+            }
         }
-        if (threadIdx.x < kc) {
-            const int c = threadIdx.x;
-            if (two && c < p.k) acc = __fadd_rn(acc, accB);
-            float* addr = p.table + (size_t)key * rowp + c;
+        // fold chain B into chain A and update the row
+        float* fold = smem;  // reuse (all consumers are done: barrier above)
+        if (accB) fold[acomp] = acc;
+        __syncthreads();
+        if (is_acc && !accB) {
+            if (two && acomp < p.k) acc = __fadd_rn(acc, fold[acomp]);
+            float* addr = p.table + (size_t)key * rowp + acomp;
             *addr = fmb::apply_update(*addr, acc, p.lr, p.mode);
         }
         __syncthreads();
@@ -231,11 +324,11 @@ __global__ void __launch_bounds__(256) fm_bwd_long_kernel(BwdParams p) {
 
 static int pick_te(int rowp, bool two) {
     int te = 256;
-    while (te > 32 && (size_t)2 * te * rowp * 4 * (two ? 2 : 1) > 96 * 1024) te >>= 1;
+    while (te > 32 && (size_t)2 * te * rowp * 4 * (two ? 2 : 1) > 80 * 1024) te >>= 1;
     return te;
 }
 static size_t tile_smem(int te, int rowp, bool two) {
-    return (size_t)2 * te * rowp * 4 * (two ? 2 : 1) + (size_t)2 * (2 * te + 1) * 4 + 16;
+    return (size_t)2 * te * rowp * 4 * (two ? 2 : 1) + (size_t)te * rowp * 4 + (size_t)2 * (2 * te + 1) * 4 + 16;
 }
 
 }  // namespace
@@ -266,13 +359,17 @@ FMB_API int fmb_fm_backward_update(const int32_t* sorted_keys, const int32_t* pe
     const bool two = use_fm2 && gvec;
     p.TE = pick_te(p.rowp, two);
     const size_t sm = tile_smem(p.TE, p.rowp, two);
-    cudaFuncSetAttribute(fm_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-    cudaFuncSetAttribute(fm_bwd_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(fm_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(fm_bwd_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr = true;
+    }
     cudaMemsetAsync(p.long_count, 0, 4, stream);
     const int grid = (int)((N + p.TE - 1) / p.TE);
     fm_bwd_tile_kernel<<<grid, 256, sm, stream>>>(p);
     FMB_CHECK_LAUNCH("fm_bwd_tile_kernel");
-    const size_t lsm = (size_t)p.TE * p.rowp * 4 * (two ? 2 : 1);
+    const size_t lsm = (size_t)2 * (2 * p.TE) * p.rowp * 4 * (two ? 2 : 1);  // double-buffered chunks of 2*TE
     fm_bwd_long_kernel<<<296, 256, lsm, stream>>>(p);
     FMB_CHECK_LAUNCH("fm_bwd_long_kernel");
     return FMB_OK;

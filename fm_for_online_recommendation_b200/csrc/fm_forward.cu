@@ -45,19 +45,23 @@ __global__ void __launch_bounds__(256) fm_forward_kernel(FwdParams p) {
     float* rows_s = smem;                          // [SB][F][rowp]
     float* x_s = rows_s + (size_t)SB * F * rowp;   // [SB][F]
     float* bi_s = x_s + SB * F;                    // [SB][k]
+    int32_t* ids_s = reinterpret_cast<int32_t*>(bi_s + SB * k);  // [SB][F]
     const int b0 = blockIdx.x * SB;
     const int nv = min(SB, p.B - b0);
     const int C = rowp >> 2;
 
-    // phase 1: gather rows (16 B per cp.async) and values
+    // phase 0: the tile's row ids and values, coalesced (one memory latency for the whole tile)
+    for (int e = threadIdx.x; e < nv * F; e += blockDim.x) {
+        ids_s[e] = __ldg(p.ids + (size_t)b0 * F + e);
+        x_s[e] = p.xv ? __ldg(p.xv + (size_t)b0 * F + e) : 1.0f;
+    }
+    __syncthreads();
+    // phase 1: gather rows, 16 B per cp.async; every row read of the tile is in flight at once
     const int nchunks = nv * F * C;
     for (int c = threadIdx.x; c < nchunks; c += blockDim.x) {
         const int ef = c / C, q = c - ef * C;  // ef = s*F + f
-        const int32_t gid = __ldg(p.ids + (size_t)b0 * F + ef);
-        cp_async16(rows_s + (size_t)ef * rowp + q * 4, p.table + (size_t)gid * rowp + q * 4);
+        cp_async16(rows_s + (size_t)ef * rowp + q * 4, p.table + (size_t)ids_s[ef] * rowp + q * 4);
     }
-    for (int e = threadIdx.x; e < nv * F; e += blockDim.x)
-        x_s[e] = p.xv ? __ldg(p.xv + (size_t)b0 * F + e) : 1.0f;
     cp_async_wait_all();
     __syncthreads();
 
@@ -133,11 +137,13 @@ FMB_API int fmb_fm_forward(const int32_t* ids, const float* xv, const float* tab
     p.B = B; p.F = F; p.k = k; p.rowp = fmb_round_up(k + 1, 4); p.kp4 = fmb_round_up(k, 4);
     p.first = first; p.S = S; p.bi = bi; p.sum_first = sum_first; p.z = z;
     p.y = y; p.loss_kind = loss_kind; p.delta = delta; p.lossv = lossv;
-    int SB = (256 + k - 1) / k;
+    int SB = (192 + p.kp4 - 1) / p.kp4;  // ~192 (sample, component) items per 256-thread CTA
     if (SB < 4) SB = 4;
     if (SB > 32) SB = 32;
-    auto bytes = [&](int sb) { return sizeof(float) * ((size_t)sb * F * p.rowp + (size_t)sb * F + (size_t)sb * k); };
-    while (SB > 1 && bytes(SB) > 64 * 1024) SB >>= 1;
+    auto bytes = [&](int sb) {
+        return sizeof(float) * ((size_t)sb * F * p.rowp + (size_t)2 * sb * F + (size_t)sb * k);
+    };
+    while (SB > 1 && bytes(SB) > 48 * 1024) SB >>= 1;
     FMB_CHECK_ARG(bytes(SB) <= 200 * 1024, "fmb_fm_forward: F*k too large for one sample tile");
     p.SB = SB;
     static bool attr_set = false;

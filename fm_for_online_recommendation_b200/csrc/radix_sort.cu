@@ -159,6 +159,109 @@ __global__ void __launch_bounds__(1024) segment_starts_kernel(const int32_t* __r
     if (threadIdx.x == 0) { *nseg = (int32_t)carry_s; seg_start[carry_s] = (int32_t)N; }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fast path: ids come as a [B,F] matrix whose column f holds ids of field f only, so the global
+// stable sort factors into F independent stable sorts of B keys each.  One CTA per field sorts its
+// column entirely in shared memory (keys 32-bit, payload = sample index 16-bit, ping-pong), with
+// as many 8-bit passes as the field's cardinality needs (0 for a single-row field), and writes
+// sorted_keys/perm at [f*B, (f+1)*B).  The result is bit-identical to the generic global sort.
+// ---------------------------------------------------------------------------------------------
+constexpr int FS_THREADS = 1024;
+constexpr int FS_WARPS = FS_THREADS / 32;
+constexpr int FS_MAX_SLOTS = 16;  // B <= 32 warps * 16 slots * 32 lanes = 16384
+
+__global__ void __launch_bounds__(FS_THREADS) sort_fields_kernel(const int32_t* __restrict__ ids, int B, int F,
+                                                                 const int32_t* __restrict__ field_off,
+                                                                 int32_t* __restrict__ skeys,
+                                                                 int32_t* __restrict__ perm) {
+    extern __shared__ __align__(16) unsigned char fs_smem[];
+    uint32_t* kbuf0 = reinterpret_cast<uint32_t*>(fs_smem);
+    uint32_t* kbuf1 = kbuf0 + B;
+    uint16_t* pbuf0 = reinterpret_cast<uint16_t*>(kbuf1 + B);
+    uint16_t* pbuf1 = pbuf0 + B + (B & 1);
+    uint16_t* cnt = pbuf1 + B + (B & 1);                 // [FS_WARPS][RADIX]
+    __shared__ uint32_t tot[RADIX];
+    const int f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int32_t off = field_off[f];
+    const uint32_t nrows = (uint32_t)(field_off[f + 1] - off);
+    int bits = 0;
+    while (bits < 31 && (1u << bits) < nrows) ++bits;
+    const int passes = (bits + RADIX_BITS - 1) / RADIX_BITS;
+    for (int i = threadIdx.x; i < B; i += FS_THREADS) {
+        kbuf0[i] = (uint32_t)(ids[(size_t)i * F + f] - off);
+        pbuf0[i] = (uint16_t)i;
+    }
+    __syncthreads();
+    uint32_t* kc = kbuf0; uint32_t* kn = kbuf1;
+    uint16_t* pc = pbuf0; uint16_t* pn = pbuf1;
+    const int slots = (B + FS_THREADS - 1) / FS_THREADS;  // per-warp slice = slots*32 consecutive keys
+    const int wbase = warp * slots * 32;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int ps = 0; ps < passes; ++ps) {
+        const int shift = ps * RADIX_BITS;
+        for (int i = threadIdx.x; i < FS_WARPS * RADIX / 2; i += FS_THREADS) reinterpret_cast<uint32_t*>(cnt)[i] = 0;
+        __syncthreads();
+        uint32_t key[FS_MAX_SLOTS];
+        uint16_t rank[FS_MAX_SLOTS];
+#pragma unroll
+        for (int s = 0; s < FS_MAX_SLOTS; ++s) {
+            if (s < slots) {
+                const int idx = wbase + s * 32 + lane;
+                const bool valid = idx < B;
+                key[s] = valid ? kc[idx] : 0u;
+                const unsigned d = valid ? ((key[s] >> shift) & (RADIX - 1)) : 0xffffffffu;
+                const unsigned m = __match_any_sync(0xffffffffu, d);
+                const int leader = __ffs(m) - 1;
+                uint32_t old = 0;
+                if (valid && lane == leader) { old = cnt[warp * RADIX + d]; cnt[warp * RADIX + d] = (uint16_t)(old + __popc(m)); }
+                old = __shfl_sync(0xffffffffu, old, leader);
+                rank[s] = (uint16_t)(old + __popc(m & lt));
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < RADIX) {
+            const int d = threadIdx.x;
+            uint32_t run = 0;
+            for (int w = 0; w < FS_WARPS; ++w) { const uint32_t t = cnt[w * RADIX + d]; cnt[w * RADIX + d] = (uint16_t)run; run += t; }
+            tot[d] = run;
+        }
+        __syncthreads();
+        if (warp == 0) {  // exclusive scan of the 256 digit totals, 8 per lane
+            uint32_t v[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v[j] = tot[lane * 8 + j]; sum += v[j]; }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            uint32_t ex = inc - sum;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { tot[lane * 8 + j] = ex; ex += v[j]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < FS_MAX_SLOTS; ++s) {
+            if (s < slots) {
+                const int idx = wbase + s * 32 + lane;
+                if (idx < B) {
+                    const unsigned d = (key[s] >> shift) & (RADIX - 1);
+                    const uint32_t pos = tot[d] + cnt[warp * RADIX + d] + rank[s];
+                    kn[pos] = key[s];
+                    pn[pos] = pc[idx];
+                }
+            }
+        }
+        __syncthreads();
+        uint32_t* tk = kc; kc = kn; kn = tk;
+        uint16_t* tp = pc; pc = pn; pn = tp;
+    }
+    for (int i = threadIdx.x; i < B; i += FS_THREADS) {
+        skeys[(size_t)f * B + i] = (int32_t)kc[i] + off;
+        perm[(size_t)f * B + i] = (int32_t)pc[i] * F + f;
+    }
+}
+
 }  // namespace
 
 static int sort_ntiles(int64_t N) { return (int)((N + TILE - 1) / TILE); }
@@ -206,5 +309,23 @@ FMB_API int fmb_sort_segment(const int32_t* keys, int64_t N, int key_bits, void*
         segment_starts_kernel<<<1, 1024, 0, stream>>>(sorted_keys, N, seg_start, nseg);
         FMB_CHECK_LAUNCH("segment_starts_kernel");
     }
+    return FMB_OK;
+}
+
+// Largest batch the per-field shared-memory sort accepts.
+FMB_API int fmb_sort_fields_max_batch(void) { return FS_WARPS * FS_MAX_SLOTS * 32; }
+
+// Stable sort of ids[B,F] (column f holds global row ids of field f, field_off[F+1] device array of
+// field offsets) -> sorted_keys[B*F], perm[B*F] (original entry index b*F+f), identical to
+// fmb_sort_segment over the flattened matrix.  One CTA per field, everything in shared memory.
+FMB_API int fmb_sort_fields(const int32_t* ids, int B, int F, const int32_t* field_off, int32_t* sorted_keys,
+                            int32_t* perm, cudaStream_t stream) {
+    FMB_CHECK_ARG(ids && field_off && sorted_keys && perm, "fmb_sort_fields: null pointer");
+    FMB_CHECK_ARG(B > 0 && B <= fmb_sort_fields_max_batch() && F > 0, "fmb_sort_fields: B=%d out of range", B);
+    const size_t sm = (size_t)2 * B * 4 + (size_t)2 * (B + (B & 1)) * 2 + (size_t)FS_WARPS * RADIX * 2;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(sort_fields_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr = true; }
+    sort_fields_kernel<<<F, FS_THREADS, sm, stream>>>(ids, B, F, field_off, sorted_keys, perm);
+    FMB_CHECK_LAUNCH("sort_fields_kernel");
     return FMB_OK;
 }

@@ -16,6 +16,8 @@ size_t fmb_sort_workspace_bytes(int64_t);
 int fmb_sort_segment(const int32_t*, int64_t, int, void*, size_t, int32_t*, int32_t*, int32_t*, int32_t*,
                      cudaStream_t);
 size_t fmb_bwd_workspace_bytes(int64_t);
+int fmb_sort_fields_max_batch(void);
+int fmb_sort_fields(const int32_t*, int, int, const int32_t*, int32_t*, int32_t*, cudaStream_t);
 int fmb_fm_backward_update(const int32_t*, const int32_t*, int64_t, const float*, float*, int, int, const float*,
                            const float*, int, const float*, float, int, void*, size_t, cudaStream_t);
 int fmb_finish_step(const float*, const float*, int, float*, float, int, float*, cudaStream_t);
@@ -39,6 +41,7 @@ struct fmb_session {
     size_t sort_ws_bytes;
     void* d_bwd_ws;
     size_t bwd_ws_bytes;
+    int32_t* d_field_off;  // [F+1] global row offset of every field (enables the per-field sort)
     // pinned host staging
     int32_t* h_ids;
     float* h_xv;
@@ -57,13 +60,15 @@ FMB_API void fmb_session_destroy(fmb_session* s) {
     if (!s) return;
     cudaFree(s->d_ids); cudaFree(s->d_xv); cudaFree(s->d_y); cudaFree(s->d_S); cudaFree(s->d_z);
     cudaFree(s->d_delta); cudaFree(s->d_lossv); cudaFree(s->d_loss); cudaFree(s->d_skeys); cudaFree(s->d_perm);
-    cudaFree(s->d_sort_ws); cudaFree(s->d_bwd_ws);
+    cudaFree(s->d_sort_ws); cudaFree(s->d_bwd_ws); cudaFree(s->d_field_off);
     cudaFreeHost(s->h_ids); cudaFreeHost(s->h_xv); cudaFreeHost(s->h_y); cudaFreeHost(s->h_loss);
     delete s;
 }
 
-// F fields, embedding size k, up to max_batch samples per step.
-FMB_API int fmb_session_create(fmb_session** out, int F, int k, int64_t max_batch) {
+// F fields, embedding size k, up to max_batch samples per step.  field_off_host [F+1] (nullable):
+// global row offset of each field; when given and B <= fmb_sort_fields_max_batch() the step uses
+// the one-kernel per-field sort instead of the generic radix sort (same result).
+FMB_API int fmb_session_create(fmb_session** out, int F, int k, int64_t max_batch, const int32_t* field_off_host) {
     FMB_CHECK_ARG(out && F > 0 && k > 0 && max_batch > 0, "fmb_session_create: bad arguments");
     FMB_CHECK_ARG(max_batch * F < ((int64_t)1 << 31), "fmb_session_create: max_batch*F must fit int32");
     fmb_session* s = new (std::nothrow) fmb_session();
@@ -83,6 +88,10 @@ FMB_API int fmb_session_create(fmb_session** out, int F, int k, int64_t max_batc
     dm(&s->d_sort_ws, s->sort_ws_bytes); dm(&s->d_bwd_ws, s->bwd_ws_bytes);
     hm((void**)&s->h_ids, N * 4); hm((void**)&s->h_xv, N * 4); hm((void**)&s->h_y, max_batch * 4);
     hm((void**)&s->h_loss, 256);
+    if (field_off_host) {
+        dm((void**)&s->d_field_off, (size_t)(F + 1) * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(s->d_field_off, field_off_host, (size_t)(F + 1) * 4, cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) {
         fmb_set_error("fmb_session_create: %s", cudaGetErrorString(e));
         fmb_session_destroy(s);
@@ -108,15 +117,19 @@ FMB_API int fmb_session_fm_step(fmb_session* s, const int32_t* ids, const float*
     int rc = fmb_fm_forward(ids, xv, table, bias, B, s->F, s->k, nullptr, s->d_S, nullptr, nullptr, s->d_z, y,
                             loss_kind, s->d_delta, s->d_lossv, stream);
     if (rc) return rc;
-    rc = fmb_sort_segment(ids, N, key_bits, s->d_sort_ws, s->sort_ws_bytes, s->d_skeys, s->d_perm, nullptr, nullptr,
-                          stream);
+    const bool by_field = s->d_field_off && B <= fmb_sort_fields_max_batch();
+    if (by_field)
+        rc = fmb_sort_fields(ids, B, s->F, s->d_field_off, s->d_skeys, s->d_perm, stream);
+    else
+        rc = fmb_sort_segment(ids, N, key_bits, s->d_sort_ws, s->sort_ws_bytes, s->d_skeys, s->d_perm, nullptr,
+                              nullptr, stream);
     if (rc) return rc;
     rc = fmb_fm_backward_update(s->d_skeys, s->d_perm, N, xv, table, s->F, s->k, s->d_S, s->d_delta, 1, nullptr, lr,
                                 mode, s->d_bwd_ws, s->bwd_ws_bytes, stream);
     if (rc) return rc;
     rc = fmb_finish_step(s->d_delta, s->d_lossv, B, bias, lr, mode, loss_dev ? loss_dev : s->d_loss, stream);
     if (rc) return rc;
-    s->launches += 1 + 3 * ((key_bits + 7) / 8) + 2 + 1;
+    s->launches += 1 + (by_field ? 1 : 3 * ((key_bits + 7) / 8)) + 2 + 1;
     return FMB_OK;
 }
 

@@ -106,6 +106,7 @@ class _DeepBase(nn.Module):
             raise ValueError("total rows must fit int32")
         self._key_bits = max(1, int(self._R - 1).bit_length())
         self._offsets_dev = torch.from_numpy(self._offsets_np[:-1].copy()).to(self.device)
+        self._field_off_dev = torch.from_numpy(self._offsets_np.astype(np.int32)).to(self.device)
 
         # parameters are drawn on the CPU in the reference's order so torch.manual_seed(s) gives the
         # same initial model as the reference (fm_adam.py:26-32, deepfm_onn.py:30-53)
@@ -240,8 +241,9 @@ class _DeepBase(nn.Module):
                 self._lib.fmb_session_destroy(self._session)
             cap = max(B, 1)
             h = C.c_void_p()
-            check(self._lib.fmb_session_create(C.byref(h), self.field_size, self.embedding_size, cap),
-                  "fmb_session_create")
+            off32 = np.ascontiguousarray(self._offsets_np.astype(np.int32))
+            check(self._lib.fmb_session_create(C.byref(h), self.field_size, self.embedding_size, cap,
+                                               off32.ctypes.data_as(C.c_void_p)), "fmb_session_create")
             self._session, self._session_cap = h, cap
         return self._session
 
@@ -340,10 +342,14 @@ class _DeepBase(nn.Module):
 
     def _sort(self, e):
         N = e.B * self.field_size
-        wsb = self._lib.fmb_sort_workspace_bytes(N)
-        ws = self._buf("sort_ws", (wsb,), torch.uint8)
         sk = self._buf("skeys", (N,), torch.int32)
         pm = self._buf("perm", (N,), torch.int32)
+        if e.B <= self._lib.fmb_sort_fields_max_batch():
+            check(self._lib.fmb_sort_fields(ptr(e.ids), e.B, self.field_size, ptr(self._field_off_dev), ptr(sk),
+                                            ptr(pm), _stream()), "fmb_sort_fields")
+            return sk, pm
+        wsb = self._lib.fmb_sort_workspace_bytes(N)
+        ws = self._buf("sort_ws", (wsb,), torch.uint8)
         check(self._lib.fmb_sort_segment(ptr(e.ids), N, self._key_bits, ptr(ws), wsb, ptr(sk), ptr(pm), None, None,
                                          _stream()), "fmb_sort_segment")
         return sk, pm

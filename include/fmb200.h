@@ -82,6 +82,12 @@ int fmb_sort_segment(const int32_t* keys_dev, int64_t N, int key_bits, void* ws_
                      int32_t* sorted_keys_dev, int32_t* perm_dev, int32_t* seg_start_dev /*[N+1], nullable*/,
                      int32_t* nseg_dev /*[1], nullable*/, fmb_stream_t stream);
 
+/* fast path for ids laid out [B,F] with column f holding field f (field_off_dev [F+1]): one CTA per
+ * field sorts its column in shared memory; output identical to fmb_sort_segment on the flat matrix */
+int fmb_sort_fields_max_batch(void);
+int fmb_sort_fields(const int32_t* ids_dev, int B, int F, const int32_t* field_off_dev, int32_t* sorted_keys_dev,
+                    int32_t* perm_dev, fmb_stream_t stream);
+
 /* ---- A6: sparse embedding gradient (segmented, in sample order) fused with the row update ------
  * replaces loss.backward() + optimizer.step() for the embedding tables (fm_adam.py:67-68,
  * deepfm_adam.py:102-103,115-116).  gs [B] = gradient on the FM logit; use_fm2 = it also flows
@@ -128,7 +134,8 @@ int fmb_hedge_apply(float* mlp_dev, const float* acc_dev, float lr, float* alpha
  *                            update_embedding (fm_adam.py:56-82, deepfm_adam.py:91-104,
  *                            nfm_adam.py:90-103, deepfm_onn.py:156-169, nfm_onn.py:158-171)
  * fmb_session_fm_step_host : the same with HOST ids/xv/y; copies in, runs, copies the loss out. */
-int fmb_session_create(fmb_session** out, int F, int k, int64_t max_batch);
+int fmb_session_create(fmb_session** out, int F, int k, int64_t max_batch,
+                       const int32_t* field_off_host /*[F+1] global row offset per field, nullable*/);
 void fmb_session_destroy(fmb_session* s);
 int64_t fmb_session_launches(const fmb_session* s);
 int fmb_session_fm_step(fmb_session* s, const int32_t* ids_dev, const float* xv_dev, const float* y_dev, int B,
