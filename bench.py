@@ -227,7 +227,7 @@ def run_ours(args):
     delta = torch.empty(B, device="cuda"); lossv = torch.empty(B, device="cuda")
     wsb = lib.fmb_sort_workspace_bytes(N); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
     sk = torch.empty(N, dtype=torch.int32, device="cuda"); pm = torch.empty(N, dtype=torch.int32, device="cuda")
-    bwsb = lib.fmb_bwd_workspace_bytes(N); bws = torch.empty(bwsb, dtype=torch.uint8, device="cuda")
+    bwsb = lib.fmb_bwd_workspace_bytes(N, k); bws = torch.empty(bwsb, dtype=torch.uint8, device="cuda")
     lossd = torch.empty(1, device="cuda")
     st = C.c_void_p(stream.cuda_stream)
     phases = {"fm_forward": 0.0, "sort": 0.0, "fm_backward_update": 0.0, "finish": 0.0}

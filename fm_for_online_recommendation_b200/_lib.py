@@ -32,7 +32,7 @@ _SIGS = {
     "fmb_finish_step": (C.c_int, [vp, vp, C.c_int, vp, C.c_float, C.c_int, vp, vp]),
     "fmb_sort_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "fmb_sort_segment": (C.c_int, [vp, C.c_int64, C.c_int, vp, C.c_size_t, vp, vp, vp, vp, vp]),
-    "fmb_bwd_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "fmb_bwd_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
     "fmb_fm_backward_update": (C.c_int, [vp, vp, C.c_int64, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, C.c_float,
                                          C.c_int, vp, C.c_size_t, vp]),
     "fmb_mlp_numel": (C.c_int64, [C.c_int, C.c_int, C.c_int]),

@@ -14,7 +14,9 @@ void fmb_set_error(const char* fmt, ...) {
 
 FMB_API const char* fmb_last_error(void) { return g_err; }
 FMB_API int fmb_version(void) { return 100; }
-FMB_API int fmb_rowp(int k) { return fmb_round_up(k + 1, 4); }
+// row pitch of the packed table in floats: rows are 64-byte aligned (HBM bursts are 64 B; a 48-byte row
+// at a 48-byte pitch straddles two bursts 3 times out of 4 -- measured 35 MB of DRAM reads for 15 MB of rows)
+FMB_API int fmb_rowp(int k) { return fmb_round_up(k + 1, 16); }
 FMB_API int fmb_kp4(int k) { return fmb_round_up(k, 4); }
 
 // number of visible CUDA devices (0 when there is no GPU / no driver): lets the Python side fail

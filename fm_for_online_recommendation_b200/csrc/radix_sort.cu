@@ -20,6 +20,21 @@ constexpr int TILE = SORT_THREADS * KPT;     // 2048 keys per CTA
 
 __device__ __forceinline__ int digit_of(int32_t key, int shift) { return (key >> shift) & (RADIX - 1); }
 
+// lanes of the warp whose (valid) key has the same digit as mine: what __match_any_sync returns, built
+// from one ballot per digit bit (MATCH is far slower than 9 VOTEs on sm_100: it was 46 % of the
+// sort kernel's stall samples in profiles/r1b).
+__device__ __forceinline__ unsigned digit_peers(unsigned d, bool valid) {
+    unsigned m = __ballot_sync(0xffffffffu, valid);
+    if (!valid) m = ~m;
+#pragma unroll
+    for (int b = 0; b < RADIX_BITS; ++b) {
+        const unsigned bit = (d >> b) & 1u;
+        const unsigned bal = __ballot_sync(0xffffffffu, bit);
+        m &= bit ? bal : ~bal;
+    }
+    return m;
+}
+
 // hist[d * ntiles + tile] = number of keys of `tile` whose digit is d
 __global__ void __launch_bounds__(SORT_THREADS) radix_hist_kernel(const int32_t* __restrict__ keys, int64_t N,
                                                                   int shift, int ntiles,
@@ -96,8 +111,8 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(const int32
         const int64_t idx = wbase + i * 32 + lane;
         const bool valid = idx < N;
         key[i] = valid ? keys_in[idx] : 0;
-        const unsigned d = valid ? (unsigned)digit_of(key[i], shift) : 0xffffffffu;
-        const unsigned m = __match_any_sync(0xffffffffu, d);
+        const unsigned d = valid ? (unsigned)digit_of(key[i], shift) : 0u;
+        const unsigned m = digit_peers(d, valid);
         const int leader = __ffs(m) - 1;
         uint32_t old = 0;
         if (valid && lane == leader) { old = cnt[warp][d]; cnt[warp][d] = old + __popc(m); }
@@ -185,8 +200,7 @@ __global__ void __launch_bounds__(FS_THREADS) sort_fields_kernel(const int32_t* 
     const int f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int32_t off = field_off[f];
     const uint32_t nrows = (uint32_t)(field_off[f + 1] - off);
-    int bits = 0;
-    while (bits < 31 && (1u << bits) < nrows) ++bits;
+    const int bits = nrows <= 1 ? 0 : 32 - __clz(nrows - 1);
     const int passes = (bits + RADIX_BITS - 1) / RADIX_BITS;
     for (int i = threadIdx.x; i < B; i += FS_THREADS) {
         kbuf0[i] = (uint32_t)(ids[(size_t)i * F + f] - off);
@@ -210,8 +224,8 @@ __global__ void __launch_bounds__(FS_THREADS) sort_fields_kernel(const int32_t* 
                 const int idx = wbase + s * 32 + lane;
                 const bool valid = idx < B;
                 key[s] = valid ? kc[idx] : 0u;
-                const unsigned d = valid ? ((key[s] >> shift) & (RADIX - 1)) : 0xffffffffu;
-                const unsigned m = __match_any_sync(0xffffffffu, d);
+                const unsigned d = valid ? ((key[s] >> shift) & (RADIX - 1)) : 0u;
+                const unsigned m = digit_peers(d, valid);
                 const int leader = __ffs(m) - 1;
                 uint32_t old = 0;
                 if (valid && lane == leader) { old = cnt[warp * RADIX + d]; cnt[warp * RADIX + d] = (uint16_t)(old + __popc(m)); }

@@ -15,13 +15,20 @@ int fmb_fm_forward(const int32_t*, const float*, const float*, const float*, int
 size_t fmb_sort_workspace_bytes(int64_t);
 int fmb_sort_segment(const int32_t*, int64_t, int, void*, size_t, int32_t*, int32_t*, int32_t*, int32_t*,
                      cudaStream_t);
-size_t fmb_bwd_workspace_bytes(int64_t);
+size_t fmb_bwd_workspace_bytes(int64_t, int);
 int fmb_sort_fields_max_batch(void);
 int fmb_sort_fields(const int32_t*, int, int, const int32_t*, int32_t*, int32_t*, cudaStream_t);
 int fmb_fm_backward_update(const int32_t*, const int32_t*, int64_t, const float*, float*, int, int, const float*,
                            const float*, int, const float*, float, int, void*, size_t, cudaStream_t);
 int fmb_finish_step(const float*, const float*, int, float*, float, int, float*, cudaStream_t);
 }
+
+#define FMB_GRAPH_CACHE 32
+struct StepKey {
+    const void *ids, *xv, *y, *table, *bias, *loss;
+    int B, key_bits, loss_kind, mode;
+    float lr;
+};
 
 struct fmb_session {
     int F, k, rowp, kp4;
@@ -48,6 +55,14 @@ struct fmb_session {
     float* h_y;
     float* h_loss;
     int64_t launches;  // kernels launched through this session (bench.py's gpu_launches)
+    // CUDA-graph cache of whole steps, keyed by every argument that is baked into the kernels
+    cudaStream_t st0, st1;
+    cudaEvent_t ev_fork, ev_fwd, ev_sort, ev_join;
+    int use_graph;
+    int ngraphs, next_evict;
+    StepKey gkey[FMB_GRAPH_CACHE];
+    cudaGraphExec_t gexec[FMB_GRAPH_CACHE];
+    int glaunches[FMB_GRAPH_CACHE];
 };
 
 #define CU(call)                                                                              \
@@ -62,6 +77,13 @@ FMB_API void fmb_session_destroy(fmb_session* s) {
     cudaFree(s->d_delta); cudaFree(s->d_lossv); cudaFree(s->d_loss); cudaFree(s->d_skeys); cudaFree(s->d_perm);
     cudaFree(s->d_sort_ws); cudaFree(s->d_bwd_ws); cudaFree(s->d_field_off);
     cudaFreeHost(s->h_ids); cudaFreeHost(s->h_xv); cudaFreeHost(s->h_y); cudaFreeHost(s->h_loss);
+    for (int i = 0; i < s->ngraphs; ++i) cudaGraphExecDestroy(s->gexec[i]);
+    if (s->st0) cudaStreamDestroy(s->st0);
+    if (s->st1) cudaStreamDestroy(s->st1);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_fwd) cudaEventDestroy(s->ev_fwd);
+    if (s->ev_sort) cudaEventDestroy(s->ev_sort);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
     delete s;
 }
 
@@ -74,10 +96,10 @@ FMB_API int fmb_session_create(fmb_session** out, int F, int k, int64_t max_batc
     fmb_session* s = new (std::nothrow) fmb_session();
     FMB_CHECK_ARG(s, "fmb_session_create: out of host memory");
     memset(s, 0, sizeof(*s));
-    s->F = F; s->k = k; s->rowp = fmb_round_up(k + 1, 4); s->kp4 = fmb_round_up(k, 4); s->maxB = max_batch;
+    s->F = F; s->k = k; s->rowp = fmb_round_up(k + 1, 16); s->kp4 = fmb_round_up(k, 4); s->maxB = max_batch;
     const int64_t N = max_batch * F;
     s->sort_ws_bytes = fmb_sort_workspace_bytes(N);
-    s->bwd_ws_bytes = fmb_bwd_workspace_bytes(N);
+    s->bwd_ws_bytes = fmb_bwd_workspace_bytes(N, k);
     cudaError_t e = cudaSuccess;
     auto dm = [&](void** p, size_t n) { if (e == cudaSuccess) e = cudaMalloc(p, n); };
     auto hm = [&](void** p, size_t n) { if (e == cudaSuccess) e = cudaMallocHost(p, n); };
@@ -92,6 +114,16 @@ FMB_API int fmb_session_create(fmb_session** out, int F, int k, int64_t max_batc
         dm((void**)&s->d_field_off, (size_t)(F + 1) * 4);
         if (e == cudaSuccess) e = cudaMemcpy(s->d_field_off, field_off_host, (size_t)(F + 1) * 4, cudaMemcpyHostToDevice);
     }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st0, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st1, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_fwd, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_sort, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming);
+    {
+        const char* ng = getenv("FMB_NO_GRAPH");
+        s->use_graph = !(ng && ng[0] == '1');
+    }
     if (e != cudaSuccess) {
         fmb_set_error("fmb_session_create: %s", cudaGetErrorString(e));
         fmb_session_destroy(s);
@@ -103,33 +135,83 @@ FMB_API int fmb_session_create(fmb_session** out, int F, int k, int64_t max_batc
 
 FMB_API int64_t fmb_session_launches(const fmb_session* s) { return s ? s->launches : 0; }
 
+// the kernels of one FM-only step.  `side` (nullable) is a second stream: the sort does not depend on
+// the forward pass and the bias/loss epilogue does not depend on the row updates, so they fork.
+static int fm_step_launch(fmb_session* s, const int32_t* ids, const float* xv, const float* y, int B, float* table,
+                          float* bias, int key_bits, int loss_kind, float lr, int mode, float* loss_dev,
+                          cudaStream_t main, cudaStream_t side, int* nlaunch) {
+    const int64_t N = (int64_t)B * s->F;
+    const bool by_field = s->d_field_off && B <= fmb_sort_fields_max_batch();
+    cudaStream_t sort_st = side ? side : main;
+    if (side) { cudaEventRecord(s->ev_fork, main); cudaStreamWaitEvent(side, s->ev_fork, 0); }
+    int rc = fmb_fm_forward(ids, xv, table, bias, B, s->F, s->k, nullptr, s->d_S, nullptr, nullptr, s->d_z, y,
+                            loss_kind, s->d_delta, s->d_lossv, main);
+    if (rc) return rc;
+    if (side) cudaEventRecord(s->ev_fwd, main);
+    if (by_field)
+        rc = fmb_sort_fields(ids, B, s->F, s->d_field_off, s->d_skeys, s->d_perm, sort_st);
+    else
+        rc = fmb_sort_segment(ids, N, key_bits, s->d_sort_ws, s->sort_ws_bytes, s->d_skeys, s->d_perm, nullptr,
+                              nullptr, sort_st);
+    if (rc) return rc;
+    if (side) { cudaEventRecord(s->ev_sort, side); cudaStreamWaitEvent(main, s->ev_sort, 0); }
+    rc = fmb_fm_backward_update(s->d_skeys, s->d_perm, N, xv, table, s->F, s->k, s->d_S, s->d_delta, 1, nullptr, lr,
+                                mode, s->d_bwd_ws, s->bwd_ws_bytes, main);
+    if (rc) return rc;
+    if (side) cudaStreamWaitEvent(side, s->ev_fwd, 0);
+    rc = fmb_finish_step(s->d_delta, s->d_lossv, B, bias, lr, mode, loss_dev ? loss_dev : s->d_loss,
+                         side ? side : main);
+    if (rc) return rc;
+    if (side) { cudaEventRecord(s->ev_join, side); cudaStreamWaitEvent(main, s->ev_join, 0); }
+    *nlaunch = 1 + (by_field ? 1 : 3 * ((key_bits + 7) / 8)) + 2 + 1;
+    return FMB_OK;
+}
+
 // One FM-only training step with DEVICE inputs (FMAdam.update_embedding/fit, and the
 // update_embedding of DeepFM/NFM/ONN classes whose loss is on forward_fm only).
 //   loss_kind 0: BCEWithLogits(z_fm)   (fm_adam.py:66, deepfm_adam.py:101, deepfm_onn.py:166)
 //   loss_kind 1: BCEWithLogits(sigmoid(z_fm))   (fm_adam.py:80, nfm_adam.py:100, nfm_onn.py:168)
 //   loss_dev (nullable): receives the mean loss (device scalar).
+// The step is captured once per distinct argument set into a CUDA graph (forward || sort ->
+// backward/update || bias+loss) and replayed afterwards; FMB_NO_GRAPH=1 launches the kernels directly.
 FMB_API int fmb_session_fm_step(fmb_session* s, const int32_t* ids, const float* xv, const float* y, int B,
                                 float* table, float* bias, int key_bits, int loss_kind, float lr, int mode,
                                 float* loss_dev, cudaStream_t stream) {
     FMB_CHECK_ARG(s && ids && y && table && bias, "fmb_session_fm_step: null pointer");
     FMB_CHECK_ARG(B > 0 && B <= s->maxB, "fmb_session_fm_step: B=%d exceeds session max_batch", B);
-    const int64_t N = (int64_t)B * s->F;
-    int rc = fmb_fm_forward(ids, xv, table, bias, B, s->F, s->k, nullptr, s->d_S, nullptr, nullptr, s->d_z, y,
-                            loss_kind, s->d_delta, s->d_lossv, stream);
-    if (rc) return rc;
-    const bool by_field = s->d_field_off && B <= fmb_sort_fields_max_batch();
-    if (by_field)
-        rc = fmb_sort_fields(ids, B, s->F, s->d_field_off, s->d_skeys, s->d_perm, stream);
-    else
-        rc = fmb_sort_segment(ids, N, key_bits, s->d_sort_ws, s->sort_ws_bytes, s->d_skeys, s->d_perm, nullptr,
-                              nullptr, stream);
-    if (rc) return rc;
-    rc = fmb_fm_backward_update(s->d_skeys, s->d_perm, N, xv, table, s->F, s->k, s->d_S, s->d_delta, 1, nullptr, lr,
-                                mode, s->d_bwd_ws, s->bwd_ws_bytes, stream);
-    if (rc) return rc;
-    rc = fmb_finish_step(s->d_delta, s->d_lossv, B, bias, lr, mode, loss_dev ? loss_dev : s->d_loss, stream);
-    if (rc) return rc;
-    s->launches += 1 + (by_field ? 1 : 3 * ((key_bits + 7) / 8)) + 2 + 1;
+    int nl = 0;
+    // the very first step runs eagerly: it sets the kernels' function attributes outside any capture
+    if (!s->use_graph || s->launches == 0) {
+        int rc = fm_step_launch(s, ids, xv, y, B, table, bias, key_bits, loss_kind, lr, mode, loss_dev, stream,
+                                nullptr, &nl);
+        s->launches += nl;
+        return rc;
+    }
+    StepKey key;
+    memset(&key, 0, sizeof(key));
+    key.ids = ids; key.xv = xv; key.y = y; key.table = table; key.bias = bias; key.loss = loss_dev;
+    key.B = B; key.key_bits = key_bits; key.loss_kind = loss_kind; key.mode = mode; key.lr = lr;
+    int slot = -1;
+    for (int i = 0; i < s->ngraphs; ++i)
+        if (memcmp(&s->gkey[i], &key, sizeof(key)) == 0) { slot = i; break; }
+    if (slot < 0) {
+        cudaGraph_t graph = nullptr;
+        CU(cudaStreamBeginCapture(s->st0, cudaStreamCaptureModeThreadLocal));
+        int rc = fm_step_launch(s, ids, xv, y, B, table, bias, key_bits, loss_kind, lr, mode, loss_dev, s->st0,
+                                s->st1, &nl);
+        cudaError_t e = cudaStreamEndCapture(s->st0, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) { fmb_set_error("graph capture: %s", cudaGetErrorString(e)); return FMB_ERR_CUDA; }
+        cudaGraphExec_t exec = nullptr;
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { fmb_set_error("graph instantiate: %s", cudaGetErrorString(e)); return FMB_ERR_CUDA; }
+        if (s->ngraphs < FMB_GRAPH_CACHE) slot = s->ngraphs++;
+        else { slot = s->next_evict; s->next_evict = (s->next_evict + 1) % FMB_GRAPH_CACHE; cudaGraphExecDestroy(s->gexec[slot]); }
+        s->gkey[slot] = key; s->gexec[slot] = exec; s->glaunches[slot] = nl;
+    }
+    CU(cudaGraphLaunch(s->gexec[slot], stream));
+    s->launches += s->glaunches[slot];
     return FMB_OK;
 }
 

@@ -6,7 +6,7 @@ Same class names, constructor kwargs, method names, argument meaning and return 
 lib/libfmb200.so (include/fmb200.h).  There is no CPU path: constructing a model without a visible
 CUDA device raises `FmbError`.
 
-Layout: one packed device table [R, rowp] (rowp = round_up(k+1, 4)) holds, per global row, the
+Layout: one packed device table [R, rowp] (rowp = round_up(k+1, 16): 64-byte aligned rows) holds, per global row, the
 second-order embedding (k floats), the first-order weight and padding.
 `second_order_embeddings[f].weight` / `first_order_embeddings[f].weight` are strided Parameter
 views into it, `hidden_layers[l].weight/.bias` are views into one flat MLP buffer, so
@@ -369,7 +369,7 @@ class _DeepBase(nn.Module):
                                    ptr(gmlp), ptr(gbi), self._kp4, ptr(ws), wsb, st), "fmb_mlp_backward")
         sk, pm = self._sort(e)
         N = B * F
-        bwsb = lib.fmb_bwd_workspace_bytes(N)
+        bwsb = lib.fmb_bwd_workspace_bytes(N, k)
         bws = self._buf("bwd_ws", (bwsb,), torch.uint8)
         check(lib.fmb_fm_backward_update(ptr(sk), ptr(pm), N, ptr(e.xv), ptr(self._table), F, k, ptr(o["S"]),
                                          ptr(delta), 0 if self._IS_NFM else 1, ptr(gbi), self._lr, self.update_mode,

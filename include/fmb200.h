@@ -14,7 +14,7 @@
  *     `*_host` entry points, which return after their result has been copied back.
  *   - return value: 0 = ok, <0 = error (FMB_ERR_*); fmb_last_error() returns a thread-local
  *     message.  No exceptions cross the boundary.
- *   - packed parameter table: float[R][rowp], rowp = fmb_rowp(k) = round_up(k+1, 4); row r holds
+ *   - packed parameter table: float[R][rowp], rowp = fmb_rowp(k) = round_up(k+1, 16) (64-byte aligned rows); row r holds
  *     second_order_embeddings row (k floats), then the first_order_embeddings weight, then zero
  *     padding.  R = sum of feature_sizes; global row id = field offset + per-field id.
  *   - S and gvec row pitch: kp4 = fmb_kp4(k) = round_up(k, 4).
@@ -92,7 +92,7 @@ int fmb_sort_fields(const int32_t* ids_dev, int B, int F, const int32_t* field_o
  * replaces loss.backward() + optimizer.step() for the embedding tables (fm_adam.py:67-68,
  * deepfm_adam.py:102-103,115-116).  gs [B] = gradient on the FM logit; use_fm2 = it also flows
  * through sum_j bi; gvec [B,kp4] (nullable) = gradient on bi from the MLP (deepfm_adam.py:81). */
-size_t fmb_bwd_workspace_bytes(int64_t N);
+size_t fmb_bwd_workspace_bytes(int64_t N, int k);
 int fmb_fm_backward_update(const int32_t* sorted_keys_dev, const int32_t* perm_dev, int64_t N,
                            const float* xv_dev, float* table_dev, int F, int k, const float* S_dev,
                            const float* gs_dev, int use_fm2, const float* gvec_dev, float lr, int mode,

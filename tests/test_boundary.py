@@ -49,7 +49,7 @@ def test_argument_errors_are_reported_not_thrown():
     lib = pkg.load()
     rc = lib.fmb_fm_forward(None, None, None, None, 4, 2, 4, None, None, None, None, None, None, 0, None, None, None)
     assert rc == -1 and b"fmb_fm_forward" in lib.fmb_last_error()
-    assert lib.fmb_rowp(10) == 12 and lib.fmb_rowp(64) == 68 and lib.fmb_kp4(10) == 12
+    assert lib.fmb_rowp(10) == 16 and lib.fmb_rowp(64) == 80 and lib.fmb_kp4(10) == 12
 
 
 def test_product_never_imports_the_oracle():
