@@ -185,7 +185,7 @@ def run_ours(args):
     def step(i):
         return model._fm_step(enc[i % NB], 0)
 
-    for i in range(W):
+    for i in range(max(W, NB)):  # every rotating batch once: its step graph is captured outside the timed region
         step(i)
     torch.cuda.synchronize()
     launches0 = lib.fmb_session_launches(sess)

@@ -47,6 +47,10 @@ _SIGS = {
     "fmb_hedge_accumulate": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "fmb_hedge_apply": (C.c_int, [vp, vp, C.c_float, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                   C.c_float, vp]),
+    "fmb_ftrl_fm_run": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, vp, vp, vp, vp, vp, vp, vp]),
+    "fmb_sftrl_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "fmb_sftrl_run": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, vp, vp, vp, vp, vp,
+                                vp, vp, vp, C.c_size_t, vp]),
     "fmb_session_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int64, vp]),
     "fmb_sort_fields_max_batch": (C.c_int, []),
     "fmb_sort_fields": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp]),

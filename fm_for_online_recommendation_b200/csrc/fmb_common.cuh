@@ -108,10 +108,19 @@ __device__ __forceinline__ float powf_p(float b, float e) { return expf_p(__fmul
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float adam1(float p, float g, float lr) {
     const float bc2s = 0.03162277660168381f;
+    const float a = -__fdiv_rn(lr, 0.1f);
+    // Exact shortcut.  The step is q = fl(fl(a*m)/d) with d >= 1e-8f, so |q| <= |a|*0.1*|g|*1e8*(1+2^-22).
+    // When that bound is below a quarter ulp of p the sum fl(p+q) is p itself; skipping the IEEE sqrt and
+    // the two IEEE divisions then changes nothing, and it is the common case on saturated logits, whose
+    // gradients are ~1e-30 (denormal operands send div.rn/sqrt.rn down their ~100-instruction slow paths).
+    const float ap = fabsf(p);
+    if (ap > 1e-20f) {
+        const float bound = __fmul_rn(__fmul_rn(__fmul_rn(fabsf(a), 0.1f), fabsf(g)), 1.0001e8f);
+        if (bound < __fmul_rn(ap, 1.4901161e-8f)) return p;   // 2^-26 * |p|
+    }
     float m = __fmul_rn(0.1f, g);
     float v = __fmul_rn(__fmul_rn(0.001f, g), g);
     float d = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2s), 1e-8f);
-    float a = -__fdiv_rn(lr, 0.1f);
     return __fadd_rn(p, __fdiv_rn(__fmul_rn(a, m), d));
 }
 __device__ __forceinline__ float apply_update(float p, float g, float lr, int mode) {

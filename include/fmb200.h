@@ -129,6 +129,22 @@ int fmb_hedge_accumulate(float* acc_dev, const float* gmlp_dev, const float* alp
 int fmb_hedge_apply(float* mlp_dev, const float* acc_dev, float lr, float* alpha_dev, const float* loss_sum_dev,
                     int B, int k, int L, int H, float hb, float hs, fmb_stream_t stream);
 
+/* ---- A9-A11: classical fp64 online learners, one persistent launch per stream -------------------
+ * fmb_ftrl_fm_run : FM_FTRL.online_learning (models/models_online/FM_FTRL.py:47-92)
+ * fmb_sftrl_run   : SFTRL_CCFM.online_learning (SFTRL_CCFM.py:30-121; vanila = 0) and
+ *                   SFTRL_Vanila.online_learning (SFTRL_Vanila.py:33-123; vanila = 1)
+ * X [N,d] dense fp64, y [N]; task 0 = 'reg', 1 = 'cls'; preds [N]; status [1] = 0 or (index of the
+ * first NaN score) + 1 -- the caller raises ValueError('Nan contained') like FM_FTRL.py:64-65. */
+int fmb_ftrl_fm_run(const double* X_dev, const double* y_dev, int N, int d, int m2, int task, double eta,
+                    double* w1_dev /*[d] in/out*/, double* W2_dev /*[m2,d-1] in/out*/,
+                    double* g_w1_dev /*[d] zeroed*/, double* g_W2_dev /*[m2,d-1] zeroed*/, double* preds_dev,
+                    int* status_dev, fmb_stream_t stream);
+size_t fmb_sftrl_workspace_bytes(int d, int m);
+int fmb_sftrl_run(const double* X_dev, const double* y_dev, int N, int d, int m, int task, int vanila, double eta,
+                  double* BT_P_dev /*[ds,2m]*/, double* BT_N_dev /*[ds,2m]*/, int* row_counts_dev /*[2]*/,
+                  double* w_dev /*[d], vanila*/, double* g_w_dev /*[d], vanila*/, double* preds_dev,
+                  int* status_dev, void* ws_dev, size_t ws_bytes, fmb_stream_t stream);
+
 /* ---- training session: one call per step -------------------------------------------------------
  * fmb_session_fm_step      : FMAdam.update_embedding / FMAdam.fit and every class's
  *                            update_embedding (fm_adam.py:56-82, deepfm_adam.py:91-104,

@@ -1,0 +1,81 @@
+"""Classical online learners (A9-A11): the numpy oracle is pinned against the reference's outputs
+(CPU test), the CUDA persistent kernels are compared with the oracle and the golden (GPU test).
+fp64 tolerance: 1e-9 relative on regression scores, identical +-1 decisions for 'cls'
+(dgemv/LAPACK summation orders are not mirrored; sketches are compared through BT BT^T, which is
+invariant to the sign/rotation freedom of singular vectors -- SURVEY.md section 7)."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from _util import GOLDEN
+from oracle import classical as oc
+
+CASES = ["codrna_cls_m40", "onehot_reg_m5", "onehot_cls_m3"]
+G = dict(np.load(GOLDEN + "/classical.npz"))
+
+
+def case(name):
+    eta, m, t = G[name + "_meta"]
+    return G[name + "_X"], G[name + "_y"], ("cls" if t else "reg"), float(eta), int(m)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference(name):
+    X, y, task, eta, m = case(name)
+    p, st = oc.fm_ftrl(X, y, task, eta, m, G[name + "_ftrl_w1_init"], G[name + "_ftrl_W2_init"])
+    np.testing.assert_allclose(p, G[name + "_ftrl_pred"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(st["W2"], G[name + "_ftrl_W2"], rtol=1e-12, atol=1e-14)
+    for tag, van in (("ccfm", False), ("vanila", True)):
+        p, st = oc.sftrl(X, y, task, eta, m, vanila=van)
+        np.testing.assert_allclose(p, G[f"{name}_{tag}_pred"], rtol=1e-10, atol=1e-12)
+        assert [st["row_count_p"], st["row_count_n"]] == G[f"{name}_{tag}_rc"].tolist()
+        for key, mine in (("BTP", st["BT_P"]), ("BTN", st["BT_N"])):
+            ref = G[f"{name}_{tag}_{key}"]
+            np.testing.assert_allclose(mine @ mine.T, ref @ ref.T, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_cuda_matches_oracle_and_reference(name):
+    import torch
+    import fm_for_online_recommendation_b200 as pkg
+    X, y, task, eta, m = case(name)
+    T = torch.DoubleTensor
+    with contextlib.redirect_stdout(io.StringIO()):
+        torch.manual_seed(7)
+        mdl = pkg.FM_FTRL(T(X), T(y), task, eta, m)
+        p, real, _ = mdl.online_learning()
+    np.testing.assert_allclose(p, G[name + "_ftrl_pred"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(mdl.W2.cpu().numpy(), G[name + "_ftrl_W2"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(mdl.w1.cpu().numpy(), G[name + "_ftrl_w1"], rtol=1e-9, atol=1e-12)
+    assert np.array_equal(real, y)
+    for tag, cls, van in (("ccfm", pkg.SFTRL_CCFM, False), ("vanila", pkg.SFTRL_Vanila, True)):
+        with contextlib.redirect_stdout(io.StringIO()):
+            mdl = cls(T(X), T(y), task, eta, m)
+            p, _, _ = mdl.online_learning()
+        po, st = oc.sftrl(X, y, task, eta, m, vanila=van)
+        np.testing.assert_allclose(p, po, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(p, G[f"{name}_{tag}_pred"], rtol=1e-9, atol=1e-9)
+        assert [mdl.row_count_p, mdl.row_count_n] == G[f"{name}_{tag}_rc"].tolist()
+        for key, mine in (("BTP", mdl.BT_P), ("BTN", mdl.BT_N)):
+            ref = G[f"{name}_{tag}_{key}"]
+            mine = mine.cpu().numpy()
+            np.testing.assert_allclose(mine @ mine.T, ref @ ref.T, rtol=1e-8, atol=1e-11)
+        if van:
+            np.testing.assert_allclose(mdl.w.cpu().numpy().reshape(-1), G[f"{name}_{tag}_w"].reshape(-1), rtol=1e-9,
+                                       atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_nan_raises_value_error():
+    import torch
+    import fm_for_online_recommendation_b200 as pkg
+    X = np.random.RandomState(0).uniform(-1, 1, (50, 6))
+    X[10, 2] = np.nan
+    y = np.ones(50)
+    with contextlib.redirect_stdout(io.StringIO()):
+        mdl = pkg.SFTRL_CCFM(torch.DoubleTensor(X), torch.DoubleTensor(y), "reg", 0.01, 3)
+        with pytest.raises(ValueError, match="Nan contained"):
+            mdl.online_learning()
