@@ -51,6 +51,16 @@ _SIGS = {
     "fmb_sftrl_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "fmb_sftrl_run": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, vp, vp, vp, vp, vp,
                                 vp, vp, vp, C.c_size_t, vp]),
+    "fmb_fm_backward_update_ex": (C.c_int, [vp, vp, C.c_int64, C.c_int64, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp,
+                                            C.c_int, C.c_int, vp, C.c_int32, C.c_float, C.c_int, vp, C.c_size_t, vp]),
+    "fmb_shard_pw": (C.c_int, [C.c_int]),
+    "fmb_shard_cw": (C.c_int, [C.c_int]),
+    "fmb_shard_sort_max_cap": (C.c_int, []),
+    "fmb_transpose_ids": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
+    "fmb_shard_partial_forward": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "fmb_shard_combine": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    "fmb_shard_unpack_ctx": (C.c_int, [vp, C.c_int64, C.c_int, vp, vp, vp]),
+    "fmb_shard_sort_fields": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp]),
     "fmb_session_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int64, vp]),
     "fmb_sort_fields_max_batch": (C.c_int, []),
     "fmb_sort_fields": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp]),

@@ -39,6 +39,9 @@ struct BwdParams {
     const float* gvec;
     float lr;
     int mode;
+    int s_pitch;          // row pitch of S / gvec in floats (kp4 unless they live in a gathered context)
+    int gs_stride;        // stride of gs in floats
+    int32_t key_limit;    // keys >= key_limit are padding (sharded path) and are skipped
     float* G;             // [N][cu*4] staged contributions (chain A, or the only chain)
     float* G2;            // [N][cu*4] chain B when both gradient paths are live
 };
@@ -61,18 +64,19 @@ __global__ void __launch_bounds__(256) fm_bwd_entry_kernel(BwdParams p) {
     const int64_t i = (int64_t)blockIdx.x * (256 >> p.ql_log) + (threadIdx.x >> p.ql_log);
     if (i >= p.N || q >= p.cu) return;
     const int32_t key = __ldg(p.skeys + i);
+    if (key >= p.key_limit) return;
     const int32_t kprev = i > 0 ? __ldg(p.skeys + i - 1) : -1;
     const int32_t knext = i + 1 < p.N ? __ldg(p.skeys + i + 1) : -1;
     const int32_t e = __ldg(p.perm + i);
     const int b = (int)(((unsigned long long)(unsigned)e * p.fmagic) >> p.fshift);
     const float x = p.xv ? __ldg(p.xv + e) : 1.0f;
-    const float d = __ldg(p.gs + b);
+    const float d = __ldg(p.gs + (size_t)b * p.gs_stride);
     float* rowptr = p.table + (size_t)key * p.rowp + q * 4;
     const float4 v4 = *reinterpret_cast<const float4*>(rowptr);
     float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = s4;
     if (q * 4 < p.kp4) {
-        s4 = __ldg(reinterpret_cast<const float4*>(p.S + (size_t)b * p.kp4 + q * 4));
-        if (p.gvec) g4 = __ldg(reinterpret_cast<const float4*>(p.gvec + (size_t)b * p.kp4 + q * 4));
+        s4 = __ldg(reinterpret_cast<const float4*>(p.S + (size_t)b * p.s_pitch + q * 4));
+        if (p.gvec) g4 = __ldg(reinterpret_cast<const float4*>(p.gvec + (size_t)b * p.s_pitch + q * 4));
     }
     const float v[4] = {v4.x, v4.y, v4.z, v4.w}, s[4] = {s4.x, s4.y, s4.z, s4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w};
     const bool two = p.use_fm2 && p.gvec;
@@ -122,8 +126,7 @@ __global__ void __launch_bounds__(256) fm_bwd_entry_kernel(BwdParams p) {
 
 // ---------------------------------------------------------------------------------------------
 constexpr int RING_SE = 32;  // entries per ring stage (one key per lane)
-constexpr int RING_NS = 4;   // stages
-
+constexpr int RING_NS = 8;   // stages
 
 __global__ void fm_bwd_runs_kernel(BwdParams p, int warps_per_block, int warp_f, int accs_n) {
     extern __shared__ __align__(16) float smem[];
@@ -139,24 +142,28 @@ __global__ void fm_bwd_runs_kernel(BwdParams p, int warps_per_block, int warp_f,
     int32_t* rkeys = reinterpret_cast<int32_t*>(ring + RING_NS * stage_f);  // [NS][SE]
     float* accs = reinterpret_cast<float*>(rkeys + RING_NS * RING_SE);      // [accs_n]
 
-    // runs (>= 2 entries) that start inside this warp's 32 positions
+    // keys of this warp's 32 positions and of the 32 after them (one memory latency for both)
     const int64_t pos = P0 + lane;
-    const int32_t mykey = pos < p.N ? __ldg(p.skeys + pos) : -1;
-    int32_t prev = __shfl_up_sync(0xffffffffu, mykey, 1);
-    int32_t next = __shfl_down_sync(0xffffffffu, mykey, 1);
+    const int32_t k0 = pos < p.N ? __ldg(p.skeys + pos) : -2;
+    const int32_t k1 = pos + 32 < p.N ? __ldg(p.skeys + pos + 32) : -2;
+    int32_t prev = __shfl_up_sync(0xffffffffu, k0, 1);
+    int32_t next = __shfl_down_sync(0xffffffffu, k0, 1);
+    const int32_t k1_0 = __shfl_sync(0xffffffffu, k1, 0);
     if (lane == 0) prev = P0 > 0 ? __ldg(p.skeys + P0 - 1) : -1;
-    if (lane == 31) next = P0 + 32 < p.N ? __ldg(p.skeys + P0 + 32) : -2;
-    unsigned todo = __ballot_sync(0xffffffffu, pos < p.N && mykey != prev && mykey == next);
+    if (lane == 31) next = k1_0;
+    // runs (>= 2 entries) that START inside these 32 positions
+    unsigned todo = __ballot_sync(0xffffffffu, pos < p.N && k0 >= 0 && k0 < p.key_limit && k0 != prev && k0 == next);
 
     while (todo) {
         const int bit = __ffs(todo) - 1;
         todo &= todo - 1;
         const int64_t s = P0 + bit;
-        const int32_t key = __shfl_sync(0xffffffffu, mykey, bit);
-        // leading matches among the first 32 entries of the run
-        const int64_t kp = s + lane;
-        const bool mt = kp < p.N && __ldg(p.skeys + kp) == key;
-        const unsigned mm = __ballot_sync(0xffffffffu, mt);
+        const int32_t key = __shfl_sync(0xffffffffu, k0, bit);
+        // leading matches among the first 32 entries of the run (keys are already in registers)
+        const int t = bit + lane;
+        const int32_t ka = __shfl_sync(0xffffffffu, k0, t & 31);
+        const int32_t kb = __shfl_sync(0xffffffffu, k1, t & 31);
+        const unsigned mm = __ballot_sync(0xffffffffu, (t < 32 ? ka : kb) == key);
         const int n0 = (mm == 0xffffffffu) ? 32 : __ffs(~mm) - 1;
 
         for (int v0 = 0; v0 < nv; v0 += 32) {  // one pass per group of 32 (buffer, component) lanes
@@ -165,38 +172,39 @@ __global__ void fm_bwd_runs_kernel(BwdParams p, int warps_per_block, int warp_f,
             const bool isB = vl >= kc;
             const int comp = isB ? vl - kc : vl;
             const float* src = (isB ? p.G2 : p.G) + comp;
-            float acc = 0.f;
-            // direct part: up to 32 entries straight from G, 8 loads in flight per lane
-            for (int j0 = 0; j0 < n0; j0 += 8) {
-                float t[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    t[u] = (active && j0 + u < n0) ? __ldg(src + (size_t)(s + j0 + u) * gp) : 0.f;
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (j0 + u < n0) acc = __fadd_rn(acc, t[u]);
-            }
-            // long run: stream the rest through the shared-memory ring
-            if (n0 == 32) {
-                int64_t fill = s + 32;  // next position to stage
-                auto issue = [&](int st) {
-                    float* dst = ring + (size_t)st * stage_f;
-                    // SE entries x 2^ql_log lanes: 4 (or more) issue slots per lane
-                    for (int idx = lane; idx < (RING_SE << p.ql_log); idx += 32) {
-                        const int en = idx >> p.ql_log, q = idx & ((1 << p.ql_log) - 1);
-                        const int64_t gpos = fill + en;
-                        if (q < p.cu && gpos < p.N) {
-                            cp_async16(dst + (size_t)en * gp + q * 4, p.G + (size_t)gpos * gp + q * 4);
-                            if (two) cp_async16(dst + (size_t)(RING_SE + en) * gp + q * 4, p.G2 + (size_t)gpos * gp + q * 4);
-                        }
+            // long run: start streaming entries 32.. into the shared-memory ring right away
+            int64_t fill = s + 32;
+            auto issue = [&](int st) {
+                float* dst = ring + (size_t)st * stage_f;
+                for (int idx = lane; idx < (RING_SE << p.ql_log); idx += 32) {
+                    const int en = idx >> p.ql_log, q = idx & ((1 << p.ql_log) - 1);
+                    const int64_t gpos = fill + en;
+                    if (q < p.cu && gpos < p.N) {
+                        cp_async16(dst + (size_t)en * gp + q * 4, p.G + (size_t)gpos * gp + q * 4);
+                        if (two) cp_async16(dst + (size_t)(RING_SE + en) * gp + q * 4, p.G2 + (size_t)gpos * gp + q * 4);
                     }
-                    if (fill + lane < p.N) cp_async4(rkeys + st * RING_SE + lane, p.skeys + fill + lane);
-                    else rkeys[st * RING_SE + lane] = -2;
-                    cp_async_commit();
-                    fill += RING_SE;
-                };
+                }
+                if (fill + lane < p.N) cp_async4(rkeys + st * RING_SE + lane, p.skeys + fill + lane);
+                else rkeys[st * RING_SE + lane] = -2;
+                cp_async_commit();
+                fill += RING_SE;
+            };
+            if (n0 == 32) {
 #pragma unroll
                 for (int st = 0; st < RING_NS; ++st) issue(st);
+            }
+            // direct part: up to 32 entries straight from G, 16 loads in flight per lane
+            float acc = 0.f;
+            for (int j0 = 0; j0 < n0; j0 += 16) {
+                float tv[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u)
+                    tv[u] = (active && j0 + u < n0) ? __ldg(src + (size_t)(s + j0 + u) * gp) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 16; ++u)
+                    if (j0 + u < n0) acc = __fadd_rn(acc, tv[u]);
+            }
+            if (n0 == 32) {
                 int st = 0;
                 while (true) {
                     cp_async_wait<RING_NS - 1>();
@@ -207,18 +215,18 @@ __global__ void fm_bwd_runs_kernel(BwdParams p, int warps_per_block, int warp_f,
                         const float* b = ring + (size_t)st * stage_f + (isB ? (size_t)RING_SE * gp : 0) + comp;
                         int j = 0;
                         for (; j + 8 <= n; j += 8) {
-                            float t[8];
+                            float tv[8];
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) t[u] = b[(size_t)(j + u) * gp];
+                            for (int u = 0; u < 8; ++u) tv[u] = b[(j + u) * gp];
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, t[u]);
+                            for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, tv[u]);
                         }
-                        for (; j < n; ++j) acc = __fadd_rn(acc, b[(size_t)j * gp]);
+                        for (; j < n; ++j) acc = __fadd_rn(acc, b[j * gp]);
                     }
                     __syncwarp();
                     if (n < 32) break;
                     issue(st);
-                    st = (st + 1) & (RING_NS - 1);
+                    st = (st + 1 == RING_NS) ? 0 : st + 1;
                 }
                 cp_async_wait<0>();
                 __syncwarp();
@@ -255,14 +263,19 @@ FMB_API size_t fmb_bwd_workspace_bytes(int64_t N, int k) {
 //   table [R,rowp] updated in place; S [B,kp4]; gs [B]; gvec [B,kp4] or NULL
 //   use_fm2: the scalar gs also flows through Sum_j bi (FM / DeepFM logit); 0 for NFM
 //   mode 0: fresh-Adam sign step (reference), 1: SGD
-FMB_API int fmb_fm_backward_update(const int32_t* sorted_keys, const int32_t* perm, int64_t N, const float* xv,
-                                   float* table, int F, int k, const float* S, const float* gs, int use_fm2,
-                                   const float* gvec, float lr, int mode, void* ws, size_t ws_bytes,
-                                   cudaStream_t stream) {
+// _ex adds: n_entries = 1 + the largest entry index stored in perm (B*F; the sharded path passes
+//   world*B*F), s_pitch / gs_stride (S, gvec and gs may live inside a gathered per-sample context),
+//   key_limit (sorted keys >= key_limit are padding and are skipped).
+FMB_API int fmb_fm_backward_update_ex(const int32_t* sorted_keys, const int32_t* perm, int64_t N, int64_t n_entries,
+                                      const float* xv, float* table, int F, int k, const float* S, int s_pitch,
+                                      const float* gs, int gs_stride, int use_fm2, const float* gvec,
+                                      int32_t key_limit, float lr, int mode, void* ws, size_t ws_bytes,
+                                      cudaStream_t stream) {
     FMB_CHECK_ARG(sorted_keys && perm && table && S && gs && ws, "fmb_fm_backward_update: null pointer");
     FMB_CHECK_ARG(N > 0 && F > 0 && F < 512 && k > 0 && k <= 124, "fmb_fm_backward_update: bad shape");
     FMB_CHECK_ARG(mode == 0 || mode == 1, "fmb_fm_backward_update: unknown update mode %d", mode);
     FMB_CHECK_ARG(use_fm2 || gvec, "fmb_fm_backward_update: neither gradient path enabled");
+    FMB_CHECK_ARG(n_entries > 0 && n_entries < ((int64_t)1 << 31), "fmb_fm_backward_update: n_entries out of range");
     if (ws_bytes < fmb_bwd_workspace_bytes(N, k)) { fmb_set_error("fmb_fm_backward_update: workspace too small"); return FMB_ERR_WS; }
     BwdParams p;
     p.skeys = sorted_keys; p.perm = perm; p.N = N; p.xv = xv; p.table = table;
@@ -270,12 +283,13 @@ FMB_API int fmb_fm_backward_update(const int32_t* sorted_keys, const int32_t* pe
     p.cu = (k + 1 + 3) / 4; p.ql_log = ilog2_ceil(p.cu);
     {
         int bn = 0, bf = 0;
-        while (((int64_t)1 << bn) < N) ++bn;
+        while (((int64_t)1 << bn) < n_entries) ++bn;
         while ((1 << bf) <= F) ++bf;
-        p.fshift = bn + bf;  // 2^fshift > N*F, and e*fmagic < 2^(2*bn+2) <= 2^64
+        p.fshift = bn + bf;  // 2^fshift > n_entries*F, and e*fmagic < 2^(2*bn+2) <= 2^64
         p.fmagic = ((1ULL << p.fshift) + (unsigned long long)F - 1) / (unsigned long long)F;
     }
     p.S = S; p.gs = gs; p.use_fm2 = use_fm2; p.gvec = gvec; p.lr = lr; p.mode = mode;
+    p.s_pitch = s_pitch; p.gs_stride = gs_stride; p.key_limit = key_limit;
     const size_t gbytes = ((size_t)N * p.cu * 16 + 255) / 256 * 256;
     p.G = (float*)ws;
     p.G2 = (float*)((char*)ws + gbytes);
@@ -289,7 +303,7 @@ FMB_API int fmb_fm_backward_update(const int32_t* sorted_keys, const int32_t* pe
     const int accs_n = (nv + 3) / 4 * 4;
     const int warp_f = RING_NS * RING_SE * gp * (two ? 2 : 1) + RING_NS * RING_SE + accs_n;
     int wpb = 8;
-    while (wpb > 1 && (size_t)wpb * warp_f * 4 > 64 * 1024) wpb >>= 1;
+    while (wpb > 1 && (size_t)wpb * warp_f * 4 > 56 * 1024) wpb >>= 1;
     const size_t sm = (size_t)wpb * warp_f * 4;
     FMB_CHECK_ARG(sm <= 200 * 1024, "fmb_fm_backward_update: k too large for the run ring");
     static bool attr = false;
@@ -298,4 +312,12 @@ FMB_API int fmb_fm_backward_update(const int32_t* sorted_keys, const int32_t* pe
     fm_bwd_runs_kernel<<<(unsigned)((nwarps + wpb - 1) / wpb), 32 * wpb, sm, stream>>>(p, wpb, warp_f, accs_n);
     FMB_CHECK_LAUNCH("fm_bwd_runs_kernel");
     return FMB_OK;
+}
+
+FMB_API int fmb_fm_backward_update(const int32_t* sorted_keys, const int32_t* perm, int64_t N, const float* xv,
+                                   float* table, int F, int k, const float* S, const float* gs, int use_fm2,
+                                   const float* gvec, float lr, int mode, void* ws, size_t ws_bytes,
+                                   cudaStream_t stream) {
+    return fmb_fm_backward_update_ex(sorted_keys, perm, N, N, xv, table, F, k, S, fmb_round_up(k, 4), gs, 1, use_fm2,
+                                     gvec, 0x7fffffff, lr, mode, ws, ws_bytes, stream);
 }

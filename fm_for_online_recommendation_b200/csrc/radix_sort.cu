@@ -8,6 +8,7 @@
 // Ranking inside a tile uses __match_any_sync on a warp-striped key arrangement (no atomics on the
 // ordering path, so the permutation is bit-reproducible).
 #include "fmb_common.cuh"
+#include "smem_sort.cuh"
 
 namespace {
 
@@ -20,20 +21,7 @@ constexpr int TILE = SORT_THREADS * KPT;     // 2048 keys per CTA
 
 __device__ __forceinline__ int digit_of(int32_t key, int shift) { return (key >> shift) & (RADIX - 1); }
 
-// lanes of the warp whose (valid) key has the same digit as mine: what __match_any_sync returns, built
-// from one ballot per digit bit (MATCH is far slower than 9 VOTEs on sm_100: it was 46 % of the
-// sort kernel's stall samples in profiles/r1b).
-__device__ __forceinline__ unsigned digit_peers(unsigned d, bool valid) {
-    unsigned m = __ballot_sync(0xffffffffu, valid);
-    if (!valid) m = ~m;
-#pragma unroll
-    for (int b = 0; b < RADIX_BITS; ++b) {
-        const unsigned bit = (d >> b) & 1u;
-        const unsigned bal = __ballot_sync(0xffffffffu, bit);
-        m &= bit ? bal : ~bal;
-    }
-    return m;
-}
+using fmb::digit_peers;
 
 // hist[d * ntiles + tile] = number of keys of `tile` whose digit is d
 __global__ void __launch_bounds__(SORT_THREADS) radix_hist_kernel(const int32_t* __restrict__ keys, int64_t N,
@@ -207,69 +195,8 @@ __global__ void __launch_bounds__(FS_THREADS) sort_fields_kernel(const int32_t* 
         pbuf0[i] = (uint16_t)i;
     }
     __syncthreads();
-    uint32_t* kc = kbuf0; uint32_t* kn = kbuf1;
-    uint16_t* pc = pbuf0; uint16_t* pn = pbuf1;
-    const int slots = (B + FS_THREADS - 1) / FS_THREADS;  // per-warp slice = slots*32 consecutive keys
-    const int wbase = warp * slots * 32;
-    const uint32_t lt = (1u << lane) - 1u;
-    for (int ps = 0; ps < passes; ++ps) {
-        const int shift = ps * RADIX_BITS;
-        for (int i = threadIdx.x; i < FS_WARPS * RADIX / 2; i += FS_THREADS) reinterpret_cast<uint32_t*>(cnt)[i] = 0;
-        __syncthreads();
-        uint32_t key[FS_MAX_SLOTS];
-        uint16_t rank[FS_MAX_SLOTS];
-#pragma unroll
-        for (int s = 0; s < FS_MAX_SLOTS; ++s) {
-            if (s < slots) {
-                const int idx = wbase + s * 32 + lane;
-                const bool valid = idx < B;
-                key[s] = valid ? kc[idx] : 0u;
-                const unsigned d = valid ? ((key[s] >> shift) & (RADIX - 1)) : 0u;
-                const unsigned m = digit_peers(d, valid);
-                const int leader = __ffs(m) - 1;
-                uint32_t old = 0;
-                if (valid && lane == leader) { old = cnt[warp * RADIX + d]; cnt[warp * RADIX + d] = (uint16_t)(old + __popc(m)); }
-                old = __shfl_sync(0xffffffffu, old, leader);
-                rank[s] = (uint16_t)(old + __popc(m & lt));
-                __syncwarp();
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x < RADIX) {
-            const int d = threadIdx.x;
-            uint32_t run = 0;
-            for (int w = 0; w < FS_WARPS; ++w) { const uint32_t t = cnt[w * RADIX + d]; cnt[w * RADIX + d] = (uint16_t)run; run += t; }
-            tot[d] = run;
-        }
-        __syncthreads();
-        if (warp == 0) {  // exclusive scan of the 256 digit totals, 8 per lane
-            uint32_t v[8], sum = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { v[j] = tot[lane * 8 + j]; sum += v[j]; }
-            uint32_t inc = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-            uint32_t ex = inc - sum;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { tot[lane * 8 + j] = ex; ex += v[j]; }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int s = 0; s < FS_MAX_SLOTS; ++s) {
-            if (s < slots) {
-                const int idx = wbase + s * 32 + lane;
-                if (idx < B) {
-                    const unsigned d = (key[s] >> shift) & (RADIX - 1);
-                    const uint32_t pos = tot[d] + cnt[warp * RADIX + d] + rank[s];
-                    kn[pos] = key[s];
-                    pn[pos] = pc[idx];
-                }
-            }
-        }
-        __syncthreads();
-        uint32_t* tk = kc; kc = kn; kn = tk;
-        uint16_t* tp = pc; pc = pn; pn = tp;
-    }
+    uint32_t* kc; uint16_t* pc;
+    fmb::smem_sort_passes(kbuf0, kbuf1, pbuf0, pbuf1, cnt, tot, B, passes, &kc, &pc);
     for (int i = threadIdx.x; i < B; i += FS_THREADS) {
         skeys[(size_t)f * B + i] = (int32_t)kc[i] + off;
         perm[(size_t)f * B + i] = (int32_t)pc[i] * F + f;

@@ -1,0 +1,255 @@
+// sharded.cu -- kernels of the row-sharded multi-GPU FM step (BASELINE.json configs[4]: 33 M-row
+// tables over 2/4/8 B200).
+//
+// Global row r lives on rank r % G at local row r / G.  Every rank holds its local batch of B
+// samples; one step over the global batch of G*B samples is
+//   1. all-gather of the transposed ids                      idsT_all [G][F][B]       (NCCL)
+//   2. each OWNER sums, for every one of the G*B samples, the rows it owns in field order:
+//      partial [G*B][PW] = [S | Q | first]                   shard_partial_forward_kernel
+//      and stably sorts, per field, the entries it owns by local row
+//                                                            shard_sort_fields_kernel
+//   3. all-to-all of the pooled partials (2k+1 floats per sample and peer)            (NCCL)
+//   4. each rank folds the G partials of its own samples in owner order, finishes logit, loss and
+//      delta: ctx [B][CW] = [S | delta | loss]               shard_combine_kernel
+//   5. all-gather of ctx                                                              (NCCL)
+//   6. each owner runs the ordinary segmented backward + update over ITS sorted entries
+//      (fm_backward.cu, keys >= key_limit are padding), and every rank applies the same bias step.
+// The reduction order differs from the 1-GPU path only in step 4 (owner-major instead of
+// field-major); oracle/fm_oracle.c restates it (orc_*_sharded) so multi-GPU runs are checked bit for
+// bit as well.  No float atomics, no data-dependent host synchronisation.
+#include "fmb_common.cuh"
+#include "smem_sort.cuh"
+
+namespace {
+
+__device__ __forceinline__ bool owned_by(int32_t gid, int G, int glog, int me, int32_t& local) {
+    if (glog >= 0) { local = gid >> glog; return (gid & (G - 1)) == me; }
+    local = gid / G;
+    return gid - local * G == me;
+}
+
+__global__ void transpose_ids_kernel(const int32_t* __restrict__ ids, int B, int F, int32_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * F) return;
+    const int f = (int)(i / B), b = (int)(i - (int64_t)f * B);
+    out[i] = ids[(size_t)b * F + f];
+}
+
+struct PartialParams {
+    const int32_t* idsT_all;
+    const float* table;
+    int G, glog, me, B, F, k, rowp, kp4, cu, ql_log, PW;
+    float* partial;
+};
+
+__global__ void __launch_bounds__(256) shard_partial_forward_kernel(PartialParams p) {
+    const int q = threadIdx.x & ((1 << p.ql_log) - 1);
+    const int64_t bg = (int64_t)blockIdx.x * (256 >> p.ql_log) + (threadIdx.x >> p.ql_log);
+    if (bg >= (int64_t)p.G * p.B || q >= p.cu) return;
+    const int r = (int)(bg / p.B), b = (int)(bg - (int64_t)r * p.B);
+    const int32_t* col = p.idsT_all + (size_t)r * p.F * p.B + b;
+    float S[4] = {0.f, 0.f, 0.f, 0.f}, Q[4] = {0.f, 0.f, 0.f, 0.f};
+    float first = 0.f;
+    for (int f0 = 0; f0 < p.F; f0 += 4) {
+        int32_t lr[4];
+        bool own[4];
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            own[u] = false;
+            if (f0 + u < p.F) own[u] = owned_by(__ldg(col + (size_t)(f0 + u) * p.B), p.G, p.glog, p.me, lr[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (own[u]) v[u] = *reinterpret_cast<const float4*>(p.table + (size_t)lr[u] * p.rowp + q * 4);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (!own[u]) continue;
+            const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};  // x == 1 (all-ones feature values)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int j = q * 4 + t;
+                if (j < p.k) { S[t] = __fadd_rn(S[t], e[t]); Q[t] = __fadd_rn(Q[t], __fmul_rn(e[t], e[t])); }
+                else if (j == p.k) first = __fadd_rn(first, e[t]);
+            }
+        }
+    }
+    float* out = p.partial + (size_t)bg * p.PW;
+    if (q * 4 < p.kp4) {
+        *reinterpret_cast<float4*>(out + q * 4) = make_float4(S[0], S[1], S[2], S[3]);
+        *reinterpret_cast<float4*>(out + p.kp4 + q * 4) = make_float4(Q[0], Q[1], Q[2], Q[3]);
+    }
+    if (q == p.k / 4) out[2 * p.kp4] = first;
+}
+
+__global__ void shard_combine_kernel(const float* __restrict__ recv, const float* __restrict__ bias,
+                                     const float* __restrict__ y, int G, int B, int k, int kp4, int PW, int CW,
+                                     int loss_kind, float* __restrict__ ctx, float* __restrict__ z_out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float sum_first = 0.f;
+    for (int o = 0; o < G; ++o) sum_first = __fadd_rn(sum_first, recv[((size_t)o * B + b) * PW + 2 * kp4]);
+    float* c = ctx + (size_t)b * CW;
+    for (int j = 0; j < kp4; ++j) {   // S = sum over owners, owner order (each partial is field-ordered)
+        float Sj = 0.f;
+        for (int o = 0; o < G; ++o) Sj = __fadd_rn(Sj, recv[((size_t)o * B + b) * PW + j]);
+        c[j] = Sj;
+    }
+    auto bi_of = [&](int j) {
+        float Sj = 0.f, Qj = 0.f;
+        for (int o = 0; o < G; ++o) {
+            const float* r = recv + ((size_t)o * B + b) * PW;
+            Sj = __fadd_rn(Sj, r[j]);
+            Qj = __fadd_rn(Qj, r[kp4 + j]);
+        }
+        return __fmul_rn(__fsub_rn(__fmul_rn(Sj, Sj), Qj), 0.5f);
+    };
+    const float sum_bi = fmb::aten_row_sum_small(bi_of, k);
+    const float z = __fadd_rn(__fadd_rn(sum_first, sum_bi), bias[0]);
+    if (z_out) z_out[b] = z;
+    const float yy = y[b];
+    const float fB = (float)((int64_t)G * B);
+    float in = z, pr = 0.f;
+    if (loss_kind == 1) { pr = fmb::sigmoidf_p(z); in = pr; }
+    const float ls = __fsub_rn(fminf(in, 0.f), fmb::log1pf_p(fmb::expf_p(-fabsf(in))));
+    const float lossv = __fsub_rn(__fmul_rn(__fsub_rn(1.0f, yy), in), ls);
+    float d = __fdiv_rn(__fsub_rn(fmb::sigmoidf_p(in), yy), fB);
+    if (loss_kind == 1) d = __fmul_rn(__fmul_rn(d, __fsub_rn(1.0f, pr)), pr);
+    c[kp4] = d;
+    c[kp4 + 1] = lossv;
+    c[kp4 + 2] = z;
+    c[kp4 + 3] = 0.f;
+}
+
+__global__ void shard_unpack_ctx_kernel(const float* __restrict__ ctx_all, int64_t n, int kp4, int CW,
+                                        float* __restrict__ delta, float* __restrict__ lossv) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    delta[i] = ctx_all[i * CW + kp4];
+    lossv[i] = ctx_all[i * CW + kp4 + 1];
+}
+
+// per field: stable compaction of the entries this rank owns (global sample order), then the
+// shared-memory LSD sort by local row.  Output segments are padded to `cap` with key = INT_MAX.
+__global__ void __launch_bounds__(fmb::SS_THREADS) shard_sort_fields_kernel(
+    const int32_t* __restrict__ idsT_all, int G, int glog, int me, int B, int F,
+    const int32_t* __restrict__ field_off, int cap, int32_t* __restrict__ skeys, int32_t* __restrict__ perm,
+    int32_t* __restrict__ counts, int32_t* __restrict__ overflow) {
+    extern __shared__ __align__(16) unsigned char fs_smem[];
+    uint32_t* kbuf0 = reinterpret_cast<uint32_t*>(fs_smem);
+    uint32_t* kbuf1 = kbuf0 + cap;
+    uint16_t* pbuf0 = reinterpret_cast<uint16_t*>(kbuf1 + cap);
+    uint16_t* pbuf1 = pbuf0 + cap + (cap & 1);
+    uint16_t* cnt = pbuf1 + cap + (cap & 1);
+    __shared__ uint32_t tot[fmb::SS_RADIX];
+    __shared__ int wtot[fmb::SS_WARPS];
+    __shared__ int s_count;
+    const int f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int32_t off = field_off[f];
+    const uint32_t nrows = (uint32_t)(field_off[f + 1] - off);
+    int32_t base;
+    { int32_t l; owned_by(off, G, glog, me, l); base = l; }           // floor(off / G)
+    const uint32_t nloc = nrows / (uint32_t)G + 2;                     // local rows of this field (upper bound)
+    const int bits = 32 - __clz(nloc);
+    const int passes = (bits + fmb::SS_RADIX_BITS - 1) / fmb::SS_RADIX_BITS;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    for (int r = 0; r < G; ++r) {
+        const int32_t* col = idsT_all + ((size_t)r * F + f) * B;
+        for (int b0 = 0; b0 < B; b0 += fmb::SS_THREADS) {
+            const int b = b0 + threadIdx.x;
+            int32_t local = 0;
+            const bool own = b < B && owned_by(__ldg(col + b), G, glog, me, local);
+            const unsigned bal = __ballot_sync(0xffffffffu, own);
+            if (lane == 0) wtot[warp] = __popc(bal);
+            __syncthreads();
+            int pre = s_count, all = 0;
+            for (int w = 0; w < fmb::SS_WARPS; ++w) { const int c = wtot[w]; if (w < warp) pre += c; all += c; }
+            if (own) {
+                const int o = pre + __popc(bal & ((1u << lane) - 1u));
+                if (o < cap) { kbuf0[o] = (uint32_t)(local - base); pbuf0[o] = (uint16_t)(r * B + b); }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) s_count += all;
+            __syncthreads();
+        }
+    }
+    int n = s_count;
+    if (n > cap) { if (threadIdx.x == 0) atomicMax(overflow, n); n = cap; }
+    if (threadIdx.x == 0) counts[f] = n;
+    uint32_t* kc; uint16_t* pc;
+    fmb::smem_sort_passes(kbuf0, kbuf1, pbuf0, pbuf1, cnt, tot, n, passes, &kc, &pc);
+    for (int i = threadIdx.x; i < cap; i += fmb::SS_THREADS) {
+        skeys[(size_t)f * cap + i] = i < n ? (int32_t)kc[i] + base : 0x7fffffff;
+        perm[(size_t)f * cap + i] = i < n ? (int32_t)pc[i] * F + f : 0;
+    }
+}
+
+static int ilog2_exact(int x) { int l = 0; while ((1 << l) < x) ++l; return (1 << l) == x ? l : -1; }
+static int ilog2_ceil(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
+
+}  // namespace
+
+FMB_API int fmb_shard_pw(int k) { return 2 * fmb_round_up(k, 4) + 4; }   // floats per pooled partial
+FMB_API int fmb_shard_cw(int k) { return fmb_round_up(k, 4) + 4; }       // floats per sample context
+FMB_API int fmb_shard_sort_max_cap(void) { return fmb::SS_WARPS * fmb::SS_MAX_SLOTS * 32; }
+
+// ids [B,F] -> out [F,B]
+FMB_API int fmb_transpose_ids(const int32_t* ids, int B, int F, int32_t* out, cudaStream_t stream) {
+    FMB_CHECK_ARG(ids && out && B > 0 && F > 0, "fmb_transpose_ids: bad arguments");
+    const int64_t n = (int64_t)B * F;
+    transpose_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ids, B, F, out);
+    FMB_CHECK_LAUNCH("transpose_ids_kernel");
+    return FMB_OK;
+}
+
+// step 2a: pooled partials of the rows rank `me` owns, for all G*B samples (feature values all ones)
+FMB_API int fmb_shard_partial_forward(const int32_t* idsT_all, const float* table_local, int G, int me, int B, int F,
+                                      int k, float* partial, cudaStream_t stream) {
+    FMB_CHECK_ARG(idsT_all && table_local && partial, "fmb_shard_partial_forward: null pointer");
+    FMB_CHECK_ARG(G > 0 && me >= 0 && me < G && B > 0 && F > 0 && k > 0 && k <= 124, "fmb_shard_partial_forward: bad arguments");
+    PartialParams p;
+    p.idsT_all = idsT_all; p.table = table_local; p.G = G; p.glog = ilog2_exact(G); p.me = me; p.B = B; p.F = F;
+    p.k = k; p.rowp = fmb_round_up(k + 1, 16); p.kp4 = fmb_round_up(k, 4); p.cu = (k + 1 + 3) / 4;
+    p.ql_log = ilog2_ceil(p.cu); p.PW = fmb_shard_pw(k); p.partial = partial;
+    const int spb = 256 >> p.ql_log;
+    const int64_t n = (int64_t)G * B;
+    shard_partial_forward_kernel<<<(unsigned)((n + spb - 1) / spb), 256, 0, stream>>>(p);
+    FMB_CHECK_LAUNCH("shard_partial_forward_kernel");
+    return FMB_OK;
+}
+
+// step 4: recv [G][B][PW] (block o = partials owner o computed for MY samples) -> ctx [B][CW]
+FMB_API int fmb_shard_combine(const float* recv, const float* bias, const float* y, int G, int B, int k,
+                              int loss_kind, float* ctx, float* z_out, cudaStream_t stream) {
+    FMB_CHECK_ARG(recv && bias && y && ctx && G > 0 && B > 0 && k > 0, "fmb_shard_combine: bad arguments");
+    shard_combine_kernel<<<(B + 127) / 128, 128, 0, stream>>>(recv, bias, y, G, B, k, fmb_round_up(k, 4),
+                                                            fmb_shard_pw(k), fmb_shard_cw(k), loss_kind, ctx, z_out);
+    FMB_CHECK_LAUNCH("shard_combine_kernel");
+    return FMB_OK;
+}
+
+FMB_API int fmb_shard_unpack_ctx(const float* ctx_all, int64_t n, int k, float* delta, float* lossv,
+                                 cudaStream_t stream) {
+    FMB_CHECK_ARG(ctx_all && delta && lossv && n > 0, "fmb_shard_unpack_ctx: bad arguments");
+    shard_unpack_ctx_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ctx_all, n, fmb_round_up(k, 4),
+                                                                           fmb_shard_cw(k), delta, lossv);
+    FMB_CHECK_LAUNCH("shard_unpack_ctx_kernel");
+    return FMB_OK;
+}
+
+// step 2b: per-field sorted list of the entries rank `me` owns.  skeys/perm [F][cap] (padding key
+// INT_MAX), counts [F], overflow [1] (max count seen when a field exceeded cap, else untouched).
+FMB_API int fmb_shard_sort_fields(const int32_t* idsT_all, int G, int me, int B, int F, const int32_t* field_off,
+                                  int cap, int32_t* skeys, int32_t* perm, int32_t* counts, int32_t* overflow,
+                                  cudaStream_t stream) {
+    FMB_CHECK_ARG(idsT_all && field_off && skeys && perm && counts && overflow, "fmb_shard_sort_fields: null pointer");
+    FMB_CHECK_ARG(cap > 0 && cap <= fmb_shard_sort_max_cap(), "fmb_shard_sort_fields: cap=%d out of range", cap);
+    FMB_CHECK_ARG((int64_t)G * B <= 65536, "fmb_shard_sort_fields: G*B must be <= 65536 (16-bit sample payload)");
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(shard_sort_fields_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr = true; }
+    shard_sort_fields_kernel<<<F, fmb::SS_THREADS, fmb::smem_sort_bytes(cap), stream>>>(
+        idsT_all, G, ilog2_exact(G), me, B, F, field_off, cap, skeys, perm, counts, overflow);
+    FMB_CHECK_LAUNCH("shard_sort_fields_kernel");
+    return FMB_OK;
+}

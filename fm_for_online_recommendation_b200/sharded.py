@@ -1,0 +1,282 @@
+"""Row-sharded multi-GPU FM training step (BASELINE.json configs[4]).
+
+One process per GPU (`torch.distributed`, backend nccl).  Global row r of the packed table lives on
+rank r % G at local row r // G; every rank feeds its own batch of B samples and one call performs
+the step over the global batch of G*B samples (same semantics as the single-GPU
+`update_embedding` on the concatenated batch: loss is the mean over G*B, duplicate rows are summed in
+global sample order).  Pipeline and reduction order: see csrc/sharded.cu.
+
+The reference has no distributed code; this module is the B200-native design for its Criteo-scale
+configuration.  `ShardedFM` is not a reference class, it is the engine `bench.py --gpus N` drives.
+"""
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check, ptr
+
+INT_MAX = 0x7FFFFFFF
+
+
+# ------------------------------------------------------------------ host-side shard map (CPU-testable)
+def owner_of(gid, G):
+    return gid % G
+
+
+def local_row(gid, G):
+    return gid // G
+
+
+def local_rows_count(R, G, rank):
+    """rows r in [0, R) with r % G == rank."""
+    return (R - rank + G - 1) // G if R > rank else 0
+
+
+def shard_from_full(full, G, rank):
+    """rows of a full [R, ...] array owned by `rank`, in local-row order."""
+    return full[rank::G]
+
+
+def full_from_shards(shards):
+    """inverse of shard_from_full for a list of per-rank arrays."""
+    G = len(shards)
+    R = sum(s.shape[0] for s in shards)
+    out = np.empty((R,) + tuple(shards[0].shape[1:]), dtype=shards[0].dtype)
+    for r, s in enumerate(shards):
+        out[r::G] = s
+    return out
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class ShardedFM:
+    """FM (first + second order, bias) with the embedding tables row-sharded over the process group."""
+
+    def __init__(self, feature_sizes, embedding_size, n=1e-4, b=0.99, update_mode=0, group=None, seed=0,
+                 init="normal", world=None, rank=None):
+        self._lib = _lib.require_cuda()
+        self.group = group
+        # world/rank given explicitly: no process group is touched (single-process emulation of the
+        # ranks in tests: the phases below are called rank by rank and the exchanges done by hand)
+        self.G = world if world is not None else dist.get_world_size(group)
+        self.rank = rank if rank is not None else dist.get_rank(group)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.feature_sizes = list(feature_sizes)
+        self.F, self.k = len(feature_sizes), embedding_size
+        self.rowp = self._lib.fmb_rowp(self.k)
+        self.kp4 = self._lib.fmb_kp4(self.k)
+        self.PW = self._lib.fmb_shard_pw(self.k)
+        self.CW = self._lib.fmb_shard_cw(self.k)
+        self.offsets_np = np.concatenate([[0], np.cumsum(feature_sizes)]).astype(np.int64)
+        self.R = int(self.offsets_np[-1])
+        self.R_local = local_rows_count(self.R, self.G, self.rank)
+        self.field_off_dev = torch.from_numpy(self.offsets_np.astype(np.int32)).to(self.device)
+        self.offsets_dev = torch.from_numpy(self.offsets_np[:-1].copy()).to(self.device)
+        self.lr = float(np.float32(n))
+        self.update_mode = update_mode
+        self.table = torch.zeros(self.R_local + 1, self.rowp, device=self.device)
+        if init == "normal":  # N(0,1) like nn.Embedding; drawn on the device (synthetic weights)
+            g = torch.Generator(device=self.device)
+            g.manual_seed(seed * 1000 + self.rank)
+            self.table[:self.R_local, :self.k + 1].normal_(generator=g)
+        self.bias = torch.full((1,), float(np.float32(b)), device=self.device)
+        self._ws = {}
+        self.launches = 0
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    # ---------------------------------------------------------------- parameters (tests)
+    def load_full(self, V, w1, bias):
+        V = np.asarray(V, np.float32)
+        w1 = np.asarray(w1, np.float32)
+        t = np.zeros((self.R_local + 1, self.rowp), np.float32)
+        t[:self.R_local, :self.k] = shard_from_full(V, self.G, self.rank)
+        t[:self.R_local, self.k] = shard_from_full(w1, self.G, self.rank)
+        self.table.copy_(torch.from_numpy(t))
+        self.bias.fill_(float(np.asarray(bias).reshape(-1)[0]))
+
+    def local_params(self):
+        t = self.table[:self.R_local].cpu().numpy()
+        return t[:, :self.k].copy(), t[:, self.k].copy()
+
+    # ---------------------------------------------------------------- the step
+    def _buf(self, name, shape, dtype=torch.float32):
+        n = int(np.prod(shape))
+        t = self._ws.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._ws[name] = t
+        return t[:n].view(*shape)
+
+    def encode(self, Xi_local, Y_local):
+        """per-field ids [B,F] (lists / ndarray) + labels -> device (global row ids int32, labels fp32)."""
+        a = np.asarray(Xi_local, dtype=np.int64).reshape(-1, self.F)
+        ids = torch.from_numpy((a + self.offsets_np[:-1][None, :]).astype(np.int32)).to(self.device)
+        y = torch.from_numpy(np.asarray(Y_local, dtype=np.float32).reshape(-1)).to(self.device)
+        return ids.contiguous(), y
+
+    # the step, split at the three exchanges so tests can emulate several ranks in one process
+    def phase_ids(self, ids):
+        """-> idsT [F,B] (to be all-gathered into [G,F,B])."""
+        B = ids.shape[0]
+        idsT = self._buf("idsT", (self.F, B), torch.int32)
+        check(self._lib.fmb_transpose_ids(ptr(ids), B, self.F, ptr(idsT), _stream()), "fmb_transpose_ids")
+        return idsT
+
+    def phase_owner_forward(self, idsT_all):
+        """idsT_all [G,F,B] -> partial [G,B,PW] (block r goes to rank r); also sorts the owned entries."""
+        lib, st = self._lib, _stream()
+        G, F, k = self.G, self.F, self.k
+        B = idsT_all.shape[2]
+        Btot = G * B
+        partial = self._buf("partial", (G, B, self.PW))
+        check(lib.fmb_shard_partial_forward(ptr(idsT_all), ptr(self.table), G, self.rank, B, F, k, ptr(partial), st),
+              "fmb_shard_partial_forward")
+        cap = min(lib.fmb_shard_sort_max_cap(), ((2 * Btot // G + Btot // 4 + 1023) // 1024) * 1024)
+        self._cap = cap
+        skeys = self._buf("skeys", (F, cap), torch.int32)
+        perm = self._buf("perm", (F, cap), torch.int32)
+        counts = self._buf("counts", (F,), torch.int32)
+        check(lib.fmb_shard_sort_fields(ptr(idsT_all), G, self.rank, B, F, ptr(self.field_off_dev), cap, ptr(skeys),
+                                        ptr(perm), ptr(counts), ptr(self.overflow), st), "fmb_shard_sort_fields")
+        return partial
+
+    def phase_combine(self, recv, y, loss_kind=0):
+        """recv [G,B,PW] (block o = owner o's partials for MY samples) -> ctx [B,CW]."""
+        B = recv.shape[1]
+        ctx = self._buf("ctx", (B, self.CW))
+        check(self._lib.fmb_shard_combine(ptr(recv), ptr(self.bias), ptr(y), self.G, B, self.k, loss_kind, ptr(ctx),
+                                          None, _stream()), "fmb_shard_combine")
+        return ctx
+
+    def phase_backward(self, ctx_all):
+        """ctx_all [G*B,CW] -> row updates of the owned rows, bias step; returns the mean loss."""
+        lib, st = self._lib, _stream()
+        F, k, cap = self.F, self.k, self._cap
+        Btot = ctx_all.shape[0]
+        N = F * cap
+        wsb = lib.fmb_bwd_workspace_bytes(N, k)
+        ws = self._buf("bwd_ws", (wsb,), torch.uint8)
+        gs = ctx_all.view(-1)[self.kp4:]
+        check(lib.fmb_fm_backward_update_ex(ptr(self._ws["skeys"]), ptr(self._ws["perm"]), N, Btot * F, None,
+                                            ptr(self.table), F, k, ptr(ctx_all), self.CW, ptr(gs), self.CW, 1, None,
+                                            INT_MAX, self.lr, self.update_mode, ptr(ws), wsb, st),
+              "fmb_fm_backward_update_ex")
+        delta_all = self._buf("delta_all", (Btot,))
+        lossv_all = self._buf("lossv_all", (Btot,))
+        check(lib.fmb_shard_unpack_ctx(ptr(ctx_all), Btot, k, ptr(delta_all), ptr(lossv_all), st),
+              "fmb_shard_unpack_ctx")
+        loss = torch.empty((), device=self.device)
+        check(lib.fmb_finish_step(ptr(delta_all), ptr(lossv_all), Btot, ptr(self.bias), self.lr, self.update_mode,
+                                  ptr(loss), st), "fmb_finish_step")
+        self.launches += 9
+        return loss
+
+    def update_embedding(self, ids, y, loss_kind=0):
+        """ids int32 [B,F] global row ids of THIS rank's batch (device), y fp32 [B] (device).
+        Returns the mean loss over the global batch (0-dim device tensor, identical on every rank)."""
+        G, B, F = self.G, ids.shape[0], self.F
+        idsT = self.phase_ids(ids)
+        idsT_all = self._buf("idsT_all", (G, F, B), torch.int32)
+        dist.all_gather_into_tensor(idsT_all.view(-1), idsT.view(-1), group=self.group)
+        partial = self.phase_owner_forward(idsT_all)
+        recv = self._buf("recv", (G, B, self.PW))
+        dist.all_to_all_single(recv.view(-1), partial.view(-1), group=self.group)
+        ctx = self.phase_combine(recv, y, loss_kind)
+        ctx_all = self._buf("ctx_all", (G * B, self.CW))
+        dist.all_gather_into_tensor(ctx_all.view(-1), ctx.view(-1), group=self.group)
+        return self.phase_backward(ctx_all)
+
+    def check_overflow(self):
+        v = int(self.overflow.item())
+        if v:
+            raise RuntimeError(f"a field had {v} owned entries on one rank, more than the per-field sort capacity")
+
+
+# ------------------------------------------------------------------ bench.py --gpus N (N > 1)
+def bench_main(args, sizes, config):
+    """weak scaling: every rank trains on its own batch of args.batch samples per step."""
+    from bench import ClockSampler, synth_batches  # noqa: WPS433 (bench.py is the caller)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    B, F, k = args.batch, len(sizes), 10
+    K, W = args.steps, max(args.warmup, 3)
+    model = ShardedFM(sizes, k, n=1e-4, seed=0)
+    NB = 8
+    host = synth_batches(sizes, B, NB, 1234 + rank)
+    enc = [model.encode(Xi, Y) for Xi, Y in host]
+    stream = torch.cuda.current_stream()
+    for i in range(W):
+        model.update_embedding(*enc[i % NB])
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    l0 = model.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(K):
+        model.update_embedding(*enc[(W + i) % NB])
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = model.launches - l0
+    # e2e: host ids/labels of this rank in, loss out, every step
+    hosts = [(np.ascontiguousarray((Xi + model.offsets_np[:-1][None, :]).astype(np.int32)), Y) for Xi, Y in host]
+    pin_i = torch.empty(B, F, dtype=torch.int32).pin_memory()
+    pin_y = torch.empty(B, dtype=torch.float32).pin_memory()
+    d_i = torch.empty(B, F, dtype=torch.int32, device="cuda")
+    d_y = torch.empty(B, device="cuda")
+
+    def host_step(i):
+        ids_h, y_h = hosts[i % NB]
+        pin_i.numpy()[...] = ids_h
+        pin_y.numpy()[...] = y_h
+        d_i.copy_(pin_i, non_blocking=True)
+        d_y.copy_(pin_y, non_blocking=True)
+        return float(model.update_embedding(d_i, d_y).item())
+
+    for i in range(W):
+        host_step(i)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        host_step(W + i)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e = torch.tensor([time.perf_counter() - t0], device="cuda")
+    dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop()
+    model.check_overflow()
+    if rank == 0:
+        value = world * B * K / (ms * 1e-3)
+        step_bytes = B * (8 * F * (k + 1) + 8 * F + 8)
+        line = {
+            "metric": "train samples/sec (fwd+bwd+update)", "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(config, parallelism=f"row-sharded tables over {world} GPUs (r % G), NCCL all-gather + "
+                                               "all-to-all of pooled partials", global_batch=world * B),
+            "clocks": clocks,
+            "e2e": {"value": world * B * K / float(e2e.item()), "unit": "samples/s",
+                    "h2d_bytes_per_step": 4 * B * F + 4 * B, "d2h_bytes_per_step": 4,
+                    "api": "ShardedFM.update_embedding (pinned host ids/y in, loss out, per rank)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "whole step per GPU", "achieved": step_bytes / (ms / K * 1e-3) / 1e9,
+                         "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
+                         "note": "multi-GPU line: per-kernel roofline is reported by the N=1 run"},
+        }
+        print(json.dumps(line))
+    dist.barrier()

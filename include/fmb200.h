@@ -98,6 +98,30 @@ int fmb_fm_backward_update(const int32_t* sorted_keys_dev, const int32_t* perm_d
                            const float* gs_dev, int use_fm2, const float* gvec_dev, float lr, int mode,
                            void* ws_dev, size_t ws_bytes, fmb_stream_t stream);
 
+/* extended form: n_entries = 1 + largest entry index in perm; S/gvec row pitch and gs stride (they may
+ * live inside a gathered per-sample context); sorted keys >= key_limit are padding and are skipped */
+int fmb_fm_backward_update_ex(const int32_t* sorted_keys_dev, const int32_t* perm_dev, int64_t N, int64_t n_entries,
+                              const float* xv_dev, float* table_dev, int F, int k, const float* S_dev, int s_pitch,
+                              const float* gs_dev, int gs_stride, int use_fm2, const float* gvec_dev,
+                              int32_t key_limit, float lr, int mode, void* ws_dev, size_t ws_bytes,
+                              fmb_stream_t stream);
+
+/* ---- row-sharded multi-GPU step (BASELINE.json configs[4]; no counterpart in the reference, which is
+ * single-device: SURVEY.md 8e).  Row r lives on rank r % G at local row r / G.  See csrc/sharded.cu. */
+int fmb_shard_pw(int k); /* floats per pooled partial [S | Q | first]   */
+int fmb_shard_cw(int k); /* floats per sample context [S | delta | loss | z] */
+int fmb_shard_sort_max_cap(void);
+int fmb_transpose_ids(const int32_t* ids_dev /*[B,F]*/, int B, int F, int32_t* out_dev /*[F,B]*/, fmb_stream_t stream);
+int fmb_shard_partial_forward(const int32_t* idsT_all_dev /*[G,F,B]*/, const float* table_local_dev, int G, int me,
+                              int B, int F, int k, float* partial_dev /*[G*B,PW]*/, fmb_stream_t stream);
+int fmb_shard_combine(const float* recv_dev /*[G,B,PW]*/, const float* bias_dev, const float* y_dev, int G, int B,
+                      int k, int loss_kind, float* ctx_dev /*[B,CW]*/, float* z_dev /*nullable*/, fmb_stream_t stream);
+int fmb_shard_unpack_ctx(const float* ctx_all_dev, int64_t n, int k, float* delta_dev, float* lossv_dev,
+                         fmb_stream_t stream);
+int fmb_shard_sort_fields(const int32_t* idsT_all_dev, int G, int me, int B, int F, const int32_t* field_off_dev,
+                          int cap, int32_t* sorted_keys_dev /*[F,cap]*/, int32_t* perm_dev /*[F,cap]*/,
+                          int32_t* counts_dev /*[F]*/, int32_t* overflow_dev /*[1]*/, fmb_stream_t stream);
+
 /* ---- A4/A5: MLP tower on the Bi-Interaction vector (deepfm_adam.py:79-89, nfm_adam.py:78-88,
  * deepfm_onn.py:88-102).  mlp = W0[H,k] c0[H] W1[H,H] c1[H] ... (nn.Linear layouts, concatenated);
  * act [L,B,H] post-relu activations; head [L,B] = sum_j act[l][b][j]. fp32 SIMT, k-ascending FMA. */

@@ -109,6 +109,8 @@ typedef struct {
     float* gA;        /* [R*(k+1)] */
     float* gB;        /* [R*(k+1)] */
     uint8_t* touched; /* [R] */
+    int32_t shard_G;  /* > 1: forward sums in the row-sharded multi-GPU order (owner-major), see
+                         fm_for_online_recommendation_b200/csrc/sharded.cu; 0/1: reference order */
 } orc_model;
 
 static size_t mlp_w_off(const orc_model* m, int l) {
@@ -129,20 +131,37 @@ API void orc_fm_forward(const orc_model* m, const int32_t* ids, const float* xv,
     float* bj = (float*)malloc(sizeof(float) * k);
     for (int b = 0; b < B; ++b) {
         for (int j = 0; j < k; ++j) { Sj[j] = 0.f; Qj[j] = 0.f; }
-        for (int f = 0; f < F; ++f) {
-            const int32_t r = ids[(size_t)b * F + f];
-            const float x = xv[(size_t)b * F + f];
-            fo[f] = m->w1[r] * x; /* deepfm_adam.py:50 */
-            const float* v = m->V + (size_t)r * k;
-            for (int j = 0; j < k; ++j) {
-                float e = v[j] * x;     /* deepfm_adam.py:60 */
-                Sj[j] = Sj[j] + e;      /* python sum(), left to right, :62 */
-                float sq = e * e;       /* :66 */
-                Qj[j] = Qj[j] + sq;     /* :67 */
+        const int G = m->shard_G > 1 ? m->shard_G : 1;
+        float sf_sharded = 0.f;
+        for (int o = 0; o < G; ++o) {
+            /* G == 1: the reference's left-to-right sum over fields.  G > 1: owner o first sums the rows
+             * it holds (row r lives on rank r % G) in field order, then the owners' partials are added
+             * in owner order -- the order the multi-GPU path uses. */
+            float pS[256], pQ[256], pf = 0.f;
+            for (int j = 0; j < k; ++j) { pS[j] = 0.f; pQ[j] = 0.f; }
+            for (int f = 0; f < F; ++f) {
+                const int32_t r = ids[(size_t)b * F + f];
+                if (G > 1 && r % G != o) continue;
+                const float x = xv[(size_t)b * F + f];
+                fo[f] = m->w1[r] * x; /* deepfm_adam.py:50 */
+                pf = pf + fo[f];
+                const float* v = m->V + (size_t)r * k;
+                for (int j = 0; j < k; ++j) {
+                    float e = v[j] * x;     /* deepfm_adam.py:60 */
+                    pS[j] = pS[j] + e;      /* python sum(), left to right, :62 */
+                    float sq = e * e;       /* :66 */
+                    pQ[j] = pQ[j] + sq;     /* :67 */
+                }
+            }
+            if (G > 1) {
+                for (int j = 0; j < k; ++j) { Sj[j] = Sj[j] + pS[j]; Qj[j] = Qj[j] + pQ[j]; }
+                sf_sharded = sf_sharded + pf;
+            } else {
+                for (int j = 0; j < k; ++j) { Sj[j] = pS[j]; Qj[j] = pQ[j]; }
             }
         }
         for (int j = 0; j < k; ++j) bj[j] = ((Sj[j] * Sj[j]) - Qj[j]) * 0.5f; /* :68 */
-        float sf = orc_sum_aten(fo, F);
+        float sf = G > 1 ? sf_sharded : orc_sum_aten(fo, F);
         float sb = orc_sum_aten(bj, k);
         if (first) for (int f = 0; f < F; ++f) first[(size_t)b * F + f] = fo[f];
         if (S) for (int j = 0; j < k; ++j) S[(size_t)b * k + j] = Sj[j];
