@@ -44,6 +44,7 @@ struct BwdParams {
     int32_t key_limit;    // keys >= key_limit are padding (sharded path) and are skipped
     float* G;             // [N][cu*4] staged contributions (chain A, or the only chain)
     float* G2;            // [N][cu*4] chain B when both gradient paths are live
+    long long* dbg;       // optional per-run timing records (debug builds of bench only), else NULL
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(256) fm_bwd_entry_kernel(BwdParams p) {
 constexpr int RING_SE = 32;  // entries per ring stage (one key per lane)
 constexpr int RING_NS = 8;   // stages
 
-__global__ void fm_bwd_runs_kernel(BwdParams p, int warps_per_block, int warp_f, int accs_n) {
+__global__ void __launch_bounds__(256, 3) fm_bwd_runs_kernel(BwdParams p, int warps_per_block, int warp_f, int accs_n) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t P0 = ((int64_t)blockIdx.x * warps_per_block + wib) * 32;
@@ -154,11 +155,22 @@ __global__ void fm_bwd_runs_kernel(BwdParams p, int warps_per_block, int warp_f,
     // runs (>= 2 entries) that START inside these 32 positions
     unsigned todo = __ballot_sync(0xffffffffu, pos < p.N && k0 >= 0 && k0 < p.key_limit && k0 != prev && k0 == next);
 
+    // per-lane constants of the ring fill: lane -> (entry within a group of 32>>ql_log, 16-byte chunk)
+    const int fl_q = lane & ((1 << p.ql_log) - 1);
+    const int fl_e = lane >> p.ql_log;
+    const int fl_iters = 1 << p.ql_log;                 // groups of (32 >> ql_log) entries per stage
+    const int fl_estep = 32 >> p.ql_log;
+    const bool fl_on = fl_q < p.cu;
+    const int fl_off = fl_e * gp + fl_q * 4;            // float offset inside a stage / inside G
+
     while (todo) {
         const int bit = __ffs(todo) - 1;
         todo &= todo - 1;
         const int64_t s = P0 + bit;
         const int32_t key = __shfl_sync(0xffffffffu, k0, bit);
+        long long t_start = 0, t_direct = 0, t_ring = 0;
+        if (p.dbg) t_start = clock64();
+        int run_len = 0;
         // leading matches among the first 32 entries of the run (keys are already in registers)
         const int t = bit + lane;
         const int32_t ka = __shfl_sync(0xffffffffu, k0, t & 31);
@@ -172,38 +184,62 @@ __global__ void fm_bwd_runs_kernel(BwdParams p, int warps_per_block, int warp_f,
             const bool isB = vl >= kc;
             const int comp = isB ? vl - kc : vl;
             const float* src = (isB ? p.G2 : p.G) + comp;
-            // long run: start streaming entries 32.. into the shared-memory ring right away
+            // the row's old value is needed only at the very end: fetch it now, off the critical path
+            float pold = 0.f;
+            if (v0 == 0 && lane < kc) pold = p.table[(size_t)key * p.rowp + lane];
+            // long run: start streaming entries 32.. into the shared-memory ring right away.
+            // A single warp executes this chain alone, so the fill path is kept to a handful of
+            // instructions: pointers advance by constants, bounds are checked once per stage.
             int64_t fill = s + 32;
+            const float* gsrc = p.G + (size_t)fill * gp + fl_off;
+            const float* gsrc2 = two ? p.G2 + (size_t)fill * gp + fl_off : nullptr;
             auto issue = [&](int st) {
-                float* dst = ring + (size_t)st * stage_f;
-                for (int idx = lane; idx < (RING_SE << p.ql_log); idx += 32) {
-                    const int en = idx >> p.ql_log, q = idx & ((1 << p.ql_log) - 1);
-                    const int64_t gpos = fill + en;
-                    if (q < p.cu && gpos < p.N) {
-                        cp_async16(dst + (size_t)en * gp + q * 4, p.G + (size_t)gpos * gp + q * 4);
-                        if (two) cp_async16(dst + (size_t)(RING_SE + en) * gp + q * 4, p.G2 + (size_t)gpos * gp + q * 4);
+                float* dst = ring + (size_t)st * stage_f + fl_off;
+                if (fill + RING_SE <= p.N) {
+                    if (fl_on) {
+                        for (int it = 0; it < fl_iters; ++it) {
+                            cp_async16(dst + it * fl_estep * gp, gsrc + it * fl_estep * gp);
+                            if (two) cp_async16(dst + (RING_SE + it * fl_estep) * gp, gsrc2 + it * fl_estep * gp);
+                        }
                     }
+                    cp_async4(rkeys + st * RING_SE + lane, p.skeys + fill + lane);
+                } else {
+                    for (int it = 0; it < fl_iters; ++it) {
+                        if (fl_on && fill + fl_e + it * fl_estep < p.N) {
+                            cp_async16(dst + it * fl_estep * gp, gsrc + it * fl_estep * gp);
+                            if (two) cp_async16(dst + (RING_SE + it * fl_estep) * gp, gsrc2 + it * fl_estep * gp);
+                        }
+                    }
+                    if (fill + lane < p.N) cp_async4(rkeys + st * RING_SE + lane, p.skeys + fill + lane);
+                    else rkeys[st * RING_SE + lane] = -2;
                 }
-                if (fill + lane < p.N) cp_async4(rkeys + st * RING_SE + lane, p.skeys + fill + lane);
-                else rkeys[st * RING_SE + lane] = -2;
                 cp_async_commit();
                 fill += RING_SE;
+                gsrc += RING_SE * gp;
+                if (two) gsrc2 += RING_SE * gp;
             };
             if (n0 == 32) {
 #pragma unroll
                 for (int st = 0; st < RING_NS; ++st) issue(st);
             }
-            // direct part: up to 32 entries straight from G, 16 loads in flight per lane
+            // direct part: up to 32 entries straight from G, all loads in flight at once
             float acc = 0.f;
-            for (int j0 = 0; j0 < n0; j0 += 16) {
-                float tv[16];
+            {
+                const float* sp = src + (size_t)s * gp;
+                float tv[16], tw[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) tv[u] = (active && u < n0) ? __ldg(sp + u * gp) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 16; ++u) tw[u] = (active && 16 + u < n0) ? __ldg(sp + (16 + u) * gp) : 0.f;
 #pragma unroll
                 for (int u = 0; u < 16; ++u)
-                    tv[u] = (active && j0 + u < n0) ? __ldg(src + (size_t)(s + j0 + u) * gp) : 0.f;
+                    if (u < n0) acc = __fadd_rn(acc, tv[u]);
 #pragma unroll
                 for (int u = 0; u < 16; ++u)
-                    if (j0 + u < n0) acc = __fadd_rn(acc, tv[u]);
+                    if (16 + u < n0) acc = __fadd_rn(acc, tw[u]);
             }
+            if (p.dbg) t_direct = clock64();
+            run_len = n0;
             if (n0 == 32) {
                 int st = 0;
                 while (true) {
@@ -212,18 +248,19 @@ __global__ void fm_bwd_runs_kernel(BwdParams p, int warps_per_block, int warp_f,
                     const unsigned m2 = __ballot_sync(0xffffffffu, rkeys[st * RING_SE + lane] == key);
                     const int n = (m2 == 0xffffffffu) ? 32 : __ffs(~m2) - 1;
                     if (active) {
-                        const float* b = ring + (size_t)st * stage_f + (isB ? (size_t)RING_SE * gp : 0) + comp;
-                        int j = 0;
-                        for (; j + 8 <= n; j += 8) {
-                            float tv[8];
+                        const float* b = ring + (size_t)st * stage_f + (isB ? RING_SE * gp : 0) + comp;
+#pragma unroll 1
+                        for (int h = 0; h < 32; h += 16) {
+                            float tv[16];
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) tv[u] = b[(j + u) * gp];
+                            for (int u = 0; u < 16; ++u) tv[u] = b[(h + u) * gp];
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, tv[u]);
+                            for (int u = 0; u < 16; ++u)
+                                if (h + u < n) acc = __fadd_rn(acc, tv[u]);
                         }
-                        for (; j < n; ++j) acc = __fadd_rn(acc, b[j * gp]);
                     }
                     __syncwarp();
+                    run_len += n;
                     if (n < 32) break;
                     issue(st);
                     st = (st + 1 == RING_NS) ? 0 : st + 1;
@@ -231,7 +268,9 @@ __global__ void fm_bwd_runs_kernel(BwdParams p, int warps_per_block, int warp_f,
                 cp_async_wait<0>();
                 __syncwarp();
             }
+            if (p.dbg) t_ring = clock64();
             if (active) accs[vl] = acc;
+            if (v0 == 0 && lane < kc) accs[accs_n + lane] = pold;
         }
         __syncwarp();
         // fold chain B into chain A and update the row (one lane per component)
@@ -241,10 +280,19 @@ __global__ void fm_bwd_runs_kernel(BwdParams p, int warps_per_block, int warp_f,
                 float gsum = accs[c];
                 if (two && c < p.k) gsum = __fadd_rn(gsum, accs[kc + c]);
                 float* addr = p.table + (size_t)key * p.rowp + c;
-                *addr = fmb::apply_update(*addr, gsum, p.lr, p.mode);
+                const float old = c < 32 ? accs[accs_n + c] : *addr;
+                *addr = fmb::apply_update(old, gsum, p.lr, p.mode);
             }
         }
         __syncwarp();
+        if (p.dbg && lane == 0) {
+            const unsigned long long slot = atomicAdd((unsigned long long*)p.dbg, 1ULL);
+            if (slot < 4000) {
+                long long* r = p.dbg + 8 + slot * 8;
+                r[0] = run_len; r[1] = t_start; r[2] = t_direct - t_start; r[3] = t_ring - t_direct;
+                r[4] = clock64() - t_ring; r[5] = 0; r[6] = 0; r[7] = 0;
+            }
+        }
     }
 }
 
@@ -257,6 +305,10 @@ FMB_API size_t fmb_bwd_workspace_bytes(int64_t N, int k) {
     const size_t gp = (size_t)((k + 1 + 3) / 4) * 4;
     return 2 * (((size_t)N * gp * 4 + 255) / 256 * 256) + 256;
 }
+
+static long long* g_runs_dbg = nullptr;
+// debug hook (not in the public header): device buffer of 8 + 4000*8 int64 receiving per-run cycle counts
+FMB_API void fmb_debug_set_runs_buffer(long long* dev) { g_runs_dbg = dev; }
 
 // A6 sparse backward + update (see file header).
 //   sorted_keys/perm [N]: output of fmb_sort_segment / fmb_sort_fields over ids[B*F]; xv [B*F] or NULL
@@ -290,6 +342,7 @@ FMB_API int fmb_fm_backward_update_ex(const int32_t* sorted_keys, const int32_t*
     }
     p.S = S; p.gs = gs; p.use_fm2 = use_fm2; p.gvec = gvec; p.lr = lr; p.mode = mode;
     p.s_pitch = s_pitch; p.gs_stride = gs_stride; p.key_limit = key_limit;
+    p.dbg = g_runs_dbg;
     const size_t gbytes = ((size_t)N * p.cu * 16 + 255) / 256 * 256;
     p.G = (float*)ws;
     p.G2 = (float*)((char*)ws + gbytes);
@@ -301,7 +354,7 @@ FMB_API int fmb_fm_backward_update_ex(const int32_t* sorted_keys, const int32_t*
     const int gp = p.cu * 4;
     const int nv = k + 1 + (two ? k : 0);
     const int accs_n = (nv + 3) / 4 * 4;
-    const int warp_f = RING_NS * RING_SE * gp * (two ? 2 : 1) + RING_NS * RING_SE + accs_n;
+    const int warp_f = RING_NS * RING_SE * gp * (two ? 2 : 1) + RING_NS * RING_SE + accs_n + 32;
     int wpb = 8;
     while (wpb > 1 && (size_t)wpb * warp_f * 4 > 56 * 1024) wpb >>= 1;
     const size_t sm = (size_t)wpb * warp_f * 4;
