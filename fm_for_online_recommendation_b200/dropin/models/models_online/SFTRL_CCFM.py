@@ -1,0 +1,2 @@
+"""Drop-in for the reference's models/models_online/SFTRL_CCFM.py: same import path, same class name."""
+from fm_for_online_recommendation_b200.classical import SFTRL_CCFM  # noqa: F401

@@ -1,0 +1,3 @@
+"""Drop-in for the reference's models/models_online_deep/deepfm_onn.py: same import path, same class name.
+Put fm_for_online_recommendation_b200/dropin first on sys.path and main_experiment*.py runs unchanged."""
+from fm_for_online_recommendation_b200.deep import DeepFMOnn  # noqa: F401
