@@ -63,3 +63,55 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b|#include\s+\"[^\"]*oracle", txt, flags=re.M):
                     bad.append(fn)
     assert not bad, bad
+
+
+def test_dropin_import_paths_mirror_the_reference():
+    """`from models.models_online_deep.fm_adam import FMAdam` (main_experiment.py:9-13) resolves to the
+    B200 classes once fm_for_online_recommendation_b200/dropin is first on sys.path."""
+    import importlib
+    import sys
+    dropin = os.path.join(PKG, "dropin")
+    saved = {k: v for k, v in sys.modules.items() if k == "models" or k.startswith("models.")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, dropin)
+    try:
+        import fm_for_online_recommendation_b200.classical as cl
+        import fm_for_online_recommendation_b200.deep as dp
+        for mod, name, home in [("models.models_online_deep.fm_adam", "FMAdam", dp),
+                                ("models.models_online_deep.deepfm_adam", "DeepFMAdam", dp),
+                                ("models.models_online_deep.nfm_adam", "NFMAdam", dp),
+                                ("models.models_online_deep.deepfm_onn", "DeepFMOnn", dp),
+                                ("models.models_online_deep.nfm_onn", "NFMOnn", dp),
+                                ("models.models_online.FM_FTRL", "FM_FTRL", cl),
+                                ("models.models_online.SFTRL_CCFM", "SFTRL_CCFM", cl),
+                                ("models.models_online.SFTRL_Vanila", "SFTRL_Vanila", cl)]:
+            assert getattr(importlib.import_module(mod), name) is getattr(home, name)
+    finally:
+        sys.path.remove(dropin)
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_reference_constructor_signatures_are_kept():
+    """positional order and defaults of the five deep constructors (note NFMOnn's
+    (num_classes, batch_size) order, nfm_onn.py:14-15)."""
+    import inspect
+    import fm_for_online_recommendation_b200.deep as dp
+    want = {
+        "FMAdam": ["feature_sizes", "embedding_size", "num_classes", "b", "n", "use_cuda"],
+        "DeepFMAdam": ["feature_sizes", "embedding_size", "num_hidden_layers", "neuron_per_hidden_layer", "batch_size",
+                       "num_classes", "b", "n", "use_cuda"],
+        "NFMAdam": ["feature_sizes", "embedding_size", "num_hidden_layers", "neuron_per_hidden_layer", "num_classes", "b",
+                    "n", "use_cuda"],
+        "DeepFMOnn": ["feature_sizes", "embedding_size", "num_hidden_layers", "neuron_per_hidden_layer", "batch_size",
+                      "num_classes", "b", "n", "s", "use_cuda"],
+        "NFMOnn": ["feature_sizes", "embedding_size", "num_hidden_layers", "neuron_per_hidden_layer", "num_classes",
+                   "batch_size", "b", "n", "s", "use_cuda"],
+    }
+    for name, params in want.items():
+        got = [p for p in inspect.signature(getattr(dp, name).__init__).parameters if p != "self"]
+        assert got[:len(params)] == params, (name, got)
+        sig = inspect.signature(getattr(dp, name).__init__)
+        assert sig.parameters["embedding_size"].default == 4 and sig.parameters["n"].default == 0.01
