@@ -428,21 +428,29 @@ class _DeepBase(nn.Module):
         self.eval()
         return self._predict_dev(self.encode(Xi, Xv)).cpu().numpy().astype(bool)
 
+    _KIND_ID = 0
+
     def run_experiment(self, data_Xi, data_Xv, data_Y):
-        """fm_adam.py:90-119: strictly sequential predict-then-fit per example."""
+        """fm_adam.py:90-119: strictly sequential predict-then-fit per example, as one persistent kernel
+        (csrc/online.cu); the bookkeeping below is the reference's, evaluated on the returned predictions."""
         data_size = len(data_Y)
         confusion_matrix = {"tp": 0, "fp": 0, "tn": 0, "fn": 0}
         accuracy = []
         roc = []
         start = time()
         enc = self.encode(data_Xi, data_Xv, data_Y)
-        labels = np.asarray(data_Y).reshape(-1)
+        if self._IS_ONN and self._batch_size != 1:
+            raise RuntimeError(f"shape '[{self._batch_size}]' is invalid for input of size 1")
         preds_dev = torch.empty(data_size, dtype=torch.uint8, device=self.device)
-        for i in range(data_size):
-            e = EncodedBatch(enc.ids[i:i + 1], None if enc.xv is None else enc.xv[i:i + 1], enc.y[i:i + 1])
-            preds_dev[i:i + 1] = self._predict_dev(e)
-            self.fit(e, None, None)
+        conf_dev = torch.zeros(4, dtype=torch.int64, device=self.device)
+        acc = self._buf("hedge_acc", (self._mlp.numel(),)) if self._IS_ONN else None
+        check(self._lib.fmb_online_deep_run(self._KIND_ID, ptr(enc.ids), ptr(enc.xv), ptr(enc.y), data_size,
+                                            self.field_size, self.embedding_size, self._L, self._H, ptr(self._table),
+                                            ptr(self.bias), ptr(self._mlp), ptr(getattr(self, "alpha", None)),
+                                            ptr(acc), self._lr, self._hb, self._hs, self.update_mode, ptr(preds_dev),
+                                            ptr(conf_dev), _stream()), "fmb_online_deep_run")
         preds = preds_dev.cpu().numpy().astype(bool)
+        labels = np.asarray(data_Y).reshape(-1)
         for i in range(data_size):
             pred = preds[i]
             if pred == labels[i]:
@@ -461,6 +469,7 @@ class _DeepBase(nn.Module):
                 roc.append({'tpr': tpr, 'fpr': fpr})
                 accuracy.append(((confusion_matrix['tp'] + confusion_matrix['tn']) / (i + 1) * 100))
         time_elapsed = time() - start
+        self._last_online_preds = preds
         return time_elapsed, accuracy[-1], roc[-1], confusion_matrix
 
 
@@ -485,6 +494,7 @@ class FMAdam(_DeepBase):
 
 class DeepFMAdam(_DeepBase):
     """deepfm_adam.py:12-159."""
+    _KIND_ID = 1
 
     def __init__(self, feature_sizes, embedding_size=4, num_hidden_layers=2, neuron_per_hidden_layer=32,
                  batch_size=1, num_classes=1, b=0.99, n=0.01, use_cuda=True, update_mode=UPDATE_ADAM1):
@@ -508,6 +518,7 @@ class DeepFMAdam(_DeepBase):
 class NFMAdam(_DeepBase):
     """nfm_adam.py:12-158: update_embedding uses BCEWL(sigmoid(z_fm)) (:100), fit uses BCEWL(z) (:114)."""
     _IS_NFM = True
+    _KIND_ID = 2
     _UE_LOSS = LOSS_LOGITS_OF_SIG
     _FIT_LOSS = LOSS_LOGITS
 
@@ -532,6 +543,7 @@ class NFMAdam(_DeepBase):
 class DeepFMOnn(_DeepBase):
     """deepfm_onn.py:12-210 (hedge backpropagation)."""
     _IS_ONN = True
+    _KIND_ID = 3
 
     def __init__(self, feature_sizes, embedding_size=4, num_hidden_layers=2, neuron_per_hidden_layer=32,
                  batch_size=1, num_classes=1, b=0.99, n=0.01, s=0.2, use_cuda=True, update_mode=UPDATE_ADAM1):
@@ -556,6 +568,7 @@ class NFMOnn(_DeepBase):
     """nfm_onn.py:13-212. Positional order is (..., num_classes, batch_size, ...) here (nfm_onn.py:14-15)."""
     _IS_ONN = True
     _IS_NFM = True
+    _KIND_ID = 4
     _UE_LOSS = LOSS_LOGITS_OF_SIG
 
     def __init__(self, feature_sizes, embedding_size=4, num_hidden_layers=2, neuron_per_hidden_layer=32,

@@ -153,6 +153,16 @@ int fmb_hedge_accumulate(float* acc_dev, const float* gmlp_dev, const float* alp
 int fmb_hedge_apply(float* mlp_dev, const float* acc_dev, float lr, float* alpha_dev, const float* loss_sum_dev,
                     int B, int k, int L, int H, float hb, float hs, fmb_stream_t stream);
 
+/* ---- A8: per-example online mode as one persistent kernel ---------------------------------------
+ * replaces run_experiment (fm_adam.py:90-119, same in all five classes): for each example in order,
+ * predict then fit with batch size 1 (Adam family: fm_adam.py:71-82, deepfm_adam.py:106-117,
+ * nfm_adam.py:105-116; ONN: deepfm_onn.py:109-154).  kind 0..4 = FMAdam, DeepFMAdam, NFMAdam, DeepFMOnn,
+ * NFMOnn.  preds [N] = prediction made before fitting example i; conf [4] = tp, fp, tn, fn. */
+int fmb_online_deep_run(int kind, const int32_t* ids_dev /*[N,F]*/, const float* xv_dev, const float* y_dev, int N,
+                        int F, int k, int L, int H, float* table_dev, float* bias_dev, float* mlp_dev,
+                        float* alpha_dev, float* acc_dev /*[fmb_mlp_numel], ONN*/, float lr, float hb, float hs,
+                        int mode, uint8_t* preds_dev, int64_t* conf_dev, fmb_stream_t stream);
+
 /* ---- A9-A11: classical fp64 online learners, one persistent launch per stream -------------------
  * fmb_ftrl_fm_run : FM_FTRL.online_learning (models/models_online/FM_FTRL.py:47-92)
  * fmb_sftrl_run   : SFTRL_CCFM.online_learning (SFTRL_CCFM.py:30-121; vanila = 0) and

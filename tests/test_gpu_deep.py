@@ -1,0 +1,138 @@
+"""GPU parity of the tower models (A4-A8): DeepFM / NFM `fit`, hedge-backprop `fit`, predict and the
+persistent per-example `run_experiment`, CUDA vs the CPU oracle (bit-exact: the SIMT tower accumulates
+every contraction left to right with one FMA per term, like oracle/fm_oracle.c), plus replays of the
+reference-generated golden fixtures (tolerance 1e-5, see tests/test_oracle_vs_golden.py)."""
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from _util import GOLDEN_DEEP, load_golden, rel_err, synth
+from test_gpu_fm import _pair, assert_same_params, pull, push
+
+pytestmark = pytest.mark.gpu
+
+SMALL = [7, 5, 11, 3, 13, 4]
+
+
+def same_all(m, orc):
+    assert_same_params(m, orc, exact=True)
+    p = pull(m)
+    if orc.L:
+        assert np.array_equal(p["mlp"], orc.mlp), int((p["mlp"] != orc.mlp).sum())
+    if hasattr(m, "alpha"):
+        assert np.array_equal(p["alpha"], orc.alpha[:orc.L])
+
+
+@pytest.mark.parametrize("kind,k,L,H,B", [("DeepFMAdam", 10, 3, 16, 64), ("NFMAdam", 64, 1, 64, 32),
+                                          ("DeepFMAdam", 10, 5, 10, 250), ("NFMAdam", 8, 2, 24, 1),
+                                          ("DeepFMAdam", 10, 3, 400, 96)])
+def test_tower_forward_fit_update_bit_exact(kind, k, L, H, B):
+    m, orc = _pair(kind, SMALL, k, L, H, lr=0.001, scale=0.2)
+    for step in range(3):
+        Xi, Xv, Y = synth(SMALL, B, 20 + step, real_xv=True, zipf=(step == 1))
+        assert np.array_equal(m.forward(Xi, Xv).cpu().numpy(), orc.forward(Xi, Xv))
+        assert np.array_equal(m.predict(Xi, Xv), orc.predict(Xi, Xv))
+        m.fit(Xi, Xv, Y)
+        orc.fit(Xi, Xv, Y)
+        same_all(m, orc)
+        got = float(m.update_embedding(Xi, Xv, Y).cpu())
+        assert np.float32(got) == np.float32(orc.update_embedding(Xi, Xv, Y))
+        same_all(m, orc)
+
+
+@pytest.mark.parametrize("kind,bs", [("DeepFMOnn", 1), ("NFMOnn", 1), ("NFMOnn", 8), ("DeepFMOnn", 5)])
+def test_hedge_fit_bit_exact(kind, bs):
+    m, orc = _pair(kind, SMALL, 10, 5, 10, lr=0.01, scale=0.2, batch_size=bs)
+    for step in range(4):
+        Xi, Xv, Y = synth(SMALL, bs, 30 + step, real_xv=True)
+        out, layers = m.forward(Xi, Xv)
+        ro, rl = orc.forward(Xi, Xv)
+        assert np.array_equal(out.cpu().numpy(), ro) and np.array_equal(layers.cpu().numpy(), rl)
+        m.fit(Xi, Xv, Y)
+        orc.fit(Xi, Xv, Y)
+        same_all(m, orc)
+    with pytest.raises(RuntimeError):
+        m.fit(*synth(SMALL, bs + 1, 1))
+
+
+@pytest.mark.parametrize("kind,L,H", [("FMAdam", 0, 0), ("DeepFMAdam", 3, 16), ("NFMAdam", 2, 10), ("DeepFMOnn", 5, 10),
+                                      ("NFMOnn", 5, 10)])
+def test_run_experiment_persistent_kernel_bit_exact(kind, L, H):
+    m, orc = _pair(kind, SMALL, 10, L, H, lr=0.001, scale=0.2)
+    Xi, Xv, Y = synth(SMALL, 300, 77, real_xv=True)
+    _, acc, roc, conf = m.run_experiment(Xi.tolist(), Xv.tolist(), [int(v) for v in Y])
+    oconf, opreds = orc.run_experiment(Xi, Xv, Y)
+    assert conf == oconf
+    assert np.array_equal(m._last_online_preds, opreds)
+    same_all(m, orc)
+    assert abs(acc - (conf["tp"] + conf["tn"]) / 300 * 100) < 1e-9 and set(roc) == {"tpr", "fpr"}
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_DEEP))
+def test_golden_replay_against_reference_outputs(name):
+    """the CUDA classes replay what the reference itself did (fixtures from tests/golden/make_golden.py)."""
+    import fm_for_online_recommendation_b200 as pkg
+    kind, kw = GOLDEN_DEEP[name]
+    g = load_golden(name)
+    ckw = dict(embedding_size=kw["k"], n=float(g["lr"]))
+    if kind != "FMAdam":
+        ckw.update(num_hidden_layers=kw["L"], neuron_per_hidden_layer=kw["H"])
+    if "batch_size" in kw:
+        ckw["batch_size"] = kw["batch_size"]
+    m = getattr(pkg, kind)(g["feature_sizes"].tolist(), **ckw)
+
+    class O:  # parameter carrier with the oracle's attribute names
+        pass
+    o = O()
+    o.k, o.L = kw["k"], kw.get("L", 0)
+    o.V, o.w1, o.bias, o.mlp = g["init_V"], g["init_w1"], g["init_bias"], g["init_mlp"]
+    o.alpha = g.get("init_alpha", np.zeros(1, np.float32))
+    push(m, o)
+    f = m.forward(g["Xi"].tolist(), g["Xv"].tolist())
+    f0 = (f[0] if isinstance(f, tuple) else f).cpu().numpy()
+    np.testing.assert_allclose(f0, g["fwd0"], rtol=1e-5, atol=1e-5)
+    if "fwd_fm0" in g:
+        assert np.array_equal(m.forward_fm(g["Xi"], g["Xv"]).cpu().numpy(), g["fwd_fm0"])  # logits: bit-exact
+    assert np.array_equal(m.predict(g["Xi"].tolist(), g["Xv"].tolist()), g["pred0"].reshape(-1))
+    losses = [float(m.update_embedding(g["ue_Xi"][s].tolist(), g["ue_Xv"][s].tolist(), g["ue_Y"][s].tolist()).cpu())
+              for s in range(int(g["steps"]))]
+    np.testing.assert_allclose(losses, g["ue_loss"], rtol=1e-5)
+    for s in range(int(g["steps"])):
+        m.fit(g["fit_Xi"][s].tolist(), g["fit_Xv"][s].tolist(), g["fit_Y"][s].tolist())
+    p = pull(m)
+    assert rel_err(p["V"], g["after_fit_V"]) <= 1e-5 and rel_err(p["w1"], g["after_fit_w1"]) <= 1e-5
+    assert rel_err(p["bias"], g["after_fit_bias"]) <= 1e-5
+    if o.L:
+        assert rel_err(p["mlp"], g["after_fit_mlp"]) <= 1e-5
+    if "on_Xi" in g:
+        _, _, _, conf = m.run_experiment(g["on_Xi"].tolist(), g["on_Xv"].tolist(), [int(v) for v in g["on_Y"]])
+        assert [conf["tp"], conf["fp"], conf["tn"], conf["fn"]] == g["on_conf"].tolist()
+        p = pull(m)
+        assert rel_err(p["V"], g["after_on_V"]) <= 1e-5
+
+
+def test_pickle_roundtrip_and_str():
+    import fm_for_online_recommendation_b200 as pkg
+    torch.manual_seed(3)
+    m = pkg.DeepFMOnn(SMALL, embedding_size=10, num_hidden_layers=5, neuron_per_hidden_layer=10, n=1e-4)
+    assert str(m).split("-")[0] == "DeepFMOnn"  # main_experiment.py:86
+    Xi, Xv, Y = synth(SMALL, 16, 5)
+    m.update_embedding(Xi, Xv, Y)
+    m2 = pickle.loads(pickle.dumps(m))          # main_experiment.py:160-162
+    assert torch.equal(m2._table, m._table) and torch.equal(m2._mlp, m._mlp) and torch.equal(m2.alpha, m.alpha)
+    assert np.array_equal(m2.predict(Xi, Xv), m.predict(Xi, Xv))
+    names = [n for n, _ in m.named_parameters()]
+    assert "first_order_embeddings.0.weight" in names and "hidden_layers.4.bias" in names
+    assert m.second_order_embeddings[2].weight.shape == (SMALL[2], 10)
+
+
+def test_same_seed_same_init_as_reference_rng_order():
+    """parameters are drawn on the CPU in the reference's construction order (fm_adam.py:26-32)."""
+    import fm_for_online_recommendation_b200 as pkg
+    g = load_golden("fm_cfg1")
+    torch.manual_seed(0)
+    m = pkg.FMAdam([943, 1682], embedding_size=10, n=0.01)
+    p = pull(m)
+    assert np.array_equal(p["V"], g["init_V"]) and np.array_equal(p["w1"], g["init_w1"])
