@@ -126,22 +126,49 @@ __global__ void __launch_bounds__(256) fm_bwd_entry_kernel(BwdParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-constexpr int RING_SE = 32;  // entries per ring stage (one key per lane)
-constexpr int RING_NS = 8;   // stages
+constexpr int RING_SE = 64;  // entries per ring stage
+constexpr int RING_NS = 4;   // stages
 
+// ---- mbarrier + 1-D bulk async copy (TMA) helpers -------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: returns false if the phase never completed (never expected; avoids hanging the GPU)
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    for (int spin = 0; spin < (1 << 20); ++spin) {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+// GPT > 0 fixes the staging pitch at compile time; 0 = runtime pitch.
+template <int GPT>
 __global__ void __launch_bounds__(256, 3) fm_bwd_runs_kernel(BwdParams p, int warps_per_block, int warp_f, int accs_n) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t P0 = ((int64_t)blockIdx.x * warps_per_block + wib) * 32;
     if (P0 >= p.N) return;
     const bool two = p.use_fm2 && p.gvec;
     const int nbuf = two ? 2 : 1;
-    const int gp = p.cu * 4, kc = p.k + 1;
+    const int gp = GPT > 0 ? GPT : p.cu * 4, kc = p.k + 1;
     const int nv = kc + (two ? p.k : 0);          // virtual lanes: chain A comps, then chain B comps
     const int stage_f = RING_SE * gp * nbuf;
     float* ring = smem + (size_t)wib * warp_f;    // [NS][nbuf][SE][gp]
-    int32_t* rkeys = reinterpret_cast<int32_t*>(ring + RING_NS * stage_f);  // [NS][SE]
-    float* accs = reinterpret_cast<float*>(rkeys + RING_NS * RING_SE);      // [accs_n]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + RING_NS * stage_f);   // [NS] mbarriers
+    float* accs = reinterpret_cast<float*>(bars + RING_NS);                   // [accs_n + 32]
 
     // keys of this warp's 32 positions and of the 32 after them (one memory latency for both)
     const int64_t pos = P0 + lane;
@@ -154,21 +181,15 @@ __global__ void __launch_bounds__(256, 3) fm_bwd_runs_kernel(BwdParams p, int wa
     if (lane == 31) next = k1_0;
     // runs (>= 2 entries) that START inside these 32 positions
     unsigned todo = __ballot_sync(0xffffffffu, pos < p.N && k0 >= 0 && k0 < p.key_limit && k0 != prev && k0 == next);
-
-    // per-lane constants of the ring fill: lane -> (entry within a group of 32>>ql_log, 16-byte chunk)
-    const int fl_q = lane & ((1 << p.ql_log) - 1);
-    const int fl_e = lane >> p.ql_log;
-    const int fl_iters = 1 << p.ql_log;                 // groups of (32 >> ql_log) entries per stage
-    const int fl_estep = 32 >> p.ql_log;
-    const bool fl_on = fl_q < p.cu;
-    const int fl_off = fl_e * gp + fl_q * 4;            // float offset inside a stage / inside G
+    bool bars_ready = false;
+    unsigned phase = 0;  // bit st = parity to wait for on bars[st]
 
     while (todo) {
         const int bit = __ffs(todo) - 1;
         todo &= todo - 1;
         const int64_t s = P0 + bit;
         const int32_t key = __shfl_sync(0xffffffffu, k0, bit);
-        long long t_start = 0, t_direct = 0, t_ring = 0;
+        long long t_start = 0, t_direct = 0, t_ring = 0, c_wait = 0, c_cons = 0, c_issue = 0;
         if (p.dbg) t_start = clock64();
         int run_len = 0;
         // leading matches among the first 32 entries of the run (keys are already in registers)
@@ -177,6 +198,18 @@ __global__ void __launch_bounds__(256, 3) fm_bwd_runs_kernel(BwdParams p, int wa
         const int32_t kb = __shfl_sync(0xffffffffu, k1, t & 31);
         const unsigned mm = __ballot_sync(0xffffffffu, (t < 32 ? ka : kb) == key);
         const int n0 = (mm == 0xffffffffu) ? 32 : __ffs(~mm) - 1;
+        // long run: probe its extent.  Keys are sorted, so "key at the end of 32-entry block b still matches"
+        // is a prefix property: one load per lane covers the next 1024 entries.
+        int32_t probe = -2;
+        if (n0 == 32) { const int64_t q = s + 32 + 32 * (int64_t)(lane + 1) - 1; probe = q < p.N ? __ldg(p.skeys + q) : -2; }
+        if (n0 == 32 && !bars_ready) {
+            if (lane == 0) {
+                for (int st = 0; st < RING_NS; ++st) mbar_init(bars + st, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+            }
+            __syncwarp();
+            bars_ready = true;
+        }
 
         for (int v0 = 0; v0 < nv; v0 += 32) {  // one pass per group of 32 (buffer, component) lanes
             const int vl = v0 + lane;
@@ -187,41 +220,6 @@ __global__ void __launch_bounds__(256, 3) fm_bwd_runs_kernel(BwdParams p, int wa
             // the row's old value is needed only at the very end: fetch it now, off the critical path
             float pold = 0.f;
             if (v0 == 0 && lane < kc) pold = p.table[(size_t)key * p.rowp + lane];
-            // long run: start streaming entries 32.. into the shared-memory ring right away.
-            // A single warp executes this chain alone, so the fill path is kept to a handful of
-            // instructions: pointers advance by constants, bounds are checked once per stage.
-            int64_t fill = s + 32;
-            const float* gsrc = p.G + (size_t)fill * gp + fl_off;
-            const float* gsrc2 = two ? p.G2 + (size_t)fill * gp + fl_off : nullptr;
-            auto issue = [&](int st) {
-                float* dst = ring + (size_t)st * stage_f + fl_off;
-                if (fill + RING_SE <= p.N) {
-                    if (fl_on) {
-                        for (int it = 0; it < fl_iters; ++it) {
-                            cp_async16(dst + it * fl_estep * gp, gsrc + it * fl_estep * gp);
-                            if (two) cp_async16(dst + (RING_SE + it * fl_estep) * gp, gsrc2 + it * fl_estep * gp);
-                        }
-                    }
-                    cp_async4(rkeys + st * RING_SE + lane, p.skeys + fill + lane);
-                } else {
-                    for (int it = 0; it < fl_iters; ++it) {
-                        if (fl_on && fill + fl_e + it * fl_estep < p.N) {
-                            cp_async16(dst + it * fl_estep * gp, gsrc + it * fl_estep * gp);
-                            if (two) cp_async16(dst + (RING_SE + it * fl_estep) * gp, gsrc2 + it * fl_estep * gp);
-                        }
-                    }
-                    if (fill + lane < p.N) cp_async4(rkeys + st * RING_SE + lane, p.skeys + fill + lane);
-                    else rkeys[st * RING_SE + lane] = -2;
-                }
-                cp_async_commit();
-                fill += RING_SE;
-                gsrc += RING_SE * gp;
-                if (two) gsrc2 += RING_SE * gp;
-            };
-            if (n0 == 32) {
-#pragma unroll
-                for (int st = 0; st < RING_NS; ++st) issue(st);
-            }
             // direct part: up to 32 entries straight from G, all loads in flight at once
             float acc = 0.f;
             {
@@ -241,32 +239,70 @@ __global__ void __launch_bounds__(256, 3) fm_bwd_runs_kernel(BwdParams p, int wa
             if (p.dbg) t_direct = clock64();
             run_len = n0;
             if (n0 == 32) {
-                int st = 0;
-                while (true) {
-                    cp_async_wait<RING_NS - 1>();
-                    __syncwarp();
-                    const unsigned m2 = __ballot_sync(0xffffffffu, rkeys[st * RING_SE + lane] == key);
-                    const int n = (m2 == 0xffffffffu) ? 32 : __ffs(~m2) - 1;
-                    if (active) {
-                        const float* b = ring + (size_t)st * stage_f + (isB ? RING_SE * gp : 0) + comp;
-#pragma unroll 1
-                        for (int h = 0; h < 32; h += 16) {
-                            float tv[16];
-#pragma unroll
-                            for (int u = 0; u < 16; ++u) tv[u] = b[(h + u) * gp];
-#pragma unroll
-                            for (int u = 0; u < 16; ++u)
-                                if (h + u < n) acc = __fadd_rn(acc, tv[u]);
-                        }
+                // stream the rest in windows of up to 1024 entries: [c0, c0 + wlen)
+                int64_t c0 = s + 32;
+                int32_t pr = probe;
+                bool ok = true;
+                while (ok) {
+                    const unsigned pm = __ballot_sync(0xffffffffu, pr == key);
+                    const int full = (pm == 0xffffffffu) ? 32 : __ffs(~pm) - 1;   // full 32-entry blocks
+                    int part = 0;
+                    if (full < 32) {
+                        const int64_t q = c0 + 32 * (int64_t)full + lane;
+                        const unsigned m3 = __ballot_sync(0xffffffffu, q < p.N && __ldg(p.skeys + q) == key);
+                        part = (m3 == 0xffffffffu) ? 32 : __ffs(~m3) - 1;
                     }
-                    __syncwarp();
-                    run_len += n;
-                    if (n < 32) break;
-                    issue(st);
-                    st = (st + 1 == RING_NS) ? 0 : st + 1;
+                    const int wlen = 32 * full + part;
+                    const int T = (wlen + RING_SE - 1) / RING_SE;
+                    // prologue: fill the ring with bulk copies (one instruction per stage and buffer)
+                    auto issue = [&](int tstage) {
+                        if (lane == 0) {
+                            const int st = tstage & (RING_NS - 1);
+                            const int n = min(RING_SE, wlen - RING_SE * tstage);
+                            const unsigned bytes = (unsigned)(n * gp * 4);
+                            float* dst = ring + (size_t)st * stage_f;
+                            mbar_expect_tx(bars + st, bytes * nbuf);
+                            bulk_g2s(dst, p.G + (size_t)(c0 + RING_SE * (int64_t)tstage) * gp, bytes, bars + st);
+                            if (two) bulk_g2s(dst + RING_SE * gp, p.G2 + (size_t)(c0 + RING_SE * (int64_t)tstage) * gp, bytes, bars + st);
+                        }
+                    };
+                    for (int ts = 0; ts < T && ts < RING_NS; ++ts) issue(ts);
+                    // next window's probe (only needed when this window is completely full)
+                    int32_t pr_next = -2;
+                    if (full == 32) { const int64_t q = c0 + 1024 + 32 * (int64_t)(lane + 1) - 1; pr_next = q < p.N ? __ldg(p.skeys + q) : -2; }
+                    for (int ts = 0; ts < T; ++ts) {
+                        const int st = ts & (RING_NS - 1);
+                        long long w0 = 0;
+                        if (p.dbg) w0 = clock64();
+                        if (!mbar_wait(bars + st, (phase >> st) & 1u)) { ok = false; break; }
+                        phase ^= 1u << st;
+                        long long w1 = 0;
+                        if (p.dbg) { w1 = clock64(); c_wait += w1 - w0; }
+                        const int n = min(RING_SE, wlen - RING_SE * ts);
+                        if (active) {
+                            const float* b = ring + (size_t)st * stage_f + (isB ? RING_SE * gp : 0) + comp;
+                            int done = 0;
+#pragma unroll 1
+                            for (; done + 32 <= n; done += 32) {   // 32 loads in flight, then the bare 32-add chain
+                                float tv[32];
+#pragma unroll
+                                for (int u = 0; u < 32; ++u) tv[u] = b[(done + u) * gp];
+#pragma unroll
+                                for (int u = 0; u < 32; ++u) acc = __fadd_rn(acc, tv[u]);
+                            }
+                            for (int u = done; u < n; ++u) acc = __fadd_rn(acc, b[u * gp]);
+                        }
+                        __syncwarp();
+                        long long w2 = 0;
+                        if (p.dbg) { w2 = clock64(); c_cons += w2 - w1; }
+                        if (ts + RING_NS < T) issue(ts + RING_NS);
+                        if (p.dbg) c_issue += clock64() - w2;
+                    }
+                    run_len += wlen;
+                    if (full < 32) break;
+                    c0 += 1024;
+                    pr = pr_next;
                 }
-                cp_async_wait<0>();
-                __syncwarp();
             }
             if (p.dbg) t_ring = clock64();
             if (active) accs[vl] = acc;
@@ -290,7 +326,7 @@ __global__ void __launch_bounds__(256, 3) fm_bwd_runs_kernel(BwdParams p, int wa
             if (slot < 4000) {
                 long long* r = p.dbg + 8 + slot * 8;
                 r[0] = run_len; r[1] = t_start; r[2] = t_direct - t_start; r[3] = t_ring - t_direct;
-                r[4] = clock64() - t_ring; r[5] = 0; r[6] = 0; r[7] = 0;
+                r[4] = clock64() - t_ring; r[5] = c_issue; r[6] = c_wait; r[7] = c_cons;
             }
         }
     }
@@ -354,15 +390,29 @@ FMB_API int fmb_fm_backward_update_ex(const int32_t* sorted_keys, const int32_t*
     const int gp = p.cu * 4;
     const int nv = k + 1 + (two ? k : 0);
     const int accs_n = (nv + 3) / 4 * 4;
-    const int warp_f = RING_NS * RING_SE * gp * (two ? 2 : 1) + RING_NS * RING_SE + accs_n + 32;
+    // ring (multiple of 128 B per warp) + NS mbarriers (8 B each) + accumulators + prefetched old row
+    const int warp_f = fmb_round_up(RING_NS * RING_SE * gp * (two ? 2 : 1) + 2 * RING_NS + accs_n + 32, 32);
     int wpb = 8;
     while (wpb > 1 && (size_t)wpb * warp_f * 4 > 56 * 1024) wpb >>= 1;
     const size_t sm = (size_t)wpb * warp_f * 4;
     FMB_CHECK_ARG(sm <= 200 * 1024, "fmb_fm_backward_update: k too large for the run ring");
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(fm_bwd_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
     const int64_t nwarps = (N + 31) / 32;
-    fm_bwd_runs_kernel<<<(unsigned)((nwarps + wpb - 1) / wpb), 32 * wpb, sm, stream>>>(p, wpb, warp_f, accs_n);
+    const unsigned grid = (unsigned)((nwarps + wpb - 1) / wpb);
+#define FMB_LAUNCH_RUNS(GPV)                                                                                      \
+    do {                                                                                                          \
+        static bool attr = false;                                                                                 \
+        if (!attr) { cudaFuncSetAttribute(fm_bwd_runs_kernel<GPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; } \
+        fm_bwd_runs_kernel<GPV><<<grid, 32 * wpb, sm, stream>>>(p, wpb, warp_f, accs_n);                          \
+    } while (0)
+    switch (gp) {
+        case 8: FMB_LAUNCH_RUNS(8); break;
+        case 12: FMB_LAUNCH_RUNS(12); break;
+        case 16: FMB_LAUNCH_RUNS(16); break;
+        case 20: FMB_LAUNCH_RUNS(20); break;
+        case 68: FMB_LAUNCH_RUNS(68); break;
+        default: FMB_LAUNCH_RUNS(0); break;
+    }
+#undef FMB_LAUNCH_RUNS
     FMB_CHECK_LAUNCH("fm_bwd_runs_kernel");
     return FMB_OK;
 }
