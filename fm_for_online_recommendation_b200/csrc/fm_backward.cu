@@ -45,19 +45,8 @@ struct BwdParams {
     float* G;             // [N][cu*4] staged contributions (chain A, or the only chain)
     float* G2;            // [N][cu*4] chain B when both gradient paths are live
     long long* dbg;       // optional per-run timing records (debug builds of bench only), else NULL
+    float astep;          // -(lr/0.1f): Adam step size, computed once on the host (same IEEE division)
 };
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fm_bwd_entry_kernel(BwdParams p) {
@@ -103,9 +92,9 @@ __global__ void __launch_bounds__(256) fm_bwd_entry_kernel(BwdParams p) {
             if (j < p.k) {
                 const float gr = two ? __fadd_rn(__fadd_rn(0.f, a[t]), __fadd_rn(0.f, c[t]))
                                      : __fadd_rn(0.f, p.gvec ? c[t] : a[t]);
-                o[t] = fmb::apply_update(v[t], gr, p.lr, p.mode);
+                o[t] = fmb::apply_update_a(v[t], gr, p.lr, p.astep, p.mode);
             } else if (j == p.k) {
-                o[t] = fmb::apply_update(v[t], __fadd_rn(0.f, a[t]), p.lr, p.mode);
+                o[t] = fmb::apply_update_a(v[t], __fadd_rn(0.f, a[t]), p.lr, p.astep, p.mode);
             } else {
                 o[t] = v[t];
             }
@@ -121,6 +110,83 @@ __global__ void __launch_bounds__(256) fm_bwd_entry_kernel(BwdParams p) {
 #pragma unroll
             for (int t = 0; t < 4; ++t) m[t] = (p.gvec && q * 4 + t < p.k) ? c[t] : a[t];
             *reinterpret_cast<float4*>(p.G + (size_t)i * gp + q * 4) = make_float4(m[0], m[1], m[2], m[3]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Thread-per-entry version for rows of at most 4 chunks (k <= 15): the per-entry bookkeeping (three key
+// loads, permutation, sample index, delta, feature value) is paid once per entry instead of once per
+// 16-byte chunk, which is what made the lane-per-chunk kernel instruction-bound (75 % issue utilisation,
+// ~450 instructions per lane: profiles/r1g).  Row and S reads are random per entry either way.
+template <int CU>
+__global__ void __launch_bounds__(256) fm_bwd_entry1_kernel(BwdParams p) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= p.N) return;
+    const int32_t key = __ldg(p.skeys + i);
+    if (key >= p.key_limit) return;
+    const int32_t kprev = i > 0 ? __ldg(p.skeys + i - 1) : -1;
+    const int32_t knext = i + 1 < p.N ? __ldg(p.skeys + i + 1) : -1;
+    const int32_t e = __ldg(p.perm + i);
+    const int b = (int)(((unsigned long long)(unsigned)e * p.fmagic) >> p.fshift);
+    const float x = p.xv ? __ldg(p.xv + e) : 1.0f;
+    const float d = __ldg(p.gs + (size_t)b * p.gs_stride);
+    float* rowptr = p.table + (size_t)key * p.rowp;
+    float v[CU * 4], s[CU * 4], g[CU * 4];
+#pragma unroll
+    for (int q = 0; q < CU; ++q) {
+        const float4 v4 = *reinterpret_cast<const float4*>(rowptr + q * 4);
+        v[q * 4] = v4.x; v[q * 4 + 1] = v4.y; v[q * 4 + 2] = v4.z; v[q * 4 + 3] = v4.w;
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = s4;
+        if (q * 4 < p.kp4) {
+            s4 = __ldg(reinterpret_cast<const float4*>(p.S + (size_t)b * p.s_pitch + q * 4));
+            if (p.gvec) g4 = __ldg(reinterpret_cast<const float4*>(p.gvec + (size_t)b * p.s_pitch + q * 4));
+        }
+        s[q * 4] = s4.x; s[q * 4 + 1] = s4.y; s[q * 4 + 2] = s4.z; s[q * 4 + 3] = s4.w;
+        g[q * 4] = g4.x; g[q * 4 + 1] = g4.y; g[q * 4 + 2] = g4.z; g[q * 4 + 3] = g4.w;
+    }
+    const bool two = p.use_fm2 && p.gvec;
+    const bool single = key != kprev && key != knext;
+    float o[CU * 4], o2[CU * 4];
+#pragma unroll
+    for (int j = 0; j < CU * 4; ++j) {
+        float a = 0.f, c = 0.f;
+        if (j < p.k) {
+            const float ej = __fmul_rn(v[j], x);
+            if (p.use_fm2) a = __fmul_rn(__fsub_rn(__fmul_rn(d, s[j]), __fmul_rn(d, ej)), x);
+            if (p.gvec) c = __fmul_rn(__fsub_rn(__fmul_rn(g[j], s[j]), __fmul_rn(g[j], ej)), x);
+        } else if (j == p.k) {
+            a = __fmul_rn(d, x);
+        }
+        if (single) {
+            // the only entry of its row: sum = 0 + contribution; update from registers
+            if (j < p.k) {
+                const float gr = two ? __fadd_rn(__fadd_rn(0.f, a), __fadd_rn(0.f, c)) : __fadd_rn(0.f, p.gvec ? c : a);
+                o[j] = fmb::apply_update_a(v[j], gr, p.lr, p.astep, p.mode);
+            } else if (j == p.k) {
+                o[j] = fmb::apply_update_a(v[j], __fadd_rn(0.f, a), p.lr, p.astep, p.mode);
+            } else {
+                o[j] = v[j];
+            }
+        } else {
+            o[j] = two ? a : ((p.gvec && j < p.k) ? c : a);
+            o2[j] = c;
+        }
+    }
+    if (single) {
+#pragma unroll
+        for (int q = 0; q < CU; ++q)
+            *reinterpret_cast<float4*>(rowptr + q * 4) = make_float4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+    } else {
+        float* gd = p.G + (size_t)i * (CU * 4);
+#pragma unroll
+        for (int q = 0; q < CU; ++q)
+            *reinterpret_cast<float4*>(gd + q * 4) = make_float4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+        if (two) {
+            float* gd2 = p.G2 + (size_t)i * (CU * 4);
+#pragma unroll
+            for (int q = 0; q < CU; ++q)
+                *reinterpret_cast<float4*>(gd2 + q * 4) = make_float4(o2[q * 4], o2[q * 4 + 1], o2[q * 4 + 2], o2[q * 4 + 3]);
         }
     }
 }
@@ -317,7 +383,7 @@ __global__ void __launch_bounds__(256, 3) fm_bwd_runs_kernel(BwdParams p, int wa
                 if (two && c < p.k) gsum = __fadd_rn(gsum, accs[kc + c]);
                 float* addr = p.table + (size_t)key * p.rowp + c;
                 const float old = c < 32 ? accs[accs_n + c] : *addr;
-                *addr = fmb::apply_update(old, gsum, p.lr, p.mode);
+                *addr = fmb::apply_update_a(old, gsum, p.lr, p.astep, p.mode);
             }
         }
         __syncwarp();
@@ -378,13 +444,23 @@ FMB_API int fmb_fm_backward_update_ex(const int32_t* sorted_keys, const int32_t*
     }
     p.S = S; p.gs = gs; p.use_fm2 = use_fm2; p.gvec = gvec; p.lr = lr; p.mode = mode;
     p.s_pitch = s_pitch; p.gs_stride = gs_stride; p.key_limit = key_limit;
+    p.astep = -(lr / 0.1f);
     p.dbg = g_runs_dbg;
     const size_t gbytes = ((size_t)N * p.cu * 16 + 255) / 256 * 256;
     p.G = (float*)ws;
     p.G2 = (float*)((char*)ws + gbytes);
     const bool two = use_fm2 && gvec;
-    const int epb = 256 >> p.ql_log;
-    fm_bwd_entry_kernel<<<(unsigned)((N + epb - 1) / epb), 256, 0, stream>>>(p);
+    const unsigned grid1 = (unsigned)((N + 255) / 256);
+    switch (p.cu) {
+        case 1: fm_bwd_entry1_kernel<1><<<grid1, 256, 0, stream>>>(p); break;
+        case 2: fm_bwd_entry1_kernel<2><<<grid1, 256, 0, stream>>>(p); break;
+        case 3: fm_bwd_entry1_kernel<3><<<grid1, 256, 0, stream>>>(p); break;
+        case 4: fm_bwd_entry1_kernel<4><<<grid1, 256, 0, stream>>>(p); break;
+        default: {
+            const int epb = 256 >> p.ql_log;
+            fm_bwd_entry_kernel<<<(unsigned)((N + epb - 1) / epb), 256, 0, stream>>>(p);
+        }
+    }
     FMB_CHECK_LAUNCH("fm_bwd_entry_kernel");
     // runs kernel: per-warp shared memory = ring + keys + accumulators
     const int gp = p.cu * 4;

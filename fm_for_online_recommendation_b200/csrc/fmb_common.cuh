@@ -106,9 +106,11 @@ __device__ __forceinline__ float powf_p(float b, float e) { return expf_p(__fmul
 // update rules.  mode 0: torch.optim.Adam, first step with fresh
 // state, lr an fp32 scalar; mode 1: plain SGD p -= lr*g.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float adam1(float p, float g, float lr) {
+// astep = -(lr / 0.1f), the (negated) bias-corrected step size: loop-invariant, so callers that update many
+// parameters compute it once (adam_astep) and call adam1_a.
+__device__ __forceinline__ float adam_astep(float lr) { return -__fdiv_rn(lr, 0.1f); }
+__device__ __forceinline__ float adam1_a(float p, float g, float a) {
     const float bc2s = 0.03162277660168381f;
-    const float a = -__fdiv_rn(lr, 0.1f);
     // Exact shortcut.  The step is q = fl(fl(a*m)/d) with d >= 1e-8f, so |q| <= |a|*0.1*|g|*1e8*(1+2^-22).
     // When that bound is below a quarter ulp of p the sum fl(p+q) is p itself; skipping the IEEE sqrt and
     // the two IEEE divisions then changes nothing, and it is the common case on saturated logits, whose
@@ -123,8 +125,13 @@ __device__ __forceinline__ float adam1(float p, float g, float lr) {
     float d = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2s), 1e-8f);
     return __fadd_rn(p, __fdiv_rn(__fmul_rn(a, m), d));
 }
+__device__ __forceinline__ float adam1(float p, float g, float lr) { return adam1_a(p, g, adam_astep(lr)); }
 __device__ __forceinline__ float apply_update(float p, float g, float lr, int mode) {
     return mode == 0 ? adam1(p, g, lr) : __fsub_rn(p, __fmul_rn(lr, g));
+}
+// same with the Adam step size precomputed
+__device__ __forceinline__ float apply_update_a(float p, float g, float lr, float astep, int mode) {
+    return mode == 0 ? adam1_a(p, g, astep) : __fsub_rn(p, __fmul_rn(lr, g));
 }
 
 // ---------------------------------------------------------------------------------------------

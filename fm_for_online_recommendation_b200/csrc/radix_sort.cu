@@ -9,6 +9,8 @@
 // ordering path, so the permutation is bit-reproducible).
 #include "fmb_common.cuh"
 #include "smem_sort.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -203,7 +205,208 @@ __global__ void __launch_bounds__(FS_THREADS) sort_fields_kernel(const int32_t* 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Cluster version of the per-field sort: a thread-block cluster of CL CTAs (CL SMs) sorts one
+// field.  CTA r keeps positions [r*Bq, (r+1)*Bq) of the field's current ordering in its shared
+// memory; every pass ranks its keys locally, exchanges the 256 digit totals through distributed
+// shared memory, and scatters (key, payload) straight into the destination CTA's shared memory.
+// Same result as sort_fields_kernel on 4x the SMs (39 CTAs of 1024 threads left 109 SMs idle and
+// were issue-bound: profiles/r1c), and batches up to 65536.
+// ---------------------------------------------------------------------------------------------
+constexpr int CL = 4;
+__device__ long long* g_sort_dbg = nullptr;   // debug: per-phase cycle counts of one CTA
+#define SORT_PROBE(slot) do { if (dbg && threadIdx.x == 0) { long long t_ = clock64(); dbg[slot] += t_ - tlast; tlast = t_; } } while (0)
+
+// THREADS = 256 for batches up to 16384 (8 warps x <= 16 slots per CTA: the per-pass fixed work -- counter
+// reset, per-digit prefix over warps -- scales with the warp count and dominated the 1024-thread version),
+// 1024 above that.
+// STAGED: keys are first scattered into a LOCAL staging buffer in digit order, then copied to their destination
+// CTAs with lane-contiguous (coalesced) distributed-shared-memory stores; the direct version issued two
+// scattered 4-/2-byte remote stores per key, which is what bounded it (profiles/r1g).
+template <int THREADS, bool STAGED>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS)
+sort_fields_cluster_kernel(const int32_t* __restrict__ ids, int B, int F, const int32_t* __restrict__ field_off,
+                           int32_t* __restrict__ skeys, int32_t* __restrict__ perm, int Bq) {
+    constexpr int WARPS = THREADS / 32;
+    extern __shared__ __align__(16) unsigned char fs_smem[];
+    uint32_t* kbuf0 = reinterpret_cast<uint32_t*>(fs_smem);
+    uint32_t* kbuf1 = kbuf0 + Bq;
+    uint16_t* pbuf0 = reinterpret_cast<uint16_t*>(kbuf1 + Bq);
+    uint16_t* pbuf1 = pbuf0 + Bq + (Bq & 1);
+    uint16_t* cnt = pbuf1 + Bq + (Bq & 1);               // [WARPS][RADIX] (sized for 32 warps)
+    uint32_t* kstage = reinterpret_cast<uint32_t*>(cnt + 32 * RADIX);   // [Bq]  (STAGED only)
+    uint16_t* pstage = reinterpret_cast<uint16_t*>(kstage + Bq);        // [Bq]
+    __shared__ uint32_t lstart[RADIX];                   // start of each digit inside the local staging order
+    __shared__ uint32_t tot[RADIX];                      // my digit totals (read by the other CTAs)
+    __shared__ uint32_t before_s[RADIX];                 // same-digit keys held by lower-ranked CTAs
+    __shared__ uint32_t base[RADIX];                     // field-wide start of each digit
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank();
+    const int f = blockIdx.x / CL, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int32_t off = field_off[f];
+    const uint32_t nrows = (uint32_t)(field_off[f + 1] - off);
+    const int bits = nrows <= 1 ? 0 : 32 - __clz(nrows - 1);
+    const int passes = (bits + RADIX_BITS - 1) / RADIX_BITS;
+    const int g0 = crank * Bq;                            // first field position held by this CTA
+    const int n = max(0, min(Bq, B - g0));                // entries held by this CTA
+    long long* dbg = (g_sort_dbg && blockIdx.x == (unsigned)(F - 1) * CL) ? g_sort_dbg : nullptr;
+    long long tlast = clock64();
+    for (int i = threadIdx.x; i < n; i += THREADS) {
+        kbuf0[i] = (uint32_t)(ids[(size_t)(g0 + i) * F + f] - off);
+        pbuf0[i] = (uint16_t)(g0 + i);
+    }
+    __syncthreads();
+    SORT_PROBE(0);
+    uint32_t* kc = kbuf0; uint32_t* kn = kbuf1;
+    uint16_t* pc = pbuf0; uint16_t* pn = pbuf1;
+    const int slots = (Bq + THREADS - 1) / THREADS;
+    const int wbase = warp * slots * 32;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int ps = 0; ps < passes; ++ps) {
+        const int shift = ps * RADIX_BITS;
+        for (int i = threadIdx.x; i < WARPS * RADIX / 2; i += THREADS) reinterpret_cast<uint32_t*>(cnt)[i] = 0;
+        __syncthreads();
+        uint32_t key[FS_MAX_SLOTS];
+        uint16_t rank[FS_MAX_SLOTS];
+        unsigned peers[FS_MAX_SLOTS];
+        // peer masks of all slots first: the ballots of different slots are independent, so their latencies
+        // overlap (issued slot after slot they were 560 cycles per slot: 9 dependent VOTEs each)
+#pragma unroll
+        for (int s = 0; s < FS_MAX_SLOTS; ++s) {
+            if (s < slots) {
+                const int idx = wbase + s * 32 + lane;
+                const bool valid = idx < n;
+                key[s] = valid ? kc[idx] : 0u;
+                peers[s] = digit_peers(valid ? ((key[s] >> shift) & (RADIX - 1)) : 0u, valid);
+            }
+        }
+        // then the (short) serial part: per-warp digit counters
+#pragma unroll
+        for (int s = 0; s < FS_MAX_SLOTS; ++s) {
+            if (s < slots) {
+                const int idx = wbase + s * 32 + lane;
+                const bool valid = idx < n;
+                const unsigned d = (key[s] >> shift) & (RADIX - 1);
+                const unsigned m = peers[s];
+                const int leader = __ffs(m) - 1;
+                uint32_t old = 0;
+                if (valid && lane == leader) { old = cnt[warp * RADIX + d]; cnt[warp * RADIX + d] = (uint16_t)(old + __popc(m)); }
+                old = __shfl_sync(0xffffffffu, old, leader);
+                rank[s] = (uint16_t)(old + __popc(m & lt));
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        SORT_PROBE(1);
+        if (threadIdx.x < RADIX) {
+            const int d = threadIdx.x;
+            uint32_t run = 0;
+            for (int w = 0; w < WARPS; ++w) { const uint32_t t = cnt[w * RADIX + d]; cnt[w * RADIX + d] = (uint16_t)run; run += t; }
+            tot[d] = run;
+        }
+        if (STAGED) {
+            __syncthreads();
+            SORT_PROBE(2);
+            if (warp == 0) {  // exclusive scan of MY digit totals -> local staging order
+                uint32_t v[8], sum = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { v[j] = tot[lane * 8 + j]; sum += v[j]; }
+                uint32_t inc = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                uint32_t ex = inc - sum;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { lstart[lane * 8 + j] = ex; ex += v[j]; }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int s = 0; s < FS_MAX_SLOTS; ++s) {
+                if (s < slots) {
+                    const int idx = wbase + s * 32 + lane;
+                    if (idx < n) {
+                        const unsigned d = (key[s] >> shift) & (RADIX - 1);
+                        const uint32_t lp = lstart[d] + cnt[warp * RADIX + d] + rank[s];
+                        kstage[lp] = key[s];
+                        pstage[lp] = pc[idx];
+                    }
+                }
+            }
+        }
+        SORT_PROBE(3);
+        cluster.sync();   // every CTA's totals are published; the previous pass's remote scatter is complete
+        SORT_PROBE(4);
+        if (threadIdx.x < RADIX) {
+            const int d = threadIdx.x;
+            uint32_t all = 0, before = 0;
+#pragma unroll
+            for (int r = 0; r < CL; ++r) {
+                const uint32_t t = *cluster.map_shared_rank(&tot[d], r);
+                all += t;
+                if (r < crank) before += t;
+            }
+            base[d] = all;
+            before_s[d] = before;
+        }
+        __syncthreads();
+        if (warp == 0) {  // exclusive scan of the 256 column totals, 8 per lane
+            uint32_t v[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v[j] = base[lane * 8 + j]; sum += v[j]; }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            uint32_t ex = inc - sum;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { base[lane * 8 + j] = ex + before_s[lane * 8 + j]; ex += v[j]; }
+        }
+        __syncthreads();
+        SORT_PROBE(5);
+        if (STAGED) {
+            // staged order -> destination CTAs: consecutive lanes write consecutive remote addresses
+            for (int i = threadIdx.x; i < n; i += THREADS) {
+                const uint32_t kk = kstage[i];
+                const unsigned d = (kk >> shift) & (RADIX - 1);
+                const uint32_t pos = base[d] + ((uint32_t)i - lstart[d]);
+                const int dest = (pos >= (uint32_t)Bq) + (pos >= 2u * (uint32_t)Bq) + (pos >= 3u * (uint32_t)Bq);
+                const uint32_t li = pos - (uint32_t)dest * (uint32_t)Bq;
+                cluster.map_shared_rank(kn, dest)[li] = kk;
+                cluster.map_shared_rank(pn, dest)[li] = pstage[i];
+            }
+        } else {
+            // scatter (key, payload) straight into the destination CTA's next buffer
+#pragma unroll
+            for (int s = 0; s < FS_MAX_SLOTS; ++s) {
+                if (s < slots) {
+                    const int idx = wbase + s * 32 + lane;
+                    if (idx < n) {
+                        const unsigned d = (key[s] >> shift) & (RADIX - 1);
+                        const uint32_t pos = base[d] + cnt[warp * RADIX + d] + rank[s];
+                        const int dest = (pos >= (uint32_t)Bq) + (pos >= 2u * (uint32_t)Bq) + (pos >= 3u * (uint32_t)Bq);
+                        const uint32_t li = pos - (uint32_t)dest * (uint32_t)Bq;
+                        cluster.map_shared_rank(kn, dest)[li] = key[s];
+                        cluster.map_shared_rank(pn, dest)[li] = pc[idx];
+                    }
+                }
+            }
+        }
+        SORT_PROBE(6);
+        cluster.sync();   // all remote writes of this pass have landed (tot[] may be overwritten again)
+        SORT_PROBE(7);
+        uint32_t* tk = kc; kc = kn; kn = tk;
+        uint16_t* tp = pc; pc = pn; pn = tp;
+    }
+    for (int i = threadIdx.x; i < n; i += THREADS) {
+        skeys[(size_t)f * B + g0 + i] = (int32_t)kc[i] + off;
+        perm[(size_t)f * B + g0 + i] = (int32_t)pc[i] * F + f;
+    }
+    SORT_PROBE(8);
+}
+
 }  // namespace
+
+// debug hook (not in the public header)
+FMB_API void fmb_debug_set_sort_buffer(long long* dev) { cudaMemcpyToSymbol(g_sort_dbg, &dev, sizeof(dev)); }
 
 static int sort_ntiles(int64_t N) { return (int)((N + TILE - 1) / TILE); }
 
@@ -253,20 +456,37 @@ FMB_API int fmb_sort_segment(const int32_t* keys, int64_t N, int key_bits, void*
     return FMB_OK;
 }
 
-// Largest batch the per-field shared-memory sort accepts.
-FMB_API int fmb_sort_fields_max_batch(void) { return FS_WARPS * FS_MAX_SLOTS * 32; }
+// Largest batch the per-field shared-memory sort accepts (cluster of 4 CTAs, 16-bit sample payload).
+FMB_API int fmb_sort_fields_max_batch(void) { return 65536; }
 
 // Stable sort of ids[B,F] (column f holds global row ids of field f, field_off[F+1] device array of
 // field offsets) -> sorted_keys[B*F], perm[B*F] (original entry index b*F+f), identical to
-// fmb_sort_segment over the flattened matrix.  One CTA per field, everything in shared memory.
+// fmb_sort_segment over the flattened matrix.  Everything stays in shared memory: one CTA per field for
+// B <= 2048, otherwise a 4-CTA thread-block cluster per field exchanging through distributed shared memory.
 FMB_API int fmb_sort_fields(const int32_t* ids, int B, int F, const int32_t* field_off, int32_t* sorted_keys,
                             int32_t* perm, cudaStream_t stream) {
     FMB_CHECK_ARG(ids && field_off && sorted_keys && perm, "fmb_sort_fields: null pointer");
     FMB_CHECK_ARG(B > 0 && B <= fmb_sort_fields_max_batch() && F > 0, "fmb_sort_fields: B=%d out of range", B);
-    const size_t sm = (size_t)2 * B * 4 + (size_t)2 * (B + (B & 1)) * 2 + (size_t)FS_WARPS * RADIX * 2;
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(sort_fields_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr = true; }
-    sort_fields_kernel<<<F, FS_THREADS, sm, stream>>>(ids, B, F, field_off, sorted_keys, perm);
-    FMB_CHECK_LAUNCH("sort_fields_kernel");
+    if (!attr) {
+        cudaFuncSetAttribute(sort_fields_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(sort_fields_cluster_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(sort_fields_cluster_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        attr = true;
+    }
+    if (B <= 2048) {
+        sort_fields_kernel<<<F, FS_THREADS, fmb::smem_sort_bytes(B), stream>>>(ids, B, F, field_off, sorted_keys, perm);
+        FMB_CHECK_LAUNCH("sort_fields_kernel");
+    } else {
+        int Bq = (B + CL - 1) / CL;
+        Bq = (Bq + 31) / 32 * 32;
+        if (Bq <= 256 * FS_MAX_SLOTS)
+            sort_fields_cluster_kernel<256, true><<<F * CL, 256, fmb::smem_sort_bytes(Bq) + (size_t)Bq * 6 + 16, stream>>>(ids, B, F, field_off,
+                                                                                             sorted_keys, perm, Bq);
+        else
+            sort_fields_cluster_kernel<1024, false><<<F * CL, 1024, fmb::smem_sort_bytes(Bq), stream>>>(ids, B, F, field_off,
+                                                                                               sorted_keys, perm, Bq);
+        FMB_CHECK_LAUNCH("sort_fields_cluster_kernel");
+    }
     return FMB_OK;
 }

@@ -115,7 +115,7 @@ def test_sort_and_segments_bit_exact(N, bits, dist):
     assert np.array_equal(seg.cpu().numpy()[:n], starts) and int(seg[n].item()) == N
 
 
-@pytest.mark.parametrize("B", [1, 33, 1000, 8192, 16384])
+@pytest.mark.parametrize("B", [1, 33, 1000, 2048, 2049, 8192, 16384, 40001, 65536])
 def test_sort_fields_matches_global_stable_sort(B):
     """per-field shared-memory sort == stable argsort of the flattened [B,F] id matrix (bit-exact)."""
     import fm_for_online_recommendation_b200 as pkg
