@@ -69,6 +69,9 @@ _SIGS = {
     "fmb_session_destroy": (None, [vp]),
     "fmb_session_launches": (C.c_int64, [vp]),
     "fmb_session_fm_step": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp]),
+    "fmb_session_fm_step_host_async": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_float,
+                                                 C.c_int, vp]),
+    "fmb_session_wait_loss": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float)]),
     "fmb_session_fm_step_host": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_float, C.c_int,
                                            C.POINTER(C.c_float), vp]),
 }

@@ -54,6 +54,12 @@ struct fmb_session {
     float* h_xv;
     float* h_y;
     float* h_loss;
+    // second input slot + copy stream for the pipelined host entry point (slot 0 = the buffers above)
+    int32_t* d_ids2; float* d_xv2; float* d_y2; float* d_loss2;
+    int32_t* h_ids2; float* h_xv2; float* h_y2;
+    cudaStream_t st_copy;
+    cudaEvent_t ev_h2d[2], ev_done[2];
+    int slot_used[2];
     int64_t launches;  // kernels launched through this session (bench.py's gpu_launches)
     // CUDA-graph cache of whole steps, keyed by every argument that is baked into the kernels
     cudaStream_t st0, st1;
@@ -77,6 +83,10 @@ FMB_API void fmb_session_destroy(fmb_session* s) {
     cudaFree(s->d_delta); cudaFree(s->d_lossv); cudaFree(s->d_loss); cudaFree(s->d_skeys); cudaFree(s->d_perm);
     cudaFree(s->d_sort_ws); cudaFree(s->d_bwd_ws); cudaFree(s->d_field_off);
     cudaFreeHost(s->h_ids); cudaFreeHost(s->h_xv); cudaFreeHost(s->h_y); cudaFreeHost(s->h_loss);
+    cudaFree(s->d_ids2); cudaFree(s->d_xv2); cudaFree(s->d_y2); cudaFree(s->d_loss2);
+    cudaFreeHost(s->h_ids2); cudaFreeHost(s->h_xv2); cudaFreeHost(s->h_y2);
+    if (s->st_copy) cudaStreamDestroy(s->st_copy);
+    for (int i = 0; i < 2; ++i) { if (s->ev_h2d[i]) cudaEventDestroy(s->ev_h2d[i]); if (s->ev_done[i]) cudaEventDestroy(s->ev_done[i]); }
     for (int i = 0; i < s->ngraphs; ++i) cudaGraphExecDestroy(s->gexec[i]);
     if (s->st0) cudaStreamDestroy(s->st0);
     if (s->st1) cudaStreamDestroy(s->st1);
@@ -110,6 +120,14 @@ FMB_API int fmb_session_create(fmb_session** out, int F, int k, int64_t max_batc
     dm(&s->d_sort_ws, s->sort_ws_bytes); dm(&s->d_bwd_ws, s->bwd_ws_bytes);
     hm((void**)&s->h_ids, N * 4); hm((void**)&s->h_xv, N * 4); hm((void**)&s->h_y, max_batch * 4);
     hm((void**)&s->h_loss, 256);
+    dm((void**)&s->d_ids2, N * 4); dm((void**)&s->d_xv2, N * 4); dm((void**)&s->d_y2, max_batch * 4);
+    dm((void**)&s->d_loss2, 256);
+    hm((void**)&s->h_ids2, N * 4); hm((void**)&s->h_xv2, N * 4); hm((void**)&s->h_y2, max_batch * 4);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st_copy, cudaStreamNonBlocking);
+    for (int i = 0; i < 2; ++i) {
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_h2d[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_done[i], cudaEventDisableTiming);
+    }
     if (field_off_host) {
         dm((void**)&s->d_field_off, (size_t)(F + 1) * 4);
         if (e == cudaSuccess) e = cudaMemcpy(s->d_field_off, field_off_host, (size_t)(F + 1) * 4, cudaMemcpyHostToDevice);
@@ -212,6 +230,62 @@ FMB_API int fmb_session_fm_step(fmb_session* s, const int32_t* ids, const float*
     }
     CU(cudaGraphLaunch(s->gexec[slot], stream));
     s->launches += s->glaunches[slot];
+    return FMB_OK;
+}
+
+// true when `p` is page-locked host memory the copy engine can read directly (no staging copy needed)
+static bool host_ptr_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// Pipelined step with HOST inputs.  `slot` (0 or 1) selects one of two device input buffers: the copies of
+// step t+1 (on the session's copy stream) overlap the kernels of step t (on `stream`).  Pinned / registered
+// host buffers are read in place, pageable ones go through the session's pinned staging area.  The loss
+// arrives in pinned memory; fmb_session_wait_loss(slot) waits for it.  Every step still moves its own
+// 4*B*F (+4*B*F) + 4*B bytes in and 4 bytes out.
+FMB_API int fmb_session_fm_step_host_async(fmb_session* s, int slot, const int32_t* ids_host, const float* xv_host,
+                                           const float* y_host, int B, float* table, float* bias, int key_bits,
+                                           int loss_kind, float lr, int mode, cudaStream_t stream) {
+    FMB_CHECK_ARG(s && ids_host && y_host && table && bias, "fmb_session_fm_step_host_async: null pointer");
+    FMB_CHECK_ARG(slot == 0 || slot == 1, "fmb_session_fm_step_host_async: slot must be 0 or 1");
+    FMB_CHECK_ARG(B > 0 && B <= s->maxB, "fmb_session_fm_step_host_async: B=%d exceeds session max_batch", B);
+    const size_t N = (size_t)B * s->F;
+    int32_t* d_ids = slot ? s->d_ids2 : s->d_ids;
+    float* d_xv = slot ? s->d_xv2 : s->d_xv;
+    float* d_y = slot ? s->d_y2 : s->d_y;
+    float* d_loss = slot ? s->d_loss2 : s->d_loss;
+    int32_t* h_ids = slot ? s->h_ids2 : s->h_ids;
+    float* h_xv = slot ? s->h_xv2 : s->h_xv;
+    float* h_y = slot ? s->h_y2 : s->h_y;
+    // the previous user of this slot (two steps ago) must be done with the device buffers and the staging area
+    if (s->slot_used[slot]) CU(cudaEventSynchronize(s->ev_done[slot]));
+    const void* src_ids = ids_host;
+    const void* src_y = y_host;
+    const void* src_xv = xv_host;
+    if (!host_ptr_is_pinned(ids_host)) { memcpy(h_ids, ids_host, N * 4); src_ids = h_ids; }
+    if (!host_ptr_is_pinned(y_host)) { memcpy(h_y, y_host, (size_t)B * 4); src_y = h_y; }
+    if (xv_host && !host_ptr_is_pinned(xv_host)) { memcpy(h_xv, xv_host, N * 4); src_xv = h_xv; }
+    CU(cudaMemcpyAsync(d_ids, src_ids, N * 4, cudaMemcpyHostToDevice, s->st_copy));
+    CU(cudaMemcpyAsync(d_y, src_y, (size_t)B * 4, cudaMemcpyHostToDevice, s->st_copy));
+    if (xv_host) CU(cudaMemcpyAsync(d_xv, src_xv, N * 4, cudaMemcpyHostToDevice, s->st_copy));
+    CU(cudaEventRecord(s->ev_h2d[slot], s->st_copy));
+    CU(cudaStreamWaitEvent(stream, s->ev_h2d[slot], 0));
+    int rc = fmb_session_fm_step(s, d_ids, xv_host ? d_xv : nullptr, d_y, B, table, bias, key_bits, loss_kind, lr,
+                                 mode, d_loss, stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(s->h_loss + 8 * slot, d_loss, 4, cudaMemcpyDeviceToHost, stream));
+    CU(cudaEventRecord(s->ev_done[slot], stream));
+    s->slot_used[slot] = 1;
+    return FMB_OK;
+}
+
+// waits for the step last submitted on `slot` and returns its mean loss
+FMB_API int fmb_session_wait_loss(fmb_session* s, int slot, float* loss_host) {
+    FMB_CHECK_ARG(s && (slot == 0 || slot == 1) && s->slot_used[slot], "fmb_session_wait_loss: nothing submitted on slot %d", slot);
+    CU(cudaEventSynchronize(s->ev_done[slot]));
+    if (loss_host) *loss_host = s->h_loss[8 * slot];
     return FMB_OK;
 }
 

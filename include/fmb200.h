@@ -195,6 +195,14 @@ int fmb_session_fm_step_host(fmb_session* s, const int32_t* ids_host, const floa
                              int B, float* table_dev, float* bias_dev, int key_bits, int loss_kind, float lr,
                              int mode, float* loss_host, fmb_stream_t stream);
 
+/* pipelined host entry point: two input slots; the H2D copies of step t+1 run on the session's copy stream
+ * while step t computes.  Pinned / registered host buffers are read in place.  fmb_session_wait_loss
+ * blocks until the step last submitted on `slot` has finished and returns its mean loss. */
+int fmb_session_fm_step_host_async(fmb_session* s, int slot, const int32_t* ids_host, const float* xv_host,
+                                   const float* y_host, int B, float* table_dev, float* bias_dev, int key_bits,
+                                   int loss_kind, float lr, int mode, fmb_stream_t stream);
+int fmb_session_wait_loss(fmb_session* s, int slot, float* loss_host);
+
 #ifdef __cplusplus
 }
 #endif
