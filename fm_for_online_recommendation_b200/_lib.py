@@ -68,9 +68,11 @@ _SIGS = {
     "fmb_sort_fields": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp]),
     "fmb_session_destroy": (None, [vp]),
     "fmb_session_launches": (C.c_int64, [vp]),
+    "fmb_session_graph_count": (C.c_int, [vp]),
     "fmb_session_fm_step": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp]),
     "fmb_session_fm_step_host_async": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_float,
                                                  C.c_int, vp]),
+    "fmb_session_presort": (C.c_int, [vp, vp, C.c_int, C.c_int]),
     "fmb_session_wait_loss": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float)]),
     "fmb_session_fm_step_host": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_float, C.c_int,
                                            C.POINTER(C.c_float), vp]),

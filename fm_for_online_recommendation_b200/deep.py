@@ -335,6 +335,12 @@ class _DeepBase(nn.Module):
     _UE_LOSS = LOSS_LOGITS
     _FIT_LOSS = LOSS_LOGITS_OF_SIG
 
+    def presort(self, batch):
+        """Start sorting the ids of `batch` (an EncodedBatch that will be passed to the NEXT update_embedding /
+        FMAdam.fit) on a side stream, overlapping the step in flight (the sort depends on the ids only)."""
+        s = self._get_session(batch.B)
+        check(self._lib.fmb_session_presort(s, ptr(batch.ids), batch.B, self._key_bits), "fmb_session_presort")
+
     def update_embedding(self, Xi, Xv, Y):
         """fm_adam.py:56-69 and the same method of the other four classes: loss on forward_fm only."""
         self.train()

@@ -188,12 +188,18 @@ int fmb_session_create(fmb_session** out, int F, int k, int64_t max_batch,
                        const int32_t* field_off_host /*[F+1] global row offset per field, nullable*/);
 void fmb_session_destroy(fmb_session* s);
 int64_t fmb_session_launches(const fmb_session* s);
+int fmb_session_graph_count(const fmb_session* s); /* step graphs currently cached */
 int fmb_session_fm_step(fmb_session* s, const int32_t* ids_dev, const float* xv_dev, const float* y_dev, int B,
                         float* table_dev, float* bias_dev, int key_bits, int loss_kind, float lr, int mode,
                         float* loss_dev, fmb_stream_t stream);
 int fmb_session_fm_step_host(fmb_session* s, const int32_t* ids_host, const float* xv_host, const float* y_host,
                              int B, float* table_dev, float* bias_dev, int key_bits, int loss_kind, float lr,
                              int mode, float* loss_host, fmb_stream_t stream);
+
+/* pre-sort: the sort of a batch depends on its ids only.  fmb_session_presort(ids) sorts them now on a side
+ * stream (overlapping the step in flight); the next fmb_session_fm_step called with the same ids pointer and
+ * B skips its own sort.  The ids must stay unchanged until that step has been submitted. */
+int fmb_session_presort(fmb_session* s, const int32_t* ids_dev, int B, int key_bits);
 
 /* pipelined host entry point: two input slots; the H2D copies of step t+1 run on the session's copy stream
  * while step t computes.  Pinned / registered host buffers are read in place.  fmb_session_wait_loss

@@ -221,6 +221,25 @@ def test_host_entry_point_matches_device_entry_point():
     assert_same_params(m, orc, exact=True)
 
 
+def test_presorted_steps_bit_exact():
+    """step(i); presort(i+1) -- the pre-sorted path must give the oracle's bits, also when a step arrives
+    without (or with a stale) pre-sort."""
+    sizes, k, B = [300, 40, 7, 2000, 3], 10, 700
+    m, orc = _pair("FMAdam", sizes, k, lr=1e-3, scale=0.2)
+    batches = [synth(sizes, B, 60 + i, zipf=(i % 2 == 1)) for i in range(7)]
+    enc = [m.encode(*b) for b in batches]
+    m.presort(enc[0])
+    for i in range(7):
+        loss = m._fm_step(enc[i], 0)
+        if i in (0, 1, 3, 4):          # steps 3 and 6 run without a matching pre-sort
+            m.presort(enc[i + 1])
+        if i == 4:
+            m.presort(enc[6])          # stale: batch 5 comes next
+        want = orc.update_embedding(*batches[i])
+        assert np.float32(loss.item()) == np.float32(want), i
+        assert_same_params(m, orc, exact=True)
+
+
 def test_pipelined_host_entry_point_bit_exact():
     """fmb_session_fm_step_host_async (two slots, pinned and pageable sources) == oracle, step after step."""
     import fm_for_online_recommendation_b200 as pkg
