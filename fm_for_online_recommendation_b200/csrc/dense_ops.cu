@@ -31,86 +31,92 @@ __global__ void update_dense_kernel(float* __restrict__ p, const float* __restri
     if (i < n) p[i] = fmb::apply_update(p[i], g[i], lr, mode);
 }
 
-// ATen-order sum of x[0:n] by one warp, with the data staged through shared memory in chunks of
-// FIN_CHUNK floats by the whole CTA (coalesced, one latency per chunk) so the serial chain reads
-// shared memory instead of L2.  Chunk boundaries are multiples of 32*16, so the cascade state
-// simply carries over; bit-identical to fmb::aten_row_sum_warp.
-constexpr int FIN_CHUNK = 4096;  // 128 rows of 32: a multiple of every cascade step <= 128
-struct AtenAcc {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-};
+// ATen-order sum of x[0:n], parallel where the order allows it.  ATen's cascade (SumKernel.cpp multi_row_sum)
+// adds rows of 32 floats (4 ilp x 8 lanes) in blocks of `level_step` rows: a block's sum is
+// ((0 + r0) + r1) + ... and depends on nothing else, only the way block sums are folded upwards is serial.
+// So: phase A, every warp computes block sums (one lane per accumulator, 16 loads in flight); phase B, one warp
+// folds the block sums through levels 1..3 exactly like the serial loop, adds the left-over rows, the left-over
+// vectors and the scalar tail.  Bit-identical to fmb::aten_row_sum_warp / orc_sum_aten.
+constexpr int FIN_THREADS = 1024;
+constexpr int FIN_MAX_BLOCKS = 2048;   // block sums kept in shared memory per array (n <= 2048*16*32 = 1 M)
 
-__global__ void __launch_bounds__(1024) finish_step_kernel(const float* __restrict__ delta,
-                                                           const float* __restrict__ lossv, int B, float* bias,
-                                                           float lr, int mode, float* loss_out) {
-    __shared__ float buf[2][FIN_CHUNK];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float* src[2] = {bias ? delta : nullptr, (loss_out && lossv) ? lossv : nullptr};
-    const int64_t n = B;
-    const int64_t vec_size = n >> 3, size_ilp = vec_size >> 2;   // rows of 32 floats handled by the cascade
+__device__ float aten_sum_cta(const float* __restrict__ x, int64_t n, float* bs /*[FIN_MAX_BLOCKS][32]*/, int w0,
+                              int nw) {
+    // called by warps [w0, w0+nw) of the CTA with the same arguments; result valid in warp w0
+    const int warp = (threadIdx.x >> 5) - w0, lane = threadIdx.x & 31;
+    const int64_t vec_size = n >> 3, size_ilp = vec_size >> 2;
     int lp = 0;
     while (((int64_t)1 << lp) < size_ilp) ++lp;
     lp >>= 2;
     const int level_power = lp > 4 ? lp : 4;
     const int64_t level_step = (int64_t)1 << level_power, level_mask = level_step - 1;
-    AtenAcc acc;
-    const bool small = n < 8;
-    for (int64_t base = 0; base < n; base += FIN_CHUNK) {
-        const int m = (int)min((int64_t)FIN_CHUNK, n - base);
-        for (int i = threadIdx.x; i < m; i += blockDim.x) {
-            if (src[0]) buf[0][i] = src[0][base + i];
-            if (src[1]) buf[1][i] = src[1][base + i];
-        }
-        __syncthreads();
-        if (warp < 2 && src[warp] && !small) {
-            const float* b = buf[warp];
-            // rows [base/32, ...) that lie fully inside both the chunk and the cascade range
-            const int64_t r0 = base >> 5;
-            const int64_t r1 = min(size_ilp, (base + m) >> 5);
-            const int64_t full_limit = (size_ilp / level_step) * level_step;
-            const int64_t rf = min(r1, full_limit);
-            int64_t i = r0;
-            while (i + level_step <= rf) {  // chunk boundaries are multiples of level_step rows
-                for (int64_t j = 0; j < level_step; j += 16, i += 16) {  // level_step is a multiple of 16
-                    float v[16];
+    const int64_t nblocks = size_ilp / level_step;
+    // phase A: block sums
+    for (int64_t bi = warp; bi < nblocks; bi += nw) {
+        const float* r = x + bi * level_step * 32 + lane;
+        float a = 0.f;
+        for (int64_t j = 0; j < level_step; j += 16) {
+            float v[16];
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) v[u] = b[((i + u) << 5) - base + lane];
+            for (int u = 0; u < 16; ++u) v[u] = r[(j + u) * 32];
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) acc.a0 = __fadd_rn(acc.a0, v[u]);
-                }
-                acc.a1 = __fadd_rn(acc.a1, acc.a0); acc.a0 = 0.f;
-                if ((i & (level_mask << level_power)) == 0) {
-                    acc.a2 = __fadd_rn(acc.a2, acc.a1); acc.a1 = 0.f;
-                    if ((i & (level_mask << (2 * level_power))) == 0) { acc.a3 = __fadd_rn(acc.a3, acc.a2); acc.a2 = 0.f; }
-                }
-            }
-            for (; i < r1; ++i) acc.a0 = __fadd_rn(acc.a0, b[(i << 5) - base + lane]);
+            for (int u = 0; u < 16; ++u) a = __fadd_rn(a, v[u]);
         }
-        __syncthreads();
+        bs[bi * 32 + lane] = a;
     }
-    if (warp < 2 && src[warp]) {
-        float total;
-        if (small) {
-            total = fmb::aten_row_sum_warp(src[warp], n);
-        } else {
-            float a = __fadd_rn(__fadd_rn(__fadd_rn(acc.a0, acc.a1), acc.a2), acc.a3);
-            const float* x = src[warp];
-            if (lane < 8)
-                for (int64_t v = size_ilp << 2; v < vec_size; ++v) a = __fadd_rn(a, x[v * 8 + lane]);
-            const float t1 = __shfl_down_sync(0xffffffffu, a, 8);
-            const float t2 = __shfl_down_sync(0xffffffffu, a, 16);
-            const float t3 = __shfl_down_sync(0xffffffffu, a, 24);
-            const float folded = __fadd_rn(__fadd_rn(__fadd_rn(a, t1), t2), t3);
-            float fin = 0.f;
-            for (int64_t q = vec_size << 3; q < n; ++q) fin = __fadd_rn(fin, x[q]);
+    // all participating warps must have written their block sums
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + (w0 ? 1 : 0)), "r"(nw * 32));
+    float total = 0.f;
+    if (warp == 0) {
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        for (int64_t bi = 0; bi < nblocks; ++bi) {
+            const int64_t i = (bi + 1) * level_step;   // rows consumed so far
+            acc1 = __fadd_rn(acc1, bs[bi * 32 + lane]);
+            if ((i & (level_mask << level_power)) == 0) {
+                acc2 = __fadd_rn(acc2, acc1); acc1 = 0.f;
+                if ((i & (level_mask << (2 * level_power))) == 0) { acc3 = __fadd_rn(acc3, acc2); acc2 = 0.f; }
+            }
+        }
+        for (int64_t i = nblocks * level_step; i < size_ilp; ++i) acc0 = __fadd_rn(acc0, x[i * 32 + lane]);
+        float a = __fadd_rn(__fadd_rn(__fadd_rn(acc0, acc1), acc2), acc3);
+        if (lane < 8)
+            for (int64_t v = size_ilp << 2; v < vec_size; ++v) a = __fadd_rn(a, x[v * 8 + lane]);
+        const float t1 = __shfl_down_sync(0xffffffffu, a, 8);
+        const float t2 = __shfl_down_sync(0xffffffffu, a, 16);
+        const float t3 = __shfl_down_sync(0xffffffffu, a, 24);
+        const float folded = __fadd_rn(__fadd_rn(__fadd_rn(a, t1), t2), t3);
+        float fin = 0.f;
+        for (int64_t q = vec_size << 3; q < n; ++q) fin = __fadd_rn(fin, x[q]);
 #pragma unroll
-            for (int l = 0; l < 8; ++l) fin = __fadd_rn(fin, __shfl_sync(0xffffffffu, folded, l));
-            total = fin;
-        }
-        if (lane == 0) {
-            if (warp == 0) bias[0] = fmb::apply_update(bias[0], total, lr, mode);
-            else loss_out[0] = __fdiv_rn(total, (float)B);
-        }
+        for (int l = 0; l < 8; ++l) fin = __fadd_rn(fin, __shfl_sync(0xffffffffu, folded, l));
+        total = fin;
+    }
+    return total;
+}
+
+// warps 0..15: bias -= step(sum(delta));  warps 16..31: loss_out = sum(lossv) / B
+__global__ void __launch_bounds__(FIN_THREADS) finish_step_kernel(const float* __restrict__ delta,
+                                                                  const float* __restrict__ lossv, int B, float* bias,
+                                                                  float lr, int mode, float* loss_out,
+                                                                  float* scratch /*[2][nblocks*32] or NULL*/) {
+    extern __shared__ __align__(16) float fin_sm[];
+    const int half = (threadIdx.x >> 5) >= 16 ? 1 : 0;
+    const float* src = half == 0 ? (bias ? delta : nullptr) : ((loss_out && lossv) ? lossv : nullptr);
+    if (!src) return;
+    const int64_t n = B;
+    const int lane = threadIdx.x & 31;
+    float total;
+    if (n < 8) {
+        if ((threadIdx.x >> 5) != half * 16) return;
+        total = fmb::aten_row_sum_warp(src, n);
+    } else {
+        float* bs = scratch ? scratch + (size_t)half * FIN_MAX_BLOCKS * 32 : fin_sm + (size_t)half * 512 * 32;
+        total = aten_sum_cta(src, n, bs, half * 16, 16);
+        if ((threadIdx.x >> 5) != half * 16) return;
+    }
+    if (lane == 0) {
+        if (half == 0) bias[0] = fmb::apply_update(bias[0], total, lr, mode);
+        else loss_out[0] = __fdiv_rn(total, (float)B);
     }
 }
 
@@ -144,11 +150,29 @@ FMB_API int fmb_update_dense(float* p, const float* g, int64_t n, float lr, int 
     return FMB_OK;
 }
 
-// end of a training step: bias update from sum(delta) (bias nullable) and mean loss (loss_out nullable)
+// end of a training step: bias update from sum(delta) (bias nullable) and mean loss (loss_out nullable).
+// B <= 1 M samples (block sums are staged in shared memory up to 256 K samples, in `fmb_finish_scratch` above).
+static float* g_fin_scratch = nullptr;
 FMB_API int fmb_finish_step(const float* delta, const float* lossv, int B, float* bias, float lr, int mode,
                             float* loss_out, cudaStream_t stream) {
     FMB_CHECK_ARG(delta && B > 0, "fmb_finish_step: bad arguments");
-    finish_step_kernel<<<1, 1024, 0, stream>>>(delta, lossv, B, bias, lr, mode, loss_out);
+    FMB_CHECK_ARG((int64_t)B <= (int64_t)FIN_MAX_BLOCKS * 16 * 32, "fmb_finish_step: B=%d too large", B);
+    // block sums: 2 arrays x (B/512) blocks x 32 floats; shared memory up to 512 blocks per array (128 KB total)
+    const int64_t nblocks = ((int64_t)B >> 5) / 16;
+    float* scratch = nullptr;
+    size_t smem = 0;
+    if (nblocks <= 512) {
+        smem = (size_t)2 * 512 * 32 * sizeof(float);
+    } else {
+        if (!g_fin_scratch && cudaMalloc(&g_fin_scratch, (size_t)2 * FIN_MAX_BLOCKS * 32 * sizeof(float)) != cudaSuccess) {
+            fmb_set_error("fmb_finish_step: scratch allocation failed");
+            return FMB_ERR_CUDA;
+        }
+        scratch = g_fin_scratch;
+    }
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(finish_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024); attr = true; }
+    finish_step_kernel<<<1, FIN_THREADS, smem, stream>>>(delta, lossv, B, bias, lr, mode, loss_out, scratch);
     FMB_CHECK_LAUNCH("finish_step_kernel");
     return FMB_OK;
 }

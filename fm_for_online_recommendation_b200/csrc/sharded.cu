@@ -152,28 +152,39 @@ __global__ void __launch_bounds__(fmb::SS_THREADS) shard_sort_fields_kernel(
     const uint32_t nloc = nrows / (uint32_t)G + 2;                     // local rows of this field (upper bound)
     const int bits = 32 - __clz(nloc);
     const int passes = (bits + fmb::SS_RADIX_BITS - 1) / fmb::SS_RADIX_BITS;
-    if (threadIdx.x == 0) s_count = 0;
-    __syncthreads();
-    for (int r = 0; r < G; ++r) {
-        const int32_t* col = idsT_all + ((size_t)r * F + f) * B;
-        for (int b0 = 0; b0 < B; b0 += fmb::SS_THREADS) {
-            const int b = b0 + threadIdx.x;
-            int32_t local = 0;
-            const bool own = b < B && owned_by(__ldg(col + b), G, glog, me, local);
-            const unsigned bal = __ballot_sync(0xffffffffu, own);
-            if (lane == 0) wtot[warp] = __popc(bal);
-            __syncthreads();
-            int pre = s_count, all = 0;
-            for (int w = 0; w < fmb::SS_WARPS; ++w) { const int c = wtot[w]; if (w < warp) pre += c; all += c; }
-            if (own) {
-                const int o = pre + __popc(bal & ((1u << lane) - 1u));
-                if (o < cap) { kbuf0[o] = (uint32_t)(local - base); pbuf0[o] = (uint16_t)(r * B + b); }
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) s_count += all;
-            __syncthreads();
-        }
+    // stable compaction of the owned entries, two syncs in total: every warp owns a contiguous slice of the
+    // global sample order (r-major, then b), counts its owned entries, the 32 counts are scanned, and the warp
+    // then writes its entries behind those of the warps before it.
+    const int64_t total = (int64_t)G * B;
+    const int64_t per_warp = ((total + fmb::SS_WARPS - 1) / fmb::SS_WARPS + 31) / 32 * 32;
+    const int64_t g_lo = min(total, (int64_t)warp * per_warp), g_hi = min(total, g_lo + per_warp);
+    const int32_t* fbase = idsT_all + (size_t)f * B;
+    const size_t rstride = (size_t)F * B;
+    int mycount = 0;
+    for (int64_t gb = g_lo; gb < g_hi; gb += 32) {   // warp-uniform trip count
+        const int64_t g = gb + lane;
+        bool own = false;
+        if (g < g_hi) { const int r = (int)(g / B); int32_t l; own = owned_by(__ldg(fbase + r * rstride + (g - (int64_t)r * B)), G, glog, me, l); }
+        mycount += __popc(__ballot_sync(0xffffffffu, own));
     }
+    if (lane == 0) wtot[warp] = mycount;
+    __syncthreads();
+    int pre = 0, all = 0;
+    for (int w = 0; w < fmb::SS_WARPS; ++w) { const int c = wtot[w]; if (w < warp) pre += c; all += c; }
+    if (threadIdx.x == 0) s_count = all;
+    for (int64_t gb = g_lo; gb < g_hi; gb += 32) {
+        const int64_t g = gb + lane;
+        bool own = false;
+        int32_t local = 0;
+        if (g < g_hi) { const int r = (int)(g / B); own = owned_by(__ldg(fbase + r * rstride + (g - (int64_t)r * B)), G, glog, me, local); }
+        const unsigned bal = __ballot_sync(0xffffffffu, own);
+        if (own) {
+            const int o = pre + __popc(bal & ((1u << lane) - 1u));
+            if (o < cap) { kbuf0[o] = (uint32_t)(local - base); pbuf0[o] = (uint16_t)g; }
+        }
+        pre += __popc(bal);
+    }
+    __syncthreads();
     int n = s_count;
     if (n > cap) { if (threadIdx.x == 0) atomicMax(overflow, n); n = cap; }
     if (threadIdx.x == 0) counts[f] = n;

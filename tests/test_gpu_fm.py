@@ -139,7 +139,7 @@ def test_sort_fields_matches_global_stable_sort(B):
     assert np.array_equal(sk.cpu().numpy(), flat[order])
 
 
-@pytest.mark.parametrize("n", [1, 5, 7, 8, 39, 511, 512, 2500, 4096, 8192, 20000, 100003])
+@pytest.mark.parametrize("n", [1, 5, 7, 8, 39, 511, 512, 513, 2500, 4096, 8192, 20000, 100003, 600001])
 def test_finish_step_sums_in_aten_order(n):
     import fm_for_online_recommendation_b200 as pkg
     from oracle.deep import lib as olib
