@@ -89,6 +89,7 @@ class ShardedFM:
             self.table[:self.R_local, :self.k + 1].normal_(generator=g)
         self.bias = torch.full((1,), float(np.float32(b)), device=self.device)
         self._ws = {}
+        self._side = torch.cuda.Stream()   # owner-side sort and bias/loss epilogue run beside the main chain
         self.launches = 0
         self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
 
@@ -144,8 +145,14 @@ class ShardedFM:
         skeys = self._buf("skeys", (F, cap), torch.int32)
         perm = self._buf("perm", (F, cap), torch.int32)
         counts = self._buf("counts", (F,), torch.int32)
-        check(lib.fmb_shard_sort_fields(ptr(idsT_all), G, self.rank, B, F, ptr(self.field_off_dev), cap, ptr(skeys),
-                                        ptr(perm), ptr(counts), ptr(self.overflow), st), "fmb_shard_sort_fields")
+        # the sort needs the ids only: it runs on the side stream, next to the partial forward, the all-to-all,
+        # the combine and the context all-gather; phase_backward joins it
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            check(lib.fmb_shard_sort_fields(ptr(idsT_all), G, self.rank, B, F, ptr(self.field_off_dev), cap,
+                                            ptr(skeys), ptr(perm), ptr(counts), ptr(self.overflow), _stream()),
+                  "fmb_shard_sort_fields")
         return partial
 
     def phase_combine(self, recv, y, loss_kind=0):
@@ -162,21 +169,27 @@ class ShardedFM:
         F, k, cap = self.F, self.k, self._cap
         Btot = ctx_all.shape[0]
         N = F * cap
+        main = torch.cuda.current_stream()
+        main.wait_stream(self._side)      # sorted keys / permutation are ready
         wsb = lib.fmb_bwd_workspace_bytes(N, k)
         ws = self._buf("bwd_ws", (wsb,), torch.uint8)
         gs = ctx_all.view(-1)[self.kp4:]
+        # bias step + mean loss depend on ctx_all only: side stream, beside the row updates
+        delta_all = self._buf("delta_all", (Btot,))
+        lossv_all = self._buf("lossv_all", (Btot,))
+        loss = torch.empty((), device=self.device)
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            check(lib.fmb_shard_unpack_ctx(ptr(ctx_all), Btot, k, ptr(delta_all), ptr(lossv_all), _stream()),
+                  "fmb_shard_unpack_ctx")
+            check(lib.fmb_finish_step(ptr(delta_all), ptr(lossv_all), Btot, ptr(self.bias), self.lr,
+                                      self.update_mode, ptr(loss), _stream()), "fmb_finish_step")
+        self.launches += 9
         check(lib.fmb_fm_backward_update_ex(ptr(self._ws["skeys"]), ptr(self._ws["perm"]), N, Btot * F, None,
                                             ptr(self.table), F, k, ptr(ctx_all), self.CW, ptr(gs), self.CW, 1, None,
                                             INT_MAX, self.lr, self.update_mode, ptr(ws), wsb, st),
               "fmb_fm_backward_update_ex")
-        delta_all = self._buf("delta_all", (Btot,))
-        lossv_all = self._buf("lossv_all", (Btot,))
-        check(lib.fmb_shard_unpack_ctx(ptr(ctx_all), Btot, k, ptr(delta_all), ptr(lossv_all), st),
-              "fmb_shard_unpack_ctx")
-        loss = torch.empty((), device=self.device)
-        check(lib.fmb_finish_step(ptr(delta_all), ptr(lossv_all), Btot, ptr(self.bias), self.lr, self.update_mode,
-                                  ptr(loss), st), "fmb_finish_step")
-        self.launches += 9
+        main.wait_stream(self._side)      # join: the step is complete when both branches are
         return loss
 
     def update_embedding(self, ids, y, loss_kind=0):
