@@ -300,6 +300,18 @@ def run_ours(args):
         "sort": B * F * 8 * 2 * ((model._key_bits + 7) // 8),
     }
     dom = max(("fm_forward", "fm_backward_update"), key=lambda n: phases[n])
+    # DRAM traffic of the dominant phase's kernels from the last `ncu --set full` capture (profiles/), per launch
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_final_dram_traffic.json")) as f:
+            tr = json.load(f)
+        pick = ("fm_forward",) if dom == "fm_forward" else ("fm_bwd_entry", "fm_bwd_runs")
+        traffic = int(sum(v["dram_read_bytes"] + v["dram_write_bytes"] for kname, v in tr.items()
+                          if kname.startswith(pick)))
+    except Exception:
+        traffic = None
+    dom_kernels = {"fm_forward": "fm_forward_kernel",
+                   "fm_backward_update": "fm_bwd_entry1_kernel + fm_bwd_runs_kernel (fmb_fm_backward_update)"}[dom]
     achieved = alg_bytes[dom] / (phases[dom] * 1e-3) / 1e9
     step_bytes = B * (8 * F * kp1 + 8 * F + 8)
 
@@ -316,8 +328,9 @@ def run_ours(args):
                        "two slots: copies of step t+1 overlap step t)",
                 "blocking_value": B * K / e2e_blocking_s},
         "gpu_launches": int(launches), "step_graphs_cached": int(lib.fmb_session_graph_count(sess)),
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": dom_kernels, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
+                     "traffic_source": "profiles/r1_final_dram_traffic.json (ncu --set full, cold cache, B=8192)",
                      "algorithmic_bytes_per_launch": alg_bytes[dom],
                      "phase_ms": phases,
                      "whole_step_GBps": step_bytes / (ms / K * 1e-3) / 1e9},
