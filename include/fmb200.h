@@ -134,6 +134,14 @@ size_t fmb_mlp_bwd_workspace_bytes(int B, int H);
 int fmb_mlp_backward(const float* bi_dev, int ldbi, const float* mlp_dev, const float* act_dev,
                      const float* gtop_dev, int top, int B, int k, int L, int H, float* gmlp_dev, float* gbi_dev,
                      int ldgbi, void* ws_dev, size_t ws_bytes, fmb_stream_t stream);
+/* Contractions of >= 2^25 multiply-adds (cfg4: B = 8192, H = 400) run on the tcgen05 tensor cores as 3xTF32
+ * with fp32 accumulation in tensor memory (csrc/gemm_tc.cu, ~1e-6 relative); smaller ones -- every shape of the
+ * reference's scripts -- on the exact SIMT kernel.  fmb_set_tensor_cores(0) (or FMB_TC=0) forces the exact path. */
+void fmb_set_tensor_cores(int on);
+int fmb_tensor_core_threshold_log2(void);
+int fmb_gemm_tc_nt(const float* A_dev /*[M,K]*/, const float* B_dev /*[N,K]*/, float* C_dev /*[M,N]*/, int M, int N,
+                   int K, fmb_stream_t stream); /* C = A B^T on the tensor cores (tests) */
+int fmb_gemm_tc_error(void);
 /* z = base + head, base = z_fm (DeepFM, deepfm_adam.py:88) or sum_first + bias (NFM, nfm_adam.py:79,87) */
 int fmb_combine_logit(int nfm, const float* z_fm_dev, const float* sum_first_dev, const float* bias_dev,
                       const float* head_dev, int B, float* z_dev, fmb_stream_t stream);

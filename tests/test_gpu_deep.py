@@ -136,3 +136,51 @@ def test_same_seed_same_init_as_reference_rng_order():
     m = pkg.FMAdam([943, 1682], embedding_size=10, n=0.01)
     p = pull(m)
     assert np.array_equal(p["V"], g["init_V"]) and np.array_equal(p["w1"], g["init_w1"])
+
+
+def test_tensor_core_gemm_3xtf32_within_tolerance():
+    """csrc/gemm_tc.cu: tcgen05.mma kind::tf32 x3 with fp32 TMEM accumulation vs an fp64 reference."""
+    import ctypes as C
+    import fm_for_online_recommendation_b200 as pkg
+    lib = pkg.require_cuda()
+    torch.manual_seed(0)
+    for (M, N, K) in [(128, 128, 32), (300, 400, 400), (8192, 400, 10), (1000, 72, 8192)]:
+        A = torch.randn(M, K, device="cuda")
+        B = torch.randn(N, K, device="cuda")
+        Cc = torch.zeros(M, N, device="cuda")
+        assert lib.fmb_gemm_tc_nt(C.c_void_p(A.data_ptr()), C.c_void_p(B.data_ptr()), C.c_void_p(Cc.data_ptr()), M, N,
+                                  K, None) == 0
+        torch.cuda.synchronize()
+        assert lib.fmb_gemm_tc_error() == 0
+        ref = (A.double() @ B.double().t())
+        rel = ((Cc.double() - ref).abs().max() / ref.abs().max()).item()
+        # the tensor core's fp32 accumulator truncates, so the error grows ~linearly with the K accumulated
+        # in one TMEM pass
+        assert rel < 1e-5 * max(1.0, K / 1024), (M, N, K, rel)
+
+
+def test_cfg4_tower_fit_tensor_cores_vs_exact_simt():
+    """BASELINE configs[3] shape (B = 8192, k = 10, 400-400-400): one DeepFMAdam.fit with the tcgen05 tower must
+    agree with the exact SIMT tower (which is bit-identical to the oracle) within 1e-5 on the logits, and the
+    sign-step updates of the tables must agree on >= 99.9 % of the touched coordinates."""
+    import fm_for_online_recommendation_b200 as pkg
+    from test_gpu_fm import CRITEO
+    lib = pkg.require_cuda()
+    B = 8192
+    Xi, Xv, Y = synth(CRITEO, B, 7)
+    outs = []
+    for tc in (1, 0):
+        lib.fmb_set_tensor_cores(tc)
+        torch.manual_seed(5)
+        m = pkg.DeepFMAdam(CRITEO, embedding_size=10, num_hidden_layers=3, neuron_per_hidden_layer=400, n=1e-4)
+        with torch.no_grad():
+            m._table[:, :11].mul_(0.1)
+        e = m.encode(Xi, Xv, Y)
+        z0 = m.forward(e, None).clone()
+        m.fit(e, None, None)
+        outs.append((z0.cpu().numpy(), m._table.cpu().numpy().copy(), m._mlp.cpu().numpy().copy()))
+    lib.fmb_set_tensor_cores(1)
+    np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=1e-5, atol=1e-5)
+    same = (outs[0][1] == outs[1][1]).mean()
+    assert same > 0.999, same
+    assert np.abs(outs[0][2] - outs[1][2]).max() <= 2.1e-4   # an MLP weight moves by +-lr at most
