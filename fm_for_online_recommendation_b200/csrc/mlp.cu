@@ -96,16 +96,18 @@ int fmb_gemm_tc_launch(const float* A, int64_t sam, int64_t sak, const float* B,
                        int64_t scm, int M, int N, int K, int epi, const float* bias, const float* mask, int64_t smm,
                        float* colsum, cudaStream_t stream);
 static int g_use_tc = -1;   // -1: read FMB_TC from the environment on first use
-// Products of at least 2^25 multiply-adds go to the tcgen05 3xTF32 kernel (gemm_tc.cu); smaller ones -- every
-// shape of the reference's own scripts (H = 10, main_experiment.py:50-54) -- stay on the exact SIMT kernel.
+// Products of at least 2^24 multiply-adds (every product of the cfg4 tower, including the K = batch weight
+// gradient of the k-wide first layer) go to the tcgen05 3xTF32 kernel (gemm_tc.cu); smaller ones -- every
+// shape of the reference's own scripts (H = 10, B <= 2500, main_experiment.py:50-54) -- stay on the exact SIMT kernel.
+constexpr int TC_THRESHOLD_LOG2 = 24;
 FMB_API void fmb_set_tensor_cores(int on) { g_use_tc = on ? 1 : 0; }
-FMB_API int fmb_tensor_core_threshold_log2(void) { return 25; }
+FMB_API int fmb_tensor_core_threshold_log2(void) { return TC_THRESHOLD_LOG2; }
 
 namespace {
 
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
     if (g_use_tc < 0) { const char* e = getenv("FMB_TC"); g_use_tc = (e && e[0] == '0') ? 0 : 1; }
-    if (g_use_tc && (int64_t)p.M * p.N * p.K >= ((int64_t)1 << 25))
+    if (g_use_tc && (int64_t)p.M * p.N * p.K >= ((int64_t)1 << TC_THRESHOLD_LOG2))
         return fmb_gemm_tc_launch(p.A, p.sam, p.sak, p.B, p.sbk, p.sbn, p.C, p.scm, p.M, p.N, p.K, p.epi, p.bias, p.mask,
                                   p.smm, p.colsum, stream);
     dim3 grid((p.N + TN - 1) / TN, (p.M + TM - 1) / TM);

@@ -134,13 +134,19 @@ size_t fmb_mlp_bwd_workspace_bytes(int B, int H);
 int fmb_mlp_backward(const float* bi_dev, int ldbi, const float* mlp_dev, const float* act_dev,
                      const float* gtop_dev, int top, int B, int k, int L, int H, float* gmlp_dev, float* gbi_dev,
                      int ldgbi, void* ws_dev, size_t ws_bytes, fmb_stream_t stream);
-/* Contractions of >= 2^25 multiply-adds (cfg4: B = 8192, H = 400) run on the tcgen05 tensor cores as 3xTF32
+/* Contractions of >= 2^24 multiply-adds (cfg4: B = 8192, H = 400) run on the tcgen05 tensor cores as 3xTF32
  * with fp32 accumulation in tensor memory (csrc/gemm_tc.cu, ~1e-6 relative); smaller ones -- every shape of the
  * reference's scripts -- on the exact SIMT kernel.  fmb_set_tensor_cores(0) (or FMB_TC=0) forces the exact path. */
 void fmb_set_tensor_cores(int on);
 int fmb_tensor_core_threshold_log2(void);
 int fmb_gemm_tc_nt(const float* A_dev /*[M,K]*/, const float* B_dev /*[N,K]*/, float* C_dev /*[M,N]*/, int M, int N,
                    int K, fmb_stream_t stream); /* C = A B^T on the tensor cores (tests) */
+/* General form: C[m*scm + n] = epi( sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] ), epi 0 none / 1 relu(x + bias[n]) /
+ * 2 keep where mask[m*smm + n] > 0; colsum[m] = sum_k A(m,k) (nullable).  The three tower products
+ * (mlp.cu: forward NT, dX NN, dW TN with K = batch split across CTAs) are this call. */
+int fmb_gemm_tc_strided(const float* A_dev, int64_t sam, int64_t sak, const float* B_dev, int64_t sbk, int64_t sbn,
+                        float* C_dev, int64_t scm, int M, int N, int K, int epi, const float* bias_dev,
+                        const float* mask_dev, int64_t smm, float* colsum_dev, fmb_stream_t stream);
 int fmb_gemm_tc_error(void);
 /* z = base + head, base = z_fm (DeepFM, deepfm_adam.py:88) or sum_first + bias (NFM, nfm_adam.py:79,87) */
 int fmb_combine_logit(int nfm, const float* z_fm_dev, const float* sum_first_dev, const float* bias_dev,
