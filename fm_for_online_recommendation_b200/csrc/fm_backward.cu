@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(256, 3) fm_bwd_runs_kernel(BwdParams p, int wa
             }
         }
         __syncwarp();
-        if (p.dbg && lane == 0) {
+        if (p.dbg && lane == 0 && run_len >= p.dbg[1]) {   // dbg[1] = shortest run to record
             const unsigned long long slot = atomicAdd((unsigned long long*)p.dbg, 1ULL);
             if (slot < 4000) {
                 long long* r = p.dbg + 8 + slot * 8;

@@ -90,6 +90,8 @@ class ShardedFM:
         self.bias = torch.full((1,), float(np.float32(b)), device=self.device)
         self._ws = {}
         self._side = torch.cuda.Stream()   # owner-side sort and bias/loss epilogue run beside the main chain
+        self._pre = torch.cuda.Stream()    # pipelined mode: the NEXT batch's owner-side sort
+        self._slot = 0                     # pipelined mode: which buffer set holds the current batch
         self.launches = 0
         self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
 
@@ -124,35 +126,47 @@ class ShardedFM:
         return ids.contiguous(), y
 
     # the step, split at the three exchanges so tests can emulate several ranks in one process
-    def phase_ids(self, ids):
+    def phase_ids(self, ids, slot=0):
         """-> idsT [F,B] (to be all-gathered into [G,F,B])."""
         B = ids.shape[0]
-        idsT = self._buf("idsT", (self.F, B), torch.int32)
+        idsT = self._buf(f"idsT{slot}", (self.F, B), torch.int32)
         check(self._lib.fmb_transpose_ids(ptr(ids), B, self.F, ptr(idsT), _stream()), "fmb_transpose_ids")
         return idsT
 
-    def phase_owner_forward(self, idsT_all):
-        """idsT_all [G,F,B] -> partial [G,B,PW] (block r goes to rank r); also sorts the owned entries."""
+    def phase_partial(self, idsT_all):
+        """idsT_all [G,F,B] -> partial [G,B,PW] (block r goes to rank r): per sample, the rows this rank owns."""
         lib, st = self._lib, _stream()
         G, F, k = self.G, self.F, self.k
         B = idsT_all.shape[2]
-        Btot = G * B
         partial = self._buf("partial", (G, B, self.PW))
         check(lib.fmb_shard_partial_forward(ptr(idsT_all), ptr(self.table), G, self.rank, B, F, k, ptr(partial), st),
               "fmb_shard_partial_forward")
+        return partial
+
+    def _sort_owned(self, idsT_all, slot):
+        """stable per-field sort of the entries this rank owns, on the CURRENT stream, into buffer set `slot`."""
+        lib = self._lib
+        G, F = self.G, self.F
+        B = idsT_all.shape[2]
+        Btot = G * B
         cap = min(lib.fmb_shard_sort_max_cap(), ((2 * Btot // G + Btot // 4 + 1023) // 1024) * 1024)
         self._cap = cap
-        skeys = self._buf("skeys", (F, cap), torch.int32)
-        perm = self._buf("perm", (F, cap), torch.int32)
-        counts = self._buf("counts", (F,), torch.int32)
+        skeys = self._buf(f"skeys{slot}", (F, cap), torch.int32)
+        perm = self._buf(f"perm{slot}", (F, cap), torch.int32)
+        counts = self._buf(f"counts{slot}", (F,), torch.int32)
+        check(lib.fmb_shard_sort_fields(ptr(idsT_all), G, self.rank, B, F, ptr(self.field_off_dev), cap,
+                                        ptr(skeys), ptr(perm), ptr(counts), ptr(self.overflow), _stream()),
+              "fmb_shard_sort_fields")
+
+    def phase_owner_forward(self, idsT_all):
+        """idsT_all [G,F,B] -> partial [G,B,PW] (block r goes to rank r); also sorts the owned entries."""
+        partial = self.phase_partial(idsT_all)
         # the sort needs the ids only: it runs on the side stream, next to the partial forward, the all-to-all,
         # the combine and the context all-gather; phase_backward joins it
         main = torch.cuda.current_stream()
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side):
-            check(lib.fmb_shard_sort_fields(ptr(idsT_all), G, self.rank, B, F, ptr(self.field_off_dev), cap,
-                                            ptr(skeys), ptr(perm), ptr(counts), ptr(self.overflow), _stream()),
-                  "fmb_shard_sort_fields")
+            self._sort_owned(idsT_all, 0)
         return partial
 
     def phase_combine(self, recv, y, loss_kind=0):
@@ -163,14 +177,16 @@ class ShardedFM:
                                           None, _stream()), "fmb_shard_combine")
         return ctx
 
-    def phase_backward(self, ctx_all):
-        """ctx_all [G*B,CW] -> row updates of the owned rows, bias step; returns the mean loss."""
+    def phase_backward(self, ctx_all, slot=0, join_sort=True):
+        """ctx_all [G*B,CW] -> row updates of the owned rows (sorted entries of buffer set `slot`), bias step;
+        returns the mean loss."""
         lib, st = self._lib, _stream()
         F, k, cap = self.F, self.k, self._cap
         Btot = ctx_all.shape[0]
         N = F * cap
         main = torch.cuda.current_stream()
-        main.wait_stream(self._side)      # sorted keys / permutation are ready
+        if join_sort:
+            main.wait_stream(self._side)  # sorted keys / permutation are ready (phase_owner_forward put them there)
         wsb = lib.fmb_bwd_workspace_bytes(N, k)
         ws = self._buf("bwd_ws", (wsb,), torch.uint8)
         gs = ctx_all.view(-1)[self.kp4:]
@@ -185,7 +201,7 @@ class ShardedFM:
             check(lib.fmb_finish_step(ptr(delta_all), ptr(lossv_all), Btot, ptr(self.bias), self.lr,
                                       self.update_mode, ptr(loss), _stream()), "fmb_finish_step")
         self.launches += 9
-        check(lib.fmb_fm_backward_update_ex(ptr(self._ws["skeys"]), ptr(self._ws["perm"]), N, Btot * F, None,
+        check(lib.fmb_fm_backward_update_ex(ptr(self._ws[f"skeys{slot}"]), ptr(self._ws[f"perm{slot}"]), N, Btot * F, None,
                                             ptr(self.table), F, k, ptr(ctx_all), self.CW, ptr(gs), self.CW, 1, None,
                                             INT_MAX, self.lr, self.update_mode, ptr(ws), wsb, st),
               "fmb_fm_backward_update_ex")
@@ -206,6 +222,48 @@ class ShardedFM:
         ctx_all = self._buf("ctx_all", (G * B, self.CW))
         dist.all_gather_into_tensor(ctx_all.view(-1), ctx.view(-1), group=self.group)
         return self.phase_backward(ctx_all)
+
+    # ---------------------------------------------------------------- pipelined steps
+    # The exchange of the ids and the owner-side sort depend on the ids only, so they can be done one step ahead:
+    # step t runs while the ids of batch t+1 are all-gathered (NCCL stream, under step t's partial forward) and
+    # sorted (stream _pre, under step t's exchanges and backward).  Same kernels, same arithmetic, same results.
+    def _prepare(self, ids, slot):
+        G, B, F = self.G, ids.shape[0], self.F
+        main = torch.cuda.current_stream()
+        idsT = self.phase_ids(ids, slot)
+        idsT_all = self._buf(f"idsT_all{slot}", (G, F, B), torch.int32)
+        work = dist.all_gather_into_tensor(idsT_all.view(-1), idsT.view(-1), group=self.group, async_op=True)
+        self._pre.wait_stream(main)   # every earlier reader of this buffer set was enqueued on main before now
+        with torch.cuda.stream(self._pre):
+            work.wait()               # _pre (not main) waits for the collective
+            self._sort_owned(idsT_all, slot)
+
+    def prepare(self, ids):
+        """start the pipeline: exchange and sort the FIRST batch's ids (the batch the next step trains on)."""
+        self._slot = 0
+        self._prepare(ids, 0)
+        torch.cuda.current_stream().wait_stream(self._pre)
+
+    def update_embedding_pipelined(self, y, ids_next, loss_kind=0):
+        """train on the batch whose ids were given to the previous call (or to prepare()), labels `y`; meanwhile
+        exchange and sort `ids_next` (None at the end of the stream).  Returns the mean loss of the trained batch."""
+        G, F = self.G, self.F
+        p = self._slot
+        main = torch.cuda.current_stream()
+        if ids_next is not None:
+            self._prepare(ids_next, 1 - p)
+        idsT_all = self._ws[f"idsT_all{p}"]
+        B = idsT_all.numel() // (G * F)
+        partial = self.phase_partial(idsT_all.view(G, F, B))
+        recv = self._buf("recv", (G, B, self.PW))
+        dist.all_to_all_single(recv.view(-1), partial.view(-1), group=self.group)
+        ctx = self.phase_combine(recv, y, loss_kind)
+        ctx_all = self._buf("ctx_all", (G * B, self.CW))
+        dist.all_gather_into_tensor(ctx_all.view(-1), ctx.view(-1), group=self.group)
+        loss = self.phase_backward(ctx_all, p, join_sort=False)   # sorted one call earlier
+        main.wait_stream(self._pre)   # the call is complete when the next batch is sorted too
+        self._slot = 1 - p
+        return loss
 
     # ---------------------------------------------------------------- CUDA-graph replay of the whole step
     def capture(self, ids, y, loss_kind=0):
@@ -232,6 +290,39 @@ class ShardedFM:
         self._graph.replay()
         return self._g_loss
 
+    def capture_pipelined(self, ids, y, loss_kind=0):
+        """Capture the pipelined step for both buffer-set parities.  `ids`/`y` seed the static buffers; two eager
+        warm-up steps run first (they do train).  Afterwards call prepare(first ids), then step_graphed_pipelined."""
+        self._g_ids = ids.clone()
+        self._g_y = y.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.prepare(self._g_ids)
+            for _ in range(2):
+                self.update_embedding_pipelined(self._g_y, self._g_ids, loss_kind)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._pgraphs, self._pg_loss = [], []
+        for parity in (0, 1):
+            self._slot = parity
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                loss = self.update_embedding_pipelined(self._g_y, self._g_ids, loss_kind)
+            self._pgraphs.append(g)
+            self._pg_loss.append(loss)
+        self._slot = 0
+        return self
+
+    def step_graphed_pipelined(self, y, ids_next):
+        """update_embedding_pipelined(y, ids_next) through the captured graphs."""
+        self._g_y.copy_(y, non_blocking=True)
+        self._g_ids.copy_(ids_next, non_blocking=True)
+        p = self._slot
+        self._pgraphs[p].replay()
+        self._slot = 1 - p
+        return self._pg_loss[p]
+
     def check_overflow(self):
         v = int(self.overflow.item())
         if v:
@@ -252,13 +343,29 @@ def bench_main(args, sizes, config):
     enc = [model.encode(Xi, Y) for Xi, Y in host]
     stream = torch.cuda.current_stream()
     use_graph = os.environ.get("FMB_NO_GRAPH", "0") != "1"
-    if use_graph:
-        model.capture(*enc[0])
-        step = model.step_graphed
+    pipelined = os.environ.get("FMB_SHARD_PIPELINE", "1") != "0"
+    if pipelined:
+        # step i trains on batch i while batch i+1's ids are exchanged and sorted (update_embedding_pipelined)
+        if use_graph:
+            model.capture_pipelined(*enc[0])
+            run = model.step_graphed_pipelined
+        else:
+            run = model.update_embedding_pipelined
+        model.prepare(enc[0][0])
+
+        def step(i):
+            return run(enc[i % NB][1], enc[(i + 1) % NB][0])
     else:
-        step = model.update_embedding
+        if use_graph:
+            model.capture(*enc[0])
+            run = model.step_graphed
+        else:
+            run = model.update_embedding
+
+        def step(i):
+            return run(*enc[i % NB])
     for i in range(W):
-        step(*enc[i % NB])
+        step(i)
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
@@ -267,7 +374,7 @@ def bench_main(args, sizes, config):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for i in range(K):
-        step(*enc[(W + i) % NB])
+        step(W + i)
     ev1.record(stream)
     torch.cuda.synchronize()
     dist.barrier()
@@ -284,13 +391,16 @@ def bench_main(args, sizes, config):
     d_y = torch.empty(B, device="cuda")
 
     def host_step(i):
-        ids_h, y_h = hosts[i % NB]
+        # this step's labels and (pipelined) the NEXT batch's ids come from pinned host memory every step
+        ids_h = hosts[(i + 1) % NB][0] if pipelined else hosts[i % NB][0]
         pin_i.numpy()[...] = ids_h
-        pin_y.numpy()[...] = y_h
+        pin_y.numpy()[...] = hosts[i % NB][1]
         d_i.copy_(pin_i, non_blocking=True)
         d_y.copy_(pin_y, non_blocking=True)
-        return float(step(d_i, d_y).item())
+        return float((run(d_y, d_i) if pipelined else run(d_i, d_y)).item())
 
+    if pipelined:   # the e2e sequence starts over at batch 0: restart the pipeline there
+        model.prepare(enc[0][0])
     for i in range(W):
         host_step(i)
     torch.cuda.synchronize()
@@ -313,11 +423,14 @@ def bench_main(args, sizes, config):
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(config, parallelism=f"row-sharded tables over {world} GPUs (r % G), NCCL all-gather + "
-                                               "all-to-all of pooled partials", global_batch=world * B),
+                                               "all-to-all of pooled partials" +
+                                               ("; next batch's id exchange + owner sort overlapped" if pipelined else ""),
+                          global_batch=world * B),
             "clocks": clocks,
             "e2e": {"value": world * B * K / float(e2e.item()), "unit": "samples/s",
                     "h2d_bytes_per_step": 4 * B * F + 4 * B, "d2h_bytes_per_step": 4,
-                    "api": "ShardedFM.update_embedding (pinned host ids/y in, loss out, per rank)"},
+                    "api": ("ShardedFM.update_embedding_pipelined" if pipelined else "ShardedFM.update_embedding") +
+                           " (pinned host ids/y in, loss out, per rank)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "whole step per GPU", "achieved": step_bytes / (ms / K * 1e-3) / 1e9,
                          "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
