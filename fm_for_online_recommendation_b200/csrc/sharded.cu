@@ -17,6 +17,14 @@
 // The reduction order differs from the 1-GPU path only in step 4 (owner-major instead of
 // field-major); oracle/fm_oracle.c restates it (orc_*_sharded) so multi-GPU runs are checked bit for
 // bit as well.  No float atomics, no data-dependent host synchronisation.
+//
+// Peer-memory exchange (the *_peers entry points): with the three exchange buffers in symmetric memory (every
+// rank maps every peer's copy), the producers of steps 1, 3 and 5 store their blocks straight into the
+// consumers' buffers over NVLink -- the transpose writes its [F][B] slab into all G ranks' idsT_all, the partial
+// forward writes block r into rank r's recv, the combine writes its ctx rows into all G ranks' ctx_all -- and a
+// one-warp kernel (shard_signal_kernel) publishes a per-channel epoch to the peers' flag words (fence.sys +
+// st.release.sys) and/or waits until all G peers have published theirs (ld.acquire.sys).  No NCCL call is left
+// in the step; same values in the same places, so the arithmetic and the results are unchanged.
 #include "fmb_common.cuh"
 #include "smem_sort.cuh"
 
@@ -196,6 +204,100 @@ __global__ void __launch_bounds__(fmb::SS_THREADS) shard_sort_fields_kernel(
     }
 }
 
+
+struct PeerPtrs { void* p[8]; };
+
+// ids [B,F] -> slab `me` of every rank's idsT_all [G][F][B]
+__global__ void transpose_ids_peers_kernel(const int32_t* __restrict__ ids, int B, int F, int G, int me, PeerPtrs dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * F) return;
+    const int f = (int)(i / B), b = (int)(i - (int64_t)f * B);
+    const int32_t v = ids[(size_t)b * F + f];
+    const size_t o = (size_t)me * F * B + i;
+    for (int r = 0; r < G; ++r) static_cast<int32_t*>(dst.p[r])[o] = v;
+}
+
+// shard_partial_forward_kernel with block r of the result stored into rank r's recv [G][B][PW] at block `me`
+__global__ void __launch_bounds__(256) shard_partial_forward_peers_kernel(PartialParams p, PeerPtrs dst) {
+    const int q = threadIdx.x & ((1 << p.ql_log) - 1);
+    const int64_t bg = (int64_t)blockIdx.x * (256 >> p.ql_log) + (threadIdx.x >> p.ql_log);
+    if (bg >= (int64_t)p.G * p.B || q >= p.cu) return;
+    const int r = (int)(bg / p.B), b = (int)(bg - (int64_t)r * p.B);
+    const int32_t* col = p.idsT_all + (size_t)r * p.F * p.B + b;
+    float S[4] = {0.f, 0.f, 0.f, 0.f}, Q[4] = {0.f, 0.f, 0.f, 0.f};
+    float first = 0.f;
+    for (int f0 = 0; f0 < p.F; f0 += 4) {
+        int32_t lr[4];
+        bool own[4];
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            own[u] = false;
+            if (f0 + u < p.F) own[u] = owned_by(__ldg(col + (size_t)(f0 + u) * p.B), p.G, p.glog, p.me, lr[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (own[u]) v[u] = *reinterpret_cast<const float4*>(p.table + (size_t)lr[u] * p.rowp + q * 4);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (!own[u]) continue;
+            const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};  // x == 1 (all-ones feature values)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int j = q * 4 + t;
+                if (j < p.k) { S[t] = __fadd_rn(S[t], e[t]); Q[t] = __fadd_rn(Q[t], __fmul_rn(e[t], e[t])); }
+                else if (j == p.k) first = __fadd_rn(first, e[t]);
+            }
+        }
+    }
+    float* out = static_cast<float*>(dst.p[r]) + ((size_t)p.me * p.B + b) * p.PW;
+    if (q * 4 < p.kp4) {
+        *reinterpret_cast<float4*>(out + q * 4) = make_float4(S[0], S[1], S[2], S[3]);
+        *reinterpret_cast<float4*>(out + p.kp4 + q * 4) = make_float4(Q[0], Q[1], Q[2], Q[3]);
+    }
+    if (q == p.k / 4) out[2 * p.kp4] = first;
+}
+
+// rows [me*B, (me+1)*B) of ctx_all, copied from the local ctx [B][CW] into every rank's ctx_all (16-byte chunks)
+__global__ void ctx_bcast_peers_kernel(const float4* __restrict__ ctx, int64_t n4, int64_t off4, int G, PeerPtrs dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = ctx[i];
+    for (int r = 0; r < G; ++r) static_cast<float4*>(dst.p[r])[off4 + i] = v;
+}
+
+// mode bit 0: publish my next epoch of `channel` to every peer's flag word [channel][me];
+// mode bit 1: wait until every peer's epoch of `channel` has reached mine.
+__global__ void shard_signal_kernel(PeerPtrs peer_flags, uint32_t* flags_local, uint32_t* epoch_local, int channel, int G,
+                                    int me, int mode, int* error) {
+    const int lane = threadIdx.x;
+    uint32_t e = epoch_local[channel];
+    if (mode & 1) {
+        e += 1;
+        __threadfence_system();   // the producer kernels before this one in the stream: their peer stores first
+        if (lane < G) {
+            uint32_t* f = static_cast<uint32_t*>(peer_flags.p[lane]) + channel * 8 + me;
+            asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(f), "r"(e) : "memory");
+        }
+        __syncwarp();
+        if (lane == 0) epoch_local[channel] = e;
+    }
+    if (mode & 2) {
+        if (lane < G) {
+            const uint32_t* f = flags_local + channel * 8 + lane;
+            bool ok = false;
+            for (long long spin = 0; spin < (1ll << 26) && !ok; ++spin) {
+                uint32_t v;
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(f) : "memory");
+                ok = (int32_t)(v - e) >= 0;
+            }
+            if (!ok && error) *error = 1 + channel;
+        }
+        __syncwarp();
+        __threadfence_system();
+    }
+}
+
 static int ilog2_exact(int x) { int l = 0; while ((1 << l) < x) ++l; return (1 << l) == x ? l : -1; }
 static int ilog2_ceil(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
 
@@ -262,5 +364,73 @@ FMB_API int fmb_shard_sort_fields(const int32_t* idsT_all, int G, int me, int B,
     shard_sort_fields_kernel<<<F, fmb::SS_THREADS, fmb::smem_sort_bytes(cap), stream>>>(
         idsT_all, G, ilog2_exact(G), me, B, F, field_off, cap, skeys, perm, counts, overflow);
     FMB_CHECK_LAUNCH("shard_sort_fields_kernel");
+    return FMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- peer-memory exchange
+// `dst`/`peer_flags`: HOST arrays of G device pointers, entry r = the address at which THIS device maps rank r's
+// copy of the buffer (torch symmetric memory `buffer_ptrs`, or CUDA IPC mappings).  G <= 8.
+static int fill_peers(PeerPtrs& pp, void* const* ptrs, int G, const char* who) {
+    if (!ptrs || G < 1 || G > 8) { fmb_set_error("%s: needs 1..8 peer pointers", who); return FMB_ERR_ARG; }
+    for (int r = 0; r < 8; ++r) pp.p[r] = r < G ? ptrs[r] : nullptr;
+    for (int r = 0; r < G; ++r)
+        if (!pp.p[r]) { fmb_set_error("%s: peer pointer %d is null", who, r); return FMB_ERR_ARG; }
+    return FMB_OK;
+}
+
+// step 1 without a collective: ids [B,F] -> slab `me` of every rank's idsT_all [G][F][B]
+FMB_API int fmb_shard_transpose_ids_peers(const int32_t* ids, int B, int F, int G, int me, void* const* dst_idsT_all,
+                                          cudaStream_t stream) {
+    FMB_CHECK_ARG(ids && B > 0 && F > 0 && me >= 0 && me < G, "fmb_shard_transpose_ids_peers: bad arguments");
+    PeerPtrs pp;
+    if (int rc = fill_peers(pp, dst_idsT_all, G, "fmb_shard_transpose_ids_peers")) return rc;
+    const int64_t n = (int64_t)B * F;
+    transpose_ids_peers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ids, B, F, G, me, pp);
+    FMB_CHECK_LAUNCH("transpose_ids_peers_kernel");
+    return FMB_OK;
+}
+
+// steps 2a + 3 without a collective: block r of the pooled partials goes straight into rank r's recv [G][B][PW]
+FMB_API int fmb_shard_partial_forward_peers(const int32_t* idsT_all, const float* table_local, int G, int me, int B,
+                                            int F, int k, void* const* dst_recv, cudaStream_t stream) {
+    FMB_CHECK_ARG(idsT_all && table_local, "fmb_shard_partial_forward_peers: null pointer");
+    FMB_CHECK_ARG(G > 0 && me >= 0 && me < G && B > 0 && F > 0 && k > 0 && k <= 124, "fmb_shard_partial_forward_peers: bad arguments");
+    PeerPtrs pp;
+    if (int rc = fill_peers(pp, dst_recv, G, "fmb_shard_partial_forward_peers")) return rc;
+    PartialParams p;
+    p.idsT_all = idsT_all; p.table = table_local; p.G = G; p.glog = ilog2_exact(G); p.me = me; p.B = B; p.F = F;
+    p.k = k; p.rowp = fmb_round_up(k + 1, 16); p.kp4 = fmb_round_up(k, 4); p.cu = (k + 1 + 3) / 4;
+    p.ql_log = ilog2_ceil(p.cu); p.PW = fmb_shard_pw(k); p.partial = nullptr;
+    const int spb = 256 >> p.ql_log;
+    const int64_t n = (int64_t)G * B;
+    shard_partial_forward_peers_kernel<<<(unsigned)((n + spb - 1) / spb), 256, 0, stream>>>(p, pp);
+    FMB_CHECK_LAUNCH("shard_partial_forward_peers_kernel");
+    return FMB_OK;
+}
+
+// step 5 without a collective: the local ctx [B][CW] becomes rows [me*B, (me+1)*B) of every rank's ctx_all
+FMB_API int fmb_shard_ctx_bcast_peers(const float* ctx, int G, int me, int B, int k, void* const* dst_ctx_all,
+                                      cudaStream_t stream) {
+    FMB_CHECK_ARG(ctx && B > 0 && k > 0 && me >= 0 && me < G, "fmb_shard_ctx_bcast_peers: bad arguments");
+    PeerPtrs pp;
+    if (int rc = fill_peers(pp, dst_ctx_all, G, "fmb_shard_ctx_bcast_peers")) return rc;
+    const int64_t n4 = (int64_t)B * fmb_shard_cw(k) / 4;
+    ctx_bcast_peers_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(ctx), n4,
+                                                                           (int64_t)me * n4, G, pp);
+    FMB_CHECK_LAUNCH("ctx_bcast_peers_kernel");
+    return FMB_OK;
+}
+
+// Epoch flags of the exchange: flag words are uint32 [channels][8] in symmetric memory, `epoch_local` uint32
+// [channels] in ordinary device memory.  mode 1 = publish (after the producer kernel, same stream), 2 = wait for
+// all G peers (before the consumer kernel), 3 = both.  error_dev (nullable) receives 1 + channel on a time-out.
+FMB_API int fmb_shard_signal(void* const* peer_flags, uint32_t* flags_local, uint32_t* epoch_local, int channel, int G,
+                             int me, int mode, int* error_dev, cudaStream_t stream) {
+    FMB_CHECK_ARG(flags_local && epoch_local && channel >= 0 && channel < 8 && me >= 0 && me < G && mode >= 1 && mode <= 3,
+                  "fmb_shard_signal: bad arguments");
+    PeerPtrs pp;
+    if (int rc = fill_peers(pp, peer_flags, G, "fmb_shard_signal")) return rc;
+    shard_signal_kernel<<<1, 32, 0, stream>>>(pp, flags_local, epoch_local, channel, G, me, mode, error_dev);
+    FMB_CHECK_LAUNCH("shard_signal_kernel");
     return FMB_OK;
 }

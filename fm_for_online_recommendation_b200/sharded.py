@@ -265,6 +265,109 @@ class ShardedFM:
         self._slot = 1 - p
         return loss
 
+    # ---------------------------------------------------------------- pipelined steps over peer memory (no NCCL)
+    # Same step, but the three exchanges are plain stores into the peers' buffers (symmetric memory over NVLink)
+    # followed by epoch flags: csrc/sharded.cu "Peer-memory exchange".  Channels of the flag block:
+    CH_IDS, CH_A2A, CH_CTX = 0, 1, 2
+
+    def _peer_setup(self, B):
+        """allocate idsT_all (two slots), recv, ctx_all and the flag block in symmetric memory and map the peers'
+        copies (collective: every rank calls it with the same B)."""
+        import torch.distributed._symmetric_memory as symm
+        G, F = self.G, self.F
+        group = self.group if self.group is not None else dist.group.WORLD
+        words = {"ids0": G * F * B, "ids1": G * F * B, "recv": G * B * self.PW, "ctx": G * B * self.CW, "flags": 64}
+        off, total = {}, 0
+        for name, n in words.items():
+            off[name] = total
+            total += (n + 63) // 64 * 64          # 256-byte aligned sub-buffers
+        arena = symm.empty(total, dtype=torch.int32, device=self.device)
+        arena.zero_()
+        hdl = symm.rendezvous(arena, group)
+        torch.cuda.synchronize()
+        dist.barrier(group=group)                  # every flag block is zero before anyone publishes
+        ptrs = {name: (C.c_void_p * G)(*[int(hdl.buffer_ptrs[r]) + 4 * o for r in range(G)]) for name, o in off.items()}
+        view = {name: arena[o:o + words[name]] for name, o in off.items()}
+        self._peer = {"B": B, "arena": arena, "hdl": hdl, "ptrs": ptrs,
+                      "ids": [view["ids0"].view(G, F, B), view["ids1"].view(G, F, B)],
+                      "recv": view["recv"].view(torch.float32).view(G, B, self.PW),
+                      "ctx": view["ctx"].view(torch.float32).view(G * B, self.CW),
+                      "flags": view["flags"],
+                      "epoch": torch.zeros(8, dtype=torch.int32, device=self.device),
+                      "error": torch.zeros(1, dtype=torch.int32, device=self.device)}
+
+    def _signal(self, channel, mode):
+        pr = self._peer
+        check(self._lib.fmb_shard_signal(pr["ptrs"]["flags"], ptr(pr["flags"]), ptr(pr["epoch"]), channel, self.G,
+                                         self.rank, mode, ptr(pr["error"]), _stream()), "fmb_shard_signal")
+
+    def _prepare_peers(self, ids, slot):
+        pr, B = self._peer, ids.shape[0]
+        main = torch.cuda.current_stream()
+        check(self._lib.fmb_shard_transpose_ids_peers(ptr(ids), B, self.F, self.G, self.rank, pr["ptrs"][f"ids{slot}"],
+                                                      _stream()), "fmb_shard_transpose_ids_peers")
+        self._signal(self.CH_IDS, 1)
+        self._pre.wait_stream(main)
+        with torch.cuda.stream(self._pre):
+            self._signal(self.CH_IDS, 2)          # every rank's slab has landed in MY idsT_all
+            self._sort_owned(pr["ids"][slot], slot)
+
+    def prepare_peers(self, ids):
+        """start the peer-memory pipeline with the first batch's ids (collective on first use: maps the buffers)."""
+        if getattr(self, "_peer", None) is None or self._peer["B"] != ids.shape[0]:
+            self._peer_setup(ids.shape[0])
+        self._slot = 0
+        self._prepare_peers(ids, 0)
+        torch.cuda.current_stream().wait_stream(self._pre)
+
+    def update_embedding_peers(self, y, ids_next, loss_kind=0):
+        """update_embedding_pipelined with every exchange done by stores into peer memory + epoch flags."""
+        pr, lib, G, F, k = self._peer, self._lib, self.G, self.F, self.k
+        p, B = self._slot, self._peer["B"]
+        main = torch.cuda.current_stream()
+        if ids_next is not None:
+            self._prepare_peers(ids_next, 1 - p)
+        check(lib.fmb_shard_partial_forward_peers(ptr(pr["ids"][p]), ptr(self.table), G, self.rank, B, F, k,
+                                                  pr["ptrs"]["recv"], _stream()), "fmb_shard_partial_forward_peers")
+        self._signal(self.CH_A2A, 3)              # my blocks are out; wait for the G blocks of MY samples
+        ctx = self.phase_combine(pr["recv"], y, loss_kind)
+        check(lib.fmb_shard_ctx_bcast_peers(ptr(ctx), G, self.rank, B, k, pr["ptrs"]["ctx"], _stream()),
+              "fmb_shard_ctx_bcast_peers")
+        self._signal(self.CH_CTX, 3)
+        loss = self.phase_backward(pr["ctx"], p, join_sort=False)
+        self.launches += 4                        # ctx broadcast + signal kernels (transpose/sort counted there)
+        main.wait_stream(self._pre)
+        self._slot = 1 - p
+        return loss
+
+    def check_exchange(self):
+        v = int(self._peer["error"].item()) if getattr(self, "_peer", None) else 0
+        if v:
+            raise RuntimeError(f"peer-memory exchange: channel {v - 1} timed out waiting for a peer's epoch flag")
+
+    def capture_peers(self, ids, y, loss_kind=0):
+        """capture_pipelined for the peer-memory step (no collective inside the graphs)."""
+        self._g_ids = ids.clone()
+        self._g_y = y.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.prepare_peers(self._g_ids)
+            for _ in range(2):
+                self.update_embedding_peers(self._g_y, self._g_ids, loss_kind)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._pgraphs, self._pg_loss = [], []
+        for parity in (0, 1):
+            self._slot = parity
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                loss = self.update_embedding_peers(self._g_y, self._g_ids, loss_kind)
+            self._pgraphs.append(g)
+            self._pg_loss.append(loss)
+        self._slot = 0
+        return self
+
     # ---------------------------------------------------------------- CUDA-graph replay of the whole step
     def capture(self, ids, y, loss_kind=0):
         """Capture one step (kernels + the three NCCL collectives) into a CUDA graph over static input
@@ -344,14 +447,17 @@ def bench_main(args, sizes, config):
     stream = torch.cuda.current_stream()
     use_graph = os.environ.get("FMB_NO_GRAPH", "0") != "1"
     pipelined = os.environ.get("FMB_SHARD_PIPELINE", "1") != "0"
+    # exchanges: "peers" = stores into peer-mapped symmetric memory + epoch flags (default), "nccl" = collectives
+    exchange = os.environ.get("FMB_SHARD_EXCHANGE", "peers") if pipelined else "nccl"
+    prepare = model.prepare_peers if exchange == "peers" else model.prepare
     if pipelined:
         # step i trains on batch i while batch i+1's ids are exchanged and sorted (update_embedding_pipelined)
         if use_graph:
-            model.capture_pipelined(*enc[0])
+            (model.capture_peers if exchange == "peers" else model.capture_pipelined)(*enc[0])
             run = model.step_graphed_pipelined
         else:
-            run = model.update_embedding_pipelined
-        model.prepare(enc[0][0])
+            run = model.update_embedding_peers if exchange == "peers" else model.update_embedding_pipelined
+        prepare(enc[0][0])
 
         def step(i):
             return run(enc[i % NB][1], enc[(i + 1) % NB][0])
@@ -400,7 +506,7 @@ def bench_main(args, sizes, config):
         return float((run(d_y, d_i) if pipelined else run(d_i, d_y)).item())
 
     if pipelined:   # the e2e sequence starts over at batch 0: restart the pipeline there
-        model.prepare(enc[0][0])
+        prepare(enc[0][0])
     for i in range(W):
         host_step(i)
     torch.cuda.synchronize()
@@ -414,6 +520,7 @@ def bench_main(args, sizes, config):
     dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
     clocks = sampler.stop()
     model.check_overflow()
+    model.check_exchange()
     dist.barrier()
     if rank == 0:
         value = world * B * K / (ms * 1e-3)
@@ -422,14 +529,17 @@ def bench_main(args, sizes, config):
             "metric": "train samples/sec (fwd+bwd+update)", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(config, parallelism=f"row-sharded tables over {world} GPUs (r % G), NCCL all-gather + "
-                                               "all-to-all of pooled partials" +
+            "config": dict(config, parallelism=f"row-sharded tables over {world} GPUs (r % G); ids / pooled partials / "
+                                               "sample contexts exchanged by " +
+                                               ("stores into peer-mapped symmetric memory + epoch flags (no NCCL in the step)"
+                                                if exchange == "peers" else "NCCL all-gather + all-to-all + all-gather") +
                                                ("; next batch's id exchange + owner sort overlapped" if pipelined else ""),
                           global_batch=world * B),
             "clocks": clocks,
             "e2e": {"value": world * B * K / float(e2e.item()), "unit": "samples/s",
                     "h2d_bytes_per_step": 4 * B * F + 4 * B, "d2h_bytes_per_step": 4,
-                    "api": ("ShardedFM.update_embedding_pipelined" if pipelined else "ShardedFM.update_embedding") +
+                    "api": ("ShardedFM.update_embedding_peers" if exchange == "peers" else
+                            "ShardedFM.update_embedding_pipelined" if pipelined else "ShardedFM.update_embedding") +
                            " (pinned host ids/y in, loss out, per rank)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "whole step per GPU", "achieved": step_bytes / (ms / K * 1e-3) / 1e9,

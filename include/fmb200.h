@@ -121,6 +121,24 @@ int fmb_shard_unpack_ctx(const float* ctx_all_dev, int64_t n, int k, float* delt
 int fmb_shard_sort_fields(const int32_t* idsT_all_dev, int G, int me, int B, int F, const int32_t* field_off_dev,
                           int cap, int32_t* sorted_keys_dev /*[F,cap]*/, int32_t* perm_dev /*[F,cap]*/,
                           int32_t* counts_dev /*[F]*/, int32_t* overflow_dev /*[1]*/, fmb_stream_t stream);
+/* The three exchanges without a collective call: with idsT_all, recv, ctx_all and a flag block in symmetric (peer
+ * mapped) memory, producers store straight into the consumers' buffers over NVLink.  Every `peers` argument is a
+ * HOST array of G (<= 8) device pointers, entry r = where THIS device maps rank r's copy of that buffer.
+ *   fmb_shard_transpose_ids_peers   ids [B,F] -> slab `me` of every rank's idsT_all [G,F,B]        (replaces all-gather 1)
+ *   fmb_shard_partial_forward_peers block r of the pooled partials -> block `me` of rank r's recv  (replaces the all-to-all)
+ *   fmb_shard_ctx_bcast_peers       local ctx [B,CW] -> rows [me*B,(me+1)*B) of every rank's ctx_all (replaces all-gather 2)
+ *   fmb_shard_signal                per-channel epoch flags, uint32 [8 channels][8 ranks] in symmetric memory;
+ *                                   mode 1 publish (fence.sys + st.release.sys to all peers), 2 wait for all G peers
+ *                                   (ld.acquire.sys, bounded spin), 3 both; epoch_local uint32 [8] ordinary device memory;
+ *                                   error_dev (nullable) receives 1 + channel on a time-out. */
+int fmb_shard_transpose_ids_peers(const int32_t* ids_dev, int B, int F, int G, int me, void* const* idsT_all_peers,
+                                  fmb_stream_t stream);
+int fmb_shard_partial_forward_peers(const int32_t* idsT_all_dev, const float* table_local_dev, int G, int me, int B,
+                                    int F, int k, void* const* recv_peers, fmb_stream_t stream);
+int fmb_shard_ctx_bcast_peers(const float* ctx_dev, int G, int me, int B, int k, void* const* ctx_all_peers,
+                              fmb_stream_t stream);
+int fmb_shard_signal(void* const* flag_peers, uint32_t* flags_local_dev, uint32_t* epoch_local_dev, int channel, int G,
+                     int me, int mode, int* error_dev, fmb_stream_t stream);
 
 /* ---- A4/A5: MLP tower on the Bi-Interaction vector (deepfm_adam.py:79-89, nfm_adam.py:78-88,
  * deepfm_onn.py:88-102).  mlp = W0[H,k] c0[H] W1[H,H] c1[H] ... (nn.Linear layouts, concatenated);
