@@ -27,6 +27,7 @@
 // in the step; same values in the same places, so the arithmetic and the results are unchanged.
 #include "fmb_common.cuh"
 #include "smem_sort.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -207,21 +208,73 @@ __global__ void __launch_bounds__(fmb::SS_THREADS) shard_sort_fields_kernel(
 
 struct PeerPtrs { void* p[8]; };
 
+// Exchange synchronisation state.  flags: uint32 [8 channels][8 ranks] in symmetric memory (peers write word
+// [channel][their rank] of MY copy); sync_local: uint32 [16] in ordinary device memory = epoch[8] | block counter[8].
+struct ExchSync {
+    PeerPtrs peer_flags;
+    uint32_t* flags_local;
+    uint32_t* sync_local;
+    int* error;
+    int G, me;
+};
+
+// Called by EVERY thread of EVERY block at the end of a producer kernel: when the last block gets here, all the
+// kernel's peer stores are ordered before the epoch it publishes to the G peers.
+__device__ __forceinline__ void publish_epoch_last_block(const ExchSync& x, int channel) {
+    __syncthreads();                 // the block's stores are ordered before thread 0's fence (barrier + cumulativity:
+    if (threadIdx.x == 0) {          // the grid-barrier idiom of cooperative groups); one fence.sys per block, not per thread
+        __threadfence_system();
+        const unsigned nb = gridDim.x * gridDim.y * gridDim.z;
+        const unsigned prev = atomicAdd(x.sync_local + 8 + channel, 1u);
+        if (prev == nb - 1) {
+            x.sync_local[8 + channel] = 0;
+            __threadfence_system();
+            const uint32_t e = x.sync_local[channel] + 1;
+            x.sync_local[channel] = e;
+            for (int r = 0; r < x.G; ++r) {   // one fence (above), then G relaxed system-scope stores
+                uint32_t* f = static_cast<uint32_t*>(x.peer_flags.p[r]) + channel * 8 + x.me;
+                asm volatile("st.relaxed.sys.global.u32 [%0], %1;\n" ::"l"(f), "r"(e) : "memory");
+            }
+        }
+    }
+}
+
+// Called by every thread of a block at the start of a consumer kernel: returns once all G peers have published
+// the epoch this rank's own producer of `channel` (earlier in the stream) has reached.
+__device__ __forceinline__ void wait_epoch(const ExchSync& x, int channel) {
+    if ((int)threadIdx.x < x.G) {
+        const uint32_t e = x.sync_local[channel];
+        const uint32_t* f = x.flags_local + channel * 8 + threadIdx.x;
+        bool ok = false;
+        for (long long spin = 0; spin < (1ll << 26) && !ok; ++spin) {
+            uint32_t v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(f) : "memory");
+            ok = (int32_t)(v - e) >= 0;
+        }
+        if (!ok && x.error) *x.error = 1 + channel;
+    }
+    __syncthreads();
+}
+
 // ids [B,F] -> slab `me` of every rank's idsT_all [G][F][B]
-__global__ void transpose_ids_peers_kernel(const int32_t* __restrict__ ids, int B, int F, int G, int me, PeerPtrs dst) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)B * F) return;
-    const int f = (int)(i / B), b = (int)(i - (int64_t)f * B);
-    const int32_t v = ids[(size_t)b * F + f];
-    const size_t o = (size_t)me * F * B + i;
-    for (int r = 0; r < G; ++r) static_cast<int32_t*>(dst.p[r])[o] = v;
+__global__ void transpose_ids_peers_kernel(const int32_t* __restrict__ ids, int B, int F, int G, int me, PeerPtrs dst,
+                                           ExchSync x, int channel) {
+    const int64_t n = (int64_t)B * F;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int f = (int)(i / B), b = (int)(i - (int64_t)f * B);
+        const int32_t v = ids[(size_t)b * F + f];
+        const size_t o = (size_t)me * F * B + i;
+        for (int r = 0; r < G; ++r) static_cast<int32_t*>(dst.p[r])[o] = v;
+    }
+    if (channel >= 0) publish_epoch_last_block(x, channel);
 }
 
 // shard_partial_forward_kernel with block r of the result stored into rank r's recv [G][B][PW] at block `me`
-__global__ void __launch_bounds__(256) shard_partial_forward_peers_kernel(PartialParams p, PeerPtrs dst) {
+__global__ void __launch_bounds__(256) shard_partial_forward_peers_kernel(PartialParams p, PeerPtrs dst, ExchSync x,
+                                                                         int channel) {
     const int q = threadIdx.x & ((1 << p.ql_log) - 1);
     const int64_t bg = (int64_t)blockIdx.x * (256 >> p.ql_log) + (threadIdx.x >> p.ql_log);
-    if (bg >= (int64_t)p.G * p.B || q >= p.cu) return;
+    if (bg < (int64_t)p.G * p.B && q < p.cu) {
     const int r = (int)(bg / p.B), b = (int)(bg - (int64_t)r * p.B);
     const int32_t* col = p.idsT_all + (size_t)r * p.F * p.B + b;
     float S[4] = {0.f, 0.f, 0.f, 0.f}, Q[4] = {0.f, 0.f, 0.f, 0.f};
@@ -256,6 +309,80 @@ __global__ void __launch_bounds__(256) shard_partial_forward_peers_kernel(Partia
         *reinterpret_cast<float4*>(out + p.kp4 + q * 4) = make_float4(Q[0], Q[1], Q[2], Q[3]);
     }
     if (q == p.k / 4) out[2 * p.kp4] = first;
+    }
+    if (channel >= 0) publish_epoch_last_block(x, channel);
+}
+
+// shard_combine_kernel fused with both of its exchanges: wait until the G owners' blocks of MY samples have
+// landed in recv, stage 32 samples' rows in shared memory with coalesced loads, fold them in owner order (the
+// arithmetic of shard_combine_kernel, term for term), store the ctx rows into every rank's ctx_all as 16-byte
+// chunks, and publish the ctx epoch from the last block.
+constexpr int CMB_SB = 32;        // samples per block
+constexpr int CMB_THREADS = 128;
+constexpr int CMB_MAXPW = 36;     // k <= 16 on this path (PW = 2*kp4 + 4)
+__global__ void __launch_bounds__(CMB_THREADS) shard_combine_peers_kernel(
+    const float* recv, const float* __restrict__ bias, const float* __restrict__ y, int G, int me, int B, int k, int kp4,
+    int PW, int CW, int loss_kind, PeerPtrs dst_ctx_all, float* ctx_local, ExchSync x, int ch_wait, int ch_publish) {
+    __shared__ float rows[8 * CMB_SB * (CMB_MAXPW + 1)];
+    __shared__ __align__(16) float ctxs[CMB_SB * 20];
+    const int b0 = blockIdx.x * CMB_SB;
+    const int nb = min(CMB_SB, B - b0);
+    const int pitch = PW + 1;
+    if (ch_wait >= 0) wait_epoch(x, ch_wait);
+    // recv[o][b0 .. b0+nb) is one contiguous run of nb*PW floats per owner
+    const int per_owner4 = nb * PW / 4;
+    for (int i = threadIdx.x; i < G * per_owner4; i += CMB_THREADS) {
+        const int o = i / per_owner4, j4 = i - o * per_owner4;
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(recv + ((size_t)o * B + b0) * PW) + j4);
+        const int e = j4 * 4, sb = e / PW, c = e - sb * PW;      // PW % 4 == 0: a chunk never straddles two samples
+        float* d = rows + (o * CMB_SB + sb) * pitch + c;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nb) {
+        const int sb = threadIdx.x, b = b0 + sb;
+        const float* r0 = rows + sb * pitch;
+        const int ostride = CMB_SB * pitch;
+        float sum_first = 0.f;
+        for (int o = 0; o < G; ++o) sum_first = __fadd_rn(sum_first, r0[o * ostride + 2 * kp4]);
+        float* c = ctxs + sb * CW;
+        for (int j = 0; j < kp4; ++j) {
+            float Sj = 0.f;
+            for (int o = 0; o < G; ++o) Sj = __fadd_rn(Sj, r0[o * ostride + j]);
+            c[j] = Sj;
+        }
+        auto bi_of = [&](int j) {
+            float Sj = 0.f, Qj = 0.f;
+            for (int o = 0; o < G; ++o) {
+                Sj = __fadd_rn(Sj, r0[o * ostride + j]);
+                Qj = __fadd_rn(Qj, r0[o * ostride + kp4 + j]);
+            }
+            return __fmul_rn(__fsub_rn(__fmul_rn(Sj, Sj), Qj), 0.5f);
+        };
+        const float sum_bi = fmb::aten_row_sum_small(bi_of, k);
+        const float z = __fadd_rn(__fadd_rn(sum_first, sum_bi), bias[0]);
+        const float yy = y[b];
+        const float fB = (float)((int64_t)G * B);
+        float in = z, pr = 0.f;
+        if (loss_kind == 1) { pr = fmb::sigmoidf_p(z); in = pr; }
+        const float ls = __fsub_rn(fminf(in, 0.f), fmb::log1pf_p(fmb::expf_p(-fabsf(in))));
+        const float lossv = __fsub_rn(__fmul_rn(__fsub_rn(1.0f, yy), in), ls);
+        float d = __fdiv_rn(__fsub_rn(fmb::sigmoidf_p(in), yy), fB);
+        if (loss_kind == 1) d = __fmul_rn(__fmul_rn(d, __fsub_rn(1.0f, pr)), pr);
+        c[kp4] = d;
+        c[kp4 + 1] = lossv;
+        c[kp4 + 2] = z;
+        c[kp4 + 3] = 0.f;
+    }
+    __syncthreads();
+    const int n4 = nb * CW / 4;
+    for (int i = threadIdx.x; i < n4; i += CMB_THREADS) {
+        const float4 v = reinterpret_cast<const float4*>(ctxs)[i];
+        const size_t o4 = ((size_t)me * B + b0) * CW / 4 + i;
+        for (int r = 0; r < G; ++r) static_cast<float4*>(dst_ctx_all.p[r])[o4] = v;
+        if (ctx_local) reinterpret_cast<float4*>(ctx_local)[(size_t)b0 * CW / 4 + i] = v;
+    }
+    if (ch_publish >= 0) publish_epoch_last_block(x, ch_publish);
 }
 
 // rows [me*B, (me+1)*B) of ctx_all, copied from the local ctx [B][CW] into every rank's ctx_all (16-byte chunks)
@@ -378,33 +505,72 @@ static int fill_peers(PeerPtrs& pp, void* const* ptrs, int G, const char* who) {
     return FMB_OK;
 }
 
-// step 1 without a collective: ids [B,F] -> slab `me` of every rank's idsT_all [G][F][B]
+static int fill_sync(ExchSync& x, void* const* flag_peers, uint32_t* flags_local, uint32_t* sync_local, int* error_dev,
+                     int G, int me, bool needed, const char* who) {
+    x.flags_local = flags_local; x.sync_local = sync_local; x.error = error_dev; x.G = G; x.me = me;
+    for (int r = 0; r < 8; ++r) x.peer_flags.p[r] = nullptr;
+    if (!needed) return FMB_OK;
+    if (!flags_local || !sync_local) { fmb_set_error("%s: flag block / sync block missing", who); return FMB_ERR_ARG; }
+    return fill_peers(x.peer_flags, flag_peers, G, who);
+}
+
+// step 1 without a collective: ids [B,F] -> slab `me` of every rank's idsT_all [G][F][B]; publish_channel >= 0:
+// the last block publishes that channel's next epoch to the peers (see fmb_shard_signal), -1: no flag.
 FMB_API int fmb_shard_transpose_ids_peers(const int32_t* ids, int B, int F, int G, int me, void* const* dst_idsT_all,
-                                          cudaStream_t stream) {
-    FMB_CHECK_ARG(ids && B > 0 && F > 0 && me >= 0 && me < G, "fmb_shard_transpose_ids_peers: bad arguments");
+                                          void* const* flag_peers, uint32_t* flags_local, uint32_t* sync_local,
+                                          int* error_dev, int publish_channel, cudaStream_t stream) {
+    FMB_CHECK_ARG(ids && B > 0 && F > 0 && me >= 0 && me < G && publish_channel < 8, "fmb_shard_transpose_ids_peers: bad arguments");
     PeerPtrs pp;
     if (int rc = fill_peers(pp, dst_idsT_all, G, "fmb_shard_transpose_ids_peers")) return rc;
+    ExchSync x;
+    if (int rc = fill_sync(x, flag_peers, flags_local, sync_local, error_dev, G, me, publish_channel >= 0, "fmb_shard_transpose_ids_peers")) return rc;
     const int64_t n = (int64_t)B * F;
-    transpose_ids_peers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ids, B, F, G, me, pp);
+    const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, 296);   // grid-stride: few blocks, few fences
+    transpose_ids_peers_kernel<<<blocks, 256, 0, stream>>>(ids, B, F, G, me, pp, x, publish_channel);
     FMB_CHECK_LAUNCH("transpose_ids_peers_kernel");
     return FMB_OK;
 }
 
 // steps 2a + 3 without a collective: block r of the pooled partials goes straight into rank r's recv [G][B][PW]
 FMB_API int fmb_shard_partial_forward_peers(const int32_t* idsT_all, const float* table_local, int G, int me, int B,
-                                            int F, int k, void* const* dst_recv, cudaStream_t stream) {
+                                            int F, int k, void* const* dst_recv, void* const* flag_peers,
+                                            uint32_t* flags_local, uint32_t* sync_local, int* error_dev,
+                                            int publish_channel, cudaStream_t stream) {
     FMB_CHECK_ARG(idsT_all && table_local, "fmb_shard_partial_forward_peers: null pointer");
-    FMB_CHECK_ARG(G > 0 && me >= 0 && me < G && B > 0 && F > 0 && k > 0 && k <= 124, "fmb_shard_partial_forward_peers: bad arguments");
+    FMB_CHECK_ARG(G > 0 && me >= 0 && me < G && B > 0 && F > 0 && k > 0 && k <= 124 && publish_channel < 8,
+                  "fmb_shard_partial_forward_peers: bad arguments");
     PeerPtrs pp;
     if (int rc = fill_peers(pp, dst_recv, G, "fmb_shard_partial_forward_peers")) return rc;
+    ExchSync x;
+    if (int rc = fill_sync(x, flag_peers, flags_local, sync_local, error_dev, G, me, publish_channel >= 0, "fmb_shard_partial_forward_peers")) return rc;
     PartialParams p;
     p.idsT_all = idsT_all; p.table = table_local; p.G = G; p.glog = ilog2_exact(G); p.me = me; p.B = B; p.F = F;
     p.k = k; p.rowp = fmb_round_up(k + 1, 16); p.kp4 = fmb_round_up(k, 4); p.cu = (k + 1 + 3) / 4;
     p.ql_log = ilog2_ceil(p.cu); p.PW = fmb_shard_pw(k); p.partial = nullptr;
     const int spb = 256 >> p.ql_log;
     const int64_t n = (int64_t)G * B;
-    shard_partial_forward_peers_kernel<<<(unsigned)((n + spb - 1) / spb), 256, 0, stream>>>(p, pp);
+    shard_partial_forward_peers_kernel<<<(unsigned)((n + spb - 1) / spb), 256, 0, stream>>>(p, pp, x, publish_channel);
     FMB_CHECK_LAUNCH("shard_partial_forward_peers_kernel");
+    return FMB_OK;
+}
+
+// steps 4 + 5 without a collective: wait_channel >= 0: first wait until all G owners have published that channel
+// (their blocks are in recv); fold; store the ctx rows into every rank's ctx_all (and ctx_local when given);
+// publish_channel >= 0: publish it from the last block.  k <= 16.
+FMB_API int fmb_shard_combine_peers(const float* recv, const float* bias, const float* y, int G, int me, int B, int k,
+                                    int loss_kind, void* const* dst_ctx_all, float* ctx_local, void* const* flag_peers,
+                                    uint32_t* flags_local, uint32_t* sync_local, int* error_dev, int wait_channel,
+                                    int publish_channel, cudaStream_t stream) {
+    FMB_CHECK_ARG(recv && bias && y && G > 0 && me >= 0 && me < G && B > 0 && k > 0, "fmb_shard_combine_peers: bad arguments");
+    FMB_CHECK_ARG(fmb_shard_pw(k) <= CMB_MAXPW && wait_channel < 8 && publish_channel < 8, "fmb_shard_combine_peers: k=%d too large for this path (k <= 16)", k);
+    PeerPtrs pp;
+    if (int rc = fill_peers(pp, dst_ctx_all, G, "fmb_shard_combine_peers")) return rc;
+    ExchSync x;
+    if (int rc = fill_sync(x, flag_peers, flags_local, sync_local, error_dev, G, me, wait_channel >= 0 || publish_channel >= 0, "fmb_shard_combine_peers")) return rc;
+    shard_combine_peers_kernel<<<(B + CMB_SB - 1) / CMB_SB, CMB_THREADS, 0, stream>>>(
+        recv, bias, y, G, me, B, k, fmb_round_up(k, 4), fmb_shard_pw(k), fmb_shard_cw(k), loss_kind, pp, ctx_local, x,
+        wait_channel, publish_channel);
+    FMB_CHECK_LAUNCH("shard_combine_peers_kernel");
     return FMB_OK;
 }
 
@@ -421,8 +587,8 @@ FMB_API int fmb_shard_ctx_bcast_peers(const float* ctx, int G, int me, int B, in
     return FMB_OK;
 }
 
-// Epoch flags of the exchange: flag words are uint32 [channels][8] in symmetric memory, `epoch_local` uint32
-// [channels] in ordinary device memory.  mode 1 = publish (after the producer kernel, same stream), 2 = wait for
+// Epoch flags of the exchange: flag words are uint32 [8 channels][8 ranks] in symmetric memory, `epoch_local` =
+// the sync block, uint32 [16] in ordinary device memory (epoch[8] | block counters[8], zero-initialised).  mode 1 = publish (after the producer kernel, same stream), 2 = wait for
 // all G peers (before the consumer kernel), 3 = both.  error_dev (nullable) receives 1 + channel on a time-out.
 FMB_API int fmb_shard_signal(void* const* peer_flags, uint32_t* flags_local, uint32_t* epoch_local, int channel, int G,
                              int me, int mode, int* error_dev, cudaStream_t stream) {

@@ -293,8 +293,12 @@ class ShardedFM:
                       "recv": view["recv"].view(torch.float32).view(G, B, self.PW),
                       "ctx": view["ctx"].view(torch.float32).view(G * B, self.CW),
                       "flags": view["flags"],
-                      "epoch": torch.zeros(8, dtype=torch.int32, device=self.device),
+                      "epoch": torch.zeros(16, dtype=torch.int32, device=self.device),   # epoch[8] | block counters[8]
                       "error": torch.zeros(1, dtype=torch.int32, device=self.device)}
+
+    def _sync_args(self):
+        pr = self._peer
+        return pr["ptrs"]["flags"], ptr(pr["flags"]), ptr(pr["epoch"]), ptr(pr["error"])
 
     def _signal(self, channel, mode):
         pr = self._peer
@@ -302,13 +306,14 @@ class ShardedFM:
                                          self.rank, mode, ptr(pr["error"]), _stream()), "fmb_shard_signal")
 
     def _prepare_peers(self, ids, slot):
+        """everything about the next batch's ids happens on the _pre stream, beside the current step."""
         pr, B = self._peer, ids.shape[0]
         main = torch.cuda.current_stream()
-        check(self._lib.fmb_shard_transpose_ids_peers(ptr(ids), B, self.F, self.G, self.rank, pr["ptrs"][f"ids{slot}"],
-                                                      _stream()), "fmb_shard_transpose_ids_peers")
-        self._signal(self.CH_IDS, 1)
-        self._pre.wait_stream(main)
+        self._pre.wait_stream(main)               # `ids` is ready; every earlier reader of this slot is behind us
         with torch.cuda.stream(self._pre):
+            check(self._lib.fmb_shard_transpose_ids_peers(ptr(ids), B, self.F, self.G, self.rank,
+                                                          pr["ptrs"][f"ids{slot}"], *self._sync_args(), self.CH_IDS,
+                                                          _stream()), "fmb_shard_transpose_ids_peers")
             self._signal(self.CH_IDS, 2)          # every rank's slab has landed in MY idsT_all
             self._sort_owned(pr["ids"][slot], slot)
 
@@ -327,15 +332,17 @@ class ShardedFM:
         main = torch.cuda.current_stream()
         if ids_next is not None:
             self._prepare_peers(ids_next, 1 - p)
+        # partial forward: stores block r into rank r's recv, its last block publishes the A2A epoch
         check(lib.fmb_shard_partial_forward_peers(ptr(pr["ids"][p]), ptr(self.table), G, self.rank, B, F, k,
-                                                  pr["ptrs"]["recv"], _stream()), "fmb_shard_partial_forward_peers")
-        self._signal(self.CH_A2A, 3)              # my blocks are out; wait for the G blocks of MY samples
-        ctx = self.phase_combine(pr["recv"], y, loss_kind)
-        check(lib.fmb_shard_ctx_bcast_peers(ptr(ctx), G, self.rank, B, k, pr["ptrs"]["ctx"], _stream()),
-              "fmb_shard_ctx_bcast_peers")
-        self._signal(self.CH_CTX, 3)
+                                                  pr["ptrs"]["recv"], *self._sync_args(), self.CH_A2A, _stream()),
+              "fmb_shard_partial_forward_peers")
+        # combine: waits for the G owners' A2A epochs, folds, stores ctx into every rank's ctx_all, publishes CTX
+        check(lib.fmb_shard_combine_peers(ptr(pr["recv"]), ptr(self.bias), ptr(y), G, self.rank, B, k, loss_kind,
+                                          pr["ptrs"]["ctx"], None, *self._sync_args(), self.CH_A2A, self.CH_CTX,
+                                          _stream()), "fmb_shard_combine_peers")
+        self._signal(self.CH_CTX, 2)              # every rank's ctx rows have landed in MY ctx_all
         loss = self.phase_backward(pr["ctx"], p, join_sort=False)
-        self.launches += 4                        # ctx broadcast + signal kernels (transpose/sort counted there)
+        self.launches += 1                        # the two wait kernels (phase_backward counts 9 for the rest)
         main.wait_stream(self._pre)
         self._slot = 1 - p
         return loss

@@ -129,15 +129,27 @@ int fmb_shard_sort_fields(const int32_t* idsT_all_dev, int G, int me, int B, int
  *   fmb_shard_ctx_bcast_peers       local ctx [B,CW] -> rows [me*B,(me+1)*B) of every rank's ctx_all (replaces all-gather 2)
  *   fmb_shard_signal                per-channel epoch flags, uint32 [8 channels][8 ranks] in symmetric memory;
  *                                   mode 1 publish (fence.sys + st.release.sys to all peers), 2 wait for all G peers
- *                                   (ld.acquire.sys, bounded spin), 3 both; epoch_local uint32 [8] ordinary device memory;
- *                                   error_dev (nullable) receives 1 + channel on a time-out. */
+ *                                   (ld.acquire.sys, bounded spin), 3 both; sync_local uint32 [16] ordinary device
+ *                                   memory, zero-initialised (epoch[8] | block counters[8]);
+ *                                   error_dev (nullable) receives 1 + channel on a time-out.
+ * The producers can publish their channel themselves from their last block (publish_channel >= 0), the fused
+ * combine can wait at its start (wait_channel >= 0): then only consumers that are not fused need fmb_shard_signal. */
 int fmb_shard_transpose_ids_peers(const int32_t* ids_dev, int B, int F, int G, int me, void* const* idsT_all_peers,
-                                  fmb_stream_t stream);
+                                  void* const* flag_peers, uint32_t* flags_local_dev, uint32_t* sync_local_dev,
+                                  int* error_dev, int publish_channel /* -1: none */, fmb_stream_t stream);
 int fmb_shard_partial_forward_peers(const int32_t* idsT_all_dev, const float* table_local_dev, int G, int me, int B,
-                                    int F, int k, void* const* recv_peers, fmb_stream_t stream);
+                                    int F, int k, void* const* recv_peers, void* const* flag_peers,
+                                    uint32_t* flags_local_dev, uint32_t* sync_local_dev, int* error_dev,
+                                    int publish_channel /* -1: none */, fmb_stream_t stream);
+/* fmb_shard_combine fused with its two exchanges: waits for `wait_channel` (the owners' partials), folds, stores
+ * the ctx rows into every rank's ctx_all (and ctx_local_dev when given), publishes `publish_channel`.  k <= 16. */
+int fmb_shard_combine_peers(const float* recv_dev, const float* bias_dev, const float* y_dev, int G, int me, int B,
+                            int k, int loss_kind, void* const* ctx_all_peers, float* ctx_local_dev /*nullable*/,
+                            void* const* flag_peers, uint32_t* flags_local_dev, uint32_t* sync_local_dev,
+                            int* error_dev, int wait_channel, int publish_channel, fmb_stream_t stream);
 int fmb_shard_ctx_bcast_peers(const float* ctx_dev, int G, int me, int B, int k, void* const* ctx_all_peers,
                               fmb_stream_t stream);
-int fmb_shard_signal(void* const* flag_peers, uint32_t* flags_local_dev, uint32_t* epoch_local_dev, int channel, int G,
+int fmb_shard_signal(void* const* flag_peers, uint32_t* flags_local_dev, uint32_t* sync_local_dev, int channel, int G,
                      int me, int mode, int* error_dev, fmb_stream_t stream);
 
 /* ---- A4/A5: MLP tower on the Bi-Interaction vector (deepfm_adam.py:79-89, nfm_adam.py:78-88,
