@@ -16,8 +16,12 @@
 //       buffer G (L2-resident).
 //   fm_bwd_runs_kernel  : one warp per 32 sorted positions finds the runs (>= 2 entries) that START
 //       there and sums each run left to right, one lane per component -- the first 32 entries straight
-//       from G, longer runs through a 4-stage cp.async ring in shared memory so the serial fp32 chain
-//       (the only part that cannot be parallelised without changing the rounding) never waits on L2.
+//       from G, longer runs through a 4-stage bulk-copy (TMA) ring in shared memory so the serial fp32
+//       chain (the only part that cannot be parallelised without changing the rounding) never waits on L2.
+// G is component-major ([component][position], SoA): a lane's chain reads ITS component of consecutive
+// entries, so the ring holds one contiguous row per lane and the chain consumes 4 entries per LDS.128
+// (the entry-major layout cost one LDS.32 per entry: 64 instructions per 32 entries, 10.6 cycles per entry
+// measured with clock64; the add chain itself is 4).
 #include "fmb_common.cuh"
 
 namespace {
@@ -42,8 +46,9 @@ struct BwdParams {
     int s_pitch;          // row pitch of S / gvec in floats (kp4 unless they live in a gathered context)
     int gs_stride;        // stride of gs in floats
     int32_t key_limit;    // keys >= key_limit are padding (sharded path) and are skipped
-    float* G;             // [N][cu*4] staged contributions (chain A, or the only chain)
-    float* G2;            // [N][cu*4] chain B when both gradient paths are live
+    float* G;             // [k+1][Npad] staged contributions, component-major (chain A, or the only chain)
+    float* G2;            // [k][Npad] chain B when both gradient paths are live
+    int64_t Npad;         // row pitch of G / G2 (positions, multiple of 4, > N + 8)
     long long* dbg;       // optional per-run timing records (debug builds of bench only), else NULL
     float astep;          // -(lr/0.1f): Adam step size, computed once on the host (same IEEE division)
 };
@@ -101,15 +106,16 @@ __global__ void __launch_bounds__(256) fm_bwd_entry_kernel(BwdParams p) {
         }
         *reinterpret_cast<float4*>(rowptr) = make_float4(o[0], o[1], o[2], o[3]);
     } else {
-        const int gp = p.cu * 4;
-        if (two) {
-            *reinterpret_cast<float4*>(p.G + (size_t)i * gp + q * 4) = make_float4(a[0], a[1], a[2], a[3]);
-            *reinterpret_cast<float4*>(p.G2 + (size_t)i * gp + q * 4) = make_float4(c[0], c[1], c[2], c[3]);
-        } else {
-            float m[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) m[t] = (p.gvec && q * 4 + t < p.k) ? c[t] : a[t];
-            *reinterpret_cast<float4*>(p.G + (size_t)i * gp + q * 4) = make_float4(m[0], m[1], m[2], m[3]);
+        for (int t = 0; t < 4; ++t) {
+            const int j = q * 4 + t;
+            if (j > p.k) continue;
+            if (two) {
+                p.G[(size_t)j * p.Npad + i] = a[t];
+                if (j < p.k) p.G2[(size_t)j * p.Npad + i] = c[t];
+            } else {
+                p.G[(size_t)j * p.Npad + i] = (p.gvec && j < p.k) ? c[t] : a[t];
+            }
         }
     }
 }
@@ -178,22 +184,20 @@ __global__ void __launch_bounds__(256) fm_bwd_entry1_kernel(BwdParams p) {
         for (int q = 0; q < CU; ++q)
             *reinterpret_cast<float4*>(rowptr + q * 4) = make_float4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
     } else {
-        float* gd = p.G + (size_t)i * (CU * 4);
 #pragma unroll
-        for (int q = 0; q < CU; ++q)
-            *reinterpret_cast<float4*>(gd + q * 4) = make_float4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
-        if (two) {
-            float* gd2 = p.G2 + (size_t)i * (CU * 4);
-#pragma unroll
-            for (int q = 0; q < CU; ++q)
-                *reinterpret_cast<float4*>(gd2 + q * 4) = make_float4(o2[q * 4], o2[q * 4 + 1], o2[q * 4 + 2], o2[q * 4 + 3]);
+        for (int j = 0; j < CU * 4; ++j) {
+            if (j > p.k) continue;
+            p.G[(size_t)j * p.Npad + i] = o[j];          // adjacent threads = adjacent positions: coalesced
+            if (two && j < p.k) p.G2[(size_t)j * p.Npad + i] = o2[j];
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-constexpr int RING_SE = 64;  // entries per ring stage
-constexpr int RING_NS = 4;   // stages
+constexpr int RING_SE = 64;            // entries per ring stage
+constexpr int RING_NS = 4;             // stages
+constexpr int RING_SEP = RING_SE + 4;  // floats per lane row of a stage: room for a start misaligned by up to 3
+                                       // entries, and a pitch of 4 banks per lane (conflict-free LDS.128)
 
 // ---- mbarrier + 1-D bulk async copy (TMA) helpers -------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -220,19 +224,17 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  : "memory");
 }
 
-// GPT > 0 fixes the staging pitch at compile time; 0 = runtime pitch.
-template <int GPT>
-__global__ void __launch_bounds__(256, 3) fm_bwd_runs_kernel(BwdParams p, int warps_per_block, int warp_f, int accs_n) {
+__global__ void __launch_bounds__(256, 3) fm_bwd_runs_kernel(BwdParams p, int warps_per_block, int warp_f, int accs_n,
+                                                             int ring_comps) {
     extern __shared__ __align__(128) float smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t P0 = ((int64_t)blockIdx.x * warps_per_block + wib) * 32;
     if (P0 >= p.N) return;
     const bool two = p.use_fm2 && p.gvec;
-    const int nbuf = two ? 2 : 1;
-    const int gp = GPT > 0 ? GPT : p.cu * 4, kc = p.k + 1;
+    const int kc = p.k + 1;
     const int nv = kc + (two ? p.k : 0);          // virtual lanes: chain A comps, then chain B comps
-    const int stage_f = RING_SE * gp * nbuf;
-    float* ring = smem + (size_t)wib * warp_f;    // [NS][nbuf][SE][gp]
+    const int stage_f = ring_comps * RING_SEP;
+    float* ring = smem + (size_t)wib * warp_f;    // [NS][ring_comps][SEP]
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + RING_NS * stage_f);   // [NS] mbarriers
     float* accs = reinterpret_cast<float*>(bars + RING_NS);                   // [accs_n + 32]
 
@@ -280,21 +282,23 @@ __global__ void __launch_bounds__(256, 3) fm_bwd_runs_kernel(BwdParams p, int wa
         for (int v0 = 0; v0 < nv; v0 += 32) {  // one pass per group of 32 (buffer, component) lanes
             const int vl = v0 + lane;
             const bool active = vl < nv;
+            const int nact = min(32, nv - v0);
             const bool isB = vl >= kc;
             const int comp = isB ? vl - kc : vl;
-            const float* src = (isB ? p.G2 : p.G) + comp;
+            // this lane's component row of the staging buffer
+            const float* src = (isB ? p.G2 : p.G) + (size_t)(active ? comp : 0) * p.Npad;
             // the row's old value is needed only at the very end: fetch it now, off the critical path
             float pold = 0.f;
             if (v0 == 0 && lane < kc) pold = p.table[(size_t)key * p.rowp + lane];
             // direct part: up to 32 entries straight from G, all loads in flight at once
             float acc = 0.f;
             {
-                const float* sp = src + (size_t)s * gp;
+                const float* sp = src + s;
                 float tv[16], tw[16];
 #pragma unroll
-                for (int u = 0; u < 16; ++u) tv[u] = (active && u < n0) ? __ldg(sp + u * gp) : 0.f;
+                for (int u = 0; u < 16; ++u) tv[u] = (active && u < n0) ? __ldg(sp + u) : 0.f;
 #pragma unroll
-                for (int u = 0; u < 16; ++u) tw[u] = (active && 16 + u < n0) ? __ldg(sp + (16 + u) * gp) : 0.f;
+                for (int u = 0; u < 16; ++u) tw[u] = (active && 16 + u < n0) ? __ldg(sp + 16 + u) : 0.f;
 #pragma unroll
                 for (int u = 0; u < 16; ++u)
                     if (u < n0) acc = __fadd_rn(acc, tv[u]);
@@ -305,8 +309,10 @@ __global__ void __launch_bounds__(256, 3) fm_bwd_runs_kernel(BwdParams p, int wa
             if (p.dbg) t_direct = clock64();
             run_len = n0;
             if (n0 == 32) {
-                // stream the rest in windows of up to 1024 entries: [c0, c0 + wlen)
+                // stream the rest in windows of up to 1024 entries: [c0, c0 + wlen).  Bulk copies need 16-byte
+                // aligned sources: every stage starts `mis` entries early (windows and stages are multiples of 4)
                 int64_t c0 = s + 32;
+                const int mis = (int)(c0 & 3);
                 int32_t pr = probe;
                 bool ok = true;
                 while (ok) {
@@ -320,17 +326,16 @@ __global__ void __launch_bounds__(256, 3) fm_bwd_runs_kernel(BwdParams p, int wa
                     }
                     const int wlen = 32 * full + part;
                     const int T = (wlen + RING_SE - 1) / RING_SE;
-                    // prologue: fill the ring with bulk copies (one instruction per stage and buffer)
+                    // one bulk copy per lane (= component row) and stage, all completing on the stage's mbarrier
                     auto issue = [&](int tstage) {
-                        if (lane == 0) {
-                            const int st = tstage & (RING_NS - 1);
-                            const int n = min(RING_SE, wlen - RING_SE * tstage);
-                            const unsigned bytes = (unsigned)(n * gp * 4);
-                            float* dst = ring + (size_t)st * stage_f;
-                            mbar_expect_tx(bars + st, bytes * nbuf);
-                            bulk_g2s(dst, p.G + (size_t)(c0 + RING_SE * (int64_t)tstage) * gp, bytes, bars + st);
-                            if (two) bulk_g2s(dst + RING_SE * gp, p.G2 + (size_t)(c0 + RING_SE * (int64_t)tstage) * gp, bytes, bars + st);
-                        }
+                        const int st = tstage & (RING_NS - 1);
+                        const int n = min(RING_SE, wlen - RING_SE * tstage);
+                        const unsigned bytes = (unsigned)(((n + mis + 3) & ~3) * 4);
+                        if (lane == 0) mbar_expect_tx(bars + st, bytes * nact);
+                        __syncwarp();
+                        if (active)
+                            bulk_g2s(ring + (size_t)st * stage_f + lane * RING_SEP, src + (c0 - mis) + RING_SE * (int64_t)tstage,
+                                     bytes, bars + st);
                     };
                     for (int ts = 0; ts < T && ts < RING_NS; ++ts) issue(ts);
                     // next window's probe (only needed when this window is completely full)
@@ -346,17 +351,39 @@ __global__ void __launch_bounds__(256, 3) fm_bwd_runs_kernel(BwdParams p, int wa
                         if (p.dbg) { w1 = clock64(); c_wait += w1 - w0; }
                         const int n = min(RING_SE, wlen - RING_SE * ts);
                         if (active) {
-                            const float* b = ring + (size_t)st * stage_f + (isB ? RING_SE * gp : 0) + comp;
-                            int done = 0;
-#pragma unroll 1
-                            for (; done + 32 <= n; done += 32) {   // 32 loads in flight, then the bare 32-add chain
-                                float tv[32];
-#pragma unroll
-                                for (int u = 0; u < 32; ++u) tv[u] = b[(done + u) * gp];
-#pragma unroll
-                                for (int u = 0; u < 32; ++u) acc = __fadd_rn(acc, tv[u]);
+                            const float4* b4 = reinterpret_cast<const float4*>(ring + (size_t)st * stage_f + lane * RING_SEP);
+                            int e = 0;
+                            const int end = mis + n;   // entries [mis, end) of this lane's row
+                            if (mis) {                 // first, partial quad
+                                const float4 q = b4[0];
+                                if (mis <= 1 && 1 < end) acc = __fadd_rn(acc, q.y);
+                                if (mis <= 2 && 2 < end) acc = __fadd_rn(acc, q.z);
+                                if (3 < end) acc = __fadd_rn(acc, q.w);
+                                e = 4;
                             }
-                            for (int u = done; u < n; ++u) acc = __fadd_rn(acc, b[u * gp]);
+#pragma unroll 1
+                            for (; e + 32 <= end; e += 32) {   // 8 LDS.128 in flight, then the bare 32-add chain
+                                float4 tv[8];
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) tv[u] = b4[(e >> 2) + u];
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) {
+                                    acc = __fadd_rn(acc, tv[u].x); acc = __fadd_rn(acc, tv[u].y);
+                                    acc = __fadd_rn(acc, tv[u].z); acc = __fadd_rn(acc, tv[u].w);
+                                }
+                            }
+#pragma unroll 1
+                            for (; e + 4 <= end; e += 4) {
+                                const float4 q = b4[e >> 2];
+                                acc = __fadd_rn(acc, q.x); acc = __fadd_rn(acc, q.y);
+                                acc = __fadd_rn(acc, q.z); acc = __fadd_rn(acc, q.w);
+                            }
+                            if (e < end) {             // last, partial quad
+                                const float4 q = b4[e >> 2];
+                                acc = __fadd_rn(acc, q.x);
+                                if (e + 1 < end) acc = __fadd_rn(acc, q.y);
+                                if (e + 2 < end) acc = __fadd_rn(acc, q.z);
+                            }
                         }
                         __syncwarp();
                         long long w2 = 0;
@@ -403,9 +430,11 @@ static int ilog2_ceil(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
 }  // namespace
 
 // workspace of fmb_fm_backward_update: the contribution staging buffers G and G2
+static int64_t bwd_npad(int64_t N) { return (N + 3) / 4 * 4 + 64; }   // row pitch of G: multiple of 4, slack for
+                                                                       // the bulk copies' rounded-up tails
 FMB_API size_t fmb_bwd_workspace_bytes(int64_t N, int k) {
-    const size_t gp = (size_t)((k + 1 + 3) / 4) * 4;
-    return 2 * (((size_t)N * gp * 4 + 255) / 256 * 256) + 256;
+    const size_t rows = (size_t)((k + 1 + 3) / 4) * 4;
+    return 2 * (((size_t)bwd_npad(N) * rows * 4 + 255) / 256 * 256) + 256;
 }
 
 static long long* g_runs_dbg = nullptr;
@@ -446,7 +475,8 @@ FMB_API int fmb_fm_backward_update_ex(const int32_t* sorted_keys, const int32_t*
     p.s_pitch = s_pitch; p.gs_stride = gs_stride; p.key_limit = key_limit;
     p.astep = -(lr / 0.1f);
     p.dbg = g_runs_dbg;
-    const size_t gbytes = ((size_t)N * p.cu * 16 + 255) / 256 * 256;
+    p.Npad = bwd_npad(N);
+    const size_t gbytes = ((size_t)p.Npad * p.cu * 16 + 255) / 256 * 256;
     p.G = (float*)ws;
     p.G2 = (float*)((char*)ws + gbytes);
     const bool two = use_fm2 && gvec;
@@ -462,33 +492,23 @@ FMB_API int fmb_fm_backward_update_ex(const int32_t* sorted_keys, const int32_t*
         }
     }
     FMB_CHECK_LAUNCH("fm_bwd_entry_kernel");
-    // runs kernel: per-warp shared memory = ring + keys + accumulators
-    const int gp = p.cu * 4;
+    // runs kernel: per-warp shared memory = ring + mbarriers + accumulators
     const int nv = k + 1 + (two ? k : 0);
     const int accs_n = (nv + 3) / 4 * 4;
+    const int ring_comps = nv < 32 ? nv : 32;
     // ring (multiple of 128 B per warp) + NS mbarriers (8 B each) + accumulators + prefetched old row
-    const int warp_f = fmb_round_up(RING_NS * RING_SE * gp * (two ? 2 : 1) + 2 * RING_NS + accs_n + 32, 32);
+    const int warp_f = fmb_round_up(RING_NS * ring_comps * RING_SEP + 2 * RING_NS + accs_n + 32, 32);
     int wpb = 8;
     while (wpb > 1 && (size_t)wpb * warp_f * 4 > 56 * 1024) wpb >>= 1;
     const size_t sm = (size_t)wpb * warp_f * 4;
     FMB_CHECK_ARG(sm <= 200 * 1024, "fmb_fm_backward_update: k too large for the run ring");
     const int64_t nwarps = (N + 31) / 32;
     const unsigned grid = (unsigned)((nwarps + wpb - 1) / wpb);
-#define FMB_LAUNCH_RUNS(GPV)                                                                                      \
-    do {                                                                                                          \
-        static bool attr = false;                                                                                 \
-        if (!attr) { cudaFuncSetAttribute(fm_bwd_runs_kernel<GPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; } \
-        fm_bwd_runs_kernel<GPV><<<grid, 32 * wpb, sm, stream>>>(p, wpb, warp_f, accs_n);                          \
-    } while (0)
-    switch (gp) {
-        case 8: FMB_LAUNCH_RUNS(8); break;
-        case 12: FMB_LAUNCH_RUNS(12); break;
-        case 16: FMB_LAUNCH_RUNS(16); break;
-        case 20: FMB_LAUNCH_RUNS(20); break;
-        case 68: FMB_LAUNCH_RUNS(68); break;
-        default: FMB_LAUNCH_RUNS(0); break;
+    {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(fm_bwd_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+        fm_bwd_runs_kernel<<<grid, 32 * wpb, sm, stream>>>(p, wpb, warp_f, accs_n, ring_comps);
     }
-#undef FMB_LAUNCH_RUNS
     FMB_CHECK_LAUNCH("fm_bwd_runs_kernel");
     return FMB_OK;
 }
