@@ -23,6 +23,7 @@
 // (the entry-major layout cost one LDS.32 per entry: 64 instructions per 32 entries, 10.6 cycles per entry
 // measured with clock64; the add chain itself is 4).
 #include "fmb_common.cuh"
+#include <cuda.h>   // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link)
 
 namespace {
 
@@ -46,9 +47,9 @@ struct BwdParams {
     int s_pitch;          // row pitch of S / gvec in floats (kp4 unless they live in a gathered context)
     int gs_stride;        // stride of gs in floats
     int32_t key_limit;    // keys >= key_limit are padding (sharded path) and are skipped
-    float* G;             // [k+1][Npad] staged contributions, component-major (chain A, or the only chain)
-    float* G2;            // [k][Npad] chain B when both gradient paths are live
-    int64_t Npad;         // row pitch of G / G2 (positions, multiple of 4, > N + 8)
+    float* G;             // [k+1 (+k)][Npad] staged contributions, component-major: rows 0..k chain A (or the only
+                          // chain), rows k+1..2k chain B when both gradient paths are live
+    int64_t Npad;         // row pitch of G (positions, multiple of 4, >= N + 64)
     long long* dbg;       // optional per-run timing records (debug builds of bench only), else NULL
     float astep;          // -(lr/0.1f): Adam step size, computed once on the host (same IEEE division)
 };
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(256) fm_bwd_entry_kernel(BwdParams p) {
             if (j > p.k) continue;
             if (two) {
                 p.G[(size_t)j * p.Npad + i] = a[t];
-                if (j < p.k) p.G2[(size_t)j * p.Npad + i] = c[t];
+                if (j < p.k) p.G[(size_t)(p.k + 1 + j) * p.Npad + i] = c[t];
             } else {
                 p.G[(size_t)j * p.Npad + i] = (p.gvec && j < p.k) ? c[t] : a[t];
             }
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(256) fm_bwd_entry1_kernel(BwdParams p) {
         for (int j = 0; j < CU * 4; ++j) {
             if (j > p.k) continue;
             p.G[(size_t)j * p.Npad + i] = o[j];          // adjacent threads = adjacent positions: coalesced
-            if (two && j < p.k) p.G2[(size_t)j * p.Npad + i] = o2[j];
+            if (two && j < p.k) p.G[(size_t)(p.k + 1 + j) * p.Npad + i] = o2[j];
         }
     }
 }
@@ -196,10 +197,11 @@ __global__ void __launch_bounds__(256) fm_bwd_entry1_kernel(BwdParams p) {
 // ---------------------------------------------------------------------------------------------
 constexpr int RING_SE = 64;            // entries per ring stage
 constexpr int RING_NS = 4;             // stages
-constexpr int RING_SEP = RING_SE + 4;  // floats per lane row of a stage: room for a start misaligned by up to 3
-                                       // entries, and a pitch of 4 banks per lane (conflict-free LDS.128)
+constexpr int RING_SEP = RING_SE + 4;  // floats per lane row of a stage = inner box of the tensor-map copy.  TMA needs
+                                       // 16-byte aligned row starts, so a stage starts up to 3 entries early (`mis`);
+                                       // the pitch of 4 banks per lane also makes the LDS.128 conflict-free
 
-// ---- mbarrier + 1-D bulk async copy (TMA) helpers -------------------------------------------------
+// ---- mbarrier + TMA helpers -------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
 }
@@ -217,14 +219,16 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, unsigned parity) {
     }
     return false;
 }
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
-                 : "memory");
+// 2-D tiled TMA: box [rows][RING_SEP entries] of the component-major staging buffer, starting at (entry x, row y)
+__device__ __forceinline__ void tma_g2s_2d(void* smem_dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+            (unsigned)__cvta_generic_to_shared(smem_dst)),
+        "l"(tmap), "r"(x), "r"(y), "r"((unsigned)__cvta_generic_to_shared(bar))
+        : "memory");
 }
 
-__global__ void __launch_bounds__(256, 3) fm_bwd_runs_kernel(BwdParams p, int warps_per_block, int warp_f, int accs_n,
+__global__ void __launch_bounds__(256, 2) fm_bwd_runs_kernel(const __grid_constant__ CUtensorMap gmap, BwdParams p, int warps_per_block, int warp_f, int accs_n,
                                                              int ring_comps) {
     extern __shared__ __align__(128) float smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -233,7 +237,7 @@ __global__ void __launch_bounds__(256, 3) fm_bwd_runs_kernel(BwdParams p, int wa
     const bool two = p.use_fm2 && p.gvec;
     const int kc = p.k + 1;
     const int nv = kc + (two ? p.k : 0);          // virtual lanes: chain A comps, then chain B comps
-    const int stage_f = ring_comps * RING_SEP;
+    const int stage_f = (ring_comps * RING_SEP + 31) & ~31;   // stages stay 128-byte aligned (TMA destination)
     float* ring = smem + (size_t)wib * warp_f;    // [NS][ring_comps][SEP]
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + RING_NS * stage_f);   // [NS] mbarriers
     float* accs = reinterpret_cast<float*>(bars + RING_NS);                   // [accs_n + 32]
@@ -282,11 +286,11 @@ __global__ void __launch_bounds__(256, 3) fm_bwd_runs_kernel(BwdParams p, int wa
         for (int v0 = 0; v0 < nv; v0 += 32) {  // one pass per group of 32 (buffer, component) lanes
             const int vl = v0 + lane;
             const bool active = vl < nv;
-            const int nact = min(32, nv - v0);
             const bool isB = vl >= kc;
             const int comp = isB ? vl - kc : vl;
             // this lane's component row of the staging buffer
-            const float* src = (isB ? p.G2 : p.G) + (size_t)(active ? comp : 0) * p.Npad;
+            const float* src = p.G + (size_t)(active ? vl : 0) * p.Npad;   // chain B rows follow chain A's (comp unused)
+            (void)isB; (void)comp;
             // the row's old value is needed only at the very end: fetch it now, off the critical path
             float pold = 0.f;
             if (v0 == 0 && lane < kc) pold = p.table[(size_t)key * p.rowp + lane];
@@ -309,8 +313,8 @@ __global__ void __launch_bounds__(256, 3) fm_bwd_runs_kernel(BwdParams p, int wa
             if (p.dbg) t_direct = clock64();
             run_len = n0;
             if (n0 == 32) {
-                // stream the rest in windows of up to 1024 entries: [c0, c0 + wlen).  Bulk copies need 16-byte
-                // aligned sources: every stage starts `mis` entries early (windows and stages are multiples of 4)
+                // stream the rest in windows of up to 1024 entries: [c0, c0 + wlen); every stage's copy starts `mis`
+                // entries early (windows and stages are multiples of 4 entries, so `mis` is the same for all of them)
                 int64_t c0 = s + 32;
                 const int mis = (int)(c0 & 3);
                 int32_t pr = probe;
@@ -326,16 +330,14 @@ __global__ void __launch_bounds__(256, 3) fm_bwd_runs_kernel(BwdParams p, int wa
                     }
                     const int wlen = 32 * full + part;
                     const int T = (wlen + RING_SE - 1) / RING_SE;
-                    // one bulk copy per lane (= component row) and stage, all completing on the stage's mbarrier
+                    // ONE tensor-map copy per stage: rows v0 .. v0+ring_comps-1 (rows past the last one are zero
+                    // filled), RING_SEP entries from the 16-byte aligned position at or before the stage's first entry
                     auto issue = [&](int tstage) {
-                        const int st = tstage & (RING_NS - 1);
-                        const int n = min(RING_SE, wlen - RING_SE * tstage);
-                        const unsigned bytes = (unsigned)(((n + mis + 3) & ~3) * 4);
-                        if (lane == 0) mbar_expect_tx(bars + st, bytes * nact);
-                        __syncwarp();
-                        if (active)
-                            bulk_g2s(ring + (size_t)st * stage_f + lane * RING_SEP, src + (c0 - mis) + RING_SE * (int64_t)tstage,
-                                     bytes, bars + st);
+                        if (lane == 0) {
+                            const int st = tstage & (RING_NS - 1);
+                            mbar_expect_tx(bars + st, (unsigned)(ring_comps * RING_SEP * 4));
+                            tma_g2s_2d(ring + (size_t)st * stage_f, &gmap, (int)(c0 - mis + RING_SE * (int64_t)tstage), v0, bars + st);
+                        }
                     };
                     for (int ts = 0; ts < T && ts < RING_NS; ++ts) issue(ts);
                     // next window's probe (only needed when this window is completely full)
@@ -352,37 +354,45 @@ __global__ void __launch_bounds__(256, 3) fm_bwd_runs_kernel(BwdParams p, int wa
                         const int n = min(RING_SE, wlen - RING_SE * ts);
                         if (active) {
                             const float4* b4 = reinterpret_cast<const float4*>(ring + (size_t)st * stage_f + lane * RING_SEP);
-                            int e = 0;
-                            const int end = mis + n;   // entries [mis, end) of this lane's row
-                            if (mis) {                 // first, partial quad
-                                const float4 q = b4[0];
-                                if (mis <= 1 && 1 < end) acc = __fadd_rn(acc, q.y);
-                                if (mis <= 2 && 2 < end) acc = __fadd_rn(acc, q.z);
-                                if (3 < end) acc = __fadd_rn(acc, q.w);
-                                e = 4;
-                            }
-#pragma unroll 1
-                            for (; e + 32 <= end; e += 32) {   // 8 LDS.128 in flight, then the bare 32-add chain
-                                float4 tv[8];
+                            if (n == RING_SE) {        // full stage: 17 LDS.128 in flight, then the bare 64-add chain
+                                float4 tv[RING_SE / 4 + 1];
 #pragma unroll
-                                for (int u = 0; u < 8; ++u) tv[u] = b4[(e >> 2) + u];
+                                for (int u = 0; u <= RING_SE / 4; ++u) tv[u] = b4[u];
+                                // entries [mis, mis + 64): part of quad 0, quads 1..15, part of quad 16
+                                if (mis == 0) acc = __fadd_rn(acc, tv[0].x);
+                                if (mis <= 1) acc = __fadd_rn(acc, tv[0].y);
+                                if (mis <= 2) acc = __fadd_rn(acc, tv[0].z);
+                                acc = __fadd_rn(acc, tv[0].w);
 #pragma unroll
-                                for (int u = 0; u < 8; ++u) {
+                                for (int u = 1; u < RING_SE / 4; ++u) {
                                     acc = __fadd_rn(acc, tv[u].x); acc = __fadd_rn(acc, tv[u].y);
                                     acc = __fadd_rn(acc, tv[u].z); acc = __fadd_rn(acc, tv[u].w);
                                 }
-                            }
+                                if (mis >= 1) acc = __fadd_rn(acc, tv[RING_SE / 4].x);
+                                if (mis >= 2) acc = __fadd_rn(acc, tv[RING_SE / 4].y);
+                                if (mis >= 3) acc = __fadd_rn(acc, tv[RING_SE / 4].z);
+                            } else {
+                                const int end = mis + n;   // entries [mis, end) of this lane's row
+                                int e = 0;
+                                if (mis) {                 // first, partial quad
+                                    const float4 q = b4[0];
+                                    if (mis <= 1 && 1 < end) acc = __fadd_rn(acc, q.y);
+                                    if (mis <= 2 && 2 < end) acc = __fadd_rn(acc, q.z);
+                                    if (3 < end) acc = __fadd_rn(acc, q.w);
+                                    e = 4;
+                                }
 #pragma unroll 1
-                            for (; e + 4 <= end; e += 4) {
-                                const float4 q = b4[e >> 2];
-                                acc = __fadd_rn(acc, q.x); acc = __fadd_rn(acc, q.y);
-                                acc = __fadd_rn(acc, q.z); acc = __fadd_rn(acc, q.w);
-                            }
-                            if (e < end) {             // last, partial quad
-                                const float4 q = b4[e >> 2];
-                                acc = __fadd_rn(acc, q.x);
-                                if (e + 1 < end) acc = __fadd_rn(acc, q.y);
-                                if (e + 2 < end) acc = __fadd_rn(acc, q.z);
+                                for (; e + 4 <= end; e += 4) {
+                                    const float4 q = b4[e >> 2];
+                                    acc = __fadd_rn(acc, q.x); acc = __fadd_rn(acc, q.y);
+                                    acc = __fadd_rn(acc, q.z); acc = __fadd_rn(acc, q.w);
+                                }
+                                if (e < end) {             // last, partial quad
+                                    const float4 q = b4[e >> 2];
+                                    acc = __fadd_rn(acc, q.x);
+                                    if (e + 1 < end) acc = __fadd_rn(acc, q.y);
+                                    if (e + 2 < end) acc = __fadd_rn(acc, q.z);
+                                }
                             }
                         }
                         __syncwarp();
@@ -429,7 +439,7 @@ static int ilog2_ceil(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
 
 }  // namespace
 
-// workspace of fmb_fm_backward_update: the contribution staging buffers G and G2
+// workspace of fmb_fm_backward_update: the component-major contribution staging buffer (chain A rows, chain B rows)
 static int64_t bwd_npad(int64_t N) { return (N + 3) / 4 * 4 + 64; }   // row pitch of G: multiple of 4, slack for
                                                                        // the bulk copies' rounded-up tails
 FMB_API size_t fmb_bwd_workspace_bytes(int64_t N, int k) {
@@ -476,9 +486,7 @@ FMB_API int fmb_fm_backward_update_ex(const int32_t* sorted_keys, const int32_t*
     p.astep = -(lr / 0.1f);
     p.dbg = g_runs_dbg;
     p.Npad = bwd_npad(N);
-    const size_t gbytes = ((size_t)p.Npad * p.cu * 16 + 255) / 256 * 256;
     p.G = (float*)ws;
-    p.G2 = (float*)((char*)ws + gbytes);
     const bool two = use_fm2 && gvec;
     const unsigned grid1 = (unsigned)((N + 255) / 256);
     switch (p.cu) {
@@ -497,7 +505,8 @@ FMB_API int fmb_fm_backward_update_ex(const int32_t* sorted_keys, const int32_t*
     const int accs_n = (nv + 3) / 4 * 4;
     const int ring_comps = nv < 32 ? nv : 32;
     // ring (multiple of 128 B per warp) + NS mbarriers (8 B each) + accumulators + prefetched old row
-    const int warp_f = fmb_round_up(RING_NS * ring_comps * RING_SEP + 2 * RING_NS + accs_n + 32, 32);
+    const int stage_f = fmb_round_up(ring_comps * RING_SEP, 32);
+    const int warp_f = fmb_round_up(RING_NS * stage_f + 2 * RING_NS + accs_n + 32, 32);
     int wpb = 8;
     while (wpb > 1 && (size_t)wpb * warp_f * 4 > 56 * 1024) wpb >>= 1;
     const size_t sm = (size_t)wpb * warp_f * 4;
@@ -505,9 +514,33 @@ FMB_API int fmb_fm_backward_update_ex(const int32_t* sorted_keys, const int32_t*
     const int64_t nwarps = (N + 31) / 32;
     const unsigned grid = (unsigned)((nwarps + wpb - 1) / wpb);
     {
+        // tensor map of the staging buffer: [nv rows][Npad] fp32, box = [ring_comps rows][RING_SEP entries]
+        typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeTiled encode = nullptr;
         static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(fm_bwd_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-        fm_bwd_runs_kernel<<<grid, 32 * wpb, sm, stream>>>(p, wpb, warp_f, accs_n, ring_comps);
+        if (!attr) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+                fmb_set_error("fmb_fm_backward_update: cuTensorMapEncodeTiled not available from the driver");
+                return FMB_ERR_CUDA;
+            }
+            encode = (EncodeTiled)fn;
+            cudaFuncSetAttribute(fm_bwd_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr = true;
+        }
+        CUtensorMap gmap;
+        const cuuint64_t gdim[2] = {(cuuint64_t)p.Npad, (cuuint64_t)nv};
+        const cuuint64_t gstride[1] = {(cuuint64_t)p.Npad * 4};
+        const cuuint32_t box[2] = {(cuuint32_t)RING_SEP, (cuuint32_t)ring_comps};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult cr = encode(&gmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, p.G, gdim, gstride, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) { fmb_set_error("fmb_fm_backward_update: cuTensorMapEncodeTiled failed (%d)", (int)cr); return FMB_ERR_CUDA; }
+        fm_bwd_runs_kernel<<<grid, 32 * wpb, sm, stream>>>(gmap, p, wpb, warp_f, accs_n, ring_comps);
     }
     FMB_CHECK_LAUNCH("fm_bwd_runs_kernel");
     return FMB_OK;
