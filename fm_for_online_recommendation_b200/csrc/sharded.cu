@@ -28,6 +28,7 @@
 #include "fmb_common.cuh"
 #include "smem_sort.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
@@ -44,6 +45,8 @@ __global__ void transpose_ids_kernel(const int32_t* __restrict__ ids, int B, int
     out[i] = ids[(size_t)b * F + f];
 }
 
+constexpr int PF_U = 4;   // fields per round of the partial forward (39 Criteo fields = 3 rounds)
+
 struct PartialParams {
     const int32_t* idsT_all;
     const float* table;
@@ -59,20 +62,22 @@ __global__ void __launch_bounds__(256) shard_partial_forward_kernel(PartialParam
     const int32_t* col = p.idsT_all + (size_t)r * p.F * p.B + b;
     float S[4] = {0.f, 0.f, 0.f, 0.f}, Q[4] = {0.f, 0.f, 0.f, 0.f};
     float first = 0.f;
-    for (int f0 = 0; f0 < p.F; f0 += 4) {
-        int32_t lr[4];
-        bool own[4];
-        float4 v[4];
+    // PF_U fields per round: all their id loads are in flight together, then the row loads of the owned ones (the
+    // kernel is two dependent memory latencies per round and nothing else: 4 fields per round left it latency-bound)
+    for (int f0 = 0; f0 < p.F; f0 += PF_U) {
+        int32_t lr[PF_U];
+        bool own[PF_U];
+        float4 v[PF_U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < PF_U; ++u) {
             own[u] = false;
             if (f0 + u < p.F) own[u] = owned_by(__ldg(col + (size_t)(f0 + u) * p.B), p.G, p.glog, p.me, lr[u]);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < PF_U; ++u)
             if (own[u]) v[u] = *reinterpret_cast<const float4*>(p.table + (size_t)lr[u] * p.rowp + q * 4);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < PF_U; ++u) {
             if (!own[u]) continue;
             const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};  // x == 1 (all-ones feature values)
 #pragma unroll
@@ -279,20 +284,22 @@ __global__ void __launch_bounds__(256) shard_partial_forward_peers_kernel(Partia
     const int32_t* col = p.idsT_all + (size_t)r * p.F * p.B + b;
     float S[4] = {0.f, 0.f, 0.f, 0.f}, Q[4] = {0.f, 0.f, 0.f, 0.f};
     float first = 0.f;
-    for (int f0 = 0; f0 < p.F; f0 += 4) {
-        int32_t lr[4];
-        bool own[4];
-        float4 v[4];
+    // PF_U fields per round: all their id loads are in flight together, then the row loads of the owned ones (the
+    // kernel is two dependent memory latencies per round and nothing else: 4 fields per round left it latency-bound)
+    for (int f0 = 0; f0 < p.F; f0 += PF_U) {
+        int32_t lr[PF_U];
+        bool own[PF_U];
+        float4 v[PF_U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < PF_U; ++u) {
             own[u] = false;
             if (f0 + u < p.F) own[u] = owned_by(__ldg(col + (size_t)(f0 + u) * p.B), p.G, p.glog, p.me, lr[u]);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < PF_U; ++u)
             if (own[u]) v[u] = *reinterpret_cast<const float4*>(p.table + (size_t)lr[u] * p.rowp + q * 4);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < PF_U; ++u) {
             if (!own[u]) continue;
             const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};  // x == 1 (all-ones feature values)
 #pragma unroll
@@ -385,6 +392,90 @@ __global__ void __launch_bounds__(CMB_THREADS) shard_combine_peers_kernel(
     if (ch_publish >= 0) publish_epoch_last_block(x, ch_publish);
 }
 
+// Warp-per-sample partial forward (k <= 31).  A block stages the ids of 64 consecutive samples ([F][64], coalesced
+// rows of the transposed ids) in shared memory; a warp then takes one sample at a time: lane f tests the ownership
+// of field f (one ballot per 32 fields), the owned fields' rows are fetched with lane j reading component j (all
+// rows of a round in flight together), and the sums run over the owned fields in field order -- the same chain of
+// fp32 adds as shard_partial_forward_kernel, which spent its time in two dependent latencies per 4 fields.
+constexpr int PW_SB = 64;          // samples per block
+constexpr int PW_MAXF = 64;        // fields handled (two ballots)
+constexpr int PW_INFLIGHT = 8;     // owned rows of one sample fetched together
+constexpr int PW_NS = 4;           // samples interleaved per warp
+__global__ void __launch_bounds__(256) shard_partial_forward_warp_kernel(PartialParams p, PeerPtrs dst, int to_peers,
+                                                                        ExchSync x, int channel) {
+    __shared__ int32_t sid[PW_MAXF * (PW_SB + 1)];   // pitch 65: lane f reads row f, bank f + sb
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t total = (int64_t)p.G * p.B;
+    const int64_t bg0 = (int64_t)blockIdx.x * PW_SB;     // B % 64 == 0: a block never straddles two ranks' slabs
+    const int r = (int)(bg0 / p.B), b0 = (int)(bg0 - (int64_t)r * p.B);
+    if (bg0 < total) {
+        const int32_t* slab = p.idsT_all + (size_t)r * p.F * p.B + b0;
+        for (int i = threadIdx.x; i < p.F * PW_SB; i += 256) {
+            const int f = i / PW_SB, sb = i - f * PW_SB;
+            sid[f * (PW_SB + 1) + sb] = __ldg(slab + (size_t)f * p.B + sb);
+        }
+    }
+    __syncthreads();
+    if (bg0 < total) {
+        // PW_NS samples per warp iteration, interleaved, so that their row latencies overlap
+        for (int sb0 = warp * PW_NS; sb0 < PW_SB; sb0 += 8 * PW_NS) {
+            int32_t l0[PW_NS], l1[PW_NS];
+            unsigned m0[PW_NS], m1[PW_NS];
+            float S[PW_NS], Q[PW_NS];   // lane j < k: components; lane k: the first-order weight (in S)
+#pragma unroll
+            for (int a = 0; a < PW_NS; ++a) {
+                const int sb = sb0 + a;
+                l0[a] = 0; l1[a] = 0;
+                const bool o0 = lane < p.F && owned_by(sid[lane * (PW_SB + 1) + sb], p.G, p.glog, p.me, l0[a]);
+                const bool o1 = 32 + lane < p.F && owned_by(sid[(32 + lane) * (PW_SB + 1) + sb], p.G, p.glog, p.me, l1[a]);
+                m0[a] = __ballot_sync(0xffffffffu, o0);
+                m1[a] = __ballot_sync(0xffffffffu, o1);
+                S[a] = 0.f; Q[a] = 0.f;
+            }
+            bool more = true;
+            while (more) {   // one round: up to PW_INFLIGHT owned rows of EACH sample in flight, then the ordered sums
+                float e[PW_NS][PW_INFLIGHT];
+                int cnt[PW_NS];
+#pragma unroll
+                for (int a = 0; a < PW_NS; ++a) {
+                    cnt[a] = 0;
+#pragma unroll
+                    for (int u = 0; u < PW_INFLIGHT; ++u) {
+                        e[a][u] = 0.f;
+                        if (m0[a] | m1[a]) {   // warp-uniform
+                            int32_t row;
+                            if (m0[a]) { const int f = __ffs(m0[a]) - 1; m0[a] &= m0[a] - 1; row = __shfl_sync(0xffffffffu, l0[a], f); }
+                            else { const int f = __ffs(m1[a]) - 1; m1[a] &= m1[a] - 1; row = __shfl_sync(0xffffffffu, l1[a], f); }
+                            if (lane <= p.k) e[a][u] = p.table[(size_t)row * p.rowp + lane];
+                            cnt[a] = u + 1;
+                        }
+                    }
+                }
+                more = false;
+#pragma unroll
+                for (int a = 0; a < PW_NS; ++a) {
+#pragma unroll
+                    for (int u = 0; u < PW_INFLIGHT; ++u)
+                        if (u < cnt[a]) { S[a] = __fadd_rn(S[a], e[a][u]); Q[a] = __fadd_rn(Q[a], __fmul_rn(e[a][u], e[a][u])); }   // x == 1
+                    more |= (m0[a] | m1[a]) != 0;
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < PW_NS; ++a) {
+                const int sb = sb0 + a;
+                float* out = to_peers ? static_cast<float*>(dst.p[r]) + ((size_t)p.me * p.B + b0 + sb) * p.PW
+                                      : p.partial + (size_t)(bg0 + sb) * p.PW;
+                if (lane < p.kp4) {
+                    out[lane] = lane < p.k ? S[a] : 0.f;
+                    out[p.kp4 + lane] = lane < p.k ? Q[a] : 0.f;
+                }
+                if (lane == p.k) out[2 * p.kp4] = S[a];
+            }
+        }
+    }
+    if (channel >= 0) publish_epoch_last_block(x, channel);
+}
+
 // rows [me*B, (me+1)*B) of ctx_all, copied from the local ctx [B][CW] into every rank's ctx_all (16-byte chunks)
 __global__ void ctx_bcast_peers_kernel(const float4* __restrict__ ctx, int64_t n4, int64_t off4, int G, PeerPtrs dst) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -425,6 +516,15 @@ __global__ void shard_signal_kernel(PeerPtrs peer_flags, uint32_t* flags_local, 
     }
 }
 
+// warp-per-sample partial forward instead of the lane-per-chunk kernel (measured: 38 vs 55 us at
+// G = 8, 33 vs 35 us at G = 2, cold L2, with four samples interleaved per warp); FMB_SHARD_WARP_PARTIAL=0/1 forces it
+static bool fmb_shard_use_warp_partial(int G, int B, int F, int k) {
+    if (!(k <= 31 && F <= PW_MAXF && B % PW_SB == 0)) return false;
+    static int forced = -2;
+    if (forced == -2) { const char* e = getenv("FMB_SHARD_WARP_PARTIAL"); forced = e ? (e[0] != '0') : -1; }
+    return forced >= 0 ? forced != 0 : G >= 2;
+}
+
 static int ilog2_exact(int x) { int l = 0; while ((1 << l) < x) ++l; return (1 << l) == x ? l : -1; }
 static int ilog2_ceil(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
 
@@ -454,7 +554,13 @@ FMB_API int fmb_shard_partial_forward(const int32_t* idsT_all, const float* tabl
     p.ql_log = ilog2_ceil(p.cu); p.PW = fmb_shard_pw(k); p.partial = partial;
     const int spb = 256 >> p.ql_log;
     const int64_t n = (int64_t)G * B;
-    shard_partial_forward_kernel<<<(unsigned)((n + spb - 1) / spb), 256, 0, stream>>>(p);
+    if (fmb_shard_use_warp_partial(G, B, F, k)) {   // warp-per-sample kernel
+        PeerPtrs none = {};
+        ExchSync nox = {};
+        shard_partial_forward_warp_kernel<<<(unsigned)(n / PW_SB), 256, 0, stream>>>(p, none, 0, nox, -1);
+    } else {
+        shard_partial_forward_kernel<<<(unsigned)((n + spb - 1) / spb), 256, 0, stream>>>(p);
+    }
     FMB_CHECK_LAUNCH("shard_partial_forward_kernel");
     return FMB_OK;
 }
@@ -549,7 +655,10 @@ FMB_API int fmb_shard_partial_forward_peers(const int32_t* idsT_all, const float
     p.ql_log = ilog2_ceil(p.cu); p.PW = fmb_shard_pw(k); p.partial = nullptr;
     const int spb = 256 >> p.ql_log;
     const int64_t n = (int64_t)G * B;
-    shard_partial_forward_peers_kernel<<<(unsigned)((n + spb - 1) / spb), 256, 0, stream>>>(p, pp, x, publish_channel);
+    if (fmb_shard_use_warp_partial(G, B, F, k))
+        shard_partial_forward_warp_kernel<<<(unsigned)(n / PW_SB), 256, 0, stream>>>(p, pp, 1, x, publish_channel);
+    else
+        shard_partial_forward_peers_kernel<<<(unsigned)((n + spb - 1) / spb), 256, 0, stream>>>(p, pp, x, publish_channel);
     FMB_CHECK_LAUNCH("shard_partial_forward_peers_kernel");
     return FMB_OK;
 }

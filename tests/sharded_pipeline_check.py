@@ -30,7 +30,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
-    B, steps = 96, 7
+    B, steps = 128, 7
     rng = np.random.RandomState(100 + rank)
     batches = []
     for _ in range(steps):

@@ -154,7 +154,7 @@ def test_sharded_decomposition_world2_gloo():
 
 # ---------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
-@pytest.mark.parametrize("G,B", [(1, 64), (2, 48), (4, 33), (8, 16), (3, 20)])
+@pytest.mark.parametrize("G,B", [(1, 64), (2, 48), (4, 33), (8, 16), (3, 20), (2, 64), (8, 128), (3, 64)])  # B % 64 == 0: warp-per-sample partial forward
 def test_cuda_ranks_emulated_bit_exact(G, B):
     steps = 3
     orc, (V0, w0, b0), batches, want_losses = _oracle(G, G * B, steps)
