@@ -12,6 +12,7 @@ configuration.  `ShardedFM` is not a reference class, it is the engine `bench.py
 import ctypes as C
 import json
 import os
+import sys
 import time
 
 import numpy as np
@@ -456,6 +457,21 @@ def bench_main(args, sizes, config):
     pipelined = os.environ.get("FMB_SHARD_PIPELINE", "1") != "0"
     # exchanges: "peers" = stores into peer-mapped symmetric memory + epoch flags (default), "nccl" = collectives
     exchange = os.environ.get("FMB_SHARD_EXCHANGE", "peers") if pipelined else "nccl"
+    if exchange == "peers":
+        # mapping the peers' buffers needs symmetric-memory support on this box; every rank must take the same path,
+        # so the ranks agree (all-reduce of a success flag) and fall back to the NCCL exchange together, loudly
+        ok = 1
+        try:
+            model._peer_setup(B)
+        except Exception as exc:  # noqa: BLE001 - any failure means "no peer mapping here"
+            ok = 0
+            print(f"[rank {rank}] symmetric-memory mapping failed ({type(exc).__name__}: {exc}); "
+                  "using the NCCL exchange", file=sys.stderr, flush=True)
+        flag = torch.tensor([ok], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            exchange = "nccl"
+            model._peer = None
     prepare = model.prepare_peers if exchange == "peers" else model.prepare
     if pipelined:
         # step i trains on batch i while batch i+1's ids are exchanged and sorted (update_embedding_pipelined)
@@ -559,6 +575,5 @@ def bench_main(args, sizes, config):
     # its work and rank 0 has printed, so a plain exit is safe.
     torch.cuda.synchronize()
     dist.barrier()
-    import sys
     sys.stdout.flush()
     os._exit(0)
