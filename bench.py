@@ -303,7 +303,7 @@ def run_ours(args):
     # DRAM traffic of the dominant phase's kernels from the last `ncu --set full` capture (profiles/), per launch
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_final_dram_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1_final2_dram_traffic.json")) as f:
             tr = json.load(f)
         pick = ("fm_forward",) if dom == "fm_forward" else ("fm_bwd_entry", "fm_bwd_runs")
         traffic = int(sum(v["dram_read_bytes"] + v["dram_write_bytes"] for kname, v in tr.items()
@@ -330,7 +330,7 @@ def run_ours(args):
         "gpu_launches": int(launches), "step_graphs_cached": int(lib.fmb_session_graph_count(sess)),
         "roofline": {"bound": "hbm", "kernel": dom_kernels, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
-                     "traffic_source": "profiles/r1_final_dram_traffic.json (ncu --set full, cold cache, B=8192)",
+                     "traffic_source": "profiles/r1_final2_dram_traffic.json (ncu --set full, cold cache, B=8192)",
                      "algorithmic_bytes_per_launch": alg_bytes[dom],
                      "phase_ms": phases,
                      "whole_step_GBps": step_bytes / (ms / K * 1e-3) / 1e9},
