@@ -40,6 +40,33 @@
  * Verified bit-exact against torch.sum on every golden fixture (tests/test_oracle_vs_golden.py).
  * This is the single reduction order used for Sum_f first[b,f], Sum_j bi[b,j], Sum_j x_l[b,j],
  * loss.mean(), the bias gradient and Sum(alpha). */
+/* ------------------------------------------------------------------ */
+/* host threads for the bench's CPU baseline                            */
+/* ------------------------------------------------------------------ */
+/* ORC_THREADS (default 1) host threads share the batch step: samples are independent in the forward pass and in
+ * the loss, fields are independent in the backward pass (see orc_fm_backward_update).  The arithmetic and the
+ * order of every sample / row are untouched, so results do not depend on the thread count (tests run both). */
+#include <pthread.h>
+typedef void (*orc_body)(int tid, int nthreads, void* ctx);
+typedef struct { orc_body fn; void* ctx; int tid, nthreads; } orc_task;
+static void* orc_tramp(void* a) { orc_task* t = (orc_task*)a; t->fn(t->tid, t->nthreads, t->ctx); return NULL; }
+static int orc_threads(void) {
+    const char* e = getenv("ORC_THREADS");
+    int n = e ? atoi(e) : 1;
+    return n < 1 ? 1 : (n > 256 ? 256 : n);
+}
+static void orc_parallel(int work_items, orc_body fn, void* ctx) {
+    int n = orc_threads();
+    if (work_items < 256 && work_items < 8 * n) n = 1;   /* tiny problems: not worth the thread start-up */
+    if (n == 1) { fn(0, 1, ctx); return; }
+    pthread_t th[256];
+    orc_task tk[256];
+    for (int t = 0; t < n; ++t) { tk[t].fn = fn; tk[t].ctx = ctx; tk[t].tid = t; tk[t].nthreads = n; }
+    for (int t = 1; t < n; ++t) pthread_create(&th[t], NULL, orc_tramp, &tk[t]);
+    fn(0, n, ctx);
+    for (int t = 1; t < n; ++t) pthread_join(th[t], NULL);
+}
+
 static int ceil_log2_i(int64_t x) {
     int r = 0;
     while (((int64_t)1 << r) < x) ++r;
@@ -122,14 +149,21 @@ static size_t mlp_c_off(const orc_model* m, int l) { return mlp_w_off(m, l) + (s
 API int64_t orc_mlp_numel(const orc_model* m) { return m->L > 0 ? (int64_t)mlp_w_off(m, m->L) : 0; }
 
 /* A1-A3: fm_adam.py:34-54, deepfm_adam.py:46-77 */
-API void orc_fm_forward(const orc_model* m, const int32_t* ids, const float* xv, int B,
-                        float* first, float* S, float* bi, float* sum_first, float* sum_bi, float* z_fm) {
+typedef struct {
+    const orc_model* m; const int32_t* ids; const float* xv; int B;
+    float *first, *S, *bi, *sum_first, *sum_bi, *z_fm;
+} fwd_ctx;
+static void fm_forward_slice(int tid, int nthreads, void* vctx) {
+    const fwd_ctx* c = (const fwd_ctx*)vctx;
+    const orc_model* m = c->m; const int32_t* ids = c->ids; const float* xv = c->xv; const int B = c->B;
+    float *first = c->first, *S = c->S, *bi = c->bi, *sum_first = c->sum_first, *sum_bi = c->sum_bi, *z_fm = c->z_fm;
+    const int b_lo = (int)((int64_t)B * tid / nthreads), b_hi = (int)((int64_t)B * (tid + 1) / nthreads);
     const int F = m->F, k = m->k;
     float* Sj = (float*)malloc(sizeof(float) * k);
     float* Qj = (float*)malloc(sizeof(float) * k);
     float* fo = (float*)malloc(sizeof(float) * F);
     float* bj = (float*)malloc(sizeof(float) * k);
-    for (int b = 0; b < B; ++b) {
+    for (int b = b_lo; b < b_hi; ++b) {
         for (int j = 0; j < k; ++j) { Sj[j] = 0.f; Qj[j] = 0.f; }
         const int G = m->shard_G > 1 ? m->shard_G : 1;
         float sf_sharded = 0.f;
@@ -171,6 +205,12 @@ API void orc_fm_forward(const orc_model* m, const int32_t* ids, const float* xv,
         if (z_fm) z_fm[b] = (sf + sb) + m->bias[0]; /* :75 */
     }
     free(Sj); free(Qj); free(fo); free(bj);
+}
+
+API void orc_fm_forward(const orc_model* m, const int32_t* ids, const float* xv, int B,
+                        float* first, float* S, float* bi, float* sum_first, float* sum_bi, float* z_fm) {
+    fwd_ctx c = {m, ids, xv, B, first, S, bi, sum_first, sum_bi, z_fm};
+    orc_parallel(B, fm_forward_slice, &c);
 }
 
 /* A4: deepfm_adam.py:82-86.  act is [L][B][H]; head[l*B+b] = Sum_j act[l][b][j] (ATen row order). */
@@ -244,10 +284,14 @@ API void orc_mlp_backward(const orc_model* m, const float* bi, const float* act,
  * kind 0: loss(z)           delta = ((sigmoid(z) - y) / B)
  * kind 1: loss(sigmoid(z))  delta = (((sigmoid(p) - y) / B) * (1 - p)) * p,  p = sigmoid(z)
  * returns mean loss (ATen row order). */
-API float orc_loss_delta(int kind, const float* z, const float* y, int B, float* delta) {
-    float* lv = (float*)malloc(sizeof(float) * B);
+typedef struct { int kind; const float* z; const float* y; int B; float* delta; float* lv; } loss_ctx;
+static void loss_slice(int tid, int nthreads, void* vctx) {
+    const loss_ctx* c = (const loss_ctx*)vctx;
+    const int kind = c->kind, B = c->B;
+    const float* z = c->z; const float* y = c->y; float* delta = c->delta; float* lv = c->lv;
     const float fB = (float)B;
-    for (int b = 0; b < B; ++b) {
+    const int b_lo = (int)((int64_t)B * tid / nthreads), b_hi = (int)((int64_t)B * (tid + 1) / nthreads);
+    for (int b = b_lo; b < b_hi; ++b) {
         float in = z[b], p = 0.f;
         if (kind == 1) { p = orc_sigmoidf(z[b]); in = p; }
         /* (1 - y) * x - log_sigmoid(x),  log_sigmoid(x) = min(x,0) - log1p(exp(-|x|)) */
@@ -257,6 +301,12 @@ API float orc_loss_delta(int kind, const float* z, const float* y, int B, float*
         if (kind == 1) d = (d * (1.0f - p)) * p; /* sigmoid_backward: grad * (1 - out) * out */
         delta[b] = d;
     }
+}
+API float orc_loss_delta(int kind, const float* z, const float* y, int B, float* delta) {
+    float* lv = (float*)malloc(sizeof(float) * B);
+    const float fB = (float)B;
+    loss_ctx c = {kind, z, y, B, delta, lv};
+    orc_parallel(B, loss_slice, &c);
     float loss = orc_sum_aten(lv, B) / fB;
     free(lv);
     return loss;
@@ -281,47 +331,95 @@ API void orc_update_dense(float* p, const float* g, int64_t n, float lr, int mod
 /* A6 sparse part: embedding_dense_backward sums duplicate rows in sample order, then one step per row.
  * gs[b]: gradient on z wrt the FM logit (first-order path, and the Sum_j bi path when use_fm2).
  * gvec[b*k+j]: gradient on bi coming from the MLP (second evaluation of second_order, deepfm_adam.py:81). */
-API void orc_fm_backward_update(orc_model* m, const int32_t* ids, const float* xv, int B, const float* S,
-                                const float* gs, int use_fm2, const float* gvec) {
+typedef struct {
+    orc_model* m; const int32_t* ids; const float* xv; int B; const float* S; const float* gs; int use_fm2;
+    const float* gvec; int32_t* tl; size_t* ntf; int by_field;
+} bwd_ctx;
+/* contribution of entry (b, f) to the gradient sums of its row */
+static inline void bwd_entry(const bwd_ctx* c, int b, int f, int32_t* tl, size_t* nt) {
+    orc_model* m = c->m;
     const int F = m->F, k = m->k, kp = k + 1;
-    int32_t* tl = (int32_t*)malloc(sizeof(int32_t) * (size_t)B * F);
-    size_t nt = 0;
-    for (int b = 0; b < B; ++b)
-        for (int f = 0; f < F; ++f) {
-            const int32_t r = ids[(size_t)b * F + f];
-            const float x = xv[(size_t)b * F + f];
-            if (!m->touched[r]) { m->touched[r] = 1; tl[nt++] = r; }
-            const float* v = m->V + (size_t)r * k;
-            float* ga = m->gA + (size_t)r * kp;
-            float* gb = m->gB + (size_t)r * kp;
-            ga[k] = ga[k] + (gs[b] * x);
-            for (int j = 0; j < k; ++j) {
-                float e = v[j] * x;
-                float s = S[(size_t)b * k + j];
-                if (use_fm2) {
-                    float ge = (gs[b] * s) - (gs[b] * e);
-                    ga[j] = ga[j] + (ge * x);
-                }
-                if (gvec) {
-                    float gv = gvec[(size_t)b * k + j];
-                    float ge = (gv * s) - (gv * e);
-                    gb[j] = gb[j] + (ge * x);
-                }
-            }
+    const int32_t r = c->ids[(size_t)b * F + f];
+    const float x = c->xv[(size_t)b * F + f];
+    if (!m->touched[r]) { m->touched[r] = 1; tl[(*nt)++] = r; }
+    const float* v = m->V + (size_t)r * k;
+    float* ga = m->gA + (size_t)r * kp;
+    float* gb = m->gB + (size_t)r * kp;
+    ga[k] = ga[k] + (c->gs[b] * x);
+    for (int j = 0; j < k; ++j) {
+        float e = v[j] * x;
+        float s = c->S[(size_t)b * k + j];
+        if (c->use_fm2) {
+            float ge = (c->gs[b] * s) - (c->gs[b] * e);
+            ga[j] = ga[j] + (ge * x);
         }
+        if (c->gvec) {
+            float gv = c->gvec[(size_t)b * k + j];
+            float ge = (gv * s) - (gv * e);
+            gb[j] = gb[j] + (ge * x);
+        }
+    }
+}
+static void bwd_rows_update(const bwd_ctx* c, const int32_t* tl, size_t nt) {
+    orc_model* m = c->m;
+    const int k = m->k, kp = k + 1;
     for (size_t t = 0; t < nt; ++t) {
         const int32_t r = tl[t];
         float* v = m->V + (size_t)r * k;
         float* ga = m->gA + (size_t)r * kp;
         float* gb = m->gB + (size_t)r * kp;
         for (int j = 0; j < k; ++j) {
-            float g = (use_fm2 && gvec) ? ga[j] + gb[j] : (gvec ? gb[j] : ga[j]);
+            float g = (c->use_fm2 && c->gvec) ? ga[j] + gb[j] : (c->gvec ? gb[j] : ga[j]);
             v[j] = upd(v[j], g, m->lr, m->update_mode);
             ga[j] = 0.f; gb[j] = 0.f;
         }
         m->w1[r] = upd(m->w1[r], ga[k], m->lr, m->update_mode);
         ga[k] = 0.f;
         m->touched[r] = 0;
+    }
+}
+/* thread t takes fields t, t + T, ...: accumulate (samples ascending), then update that field's touched rows */
+static void bwd_fields(int tid, int nthreads, void* vctx) {
+    const bwd_ctx* c = (const bwd_ctx*)vctx;
+    const int F = c->m->F, B = c->B;
+    for (int f = tid; f < F; f += nthreads) {
+        int32_t* tlf = c->tl + (size_t)f * B;
+        size_t nt = 0;
+        for (int b = 0; b < B; ++b) bwd_entry(c, b, f, tlf, &nt);
+        bwd_rows_update(c, tlf, nt);
+    }
+}
+API void orc_fm_backward_update(orc_model* m, const int32_t* ids, const float* xv, int B, const float* S,
+                                const float* gs, int use_fm2, const float* gvec) {
+    const int F = m->F;
+    int32_t* tl = (int32_t*)malloc(sizeof(int32_t) * (size_t)B * F);
+    bwd_ctx c = {m, ids, xv, B, S, gs, use_fm2, gvec, tl, NULL, 0};
+    /* A row's contributions must be added in sample order.  The reference walk is b-major, f-minor; when the rows
+     * of different fields are disjoint (global id = field offset + local id), walking field by field with the samples
+     * ascending inside gives every row the same order, and the fields become independent (one thread each).  That
+     * is only used when the batch's id ranges are disjoint and ordered field by field (checked here). */
+    int by_field = orc_threads() > 1 && B >= 256;
+    if (by_field) {
+        int32_t* lo = (int32_t*)malloc(sizeof(int32_t) * F);
+        int32_t* hi = (int32_t*)malloc(sizeof(int32_t) * F);
+        for (int f = 0; f < F; ++f) { lo[f] = ids[f]; hi[f] = ids[f]; }
+        for (int b = 1; b < B; ++b)
+            for (int f = 0; f < F; ++f) {
+                const int32_t r = ids[(size_t)b * F + f];
+                if (r < lo[f]) lo[f] = r;
+                if (r > hi[f]) hi[f] = r;
+            }
+        for (int f = 0; f + 1 < F; ++f)
+            if (hi[f] >= lo[f + 1]) by_field = 0;
+        free(lo); free(hi);
+    }
+    if (by_field) {
+        orc_parallel(B, bwd_fields, &c);
+    } else {
+        size_t nt = 0;
+        for (int b = 0; b < B; ++b)
+            for (int f = 0; f < F; ++f) bwd_entry(&c, b, f, tl, &nt);
+        bwd_rows_update(&c, tl, nt);
     }
     free(tl);
 }

@@ -132,3 +132,28 @@ def test_sum_aten_matches_torch_sum_bitwise():
         want = torch.sum(torch.from_numpy(x)).item()
         got = lib().orc_sum_aten(x.ctypes.data_as(C.POINTER(C.c_float)), n)
         assert np.float32(got) == np.float32(want), n
+
+
+def test_oracle_host_threads_do_not_change_results():
+    """oracle/fm_oracle.c splits the batch step over ORC_THREADS host threads (samples in the forward pass, fields in
+    the backward pass) for the bench's CPU baseline: every bit of the result must be the same as with one thread."""
+    import os
+    from oracle.deep import OracleDeep
+    sizes = [7, 300, 4, 1000, 50, 9]
+    outs = []
+    for threads in ("1", "4"):
+        os.environ["ORC_THREADS"] = threads
+        orc = OracleDeep("DeepFMAdam", sizes, 6, 2, 8, lr=0.01, seed=3)
+        rng = np.random.RandomState(5)
+        off = np.concatenate([[0], np.cumsum(sizes)])[:-1]
+        losses = []
+        for _ in range(3):
+            Xi = np.stack([rng.randint(0, fs, size=600) for fs in sizes], 1)
+            Xv = rng.uniform(0.5, 1.5, size=Xi.shape).astype(np.float32)
+            Y = (rng.uniform(size=600) < 0.4).astype(np.float32)
+            losses.append(orc.update_embedding(Xi, Xv, Y))
+        outs.append((np.array(losses, np.float32), orc.V.copy(), orc.w1.copy(), orc.bias.copy()))
+        del off
+    os.environ["ORC_THREADS"] = "1"
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
