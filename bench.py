@@ -110,7 +110,7 @@ def cpu_port_rate(sizes, k, B, budget_s, seed=0, threads=None):
         Xi, Y = batches[n % len(batches)]
         orc.update_embedding(Xi, ones, Y)
         n += 1
-        if time.perf_counter() - t0 > budget_s or n >= 200:
+        if time.perf_counter() - t0 > budget_s or n >= 20000:
             break
     dt = time.perf_counter() - t0
     return n * B / dt, n, dt
