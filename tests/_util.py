@@ -40,3 +40,28 @@ def synth(feature_sizes, n, seed, real_xv=False, zipf=False):
     Xv = rng.uniform(0.25, 2.0, size=Xi.shape).astype(np.float32) if real_xv else np.ones(Xi.shape, np.float32)
     Y = (rng.uniform(size=n) < 0.3).astype(np.float32)
     return Xi.astype(np.int64), Xv, Y
+
+
+def auc(scores, labels):
+    """exact ROC AUC (rank statistic with average ranks for ties), labels in {0,1} or {-1,+1}."""
+    s = np.asarray(scores, np.float64).reshape(-1)
+    y = np.asarray(labels).reshape(-1) > 0
+    order = np.argsort(s, kind="stable")
+    ranks = np.empty(len(s), np.float64)
+    ss = s[order]
+    i = 0
+    while i < len(ss):
+        j = i
+        while j + 1 < len(ss) and ss[j + 1] == ss[i]:
+            j += 1
+        ranks[order[i:j + 1]] = 0.5 * (i + j) + 1.0
+        i = j + 1
+    npos, nneg = int(y.sum()), int((~y).sum())
+    if npos == 0 or nneg == 0:
+        return float("nan")
+    return float((ranks[y].sum() - npos * (npos + 1) / 2.0) / (npos * nneg))
+
+
+def rmse(pred, target):
+    d = np.asarray(pred, np.float64).reshape(-1) - np.asarray(target, np.float64).reshape(-1)
+    return float(np.sqrt(np.mean(d * d)))

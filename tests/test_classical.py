@@ -9,7 +9,7 @@ import io
 import numpy as np
 import pytest
 
-from _util import GOLDEN
+from _util import GOLDEN, auc, rmse
 from oracle import classical as oc
 
 CASES = ["codrna_cls_m40", "onehot_reg_m5", "onehot_cls_m3"]
@@ -36,6 +36,25 @@ def test_oracle_matches_reference(name):
             np.testing.assert_allclose(mine @ mine.T, ref @ ref.T, rtol=1e-9, atol=1e-12)
 
 
+def metrics_match(pred, ref, y, task):
+    """north_star: AUC and RMSE identical to 4 decimal places (online prediction streams)."""
+    if task == "reg":
+        assert round(rmse(pred, y), 4) == round(rmse(ref, y), 4)
+    else:
+        assert round(auc(pred, y), 4) == round(auc(ref, y), 4)
+        assert np.mean(np.sign(pred) == np.sign(y)) == np.mean(np.sign(ref) == np.sign(y))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_auc_rmse_identical_to_4_decimals(name):
+    X, y, task, eta, m = case(name)
+    p, _ = oc.fm_ftrl(X, y, task, eta, m, G[name + "_ftrl_w1_init"], G[name + "_ftrl_W2_init"])
+    metrics_match(p, G[name + "_ftrl_pred"], y, task)
+    for tag, van in (("ccfm", False), ("vanila", True)):
+        p, _ = oc.sftrl(X, y, task, eta, m, vanila=van)
+        metrics_match(p, G[f"{name}_{tag}_pred"], y, task)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", CASES)
 def test_cuda_matches_oracle_and_reference(name):
@@ -48,6 +67,7 @@ def test_cuda_matches_oracle_and_reference(name):
         mdl = pkg.FM_FTRL(T(X), T(y), task, eta, m)
         p, real, _ = mdl.online_learning()
     np.testing.assert_allclose(p, G[name + "_ftrl_pred"], rtol=1e-9, atol=1e-9)
+    metrics_match(np.asarray(p), G[name + "_ftrl_pred"], y, task)
     np.testing.assert_allclose(mdl.W2.cpu().numpy(), G[name + "_ftrl_W2"], rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(mdl.w1.cpu().numpy(), G[name + "_ftrl_w1"], rtol=1e-9, atol=1e-12)
     assert np.array_equal(real, y)
@@ -58,6 +78,7 @@ def test_cuda_matches_oracle_and_reference(name):
         po, st = oc.sftrl(X, y, task, eta, m, vanila=van)
         np.testing.assert_allclose(p, po, rtol=1e-9, atol=1e-9)
         np.testing.assert_allclose(p, G[f"{name}_{tag}_pred"], rtol=1e-9, atol=1e-9)
+        metrics_match(np.asarray(p), G[f"{name}_{tag}_pred"], y, task)
         assert [mdl.row_count_p, mdl.row_count_n] == G[f"{name}_{tag}_rc"].tolist()
         for key, mine in (("BTP", mdl.BT_P), ("BTN", mdl.BT_N)):
             ref = G[f"{name}_{tag}_{key}"]

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from _util import GOLDEN_DEEP, load_golden, rel_err, synth
+from _util import GOLDEN_DEEP, auc, load_golden, rel_err, rmse, synth
 from test_gpu_fm import _pair, assert_same_params, pull, push
 
 pytestmark = pytest.mark.gpu
@@ -104,6 +104,15 @@ def test_golden_replay_against_reference_outputs(name):
     p = pull(m)
     assert rel_err(p["V"], g["after_fit_V"]) <= 1e-5 and rel_err(p["w1"], g["after_fit_w1"]) <= 1e-5
     assert rel_err(p["bias"], g["after_fit_bias"]) <= 1e-5
+    # north_star: AUC and RMSE identical to 4 decimal places (scores after the golden training trajectory)
+    f = m.forward(g["Xi"].tolist(), g["Xv"].tolist())
+    z = (f[0] if isinstance(f, tuple) else f).cpu().numpy().astype(np.float64)
+    zr, y = np.asarray(g["fwd1"], np.float64), np.asarray(g["Y"]).reshape(-1)
+    if len(np.unique(y > 0)) == 2:
+        assert round(auc(z, y), 4) == round(auc(zr, y), 4)
+    sig = lambda t: 1.0 / (1.0 + np.exp(-t))
+    pz, pr = (z, zr) if isinstance(f, tuple) else (sig(z), sig(zr))
+    assert round(rmse(pz, y), 4) == round(rmse(pr, y), 4)
     if o.L:
         assert rel_err(p["mlp"], g["after_fit_mlp"]) <= 1e-5
     if "on_Xi" in g:

@@ -12,7 +12,7 @@ batch-size-dependent) and MKL's GEMM order, hence <= 1e-5 rather than 0 on those
 import numpy as np
 import pytest
 
-from _util import GOLDEN_DEEP, load_golden, rel_err
+from _util import GOLDEN_DEEP, auc, load_golden, rel_err, rmse
 from oracle.deep import OracleDeep, lib
 
 TOL = 1e-5
@@ -157,3 +157,26 @@ def test_oracle_host_threads_do_not_change_results():
     os.environ["ORC_THREADS"] = "1"
     for a, b in zip(outs[0], outs[1]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_DEEP))
+def test_auc_and_rmse_identical_to_4_decimals(name):
+    """BASELINE.json north_star: "AUC and RMSE must be identical to 4 decimal places".  After the golden training
+    trajectory (update_embedding steps, then fit steps) the oracle's scores on the evaluation batch give the same
+    AUC and the same RMSE (of sigmoid(z) against the 0/1 labels) as the reference's recorded scores."""
+    m, g = make(name)
+    load(m, g, "init_")
+    for s in range(int(g["steps"])):
+        m.update_embedding(g["ue_Xi"][s], g["ue_Xv"][s], g["ue_Y"][s])
+    for s in range(int(g["steps"])):
+        m.fit(g["fit_Xi"][s], g["fit_Xv"][s], g["fit_Y"][s])
+    f = m.forward(g["Xi"], g["Xv"])
+    z = np.asarray(f[0] if isinstance(f, tuple) else f, np.float64)
+    zr = np.asarray(g["fwd1"], np.float64)
+    y = np.asarray(g["Y"]).reshape(-1)
+    if len(np.unique(y > 0)) == 2:
+        assert round(auc(z, y), 4) == round(auc(zr, y), 4)
+    sig = lambda t: 1.0 / (1.0 + np.exp(-t))
+    # ONN forward already returns probabilities; the Adam family returns logits
+    pz, pr = (z, zr) if isinstance(f, tuple) else (sig(z), sig(zr))
+    assert round(rmse(pz, y), 4) == round(rmse(pr, y), 4)
