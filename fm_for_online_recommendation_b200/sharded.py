@@ -369,8 +369,11 @@ class ShardedFM:
         for parity in (0, 1):
             self._slot = parity
             g = torch.cuda.CUDAGraph()
+            l0 = self.launches
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 loss = self.update_embedding_peers(self._g_y, self._g_ids, loss_kind)
+            self._graph_launches = self.launches - l0   # kernels of one replay (capturing launches nothing)
+            self.launches = l0
             self._pgraphs.append(g)
             self._pg_loss.append(loss)
         self._slot = 0
@@ -390,8 +393,11 @@ class ShardedFM:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
+        l0 = self.launches
         with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
             self._g_loss = self.update_embedding(self._g_ids, self._g_y, loss_kind)
+        self._graph_launches = self.launches - l0   # kernels of one replay (capturing launches nothing)
+        self.launches = l0
         return self
 
     def step_graphed(self, ids, y):
@@ -399,6 +405,7 @@ class ShardedFM:
         self._g_ids.copy_(ids, non_blocking=True)
         self._g_y.copy_(y, non_blocking=True)
         self._graph.replay()
+        self.launches += self._graph_launches
         return self._g_loss
 
     def capture_pipelined(self, ids, y, loss_kind=0):
@@ -418,8 +425,11 @@ class ShardedFM:
         for parity in (0, 1):
             self._slot = parity
             g = torch.cuda.CUDAGraph()
+            l0 = self.launches
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 loss = self.update_embedding_pipelined(self._g_y, self._g_ids, loss_kind)
+            self._graph_launches = self.launches - l0   # kernels of one replay (capturing launches nothing)
+            self.launches = l0
             self._pgraphs.append(g)
             self._pg_loss.append(loss)
         self._slot = 0
@@ -431,6 +441,7 @@ class ShardedFM:
         self._g_ids.copy_(ids_next, non_blocking=True)
         p = self._slot
         self._pgraphs[p].replay()
+        self.launches += self._graph_launches
         self._slot = 1 - p
         return self._pg_loss[p]
 
