@@ -72,7 +72,6 @@ _SIGS = {
                                                   C.c_int, vp]),
     "fmb_shard_combine_peers": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp,
                                           C.c_int, C.c_int, vp]),
-    "fmb_shard_ctx_bcast_peers": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "fmb_shard_signal": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "fmb_online_deep_run": (C.c_int, [C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp,
                                       vp, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp, vp]),

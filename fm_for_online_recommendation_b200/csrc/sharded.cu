@@ -476,14 +476,6 @@ __global__ void __launch_bounds__(256) shard_partial_forward_warp_kernel(Partial
     if (channel >= 0) publish_epoch_last_block(x, channel);
 }
 
-// rows [me*B, (me+1)*B) of ctx_all, copied from the local ctx [B][CW] into every rank's ctx_all (16-byte chunks)
-__global__ void ctx_bcast_peers_kernel(const float4* __restrict__ ctx, int64_t n4, int64_t off4, int G, PeerPtrs dst) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n4) return;
-    const float4 v = ctx[i];
-    for (int r = 0; r < G; ++r) static_cast<float4*>(dst.p[r])[off4 + i] = v;
-}
-
 // mode bit 0: publish my next epoch of `channel` to every peer's flag word [channel][me];
 // mode bit 1: wait until every peer's epoch of `channel` has reached mine.
 __global__ void shard_signal_kernel(PeerPtrs peer_flags, uint32_t* flags_local, uint32_t* epoch_local, int channel, int G,
@@ -680,19 +672,6 @@ FMB_API int fmb_shard_combine_peers(const float* recv, const float* bias, const 
         recv, bias, y, G, me, B, k, fmb_round_up(k, 4), fmb_shard_pw(k), fmb_shard_cw(k), loss_kind, pp, ctx_local, x,
         wait_channel, publish_channel);
     FMB_CHECK_LAUNCH("shard_combine_peers_kernel");
-    return FMB_OK;
-}
-
-// step 5 without a collective: the local ctx [B][CW] becomes rows [me*B, (me+1)*B) of every rank's ctx_all
-FMB_API int fmb_shard_ctx_bcast_peers(const float* ctx, int G, int me, int B, int k, void* const* dst_ctx_all,
-                                      cudaStream_t stream) {
-    FMB_CHECK_ARG(ctx && B > 0 && k > 0 && me >= 0 && me < G, "fmb_shard_ctx_bcast_peers: bad arguments");
-    PeerPtrs pp;
-    if (int rc = fill_peers(pp, dst_ctx_all, G, "fmb_shard_ctx_bcast_peers")) return rc;
-    const int64_t n4 = (int64_t)B * fmb_shard_cw(k) / 4;
-    ctx_bcast_peers_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(ctx), n4,
-                                                                           (int64_t)me * n4, G, pp);
-    FMB_CHECK_LAUNCH("ctx_bcast_peers_kernel");
     return FMB_OK;
 }
 

@@ -126,7 +126,7 @@ int fmb_shard_sort_fields(const int32_t* idsT_all_dev, int G, int me, int B, int
  * HOST array of G (<= 8) device pointers, entry r = where THIS device maps rank r's copy of that buffer.
  *   fmb_shard_transpose_ids_peers   ids [B,F] -> slab `me` of every rank's idsT_all [G,F,B]        (replaces all-gather 1)
  *   fmb_shard_partial_forward_peers block r of the pooled partials -> block `me` of rank r's recv  (replaces the all-to-all)
- *   fmb_shard_ctx_bcast_peers       local ctx [B,CW] -> rows [me*B,(me+1)*B) of every rank's ctx_all (replaces all-gather 2)
+ *   fmb_shard_combine_peers         fold + ctx rows -> rows [me*B,(me+1)*B) of every rank's ctx_all      (replaces all-gather 2)
  *   fmb_shard_signal                per-channel epoch flags, uint32 [8 channels][8 ranks] in symmetric memory;
  *                                   mode 1 publish (fence.sys + st.release.sys to all peers), 2 wait for all G peers
  *                                   (ld.acquire.sys, bounded spin), 3 both; sync_local uint32 [16] ordinary device
@@ -147,8 +147,6 @@ int fmb_shard_combine_peers(const float* recv_dev, const float* bias_dev, const 
                             int k, int loss_kind, void* const* ctx_all_peers, float* ctx_local_dev /*nullable*/,
                             void* const* flag_peers, uint32_t* flags_local_dev, uint32_t* sync_local_dev,
                             int* error_dev, int wait_channel, int publish_channel, fmb_stream_t stream);
-int fmb_shard_ctx_bcast_peers(const float* ctx_dev, int G, int me, int B, int k, void* const* ctx_all_peers,
-                              fmb_stream_t stream);
 int fmb_shard_signal(void* const* flag_peers, uint32_t* flags_local_dev, uint32_t* sync_local_dev, int channel, int G,
                      int me, int mode, int* error_dev, fmb_stream_t stream);
 
