@@ -64,7 +64,7 @@ _SIGS = {
     "fmb_shard_sort_max_cap": (C.c_int, []),
     "fmb_transpose_ids": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
     "fmb_shard_partial_forward": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
-    "fmb_shard_combine": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    "fmb_shard_combine": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     "fmb_shard_unpack_ctx": (C.c_int, [vp, C.c_int64, C.c_int, vp, vp, vp]),
     "fmb_shard_sort_fields": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp]),
     "fmb_shard_transpose_ids_peers": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp]),

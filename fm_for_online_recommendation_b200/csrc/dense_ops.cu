@@ -11,12 +11,9 @@ __global__ void loss_delta_kernel(int kind, const float* __restrict__ z, const f
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const float yy = y[b];
-    float in = z[b], pr = 0.f;
-    if (kind == 1) { pr = fmb::sigmoidf_p(in); in = pr; }
-    const float ls = __fsub_rn(fminf(in, 0.f), fmb::log1pf_p(fmb::expf_p(-fabsf(in))));
-    if (lossv) lossv[b] = __fsub_rn(__fmul_rn(__fsub_rn(1.0f, yy), in), ls);
-    float d = __fdiv_rn(__fsub_rn(fmb::sigmoidf_p(in), yy), (float)B);
-    if (kind == 1) d = __fmul_rn(__fmul_rn(d, __fsub_rn(1.0f, pr)), pr);
+    float lv, d;
+    fmb::bce_logits_value_grad(kind, z[b], yy, b, B, lv, d);
+    if (lossv) lossv[b] = lv;
     delta[b] = d;
 }
 

@@ -115,12 +115,9 @@ __global__ void __launch_bounds__(256) fm_forward_kernel(FwdParams p) {
         if (p.z) p.z[b] = z;
         if (p.y) {
             const float y = p.y[b];
-            float in = z, pr = 0.f;
-            if (p.loss_kind == 1) { pr = fmb::sigmoidf_p(z); in = pr; }
-            const float ls = __fsub_rn(fminf(in, 0.f), fmb::log1pf_p(fmb::expf_p(-fabsf(in))));
-            p.lossv[b] = __fsub_rn(__fmul_rn(__fsub_rn(1.0f, y), in), ls);
-            float d = __fdiv_rn(__fsub_rn(fmb::sigmoidf_p(in), y), (float)p.B);
-            if (p.loss_kind == 1) d = __fmul_rn(__fmul_rn(d, __fsub_rn(1.0f, pr)), pr);
+            float lv, d;
+            fmb::bce_logits_value_grad(p.loss_kind, z, y, b, p.B, lv, d);
+            p.lossv[b] = lv;
             p.delta[b] = d;
         }
     }

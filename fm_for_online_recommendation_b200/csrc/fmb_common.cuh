@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "fmb_aten_math.cuh"
 
 #define FMB_API extern "C" __attribute__((visibility("default")))
 
@@ -31,7 +32,9 @@ static inline int fmb_round_up(int x, int m) { return (x + m - 1) / m * m; }
 namespace fmb {
 
 // ---------------------------------------------------------------------------------------------
-// fp32 transcendental functions: the SAME algorithms as oracle/oracle_math.h, restated.
+// portable fp32 expf/logf (Cephes-style, oracle/oracle_math.h group 2): used only for nn.BCELoss values and
+// torch.pow in the hedge step (continuous updates, never sign-amplified).  sigmoid / log_sigmoid / sqrt are
+// the ATen mirrors of fmb_aten_math.cuh.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float pow2i(int n) { return __int_as_float((n + 127) << 23); }
 
@@ -99,7 +102,6 @@ __device__ __forceinline__ float log1pf_p(float u) {
     return __fsub_rn(l, c);
 }
 
-__device__ __forceinline__ float sigmoidf_p(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf_p(-x))); }
 __device__ __forceinline__ float powf_p(float b, float e) { return expf_p(__fmul_rn(e, logf_p(b))); }
 
 // ---------------------------------------------------------------------------------------------
@@ -122,7 +124,7 @@ __device__ __forceinline__ float adam1_a(float p, float g, float a) {
     }
     float m = __fmul_rn(0.1f, g);
     float v = __fmul_rn(__fmul_rn(0.001f, g), g);
-    float d = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2s), 1e-8f);
+    float d = __fadd_rn(__fdiv_rn(sqrt_mkl(v), bc2s), 1e-8f);   // exp_avg_sq.sqrt() is MKL's vsSqrt
     return __fadd_rn(p, __fdiv_rn(__fmul_rn(a, m), d));
 }
 __device__ __forceinline__ float adam1(float p, float g, float lr) { return adam1_a(p, g, adam_astep(lr)); }
@@ -132,6 +134,22 @@ __device__ __forceinline__ float apply_update(float p, float g, float lr, int mo
 // same with the Adam step size precomputed
 __device__ __forceinline__ float apply_update_a(float p, float g, float lr, float astep, int mode) {
     return mode == 0 ? adam1_a(p, g, astep) : __fsub_rn(p, __fmul_rn(lr, g));
+}
+
+// ---------------------------------------------------------------------------------------------
+// F.binary_cross_entropy_with_logits value + gradient for sample b of a batch of B.
+//   kind 0: loss(z)           delta = (sigmoid(z) - y) / B
+//   kind 1: loss(sigmoid(z))  delta = (((sigmoid(p) - y) / B) * (1 - p)) * p,  p = sigmoid(z)
+// Both sigmoids are torch.sigmoid calls on the [B] tensor, so their bits depend on the position b.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bce_logits_value_grad(int kind, float z, float y, int b, int B, float& lossv,
+                                                      float& delta) {
+    float in = z, pr = 0.f;
+    if (kind == 1) { pr = sigmoid_at(z, b, B); in = pr; }
+    lossv = __fsub_rn(__fmul_rn(__fsub_rn(1.0f, y), in), log_sigmoid(in));
+    float d = __fdiv_rn(__fsub_rn(sigmoid_at(in, b, B), y), (float)B);
+    if (kind == 1) d = __fmul_rn(__fmul_rn(d, __fsub_rn(1.0f, pr)), pr);
+    delta = d;
 }
 
 // ---------------------------------------------------------------------------------------------

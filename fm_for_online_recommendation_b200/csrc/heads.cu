@@ -21,12 +21,12 @@ __global__ void onn_heads_kernel(int nfm, const float* z_fm, const float* sum_fi
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= L * B) return;
     const int b = i % B;
-    p[i] = fmb::sigmoidf_p(__fadd_rn(base_of(nfm, z_fm, sum_first, bias, b), head[i]));
+    p[i] = fmb::sigmoid_at(__fadd_rn(base_of(nfm, z_fm, sum_first, bias, b), head[i]), b, B);   // one torch.sigmoid per layer on [B]
 }
 
 __global__ void predict_kernel(const float* z, int n, uint8_t* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = fmb::sigmoidf_p(z[i]) > 0.5f;
+    if (i < n) out[i] = fmb::sigmoid_at(z[i], i, n) > 0.5f;
 }
 
 // nn.BCELoss value and d(loss)/d(pre-sigmoid logit) of one head (deepfm_onn.py:117-120,127)

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(OT) online_deep_kernel(OnlineParams p) {
                     const float hsum = fmb::aten_row_sum_warp(act + l * H, H);
                     if (lane == 0) {
                         head[l] = hsum;
-                        if (is_onn) pl[l] = fmb::sigmoidf_p(__fadd_rn(sc[3], hsum));
+                        if (is_onn) pl[l] = fmb::sigmoid_at(__fadd_rn(sc[3], hsum), 0, 1);   // B = 1: ATen's scalar path
                         else if (l == L - 1) sc[4] = __fadd_rn(sc[3], hsum);
                     }
                 }
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(OT) online_deep_kernel(OnlineParams p) {
         // ---- predict (fm_adam.py:84-88 / deepfm_onn.py:171-175)
         const float yy = p.y[n];
         const float zout = is_onn ? pl[L - 1] : sc[4];
-        const bool pred = fmb::sigmoidf_p(zout) > 0.5f;
+        const bool pred = fmb::sigmoid_at(zout, 0, 1) > 0.5f;
         if (tid == 0) {
             p.preds[n] = pred;
             const bool pos = yy == 1.0f;
@@ -135,8 +135,8 @@ __global__ void __launch_bounds__(OT) online_deep_kernel(OnlineParams p) {
                 const float z = sc[4];
                 float in = z, pr = 0.f;
                 const int kindl = (p.kind == 2) ? 0 : 1;
-                if (kindl == 1) { pr = fmb::sigmoidf_p(z); in = pr; }
-                float d = __fdiv_rn(__fsub_rn(fmb::sigmoidf_p(in), yy), 1.0f);
+                if (kindl == 1) { pr = fmb::sigmoid_at(z, 0, 1); in = pr; }
+                float d = __fdiv_rn(__fsub_rn(fmb::sigmoid_at(in, 0, 1), yy), 1.0f);
                 if (kindl == 1) d = __fmul_rn(__fmul_rn(d, __fsub_rn(1.0f, pr)), pr);
                 sc[5] = d;
             }

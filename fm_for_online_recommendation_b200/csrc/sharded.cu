@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) shard_partial_forward_kernel(PartialParam
 }
 
 __global__ void shard_combine_kernel(const float* __restrict__ recv, const float* __restrict__ bias,
-                                     const float* __restrict__ y, int G, int B, int k, int kp4, int PW, int CW,
+                                     const float* __restrict__ y, int G, int me, int B, int k, int kp4, int PW, int CW,
                                      int loss_kind, float* __restrict__ ctx, float* __restrict__ z_out) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
@@ -122,13 +122,8 @@ __global__ void shard_combine_kernel(const float* __restrict__ recv, const float
     const float z = __fadd_rn(__fadd_rn(sum_first, sum_bi), bias[0]);
     if (z_out) z_out[b] = z;
     const float yy = y[b];
-    const float fB = (float)((int64_t)G * B);
-    float in = z, pr = 0.f;
-    if (loss_kind == 1) { pr = fmb::sigmoidf_p(z); in = pr; }
-    const float ls = __fsub_rn(fminf(in, 0.f), fmb::log1pf_p(fmb::expf_p(-fabsf(in))));
-    const float lossv = __fsub_rn(__fmul_rn(__fsub_rn(1.0f, yy), in), ls);
-    float d = __fdiv_rn(__fsub_rn(fmb::sigmoidf_p(in), yy), fB);
-    if (loss_kind == 1) d = __fmul_rn(__fmul_rn(d, __fsub_rn(1.0f, pr)), pr);
+    float lossv, d;   // sample b of rank `me` is element me*B + b of the global batch (torch.sigmoid is position-dependent)
+    fmb::bce_logits_value_grad(loss_kind, z, yy, me * B + b, G * B, lossv, d);
     c[kp4] = d;
     c[kp4 + 1] = lossv;
     c[kp4 + 2] = z;
@@ -369,13 +364,8 @@ __global__ void __launch_bounds__(CMB_THREADS) shard_combine_peers_kernel(
         const float sum_bi = fmb::aten_row_sum_small(bi_of, k);
         const float z = __fadd_rn(__fadd_rn(sum_first, sum_bi), bias[0]);
         const float yy = y[b];
-        const float fB = (float)((int64_t)G * B);
-        float in = z, pr = 0.f;
-        if (loss_kind == 1) { pr = fmb::sigmoidf_p(z); in = pr; }
-        const float ls = __fsub_rn(fminf(in, 0.f), fmb::log1pf_p(fmb::expf_p(-fabsf(in))));
-        const float lossv = __fsub_rn(__fmul_rn(__fsub_rn(1.0f, yy), in), ls);
-        float d = __fdiv_rn(__fsub_rn(fmb::sigmoidf_p(in), yy), fB);
-        if (loss_kind == 1) d = __fmul_rn(__fmul_rn(d, __fsub_rn(1.0f, pr)), pr);
+            float lossv, d;   // sample b of rank `me` is element me*B + b of the global batch (torch.sigmoid is position-dependent)
+        fmb::bce_logits_value_grad(loss_kind, z, yy, me * B + b, G * B, lossv, d);
         c[kp4] = d;
         c[kp4 + 1] = lossv;
         c[kp4 + 2] = z;
@@ -558,10 +548,10 @@ FMB_API int fmb_shard_partial_forward(const int32_t* idsT_all, const float* tabl
 }
 
 // step 4: recv [G][B][PW] (block o = partials owner o computed for MY samples) -> ctx [B][CW]
-FMB_API int fmb_shard_combine(const float* recv, const float* bias, const float* y, int G, int B, int k,
+FMB_API int fmb_shard_combine(const float* recv, const float* bias, const float* y, int G, int me, int B, int k,
                               int loss_kind, float* ctx, float* z_out, cudaStream_t stream) {
-    FMB_CHECK_ARG(recv && bias && y && ctx && G > 0 && B > 0 && k > 0, "fmb_shard_combine: bad arguments");
-    shard_combine_kernel<<<(B + 127) / 128, 128, 0, stream>>>(recv, bias, y, G, B, k, fmb_round_up(k, 4),
+    FMB_CHECK_ARG(recv && bias && y && ctx && G > 0 && me >= 0 && me < G && B > 0 && k > 0, "fmb_shard_combine: bad arguments");
+    shard_combine_kernel<<<(B + 127) / 128, 128, 0, stream>>>(recv, bias, y, G, me, B, k, fmb_round_up(k, 4),
                                                             fmb_shard_pw(k), fmb_shard_cw(k), loss_kind, ctx, z_out);
     FMB_CHECK_LAUNCH("shard_combine_kernel");
     return FMB_OK;

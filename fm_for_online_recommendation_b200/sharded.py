@@ -174,7 +174,7 @@ class ShardedFM:
         """recv [G,B,PW] (block o = owner o's partials for MY samples) -> ctx [B,CW]."""
         B = recv.shape[1]
         ctx = self._buf("ctx", (B, self.CW))
-        check(self._lib.fmb_shard_combine(ptr(recv), ptr(self.bias), ptr(y), self.G, B, self.k, loss_kind, ptr(ctx),
+        check(self._lib.fmb_shard_combine(ptr(recv), ptr(self.bias), ptr(y), self.G, self.rank, B, self.k, loss_kind, ptr(ctx),
                                           None, _stream()), "fmb_shard_combine")
         return ctx
 

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 def build(force: bool = False) -> str:
     """Compile oracle/libfm_oracle.so with gcc (idempotent). Returns the path."""
     so = os.path.join(_HERE, "libfm_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("fm_oracle.c", "oracle_math.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("fm_oracle.c", "oracle_math.h", "rsqrt14_table.inc")]
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-B", "libfm_oracle.so"], stdout=subprocess.DEVNULL)

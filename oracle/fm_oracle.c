@@ -13,11 +13,10 @@
  * committed under tests/golden (npz files).  The reference ships no tests or golden
  * vectors of its own.
  *
- * Documented deviations from torch bits (all <= a few ulp on the logit, see
- * DESIGN.md "Reduction orders"): the row reductions Sum_f first[b,f],
- * Sum_j bi[b,j], Sum_j x_l[b,j], the batch reductions (loss mean, bias gradient)
- * and exp/log use ONE fixed, ISA-independent order/algorithm, because ATen's
- * own order depends on the host's vector width.
+ * What is mirrored bit for bit (torch 2.11 CPU as it runs in the build container, one thread):
+ * torch.sum's accumulator cascade (orc_sum_aten), torch.sigmoid (Sleef vector body + glibc scalar
+ * tail, split by position in the batch), log_sigmoid, the fresh-state Adam step.  Not mirrored:
+ * MKL's sgemm order (MLP tower) and glibc logf/log1pf/powf in nn.BCELoss / torch.pow (hedge step).
  *
  * Build: gcc -O2 -fPIC -shared -ffp-contract=off -fno-fast-math (oracle/Makefile).
  */
@@ -293,11 +292,11 @@ static void loss_slice(int tid, int nthreads, void* vctx) {
     const int b_lo = (int)((int64_t)B * tid / nthreads), b_hi = (int)((int64_t)B * (tid + 1) / nthreads);
     for (int b = b_lo; b < b_hi; ++b) {
         float in = z[b], p = 0.f;
-        if (kind == 1) { p = orc_sigmoidf(z[b]); in = p; }
-        /* (1 - y) * x - log_sigmoid(x),  log_sigmoid(x) = min(x,0) - log1p(exp(-|x|)) */
-        float ls = fminf(in, 0.f) - orc_log1pf(orc_expf(-fabsf(in)));
+        if (kind == 1) { p = orc_sigmoid_at(z[b], b, B); in = p; }   /* torch.sigmoid(output), fm_adam.py:80 */
+        /* (1 - y) * x - log_sigmoid(x)  (ATen Loss.cpp binary_cross_entropy_with_logits) */
+        float ls = orc_log_sigmoid(in);
         lv[b] = ((1.0f - y[b]) * in) - ls;
-        float d = (orc_sigmoidf(in) - y[b]) / fB;
+        float d = (orc_sigmoid_at(in, b, B) - y[b]) / fB;         /* backward: (input.sigmoid() - target) * grad */
         if (kind == 1) d = (d * (1.0f - p)) * p; /* sigmoid_backward: grad * (1 - out) * out */
         delta[b] = d;
     }
@@ -317,13 +316,18 @@ static inline float adam1(float p, float g, float lr) {
     const float bc2s = 0.03162277660168381f; /* float((1 - 0.999) ** 0.5) */
     float m = 0.1f * g;                      /* lerp(0, g, 1 - beta1) */
     float v = (0.001f * g) * g;              /* addcmul(value = 1 - beta2) */
-    float d = (sqrtf(v) / bc2s) + 1e-8f;
+    float d = (orc_sqrt_mkl(v) / bc2s) + 1e-8f;  /* exp_avg_sq.sqrt(): MKL vsSqrt, not sqrtf */
     float a = -(lr / 0.1f);                  /* -(lr / bias_correction1) */
     return p + ((a * m) / d);
 }
 static inline float upd(float p, float g, float lr, int mode) {
     return mode == 0 ? adam1(p, g, lr) : p - lr * g;
 }
+/* element-wise exports for tests/test_oracle_math.py */
+API void orc_vec_sqrt_mkl(const float* x, float* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = orc_sqrt_mkl(x[i]); }
+API void orc_vec_sigmoid(const float* x, float* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = orc_sigmoid_at(x[i], i, n); }
+API void orc_vec_log_sigmoid(const float* x, float* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = orc_log_sigmoid(x[i]); }
+API void orc_vec_expf_glibc(const float* x, float* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = orc_expf_glibc(x[i]); }
 API void orc_update_dense(float* p, const float* g, int64_t n, float lr, int mode) {
     for (int64_t i = 0; i < n; ++i) p[i] = upd(p[i], g[i], lr, mode);
 }
@@ -463,7 +467,7 @@ static void full_forward(const orc_model* m, const int32_t* ids, const float* xv
     } else {
         for (int l = 0; l < m->L; ++l)
             for (int b = 0; b < B; ++b) {
-                float p = orc_sigmoidf(w->base[b] + w->head[(size_t)l * B + b]);
+                float p = orc_sigmoid_at(w->base[b] + w->head[(size_t)l * B + b], b, B);
                 if (players) players[(size_t)l * B + b] = p;
                 if (l == m->L - 1) z[b] = p;
             }
@@ -480,7 +484,7 @@ API void orc_forward(const orc_model* m, const int32_t* ids, const float* xv, in
 API void orc_predict(const orc_model* m, const int32_t* ids, const float* xv, int B, uint8_t* pred) {
     float* z = (float*)malloc(sizeof(float) * B);
     orc_forward(m, ids, xv, B, z, NULL);
-    for (int b = 0; b < B; ++b) pred[b] = orc_sigmoidf(z[b]) > 0.5f;
+    for (int b = 0; b < B; ++b) pred[b] = orc_sigmoid_at(z[b], b, B) > 0.5f;
     free(z);
 }
 
