@@ -28,6 +28,7 @@ _SIGS = {
                                  vp]),
     "fmb_loss_delta": (C.c_int, [C.c_int, vp, vp, C.c_int, vp, vp, vp]),
     "fmb_sum_aten": (C.c_int, [vp, C.c_int64, vp, vp]),
+    "fmb_math_eval": (C.c_int, [C.c_int, vp, vp, C.c_int64, vp]),
     "fmb_update_dense": (C.c_int, [vp, vp, C.c_int64, C.c_float, C.c_int, vp]),
     "fmb_finish_step": (C.c_int, [vp, vp, C.c_int, vp, C.c_float, C.c_int, vp, vp]),
     "fmb_sort_workspace_bytes": (C.c_size_t, [C.c_int64]),

@@ -17,6 +17,21 @@ __global__ void loss_delta_kernel(int kind, const float* __restrict__ z, const f
     delta[b] = d;
 }
 
+// element-wise evaluation of the ATen mirrors (fmb_aten_math.cuh), so tests can compare them with the oracle's
+__global__ void math_eval_kernel(int op, const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = x[i];
+    float r;
+    switch (op) {
+        case 0: r = fmb::sigmoid_at(v, (int)i, (int)n); break;   // torch.sigmoid of a contiguous [n] tensor
+        case 1: r = fmb::log_sigmoid(v); break;
+        case 2: r = fmb::sqrt_mkl(v); break;
+        default: r = fmb::expf_glibc(v); break;
+    }
+    y[i] = r;
+}
+
 __global__ void sum_aten_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
     const float s = fmb::aten_row_sum_warp(x, n);
     if (threadIdx.x == 0) out[0] = s;
@@ -127,6 +142,15 @@ FMB_API int fmb_loss_delta(int kind, const float* z, const float* y, int B, floa
     FMB_CHECK_ARG(kind == 0 || kind == 1, "fmb_loss_delta: unknown loss kind %d", kind);
     loss_delta_kernel<<<(B + 255) / 256, 256, 0, stream>>>(kind, z, y, B, delta, lossv);
     FMB_CHECK_LAUNCH("loss_delta_kernel");
+    return FMB_OK;
+}
+
+// y[i] = f(x[i]) for the ATen mirrors: op 0 torch.sigmoid (element i of a contiguous [n] tensor, n < 2^31),
+// 1 at::log_sigmoid, 2 Tensor.sqrt (MKL vsSqrt), 3 glibc expf.  Exists so that parity tests can sweep them.
+FMB_API int fmb_math_eval(int op, const float* x, float* y, int64_t n, cudaStream_t stream) {
+    FMB_CHECK_ARG(x && y && n > 0 && n < ((int64_t)1 << 31) && op >= 0 && op <= 3, "fmb_math_eval: bad arguments");
+    math_eval_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(op, x, y, n);
+    FMB_CHECK_LAUNCH("math_eval_kernel");
     return FMB_OK;
 }
 

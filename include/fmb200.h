@@ -67,6 +67,11 @@ int fmb_fm_forward(const int32_t* ids_dev, const float* xv_dev, const float* tab
 /* ---- A6: loss + gradient on the logit (fm_adam.py:63-67, :77-81) ------------------------------- */
 int fmb_loss_delta(int loss_kind, const float* z_dev, const float* y_dev, int B, float* delta_dev,
                    float* lossv_dev, fmb_stream_t stream);
+/* element-wise ATen mirrors (torch 2.11 CPU arithmetic restated on the device, csrc/fmb_aten_math.cuh):
+ * op 0 torch.sigmoid of element i of a contiguous [n] tensor (fm_adam.py:80,86), 1 at::log_sigmoid (inside
+ * F.binary_cross_entropy_with_logits, fm_adam.py:65), 2 Tensor.sqrt as torch.optim.Adam calls it (fm_adam.py:68),
+ * 3 glibc expf.  Exported so that parity tests can sweep them against the oracle. */
+int fmb_math_eval(int op, const float* x_dev, float* y_dev, int64_t n, fmb_stream_t stream);
 /* sum in ATen's CPU order (loss.mean(), bias gradient): out[0] = sum(x[0:n]) */
 int fmb_sum_aten(const float* x_dev, int64_t n, float* out_dev, fmb_stream_t stream);
 /* optimizer.step() on dense parameters (bias, hidden_layers): fm_adam.py:68 */

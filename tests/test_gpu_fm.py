@@ -294,3 +294,35 @@ def test_full_size_properties_cfg4():
         m.bias.copy_(b0)
     l2 = m.update_embedding(e, None, None).item()
     assert l1 == l2 and torch.equal(m._table, t1)
+
+
+@pytest.mark.parametrize("op,fn", [(0, "orc_vec_sigmoid"), (1, "orc_vec_log_sigmoid"), (2, "orc_vec_sqrt_mkl"),
+                                   (3, "orc_vec_expf_glibc")])
+def test_aten_mirrors_device_equals_oracle(op, fn):
+    """fmb_aten_math.cuh (device) == oracle_math.h (C) bit for bit: torch.sigmoid's Sleef/glibc split, log_sigmoid,
+    MKL's vsSqrt (every mantissa), glibc expf.  The oracle side is pinned on torch itself in test_oracle_math.py."""
+    import fm_for_online_recommendation_b200 as pkg
+    from oracle.deep import lib as olib
+    lib = pkg.require_cuda()
+    rng = np.random.RandomState(op)
+    if op == 2:
+        xs = [((np.uint32(e0) << np.uint32(23)) + np.arange(1 << 24, dtype=np.uint32)).view(np.float32)
+              for e0 in (1, 100, 127)]
+        xs.append(np.arange(0, 1 << 23, dtype=np.uint32).view(np.float32))
+    else:
+        xs = [(rng.standard_normal(n) * rng.choice([0.05, 1, 5, 20, 60, 120], n)).astype(np.float32)
+              for n in (1, 31, 33, 250, 8192, 8200, 1 << 22)]
+        xs.append(np.array([0.0, -0.0, 88.72, 88.73, -103.9, -103.98, -103.3, -87.4, 1e-30, 104.5, -104.5],
+                           np.float32))
+    f = getattr(olib(), fn)
+    f.restype = None
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    for x in xs:
+        x = np.ascontiguousarray(x)
+        want = np.empty_like(x)
+        f(x.ctypes.data, want.ctypes.data, x.size)
+        d = torch.from_numpy(x).cuda()
+        out = torch.empty_like(d)
+        assert lib.fmb_math_eval(op, C.c_void_p(d.data_ptr()), C.c_void_p(out.data_ptr()), x.size, None) == 0
+        got = out.cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (op, x.size)
