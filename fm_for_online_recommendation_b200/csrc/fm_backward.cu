@@ -23,6 +23,7 @@
 // (the entry-major layout cost one LDS.32 per entry: 64 instructions per 32 entries, 10.6 cycles per entry
 // measured with clock64; the add chain itself is 4).
 #include "fmb_common.cuh"
+#include <cstring>
 #include <cuda.h>   // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link)
 
 namespace {
@@ -451,6 +452,55 @@ static long long* g_runs_dbg = nullptr;
 // debug hook (not in the public header): device buffer of 8 + 4000*8 int64 receiving per-run cycle counts
 FMB_API void fmb_debug_set_runs_buffer(long long* dev) { g_runs_dbg = dev; }
 
+// launches fm_bwd_runs_kernel over the staged contributions p.G (per-warp shared memory = ring + mbarriers + accumulators)
+static int launch_runs(BwdParams& p, bool two, cudaStream_t stream) {
+    const int k = p.k;
+    const int64_t N = p.N;
+    const int nv = k + 1 + (two ? k : 0);
+    const int accs_n = (nv + 3) / 4 * 4;
+    const int ring_comps = nv < 32 ? nv : 32;
+    // ring (multiple of 128 B per warp) + NS mbarriers (8 B each) + accumulators + prefetched old row
+    const int stage_f = fmb_round_up(ring_comps * RING_SEP, 32);
+    const int warp_f = fmb_round_up(RING_NS * stage_f + 2 * RING_NS + accs_n + 32, 32);
+    int wpb = 8;
+    while (wpb > 1 && (size_t)wpb * warp_f * 4 > 56 * 1024) wpb >>= 1;
+    const size_t sm = (size_t)wpb * warp_f * 4;
+    FMB_CHECK_ARG(sm <= 200 * 1024, "fmb_fm_backward_update: k too large for the run ring");
+    const int64_t nwarps = (N + 31) / 32;
+    const unsigned grid = (unsigned)((nwarps + wpb - 1) / wpb);
+    {
+        // tensor map of the staging buffer: [nv rows][Npad] fp32, box = [ring_comps rows][RING_SEP entries]
+        typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeTiled encode = nullptr;
+        static bool attr = false;
+        if (!attr) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+                fmb_set_error("fmb_fm_backward_update: cuTensorMapEncodeTiled not available from the driver");
+                return FMB_ERR_CUDA;
+            }
+            encode = (EncodeTiled)fn;
+            cudaFuncSetAttribute(fm_bwd_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr = true;
+        }
+        CUtensorMap gmap;
+        const cuuint64_t gdim[2] = {(cuuint64_t)p.Npad, (cuuint64_t)nv};
+        const cuuint64_t gstride[1] = {(cuuint64_t)p.Npad * 4};
+        const cuuint32_t box[2] = {(cuuint32_t)RING_SEP, (cuuint32_t)ring_comps};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult cr = encode(&gmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, p.G, gdim, gstride, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) { fmb_set_error("fmb_fm_backward_update: cuTensorMapEncodeTiled failed (%d)", (int)cr); return FMB_ERR_CUDA; }
+        fm_bwd_runs_kernel<<<grid, 32 * wpb, sm, stream>>>(gmap, p, wpb, warp_f, accs_n, ring_comps);
+    }
+    FMB_CHECK_LAUNCH("fm_bwd_runs_kernel");
+    return FMB_OK;
+}
+
 // A6 sparse backward + update (see file header).
 //   sorted_keys/perm [N]: output of fmb_sort_segment / fmb_sort_fields over ids[B*F]; xv [B*F] or NULL
 //   table [R,rowp] updated in place; S [B,kp4]; gs [B]; gvec [B,kp4] or NULL
@@ -500,50 +550,27 @@ FMB_API int fmb_fm_backward_update_ex(const int32_t* sorted_keys, const int32_t*
         }
     }
     FMB_CHECK_LAUNCH("fm_bwd_entry_kernel");
-    // runs kernel: per-warp shared memory = ring + mbarriers + accumulators
-    const int nv = k + 1 + (two ? k : 0);
-    const int accs_n = (nv + 3) / 4 * 4;
-    const int ring_comps = nv < 32 ? nv : 32;
-    // ring (multiple of 128 B per warp) + NS mbarriers (8 B each) + accumulators + prefetched old row
-    const int stage_f = fmb_round_up(ring_comps * RING_SEP, 32);
-    const int warp_f = fmb_round_up(RING_NS * stage_f + 2 * RING_NS + accs_n + 32, 32);
-    int wpb = 8;
-    while (wpb > 1 && (size_t)wpb * warp_f * 4 > 56 * 1024) wpb >>= 1;
-    const size_t sm = (size_t)wpb * warp_f * 4;
-    FMB_CHECK_ARG(sm <= 200 * 1024, "fmb_fm_backward_update: k too large for the run ring");
-    const int64_t nwarps = (N + 31) / 32;
-    const unsigned grid = (unsigned)((nwarps + wpb - 1) / wpb);
-    {
-        // tensor map of the staging buffer: [nv rows][Npad] fp32, box = [ring_comps rows][RING_SEP entries]
-        typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        static EncodeTiled encode = nullptr;
-        static bool attr = false;
-        if (!attr) {
-            void* fn = nullptr;
-            cudaDriverEntryPointQueryResult qres;
-            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
-                fmb_set_error("fmb_fm_backward_update: cuTensorMapEncodeTiled not available from the driver");
-                return FMB_ERR_CUDA;
-            }
-            encode = (EncodeTiled)fn;
-            cudaFuncSetAttribute(fm_bwd_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr = true;
-        }
-        CUtensorMap gmap;
-        const cuuint64_t gdim[2] = {(cuuint64_t)p.Npad, (cuuint64_t)nv};
-        const cuuint64_t gstride[1] = {(cuuint64_t)p.Npad * 4};
-        const cuuint32_t box[2] = {(cuuint32_t)RING_SEP, (cuuint32_t)ring_comps};
-        const cuuint32_t estr[2] = {1, 1};
-        const CUresult cr = encode(&gmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, p.G, gdim, gstride, box, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) { fmb_set_error("fmb_fm_backward_update: cuTensorMapEncodeTiled failed (%d)", (int)cr); return FMB_ERR_CUDA; }
-        fm_bwd_runs_kernel<<<grid, 32 * wpb, sm, stream>>>(gmap, p, wpb, warp_f, accs_n, ring_comps);
-    }
-    FMB_CHECK_LAUNCH("fm_bwd_runs_kernel");
-    return FMB_OK;
+    return launch_runs(p, two, stream);
+}
+
+// Run kernel alone: sums the contributions staged in ws (by fmb_fm_step_fused, at sorted positions) over every run
+// of >= 2 equal keys, in sample order, and updates those rows.  Same arguments as fmb_fm_backward_update.
+FMB_API int fmb_fm_backward_runs(const int32_t* sorted_keys, int64_t N, float* table, int F, int k, float lr,
+                                 int mode, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    FMB_CHECK_ARG(sorted_keys && table && ws, "fmb_fm_backward_runs: null pointer");
+    FMB_CHECK_ARG(N > 0 && F > 0 && F < 512 && k > 0 && k <= 124, "fmb_fm_backward_runs: bad shape");
+    FMB_CHECK_ARG(mode == 0 || mode == 1, "fmb_fm_backward_runs: unknown update mode %d", mode);
+    if (ws_bytes < fmb_bwd_workspace_bytes(N, k)) { fmb_set_error("fmb_fm_backward_runs: workspace too small"); return FMB_ERR_WS; }
+    BwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.skeys = sorted_keys; p.N = N; p.table = table;
+    p.F = F; p.k = k; p.rowp = fmb_round_up(k + 1, 16); p.kp4 = fmb_round_up(k, 4);
+    p.use_fm2 = 1; p.gvec = nullptr; p.lr = lr; p.mode = mode; p.key_limit = 0x7fffffff;
+    p.astep = -(lr / 0.1f);
+    p.dbg = nullptr;
+    p.Npad = bwd_npad(N);
+    p.G = (float*)ws;
+    return launch_runs(p, false, stream);
 }
 
 FMB_API int fmb_fm_backward_update(const int32_t* sorted_keys, const int32_t* perm, int64_t N, const float* xv,
