@@ -190,10 +190,7 @@ def run_ours(args):
     def step(i):
         # step on batch i; the sort of batch i+1 (it depends on the ids only) is started right behind it on a side
         # stream, so it overlaps this step's backward kernels.  Every step still sorts exactly one batch.
-        out = model._fm_step(enc[i % NB], 0)
-        if not args.no_presort:
-            model.presort(enc[(i + 1) % NB])
-        return out
+        return model._fm_step(enc[i % NB], 0, None if args.no_presort else enc[(i + 1) % NB])
 
     sampler = ClockSampler(local)       # started before the warm-up: forking nvidia-smi must not sit in front of the timed region
     base = max(W, 2 * NB + 2)           # two epochs of the rotating batches; the timed loop CONTINUES the sequence

@@ -86,6 +86,13 @@ _SIGS = {
     "fmb_session_fm_step_host_async": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_float,
                                                  C.c_int, vp]),
     "fmb_session_presort": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+    "fmb_session_presort_invalidate": (None, [vp]),
+    "fmb_session_fm_step_next": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp,
+                                           vp]),
+    "fmb_pos_flags": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
+    "fmb_fm_step_fused": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp,
+                                    vp, C.c_size_t, vp]),
+    "fmb_fm_backward_runs": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, C.c_size_t, vp]),
     "fmb_session_wait_loss": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float)]),
     "fmb_session_fm_step_host": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_float, C.c_int,
                                            C.POINTER(C.c_float), vp]),

@@ -31,13 +31,11 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
+// The four per-batch pointers are separate kernel arguments (not members of StepParams) so that a captured CUDA
+// graph of the step can be re-pointed at another batch with cudaGraphExecKernelNodeSetParams (session.cu).
 struct StepParams {
-    const int32_t* ids;        // [B,F] global row ids
-    const float* xv;           // [B,F] or NULL (all ones)
-    const float* y;            // [B]
     float* table;              // [R,rowp]
     const float* bias;         // [1]
-    const uint32_t* posflag;   // [B*F] entry-major: sorted position of the entry | 0x80000000 if its row is hit > once
     int B, F, k, rowp, kp4, SB;
     int cu;                    // 16-byte chunks of a row that hold data: ceil((k+1)/4)
     int ql_log;                // log2 of lanes per (sample, field) in the gather phase (pow2 >= cu)
@@ -50,7 +48,11 @@ struct StepParams {
     int64_t Npad;
 };
 
-__global__ void __launch_bounds__(256) fm_step_fused_kernel(StepParams p) {
+//   ids [B,F] global row ids;  xv [B,F] or NULL (all ones);  y [B];
+//   posflag [B*F] entry-major: sorted position of the entry | 0x80000000 if its row is hit more than once
+__global__ void __launch_bounds__(256) fm_step_fused_kernel(const int32_t* __restrict__ ids, const float* __restrict__ xv,
+                                                            const float* __restrict__ y, const uint32_t* __restrict__ posflag,
+                                                            StepParams p) {
     extern __shared__ __align__(16) float smem[];
     const int F = p.F, k = p.k, SB = p.SB;
     const int rp = p.cu * 4;                       // shared-memory row pitch (floats)
@@ -66,9 +68,9 @@ __global__ void __launch_bounds__(256) fm_step_fused_kernel(StepParams p) {
 
     // phase 0: the tile's row ids, values and sorted positions, coalesced
     for (int e = threadIdx.x; e < nv * F; e += blockDim.x) {
-        ids_s[e] = __ldg(p.ids + (size_t)b0 * F + e);
-        x_s[e] = p.xv ? __ldg(p.xv + (size_t)b0 * F + e) : 1.0f;
-        pos_s[e] = __ldg(p.posflag + (size_t)b0 * F + e);
+        ids_s[e] = __ldg(ids + (size_t)b0 * F + e);
+        x_s[e] = xv ? __ldg(xv + (size_t)b0 * F + e) : 1.0f;
+        pos_s[e] = __ldg(posflag + (size_t)b0 * F + e);
     }
     __syncthreads();
     // phase 1: gather rows, 16 B per cp.async; every row read of the tile is in flight at once
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(256) fm_step_fused_kernel(StepParams p) {
         const float sb = fmb::aten_row_sum_small([&](int j) { return bs[j]; }, k);
         const float z = __fadd_rn(__fadd_rn(sf, sb), __ldg(p.bias));
         float lv, d;
-        fmb::bce_logits_value_grad(p.loss_kind, z, p.y[b], b, p.B, lv, d);
+        fmb::bce_logits_value_grad(p.loss_kind, z, y[b], b, p.B, lv, d);
         p.lossv[b] = lv;
         p.delta[b] = d;
         d_s[s] = d;
@@ -176,6 +178,10 @@ static int ilog2_ceil(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
 
 }  // namespace
 
+// host-side handle of the fused kernel, for graph-node identification in session.cu (arguments 0..3 are ids, xv, y, posflag)
+FMB_API const void* fmb_fused_kernel_fn(void) { return (const void*)fm_step_fused_kernel; }
+FMB_API const void* fmb_pos_flags_kernel_fn(void) { return (const void*)pos_flags_kernel; }
+
 // per-entry sorted position + multi-hit flag from the stable sort's output (fmb_sort_fields / fmb_sort_segment)
 FMB_API int fmb_pos_flags(const int32_t* sorted_keys, const int32_t* perm, int64_t N, uint32_t* posflag,
                           cudaStream_t stream) {
@@ -199,7 +205,7 @@ FMB_API int fmb_fm_step_fused(const int32_t* ids, const float* xv, const float* 
     const int64_t N = (int64_t)B * F;
     if (ws_bytes < fmb_bwd_workspace_bytes(N, k)) { fmb_set_error("fmb_fm_step_fused: workspace too small"); return FMB_ERR_WS; }
     StepParams p;
-    p.ids = ids; p.xv = xv; p.y = y; p.table = table; p.bias = bias; p.posflag = posflag;
+    p.table = table; p.bias = bias;
     p.B = B; p.F = F; p.k = k; p.rowp = fmb_round_up(k + 1, 16); p.kp4 = fmb_round_up(k, 4);
     p.cu = (k + 1 + 3) / 4; p.ql_log = ilog2_ceil(p.cu); p.jl_log = ilog2_ceil(p.kp4);
     p.loss_kind = loss_kind; p.mode = mode; p.lr = lr; p.astep = -(lr / 0.1f);
@@ -219,7 +225,7 @@ FMB_API int fmb_fm_step_fused(const int32_t* ids, const float* xv, const float* 
         cudaFuncSetAttribute(fm_step_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    fm_step_fused_kernel<<<(B + SB - 1) / SB, 256, bytes(SB), stream>>>(p);
+    fm_step_fused_kernel<<<(B + SB - 1) / SB, 256, bytes(SB), stream>>>(ids, xv, y, posflag, p);
     FMB_CHECK_LAUNCH("fm_step_fused_kernel");
     return FMB_OK;
 }

@@ -456,6 +456,15 @@ FMB_API int fmb_sort_segment(const int32_t* keys, int64_t N, int key_bits, void*
     return FMB_OK;
 }
 
+// host-side handles of the three per-field sort kernels (argument 0 = ids, 4 = sorted_keys, 5 = perm; 6 or 7 arguments),
+// for graph-node identification in session.cu
+FMB_API int fmb_sort_fields_kernel_fns(const void** fns, int* nparams) {
+    fns[0] = (const void*)sort_fields_kernel; nparams[0] = 6;
+    fns[1] = (const void*)sort_fields_cluster_kernel<256, true>; nparams[1] = 7;
+    fns[2] = (const void*)sort_fields_cluster_kernel<1024, false>; nparams[2] = 7;
+    return 3;
+}
+
 // Largest batch the per-field shared-memory sort accepts (cluster of 4 CTAs, 16-bit sample payload).
 FMB_API int fmb_sort_fields_max_batch(void) { return 65536; }
 

@@ -7,6 +7,7 @@
 #include "fmb_common.cuh"
 #include <cstdlib>
 #include <cstring>
+#include <cstddef>
 #include <new>
 
 extern "C" {
@@ -21,13 +22,28 @@ int fmb_sort_fields(const int32_t*, int, int, const int32_t*, int32_t*, int32_t*
 int fmb_fm_backward_update(const int32_t*, const int32_t*, int64_t, const float*, float*, int, int, const float*,
                            const float*, int, const float*, float, int, void*, size_t, cudaStream_t);
 int fmb_finish_step(const float*, const float*, int, float*, float, int, float*, cudaStream_t);
+int fmb_pos_flags(const int32_t*, const int32_t*, int64_t, uint32_t*, cudaStream_t);
+int fmb_fm_step_fused(const int32_t*, const float*, const float*, float*, const float*, const uint32_t*, int, int, int,
+                      int, float, int, float*, float*, void*, size_t, cudaStream_t);
+int fmb_fm_backward_runs(const int32_t*, int64_t, float*, int, int, float, int, void*, size_t, cudaStream_t);
+const void* fmb_fused_kernel_fn(void);
+int fmb_sort_fields_kernel_fns(const void**, int*);
 }
 
-#define FMB_GRAPH_CACHE 128
-struct StepKey {
-    const void *ids, *xv, *y, *table, *bias, *loss;
-    int B, key_bits, loss_kind, mode, sort_buf, skip_sort;
+// One captured step graph per CONFIGURATION (batch size, loss, update mode, with/without xv, sorted in the step or
+// before it, with/without the sort of the next batch riding along) -- never per batch: the per-batch pointers
+// (ids, xv, y of the fused kernel; ids of the sort kernels) are re-pointed before every launch with
+// cudaGraphExecKernelNodeSetParams, so a training loop over a device-resident dataset replays ONE graph.
+#define FMB_GRAPH_CACHE 32
+struct StepVariant {
+    int B, key_bits, loss_kind, mode, has_xv, pre, has_next, cur;
+    const void *table, *bias;
     float lr;
+    cudaGraph_t graph;        // kept alive: its nodes own the argument storage the patches start from
+    cudaGraphExec_t exec;
+    cudaGraphNode_t n_fused, n_sort_cur, n_sort_next;
+    int np_sort_cur, np_sort_next;
+    int nlaunch;
 };
 
 struct fmb_session {
@@ -46,10 +62,14 @@ struct fmb_session {
     int32_t* d_perm;
     int32_t* d_skeys_buf[2];
     int32_t* d_perm_buf[2];
+    uint32_t* d_posflag_buf[2];   // per entry: sorted position | multi-hit flag (fmb_pos_flags), one per sorted buffer
+    void* d_sort_ws2;             // radix workspace of the pre-sort (the in-step sort may be using d_sort_ws)
     // pre-sort: the sort depends on the ids only, so the sort of batch t+1 may run (on st1) while step t is
     // still in its backward kernels.  presort_ids names the batch whose sorted form sits in presort_buf.
     const int32_t* presort_ids;
     int presort_B, presort_buf, last_buf;
+    int presort_ext;     // the pending pre-sort ran outside a step graph: steps must wait for ev_presort
+    int presort_stale;   // set by fmb_session_presort_invalidate
     cudaEvent_t ev_presort, ev_buf_free[2];
     int buf_used[2];
     void* d_sort_ws;
@@ -75,9 +95,8 @@ struct fmb_session {
     cudaEvent_t ev_fork, ev_fwd, ev_sort, ev_join;
     int use_graph;
     int ngraphs, next_evict;
-    StepKey gkey[FMB_GRAPH_CACHE];
-    cudaGraphExec_t gexec[FMB_GRAPH_CACHE];
-    int glaunches[FMB_GRAPH_CACHE];
+    StepVariant gvar[FMB_GRAPH_CACHE];
+    cudaEvent_t ev_join2;
 };
 
 #define CU(call)                                                                              \
@@ -90,7 +109,9 @@ FMB_API void fmb_session_destroy(fmb_session* s) {
     if (!s) return;
     cudaFree(s->d_ids); cudaFree(s->d_xv); cudaFree(s->d_y); cudaFree(s->d_S); cudaFree(s->d_z);
     cudaFree(s->d_delta); cudaFree(s->d_lossv); cudaFree(s->d_loss);
-    for (int i = 0; i < 2; ++i) { cudaFree(s->d_skeys_buf[i]); cudaFree(s->d_perm_buf[i]); if (s->ev_buf_free[i]) cudaEventDestroy(s->ev_buf_free[i]); }
+    for (int i = 0; i < 2; ++i) { cudaFree(s->d_skeys_buf[i]); cudaFree(s->d_perm_buf[i]); cudaFree(s->d_posflag_buf[i]); if (s->ev_buf_free[i]) cudaEventDestroy(s->ev_buf_free[i]); }
+    cudaFree(s->d_sort_ws2);
+    if (s->ev_join2) cudaEventDestroy(s->ev_join2);
     if (s->ev_presort) cudaEventDestroy(s->ev_presort);
     cudaFree(s->d_sort_ws); cudaFree(s->d_bwd_ws); cudaFree(s->d_field_off);
     cudaFreeHost(s->h_ids); cudaFreeHost(s->h_xv); cudaFreeHost(s->h_y); cudaFreeHost(s->h_loss);
@@ -98,7 +119,7 @@ FMB_API void fmb_session_destroy(fmb_session* s) {
     cudaFreeHost(s->h_ids2); cudaFreeHost(s->h_xv2); cudaFreeHost(s->h_y2);
     if (s->st_copy) cudaStreamDestroy(s->st_copy);
     for (int i = 0; i < 2; ++i) { if (s->ev_h2d[i]) cudaEventDestroy(s->ev_h2d[i]); if (s->ev_done[i]) cudaEventDestroy(s->ev_done[i]); }
-    for (int i = 0; i < s->ngraphs; ++i) cudaGraphExecDestroy(s->gexec[i]);
+    for (int i = 0; i < s->ngraphs; ++i) { cudaGraphExecDestroy(s->gvar[i].exec); cudaGraphDestroy(s->gvar[i].graph); }
     if (s->st0) cudaStreamDestroy(s->st0);
     if (s->st1) cudaStreamDestroy(s->st1);
     if (s->st2) cudaStreamDestroy(s->st2);
@@ -128,7 +149,8 @@ FMB_API int fmb_session_create(fmb_session** out, int F, int k, int64_t max_batc
     dm((void**)&s->d_ids, N * 4); dm((void**)&s->d_xv, N * 4); dm((void**)&s->d_y, max_batch * 4);
     dm((void**)&s->d_S, max_batch * s->kp4 * 4); dm((void**)&s->d_z, max_batch * 4);
     dm((void**)&s->d_delta, max_batch * 4); dm((void**)&s->d_lossv, max_batch * 4); dm((void**)&s->d_loss, 256);
-    for (int i = 0; i < 2; ++i) { dm((void**)&s->d_skeys_buf[i], N * 4); dm((void**)&s->d_perm_buf[i], N * 4); }
+    for (int i = 0; i < 2; ++i) { dm((void**)&s->d_skeys_buf[i], N * 4); dm((void**)&s->d_perm_buf[i], N * 4); dm((void**)&s->d_posflag_buf[i], N * 4); }
+    if (!(field_off_host && max_batch <= fmb_sort_fields_max_batch())) dm(&s->d_sort_ws2, s->sort_ws_bytes);
     s->d_skeys = s->d_skeys_buf[0]; s->d_perm = s->d_perm_buf[0];
     dm(&s->d_sort_ws, s->sort_ws_bytes); dm(&s->d_bwd_ws, s->bwd_ws_bytes);
     hm((void**)&s->h_ids, N * 4); hm((void**)&s->h_xv, N * 4); hm((void**)&s->h_y, max_batch * 4);
@@ -153,6 +175,7 @@ FMB_API int fmb_session_create(fmb_session** out, int F, int k, int64_t max_batc
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_sort, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_presort, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_join2, cudaEventDisableTiming);
     for (int i = 0; i < 2; ++i) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_buf_free[i], cudaEventDisableTiming);
     {
         const char* ng = getenv("FMB_NO_GRAPH");
@@ -170,141 +193,246 @@ FMB_API int fmb_session_create(fmb_session** out, int F, int k, int64_t max_batc
 FMB_API int64_t fmb_session_launches(const fmb_session* s) { return s ? s->launches : 0; }
 FMB_API int fmb_session_graph_count(const fmb_session* s) { return s ? s->ngraphs : 0; }
 
-// the kernels of one FM-only step.  `side` (nullable) is a second stream: the sort does not depend on
-// the forward pass and the bias/loss epilogue does not depend on the row updates, so they fork.
+static bool by_field_sort(const fmb_session* s, int B) { return s->d_field_off && B <= fmb_sort_fields_max_batch(); }
+
+// stable sort of a batch's row ids + per-entry (sorted position | multi-hit flag) words into sorted buffer `buf`
+static int sort_launch(fmb_session* s, const int32_t* ids, int B, int key_bits, int buf, void* radix_ws,
+                       cudaStream_t st, int* nlaunch) {
+    const int64_t N = (int64_t)B * s->F;
+    int rc;
+    if (by_field_sort(s, B)) {
+        rc = fmb_sort_fields(ids, B, s->F, s->d_field_off, s->d_skeys_buf[buf], s->d_perm_buf[buf], st);
+        *nlaunch += 1;
+    } else {
+        rc = fmb_sort_segment(ids, N, key_bits, radix_ws, s->sort_ws_bytes, s->d_skeys_buf[buf], s->d_perm_buf[buf],
+                              nullptr, nullptr, st);
+        *nlaunch += 3 * ((key_bits + 7) / 8);
+    }
+    if (rc) return rc;
+    rc = fmb_pos_flags(s->d_skeys_buf[buf], s->d_perm_buf[buf], N, s->d_posflag_buf[buf], st);
+    *nlaunch += 1;
+    return rc;
+}
+
+// The kernels of one FM-only step (rows read once, see fm_step.cu):
+//   main : [sort + position words of this batch, unless pre-sorted] -> fused forward/loss/single-hit updates
+//          -> run kernel (multi-hit rows, sample order)
+//   side : bias step + mean loss (needs delta/lossv only)            side2: sort of the NEXT batch (ids only)
 static int fm_step_launch(fmb_session* s, const int32_t* ids, const float* xv, const float* y, int B, float* table,
                           float* bias, int key_bits, int loss_kind, float lr, int mode, float* loss_dev,
-                          cudaStream_t main, cudaStream_t side, int sort_buf, bool skip_sort, int* nlaunch) {
+                          const int32_t* next_ids, cudaStream_t main, cudaStream_t side, cudaStream_t side2, int cur,
+                          bool pre, int* nlaunch) {
     const int64_t N = (int64_t)B * s->F;
-    int32_t* skeys = s->d_skeys_buf[sort_buf];
-    int32_t* perm = s->d_perm_buf[sort_buf];
-    const bool by_field = s->d_field_off && B <= fmb_sort_fields_max_batch();
-    cudaStream_t sort_st = side ? side : main;
-    if (side) { cudaEventRecord(s->ev_fork, main); cudaStreamWaitEvent(side, s->ev_fork, 0); }
-    int rc = fmb_fm_forward(ids, xv, table, bias, B, s->F, s->k, nullptr, s->d_S, nullptr, nullptr, s->d_z, y,
-                            loss_kind, s->d_delta, s->d_lossv, main);
-    if (rc) return rc;
-    if (side) cudaEventRecord(s->ev_fwd, main);
-    if (!skip_sort) {
-        if (by_field)
-            rc = fmb_sort_fields(ids, B, s->F, s->d_field_off, skeys, perm, sort_st);
-        else
-            rc = fmb_sort_segment(ids, N, key_bits, s->d_sort_ws, s->sort_ws_bytes, skeys, perm, nullptr, nullptr,
-                                  sort_st);
+    int rc;
+    *nlaunch = 0;
+    cudaEventRecord(s->ev_fork, main);
+    cudaStreamWaitEvent(side, s->ev_fork, 0);
+    if (next_ids) {
+        cudaStreamWaitEvent(side2, s->ev_fork, 0);
+        rc = sort_launch(s, next_ids, B, key_bits, 1 - cur, s->d_sort_ws2, side2, nlaunch);
+        if (rc) return rc;
+        cudaEventRecord(s->ev_join2, side2);
+    }
+    if (!pre) {
+        rc = sort_launch(s, ids, B, key_bits, cur, s->d_sort_ws, main, nlaunch);
         if (rc) return rc;
     }
-    if (side) { cudaEventRecord(s->ev_sort, side); cudaStreamWaitEvent(main, s->ev_sort, 0); }
-    rc = fmb_fm_backward_update(skeys, perm, N, xv, table, s->F, s->k, s->d_S, s->d_delta, 1, nullptr, lr,
-                                mode, s->d_bwd_ws, s->bwd_ws_bytes, main);
+    rc = fmb_fm_step_fused(ids, xv, y, table, bias, s->d_posflag_buf[cur], B, s->F, s->k, loss_kind, lr, mode,
+                           s->d_delta, s->d_lossv, s->d_bwd_ws, s->bwd_ws_bytes, main);
     if (rc) return rc;
-    if (side) cudaStreamWaitEvent(side, s->ev_fwd, 0);
-    rc = fmb_finish_step(s->d_delta, s->d_lossv, B, bias, lr, mode, loss_dev ? loss_dev : s->d_loss,
-                         side ? side : main);
+    cudaEventRecord(s->ev_fwd, main);
+    cudaStreamWaitEvent(side, s->ev_fwd, 0);
+    rc = fmb_finish_step(s->d_delta, s->d_lossv, B, bias, lr, mode, loss_dev ? loss_dev : s->d_loss, side);
     if (rc) return rc;
-    if (side) { cudaEventRecord(s->ev_join, side); cudaStreamWaitEvent(main, s->ev_join, 0); }
-    *nlaunch = 1 + (skip_sort ? 0 : (by_field ? 1 : 3 * ((key_bits + 7) / 8))) + 2 + 1;
+    cudaEventRecord(s->ev_join, side);
+    rc = fmb_fm_backward_runs(s->d_skeys_buf[cur], N, table, s->F, s->k, lr, mode, s->d_bwd_ws, s->bwd_ws_bytes, main);
+    if (rc) return rc;
+    cudaStreamWaitEvent(main, s->ev_join, 0);
+    if (next_ids) cudaStreamWaitEvent(main, s->ev_join2, 0);
+    *nlaunch += 3;
     return FMB_OK;
 }
 
-// One FM-only training step with DEVICE inputs (FMAdam.update_embedding/fit, and the
-// update_embedding of DeepFM/NFM/ONN classes whose loss is on forward_fm only).
+// re-point one kernel node of an instantiated step graph at new per-batch pointers: argument i of the node is
+// replaced by *repl[i] wherever repl[i] != NULL; the other arguments keep the values captured in `graph`.
+static int patch_node(cudaGraphExec_t exec, cudaGraphNode_t node, int nparams, const void* const* repl) {
+    cudaKernelNodeParams kp;
+    CU(cudaGraphKernelNodeGetParams(node, &kp));
+    void* args[16];
+    for (int i = 0; i < nparams; ++i) args[i] = repl[i] ? const_cast<void*>(repl[i]) : kp.kernelParams[i];
+    kp.kernelParams = args;
+    kp.extra = nullptr;
+    CU(cudaGraphExecKernelNodeSetParams(exec, node, &kp));
+    return FMB_OK;
+}
+
+static int capture_variant(fmb_session* s, StepVariant* v, const int32_t* ids, const float* xv, const float* y,
+                           float* table, float* bias, const int32_t* next_ids) {
+    cudaGraph_t graph = nullptr;
+    int nl = 0;
+    CU(cudaStreamBeginCapture(s->st0, cudaStreamCaptureModeThreadLocal));
+    const int rc = fm_step_launch(s, ids, xv, y, v->B, table, bias, v->key_bits, v->loss_kind, v->lr, v->mode, s->d_loss,
+                                  next_ids, s->st0, s->st1, s->st2, v->cur, v->pre != 0, &nl);
+    cudaError_t e = cudaStreamEndCapture(s->st0, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) { fmb_set_error("graph capture: %s", cudaGetErrorString(e)); return FMB_ERR_CUDA; }
+    // find the nodes that carry per-batch pointers
+    cudaGraphNode_t nodes[64];
+    size_t nn = 64;
+    CU(cudaGraphGetNodes(graph, nodes, &nn));
+    const void* sort_fns[3];
+    int sort_np[3];
+    const int nsort = fmb_sort_fields_kernel_fns(sort_fns, sort_np);
+    v->n_fused = v->n_sort_cur = v->n_sort_next = nullptr;
+    for (size_t i = 0; i < nn; ++i) {
+        cudaGraphNodeType ty;
+        CU(cudaGraphNodeGetType(nodes[i], &ty));
+        if (ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp;
+        CU(cudaGraphKernelNodeGetParams(nodes[i], &kp));
+        if (kp.func == fmb_fused_kernel_fn()) { v->n_fused = nodes[i]; continue; }
+        for (int t = 0; t < nsort; ++t)
+            if (kp.func == sort_fns[t]) {
+                const int32_t* out = *static_cast<int32_t**>(kp.kernelParams[4]);   // sorted_keys argument
+                if (out == s->d_skeys_buf[v->cur]) { v->n_sort_cur = nodes[i]; v->np_sort_cur = sort_np[t]; }
+                else { v->n_sort_next = nodes[i]; v->np_sort_next = sort_np[t]; }
+            }
+    }
+    if (!v->n_fused || (!v->pre && !v->n_sort_cur) || (v->has_next && !v->n_sort_next)) {
+        cudaGraphDestroy(graph);
+        fmb_set_error("step graph: kernel nodes not found");
+        return FMB_ERR_CUDA;
+    }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(graph); fmb_set_error("graph instantiate: %s", cudaGetErrorString(e)); return FMB_ERR_CUDA; }
+    v->graph = graph; v->exec = exec; v->nlaunch = nl;
+    return FMB_OK;
+}
+
+// One FM-only training step with DEVICE inputs (FMAdam.update_embedding/fit, and the update_embedding of the
+// DeepFM/NFM/ONN classes whose loss is on forward_fm only).
 //   loss_kind 0: BCEWithLogits(z_fm)   (fm_adam.py:66, deepfm_adam.py:101, deepfm_onn.py:166)
 //   loss_kind 1: BCEWithLogits(sigmoid(z_fm))   (fm_adam.py:80, nfm_adam.py:100, nfm_onn.py:168)
 //   loss_dev (nullable): receives the mean loss (device scalar).
-// The step is captured once per distinct argument set into a CUDA graph (forward || sort ->
-// backward/update || bias+loss) and replayed afterwards; FMB_NO_GRAPH=1 launches the kernels directly.
-FMB_API int fmb_session_fm_step(fmb_session* s, const int32_t* ids, const float* xv, const float* y, int B,
-                                float* table, float* bias, int key_bits, int loss_kind, float lr, int mode,
-                                float* loss_dev, cudaStream_t stream) {
+//   next_ids (nullable): ids [B,F] of the batch the NEXT call will step on; their sort (it depends on the ids only)
+//   rides along on a side branch of this step, and the next call -- recognised by its ids pointer -- skips its own.
+// The step replays a CUDA graph captured once per configuration and re-pointed at this call's batch;
+// FMB_NO_GRAPH=1 (and batches too large for the per-field sort) launch the kernels directly.
+FMB_API int fmb_session_fm_step_next(fmb_session* s, const int32_t* ids, const float* xv, const float* y, int B,
+                                     float* table, float* bias, int key_bits, int loss_kind, float lr, int mode,
+                                     const int32_t* next_ids, float* loss_dev, cudaStream_t stream) {
     FMB_CHECK_ARG(s && ids && y && table && bias, "fmb_session_fm_step: null pointer");
     FMB_CHECK_ARG(B > 0 && B <= s->maxB, "fmb_session_fm_step: B=%d exceeds session max_batch", B);
     int nl = 0;
-    // sorted form of this batch: already produced by fmb_session_presort, or sorted inside the step
-    const bool pre = s->presort_ids == ids && s->presort_B == B;
-    const int buf = pre ? s->presort_buf : 1 - s->last_buf;
+    // sorted form of this batch: already produced by a previous call (next_ids / fmb_session_presort), or sorted here
+    const bool pre = s->presort_ids == ids && s->presort_B == B && !s->presort_stale;
+    s->presort_stale = 0;
+    const int cur = pre ? s->presort_buf : 1 - s->last_buf;
     if (pre) {
-        CU(cudaStreamWaitEvent(stream, s->ev_presort, 0));
-        s->presort_ids = nullptr;
+        if (s->presort_ext) CU(cudaStreamWaitEvent(stream, s->ev_presort, 0));
     } else {
-        if (s->buf_used[buf]) CU(cudaStreamWaitEvent(stream, s->ev_buf_free[buf], 0));
-        if (s->presort_ids && s->presort_buf == buf) {
-            // a pre-sort of some other batch targets the buffer this step is about to overwrite: order the
-            // step behind it and forget its result
-            CU(cudaStreamWaitEvent(stream, s->ev_presort, 0));
-            s->presort_ids = nullptr;
-        }
+        if (s->buf_used[cur]) CU(cudaStreamWaitEvent(stream, s->ev_buf_free[cur], 0));
+        if (s->presort_ids && s->presort_ext) CU(cudaStreamWaitEvent(stream, s->ev_presort, 0));   // a pre-sort nobody used
     }
-    s->last_buf = buf;
+    s->presort_ids = nullptr;
+    // the next batch is sorted into the other buffer, last read by the step before this one (already ordered: same stream)
+    if (next_ids && s->buf_used[1 - cur]) CU(cudaStreamWaitEvent(stream, s->ev_buf_free[1 - cur], 0));
+    s->last_buf = cur;
     int rc = FMB_OK;
     // the very first step runs eagerly: it sets the kernels' function attributes outside any capture
-    if (!s->use_graph || s->steps_done == 0) {
-        // direct launches; the sort (when not pre-sorted) and the bias/loss epilogue still fork to the side stream
-        rc = fm_step_launch(s, ids, xv, y, B, table, bias, key_bits, loss_kind, lr, mode, loss_dev, stream, s->st1,
-                            buf, pre, &nl);
+    if (!s->use_graph || s->steps_done == 0 || !by_field_sort(s, B)) {
+        rc = fm_step_launch(s, ids, xv, y, B, table, bias, key_bits, loss_kind, lr, mode, loss_dev, next_ids, stream,
+                            s->st1, s->st2, cur, pre, &nl);
+        if (rc) return rc;
         s->launches += nl;
     } else {
-        StepKey key;
+        StepVariant key;
         memset(&key, 0, sizeof(key));
-        key.ids = ids; key.xv = xv; key.y = y; key.table = table; key.bias = bias; key.loss = nullptr;
-        key.B = B; key.key_bits = key_bits; key.loss_kind = loss_kind; key.mode = mode; key.lr = lr;
-        key.sort_buf = buf; key.skip_sort = pre;
-        int slot = -1;
+        key.B = B; key.key_bits = key_bits; key.loss_kind = loss_kind; key.mode = mode; key.has_xv = xv != nullptr;
+        key.pre = pre; key.has_next = next_ids != nullptr; key.cur = cur; key.table = table; key.bias = bias; key.lr = lr;
+        StepVariant* v = nullptr;
+        const size_t keylen = offsetof(StepVariant, graph);
         for (int i = 0; i < s->ngraphs; ++i)
-            if (memcmp(&s->gkey[i], &key, sizeof(key)) == 0) { slot = i; break; }
-        if (slot < 0) {
-            cudaGraph_t graph = nullptr;
-            CU(cudaStreamBeginCapture(s->st0, cudaStreamCaptureModeThreadLocal));
-            // the graph always writes the loss to the session's own scalar: the caller's pointer (often a fresh
-            // allocation every step) must not be part of the cache key
-            rc = fm_step_launch(s, ids, xv, y, B, table, bias, key_bits, loss_kind, lr, mode, s->d_loss, s->st0,
-                                s->st1, buf, pre, &nl);
-            cudaError_t e = cudaStreamEndCapture(s->st0, &graph);
-            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-            if (e != cudaSuccess) { fmb_set_error("graph capture: %s", cudaGetErrorString(e)); return FMB_ERR_CUDA; }
-            cudaGraphExec_t exec = nullptr;
-            e = cudaGraphInstantiate(&exec, graph, 0);
-            cudaGraphDestroy(graph);
-            if (e != cudaSuccess) { fmb_set_error("graph instantiate: %s", cudaGetErrorString(e)); return FMB_ERR_CUDA; }
+            if (memcmp(&s->gvar[i], &key, keylen) == 0) { v = &s->gvar[i]; break; }
+        if (!v) {
+            rc = capture_variant(s, &key, ids, xv, y, table, bias, next_ids);
+            if (rc) return rc;
+            int slot;
             if (s->ngraphs < FMB_GRAPH_CACHE) slot = s->ngraphs++;
-            else { slot = s->next_evict; s->next_evict = (s->next_evict + 1) % FMB_GRAPH_CACHE; cudaGraphExecDestroy(s->gexec[slot]); }
-            s->gkey[slot] = key; s->gexec[slot] = exec; s->glaunches[slot] = nl;
+            else {
+                slot = s->next_evict; s->next_evict = (s->next_evict + 1) % FMB_GRAPH_CACHE;
+                cudaGraphExecDestroy(s->gvar[slot].exec); cudaGraphDestroy(s->gvar[slot].graph);
+            }
+            s->gvar[slot] = key;
+            v = &s->gvar[slot];
         }
-        CU(cudaGraphLaunch(s->gexec[slot], stream));
+        {
+            const void* repl[16] = {nullptr};
+            repl[0] = &ids; repl[1] = &xv; repl[2] = &y;
+            rc = patch_node(v->exec, v->n_fused, 5, repl);
+            if (rc) return rc;
+        }
+        if (!pre) {
+            const void* repl[16] = {nullptr};
+            repl[0] = &ids;
+            rc = patch_node(v->exec, v->n_sort_cur, v->np_sort_cur, repl);
+            if (rc) return rc;
+        }
+        if (next_ids) {
+            const void* repl[16] = {nullptr};
+            repl[0] = &next_ids;
+            rc = patch_node(v->exec, v->n_sort_next, v->np_sort_next, repl);
+            if (rc) return rc;
+        }
+        CU(cudaGraphLaunch(v->exec, stream));
         if (loss_dev && loss_dev != s->d_loss) CU(cudaMemcpyAsync(loss_dev, s->d_loss, 4, cudaMemcpyDeviceToDevice, stream));
-        s->launches += s->glaunches[slot];
+        s->launches += v->nlaunch;
     }
-    if (rc) return rc;
-    CU(cudaEventRecord(s->ev_buf_free[buf], stream));
-    s->buf_used[buf] = 1;
+    CU(cudaEventRecord(s->ev_buf_free[cur], stream));
+    s->buf_used[cur] = 1;
+    if (next_ids) {
+        s->presort_ids = next_ids; s->presort_B = B; s->presort_buf = 1 - cur; s->presort_ext = 0;
+        CU(cudaEventRecord(s->ev_buf_free[1 - cur], stream));
+        s->buf_used[1 - cur] = 1;
+    }
     s->steps_done += 1;
     return FMB_OK;
 }
 
-// Sort batch `ids` now, on the session's side stream, into the sorted-buffer the running step is NOT using;
-// the next fmb_session_fm_step called with the same `ids` pointer and B skips its own sort.  The sort
-// depends on the ids only, so this overlaps the backward kernels of the step in flight.  `ready` (nullable)
-// is an event the ids depend on (e.g. their H2D copy).  The ids must not change until that step has run.
+FMB_API int fmb_session_fm_step(fmb_session* s, const int32_t* ids, const float* xv, const float* y, int B,
+                                float* table, float* bias, int key_bits, int loss_kind, float lr, int mode,
+                                float* loss_dev, cudaStream_t stream) {
+    return fmb_session_fm_step_next(s, ids, xv, y, B, table, bias, key_bits, loss_kind, lr, mode, nullptr, loss_dev, stream);
+}
+
+// Sort batch `ids` now, on the session's side stream, into the sorted buffer the running step is NOT using; the
+// next fmb_session_fm_step called with the same `ids` pointer and B skips its own sort.  The sort depends on the
+// ids only, so this overlaps the kernels of the step in flight.  `ready` (nullable) is an event the ids depend on
+// (e.g. their H2D copy).  The ids must not change until that step has run.
 static int presort_impl(fmb_session* s, const int32_t* ids, int B, int key_bits, cudaEvent_t ready) {
     const int buf = 1 - s->last_buf;
     if (s->buf_used[buf]) CU(cudaStreamWaitEvent(s->st2, s->ev_buf_free[buf], 0));
     if (ready) CU(cudaStreamWaitEvent(s->st2, ready, 0));
-    const int64_t N = (int64_t)B * s->F;
-    int rc;
-    if (s->d_field_off && B <= fmb_sort_fields_max_batch())
-        rc = fmb_sort_fields(ids, B, s->F, s->d_field_off, s->d_skeys_buf[buf], s->d_perm_buf[buf], s->st2);
-    else
-        rc = fmb_sort_segment(ids, N, key_bits, s->d_sort_ws, s->sort_ws_bytes, s->d_skeys_buf[buf], s->d_perm_buf[buf],
-                              nullptr, nullptr, s->st2);
+    int nl = 0;
+    const int rc = sort_launch(s, ids, B, key_bits, buf, s->d_sort_ws2 ? s->d_sort_ws2 : s->d_sort_ws, s->st2, &nl);
     if (rc) return rc;
     CU(cudaEventRecord(s->ev_presort, s->st2));
-    s->launches += (s->d_field_off && B <= fmb_sort_fields_max_batch()) ? 1 : 3 * ((key_bits + 7) / 8);
-    s->presort_ids = ids; s->presort_B = B; s->presort_buf = buf;
+    s->launches += nl;
+    s->presort_ids = ids; s->presort_B = B; s->presort_buf = buf; s->presort_ext = 1;
     return FMB_OK;
 }
 
 FMB_API int fmb_session_presort(fmb_session* s, const int32_t* ids, int B, int key_bits) {
     FMB_CHECK_ARG(s && ids && B > 0 && B <= s->maxB, "fmb_session_presort: bad arguments");
     return presort_impl(s, ids, B, key_bits, nullptr);
+}
+
+// Forget any pre-sorted batch: the next step sorts its own ids.  Callers that cannot guarantee that the buffer
+// behind a pre-sorted ids pointer still holds the same batch (freed and re-allocated tensors) call this.
+FMB_API void fmb_session_presort_invalidate(fmb_session* s) {
+    if (!s || !s->presort_ids) return;
+    s->presort_stale = 1;
 }
 
 // true when `p` is page-locked host memory the copy engine can read directly (no staging copy needed)

@@ -148,6 +148,7 @@ class _DeepBase(nn.Module):
                                       requires_grad=False)
         self._session = None
         self._session_cap = 0
+        self._presorted = None   # the EncodedBatch whose sorted form the session holds (kept alive: its ids pointer is the key)
         self._ws = {}
 
     def _bind_embeddings(self):
@@ -245,6 +246,7 @@ class _DeepBase(nn.Module):
             check(self._lib.fmb_session_create(C.byref(h), self.field_size, self.embedding_size, cap,
                                                off32.ctypes.data_as(C.c_void_p)), "fmb_session_create")
             self._session, self._session_cap = h, cap
+            self._presorted = None
         return self._session
 
     def _buf(self, name, shape, dtype=torch.float32):
@@ -322,14 +324,21 @@ class _DeepBase(nn.Module):
         return o["z"]
 
     # ------------------------------------------------------------------ training steps (A6, A7)
-    def _fm_step(self, e, loss_kind):
+    def _fm_step(self, e, loss_kind, next_batch=None):
+        """One FM-only step on EncodedBatch `e`.  `next_batch` (an EncodedBatch of the same size, optional) is the
+        batch the following call will step on: its sort rides along with this step."""
         if e.y is None:
             raise ValueError("labels required")
         s = self._get_session(e.B)
+        if self._presorted is not None and self._presorted is not e:
+            self._lib.fmb_session_presort_invalidate(s)   # a pre-sort is only ever honoured for the very same batch object
+        nxt = next_batch if (next_batch is not None and next_batch.B == e.B) else None
         loss = torch.empty((), device=self.device)
-        check(self._lib.fmb_session_fm_step(s, ptr(e.ids), ptr(e.xv), ptr(e.y), e.B, ptr(self._table), ptr(self.bias),
-                                            self._key_bits, loss_kind, self._lr, self.update_mode, ptr(loss),
-                                            _stream()), "fmb_session_fm_step")
+        check(self._lib.fmb_session_fm_step_next(s, ptr(e.ids), ptr(e.xv), ptr(e.y), e.B, ptr(self._table),
+                                                 ptr(self.bias), self._key_bits, loss_kind, self._lr, self.update_mode,
+                                                 ptr(nxt.ids) if nxt is not None else None, ptr(loss), _stream()),
+              "fmb_session_fm_step_next")
+        self._presorted = nxt
         return loss
 
     _UE_LOSS = LOSS_LOGITS
@@ -340,11 +349,13 @@ class _DeepBase(nn.Module):
         FMAdam.fit) on a side stream, overlapping the step in flight (the sort depends on the ids only)."""
         s = self._get_session(batch.B)
         check(self._lib.fmb_session_presort(s, ptr(batch.ids), batch.B, self._key_bits), "fmb_session_presort")
+        self._presorted = batch
 
-    def update_embedding(self, Xi, Xv, Y):
-        """fm_adam.py:56-69 and the same method of the other four classes: loss on forward_fm only."""
+    def update_embedding(self, Xi, Xv, Y, next_batch=None):
+        """fm_adam.py:56-69 and the same method of the other four classes: loss on forward_fm only.
+        `next_batch` (extension, optional): the EncodedBatch the next call will be given."""
         self.train()
-        return self._fm_step(self.encode(Xi, Xv, Y), self._UE_LOSS)
+        return self._fm_step(self.encode(Xi, Xv, Y), self._UE_LOSS, next_batch)
 
     def _sort(self, e):
         N = e.B * self.field_size

@@ -93,6 +93,23 @@ int fmb_sort_fields_max_batch(void);
 int fmb_sort_fields(const int32_t* ids_dev, int B, int F, const int32_t* field_off_dev, int32_t* sorted_keys_dev,
                     int32_t* perm_dev, fmb_stream_t stream);
 
+/* ---- A1-A3 + A6 fused: the FM-only step with every row read once (csrc/fm_step.cu) ----------------
+ * replaces forward_fm + F.binary_cross_entropy_with_logits + loss.backward() + optimizer.step() of
+ * fm_adam.py:56-82 (and update_embedding of the other four classes) in three launches:
+ *   fmb_pos_flags        per entry: its position in the stable sort | "row hit more than once" flag
+ *   fmb_fm_step_fused    gather, logit, loss, gradient; rows hit once are updated from the copy in shared memory,
+ *                        the other entries stage their contribution at their sorted position in `ws`
+ *   fmb_fm_backward_runs sums every run of >= 2 equal sorted keys in sample order (torch's CPU
+ *                        embedding_dense_backward order) and updates those rows
+ * followed by fmb_finish_step (bias step, mean loss) on delta/lossv.  ws: fmb_bwd_workspace_bytes(B*F, k). */
+int fmb_pos_flags(const int32_t* sorted_keys_dev, const int32_t* perm_dev, int64_t N, uint32_t* posflag_dev,
+                  fmb_stream_t stream);
+int fmb_fm_step_fused(const int32_t* ids_dev, const float* xv_dev /*nullable*/, const float* y_dev, float* table_dev,
+                      const float* bias_dev, const uint32_t* posflag_dev, int B, int F, int k, int loss_kind, float lr,
+                      int mode, float* delta_dev, float* lossv_dev, void* ws_dev, size_t ws_bytes, fmb_stream_t stream);
+int fmb_fm_backward_runs(const int32_t* sorted_keys_dev, int64_t N, float* table_dev, int F, int k, float lr, int mode,
+                         void* ws_dev, size_t ws_bytes, fmb_stream_t stream);
+
 /* ---- A6: sparse embedding gradient (segmented, in sample order) fused with the row update ------
  * replaces loss.backward() + optimizer.step() for the embedding tables (fm_adam.py:67-68,
  * deepfm_adam.py:102-103,115-116).  gs [B] = gradient on the FM logit; use_fm2 = it also flows
@@ -247,6 +264,15 @@ int fmb_session_fm_step_host(fmb_session* s, const int32_t* ids_host, const floa
  * stream (overlapping the step in flight); the next fmb_session_fm_step called with the same ids pointer and
  * B skips its own sort.  The ids must stay unchanged until that step has been submitted. */
 int fmb_session_presort(fmb_session* s, const int32_t* ids_dev, int B, int key_bits);
+/* forget a pending pre-sort (the caller cannot vouch that the pre-sorted ids buffer still holds the same batch) */
+void fmb_session_presort_invalidate(fmb_session* s);
+/* fmb_session_fm_step with the sort of the NEXT batch riding along: next_ids_dev (nullable) are the ids the
+ * following call will step on (main_experiment.py:92-105 walks its batches in a known order); their stable sort
+ * runs on a side branch of this step's graph and the following call, recognised by its ids pointer, skips its own.
+ * One CUDA graph per configuration, re-pointed at each call's batch (cudaGraphExecKernelNodeSetParams). */
+int fmb_session_fm_step_next(fmb_session* s, const int32_t* ids_dev, const float* xv_dev, const float* y_dev, int B,
+                             float* table_dev, float* bias_dev, int key_bits, int loss_kind, float lr, int mode,
+                             const int32_t* next_ids_dev, float* loss_dev, fmb_stream_t stream);
 
 /* pipelined host entry point: two input slots; the H2D copies of step t+1 run on the session's copy stream
  * while step t computes.  Pinned / registered host buffers are read in place.  fmb_session_wait_loss

@@ -326,3 +326,23 @@ def test_aten_mirrors_device_equals_oracle(op, fn):
         assert lib.fmb_math_eval(op, C.c_void_p(d.data_ptr()), C.c_void_p(out.data_ptr()), x.size, None) == 0
         got = out.cpu().numpy()
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (op, x.size)
+
+
+@pytest.mark.parametrize("B", [512, 4096])
+def test_step_graph_is_repointed_per_batch_and_next_batch_sort_rides_along(B):
+    """fmb_session_fm_step_next: ONE graph per configuration, re-pointed at every call's batch; the sort of the
+    announced next batch rides along.  12 distinct device-resident batches, bit-exact vs the oracle step by step;
+    a wrong announcement (stepping on another batch than the one announced) must not change a bit either."""
+    import fm_for_online_recommendation_b200 as pkg
+    lib = pkg.require_cuda()
+    m, orc = _pair("FMAdam", CRITEO, 10, lr=1e-3, scale=0.1)
+    data = [synth(CRITEO, B, 100 + i, zipf=(i % 3 == 0)) for i in range(12)]
+    enc = [m.encode(Xi, Xv, Y) for Xi, Xv, Y in data]
+    order = [0, 1, 2, 3, 4, 5, 7, 6, 8, 9, 10, 11, 3, 3]      # step 6 was announced as batch 6 but batch 7 is stepped
+    announce = [1, 2, 3, 4, 5, 6, 6, 8, 9, 10, 11, None, 3, None]
+    for t, (i, nx) in enumerate(zip(order, announce)):
+        got = m._fm_step(enc[i], 0, enc[nx] if nx is not None else None)
+        want = orc.update_embedding(*data[i])
+        assert np.float32(got.item()) == np.float32(want), (t, i)
+    assert_same_params(m, orc)
+    assert lib.fmb_session_graph_count(m._session) <= 6   # (sorted before / in the step) x (with / without next) x buffer parity
