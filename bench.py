@@ -201,8 +201,10 @@ def run_ours(args):
     graphs0 = lib.fmb_session_graph_count(sess)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
+    th0 = time.perf_counter()
     for i in range(K):
         step(base + i)
+    host_ms = (time.perf_counter() - th0) * 1e3 / K     # time the host needs to SUBMIT one step (no sync inside)
     ev1.record(stream)
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
@@ -263,61 +265,60 @@ def run_ours(args):
     e2e_blocking_s = time.perf_counter() - t0
     clocks = sampler.stop()
 
-    # ---- per-phase device time (CUDA events on the launching stream) for the roofline
+    # ---- per-kernel device time (CUDA events on the launching stream, warm L2 like the real step) for the roofline
     p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
     N = B * F
-    S = torch.empty(B, model._kp4, device="cuda"); z = torch.empty(B, device="cuda")
     delta = torch.empty(B, device="cuda"); lossv = torch.empty(B, device="cuda")
     wsb = lib.fmb_sort_workspace_bytes(N); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
     sk = torch.empty(N, dtype=torch.int32, device="cuda"); pm = torch.empty(N, dtype=torch.int32, device="cuda")
+    pf = torch.empty(N, dtype=torch.int32, device="cuda")
     bwsb = lib.fmb_bwd_workspace_bytes(N, k); bws = torch.empty(bwsb, dtype=torch.uint8, device="cuda")
     lossd = torch.empty(1, device="cuda")
     st = C.c_void_p(stream.cuda_stream)
-    phases = {"fm_forward": 0.0, "sort": 0.0, "fm_backward_update": 0.0, "finish": 0.0}
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    phases = {"sort": 0.0, "pos_flags": 0.0, "fm_step_fused": 0.0, "fm_bwd_runs": 0.0, "finish": 0.0}
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
     reps = max(5, min(K, 50))
     for i in range(reps + 2):
         e = enc[i % NB]
         evs[0].record(stream)
-        lib.fmb_fm_forward(p(e.ids), None, tptr, bptr, B, F, k, None, p(S), None, None, p(z), p(e.y), 0, p(delta),
-                           p(lossv), st)
-        evs[1].record(stream)
         if B <= lib.fmb_sort_fields_max_batch():
-            lib.fmb_sort_fields(p(e.ids), B, F, p(model._field_off_dev), p(sk), p(pm), st)
+            rc = lib.fmb_sort_fields(p(e.ids), B, F, p(model._field_off_dev), p(sk), p(pm), st)
         else:
-            lib.fmb_sort_segment(p(e.ids), N, model._key_bits, p(ws), wsb, p(sk), p(pm), None, None, st)
+            rc = lib.fmb_sort_segment(p(e.ids), N, model._key_bits, p(ws), wsb, p(sk), p(pm), None, None, st)
+        assert rc == 0, lib.fmb_last_error()
+        evs[1].record(stream)
+        assert lib.fmb_pos_flags(p(sk), p(pm), N, p(pf), st) == 0
         evs[2].record(stream)
-        lib.fmb_fm_backward_update(p(sk), p(pm), N, None, tptr, F, k, p(S), p(delta), 1, None, model._lr, 0, p(bws),
-                                   bwsb, st)
+        rc = lib.fmb_fm_step_fused(p(e.ids), None, p(e.y), tptr, bptr, p(pf), B, F, k, 0, model._lr, 0, p(delta), p(lossv),
+                                   p(bws), bwsb, st)
+        assert rc == 0, lib.fmb_last_error()
         evs[3].record(stream)
-        lib.fmb_finish_step(p(delta), p(lossv), B, bptr, model._lr, 0, p(lossd), st)
+        assert lib.fmb_fm_backward_runs(p(sk), N, tptr, F, k, model._lr, 0, p(bws), bwsb, st) == 0
         evs[4].record(stream)
+        assert lib.fmb_finish_step(p(delta), p(lossv), B, bptr, model._lr, 0, p(lossd), st) == 0
+        evs[5].record(stream)
         torch.cuda.synchronize()
         if i >= 2:
             for j, name in enumerate(phases):
                 phases[name] += evs[j].elapsed_time(evs[j + 1]) / reps
     peaks, peak_src = measured_peaks()
     kp1 = k + 1
-    alg_bytes = {  # algorithmic bytes per launch (DESIGN.md "Kernels")
-        "fm_forward": B * (4 * F + 4 * F * kp1 + 4 * model._kp4 + 16),
-        "fm_backward_update": B * (8 * F + 8 * F * kp1 + 4 * model._kp4 + 4),
-        "sort": B * F * 8 * 2 * ((model._key_bits + 7) // 8),
-    }
-    dom = max(("fm_forward", "fm_backward_update"), key=lambda n: phases[n])
-    # DRAM traffic of the dominant phase's kernels from the last `ncu --set full` capture (profiles/), per launch
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_final2_dram_traffic.json")) as f:
+    # algorithmic bytes per launch of the dominant kernel: ids + position words + rows read + rows
+    # written + delta/loss = the whole step's 8F(k+1) + 8F + 8 per sample
+    step_bytes = B * (8 * F * kp1 + 8 * F + 8)
+    alg_bytes = {"fm_step_fused": step_bytes}
+    dom = "fm_step_fused"
+    traffic, traffic_src = None, None
+    try:   # DRAM bytes of that kernel from the last `ncu --set full` capture of this command (profiles/), per launch
+        with open(os.path.join(ROOT, "profiles", "r2_dram_traffic.json")) as f:
             tr = json.load(f)
-        pick = ("fm_forward",) if dom == "fm_forward" else ("fm_bwd_entry", "fm_bwd_runs")
-        traffic = int(sum(v["dram_read_bytes"] + v["dram_write_bytes"] for kname, v in tr.items()
-                          if kname.startswith(pick)))
+        if B == 8192 and args.workload == "cfg5":
+            traffic = int(tr["fm_step_fused_kernel"]["dram_read_bytes"] + tr["fm_step_fused_kernel"]["dram_write_bytes"])
+            traffic_src = "profiles/r2_dram_traffic.json (ncu --set full, cold cache, B=8192)"
     except Exception:
         traffic = None
-    dom_kernels = {"fm_forward": "fm_forward_kernel",
-                   "fm_backward_update": "fm_bwd_entry1_kernel + fm_bwd_runs_kernel (fmb_fm_backward_update)"}[dom]
+    dom_kernels = "fm_step_fused_kernel (gather + logit + loss + single-hit row updates + staging)"
     achieved = alg_bytes[dom] / (phases[dom] * 1e-3) / 1e9
-    step_bytes = B * (8 * F * kp1 + 8 * F + 8)
 
     value = B * K / (ms * 1e-3)
     line = {
@@ -331,10 +332,11 @@ def run_ours(args):
                 "api": "fmb_session_fm_step_host_async + fmb_session_wait_loss (pinned host ids/y in, loss out, "
                        "two slots: copies of step t+1 overlap step t)",
                 "blocking_value": B * K / e2e_blocking_s},
+        "host_submit_ms_per_step": host_ms,
         "gpu_launches": int(launches), "step_graphs_cached": int(lib.fmb_session_graph_count(sess)),
         "roofline": {"bound": "hbm", "kernel": dom_kernels, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
-                     "traffic_source": "profiles/r1_final2_dram_traffic.json (ncu --set full, cold cache, B=8192)",
+                     "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": alg_bytes[dom],
                      "phase_ms": phases,
                      "whole_step_GBps": step_bytes / (ms / K * 1e-3) / 1e9},

@@ -46,6 +46,8 @@ struct StepParams {
     float* lossv;              // [B] out
     float* G;                  // [k+1][Npad] staged contributions of multi-hit entries
     int64_t Npad;
+    long long* tdbg;           // debug only: per-CTA phase timestamps [grid][8] (globaltimer ns), else NULL
+    int dbg;                   // debug/attribution only (fmb_debug_set_step_flags): 1 = skip phase 4a, 2 = skip phase 4b
 };
 
 //   ids [B,F] global row ids;  xv [B,F] or NULL (all ones);  y [B];
@@ -63,16 +65,42 @@ __global__ void __launch_bounds__(256) fm_step_fused_kernel(const int32_t* __res
     float* d_s = S_s + SB * p.kp4;                 // [SB]
     int32_t* ids_s = reinterpret_cast<int32_t*>(d_s + SB);            // [SB][F]
     uint32_t* pos_s = reinterpret_cast<uint32_t*>(ids_s + SB * F);    // [SB][F]
+    uint16_t* single_s = reinterpret_cast<uint16_t*>(pos_s + SB * F); // [SB*F] entries whose row is hit once
+    uint16_t* multi_s = single_s + SB * F;                            // [SB*F] the others
+    __shared__ int n_single, n_multi;
+    if (threadIdx.x == 0) { n_single = 0; n_multi = 0; }
+    __syncthreads();
     const int b0 = blockIdx.x * SB;
     const int nv = min(SB, p.B - b0);
+#define FMB_TS(i) do { if (p.tdbg && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); p.tdbg[(size_t)blockIdx.x * 8 + (i)] = (long long)t_; } } while (0)
+    FMB_TS(0);
 
-    // phase 0: the tile's row ids, values and sorted positions, coalesced
-    for (int e = threadIdx.x; e < nv * F; e += blockDim.x) {
-        ids_s[e] = __ldg(ids + (size_t)b0 * F + e);
-        x_s[e] = xv ? __ldg(xv + (size_t)b0 * F + e) : 1.0f;
-        pos_s[e] = __ldg(posflag + (size_t)b0 * F + e);
+    // phase 0: the tile's row ids, values and sorted positions, coalesced; the entries are split into two compact
+    // lists (row hit once / several times) so that the update phase runs full warps down one code path each
+    for (int e0 = (threadIdx.x & ~31); e0 < nv * F; e0 += blockDim.x) {
+        const int e = e0 + (threadIdx.x & 31);
+        const bool valid = e < nv * F;
+        uint32_t pf = 0;
+        if (valid) {
+            ids_s[e] = __ldg(ids + (size_t)b0 * F + e);
+            x_s[e] = xv ? __ldg(xv + (size_t)b0 * F + e) : 1.0f;
+            pf = __ldg(posflag + (size_t)b0 * F + e);
+            pos_s[e] = pf;
+        }
+        const unsigned ms = __ballot_sync(0xffffffffu, valid && !(pf >> 31));
+        const unsigned mm = __ballot_sync(0xffffffffu, valid && (pf >> 31));
+        int bs = 0, bm = 0;
+        if ((threadIdx.x & 31) == 0) { bs = atomicAdd(&n_single, __popc(ms)); bm = atomicAdd(&n_multi, __popc(mm)); }
+        bs = __shfl_sync(0xffffffffu, bs, 0);
+        bm = __shfl_sync(0xffffffffu, bm, 0);
+        const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+        if (valid) {
+            if (pf >> 31) multi_s[bm + __popc(mm & lt)] = (uint16_t)e;
+            else single_s[bs + __popc(ms & lt)] = (uint16_t)e;
+        }
     }
     __syncthreads();
+    FMB_TS(1);
     // phase 1: gather rows, 16 B per cp.async; every row read of the tile is in flight at once
     {
         const int q = threadIdx.x & ((1 << p.ql_log) - 1);
@@ -83,6 +111,7 @@ __global__ void __launch_bounds__(256) fm_step_fused_kernel(const int32_t* __res
     }
     cp_async_wait_all();
     __syncthreads();
+    FMB_TS(2);
 
     // phase 2: one thread per (sample, component): S = sum_f e_f, Q = sum_f e_f^2, left to right (python sum() order)
     {
@@ -107,59 +136,91 @@ __global__ void __launch_bounds__(256) fm_step_fused_kernel(const int32_t* __res
             }
     }
     __syncthreads();
+    FMB_TS(3);
 
-    // phase 3: one thread per sample: logit in ATen's row-sum order, loss value, gradient on the logit
-    if (threadIdx.x < nv) {
-        const int s = threadIdx.x, b = b0 + s;
-        const float* r = rows_s + (size_t)s * F * rp + k;
-        const float* xs = x_s + s * F;
-        const float sf = fmb::aten_row_sum_small([&](int f) { return __fmul_rn(r[(size_t)f * rp], xs[f]); }, F);
-        const float* bs = bi_s + s * k;
-        const float sb = fmb::aten_row_sum_small([&](int j) { return bs[j]; }, k);
-        const float z = __fadd_rn(__fadd_rn(sf, sb), __ldg(p.bias));
-        float lv, d;
-        fmb::bce_logits_value_grad(p.loss_kind, z, y[b], b, p.B, lv, d);
-        p.lossv[b] = lv;
-        p.delta[b] = d;
-        d_s[s] = d;
+    // phase 3: eight lanes per sample: logit in ATen's row-sum order (the eight vector-lane chains side by side),
+    // then lane 0 of the group: loss value and gradient on the logit
+    {
+        const int s = threadIdx.x >> 3, l8 = threadIdx.x & 7;
+        const int nv8 = (nv + 3) & ~3;                        // whole warps take part in the shuffles
+        if (s < nv8) {
+            const unsigned mask = 0xffffffffu;
+            const int sc = min(s, nv - 1);                    // padding groups recompute the last sample (discarded)
+            const float* r = rows_s + (size_t)sc * F * rp + k;
+            const float* xs = x_s + sc * F;
+            const float sf = fmb::aten_row_sum_lanes8([&](int f) { return __fmul_rn(r[(size_t)f * rp], xs[f]); }, F, l8, mask);
+            const float* bs = bi_s + sc * k;
+            const float sb = fmb::aten_row_sum_lanes8([&](int j) { return bs[j]; }, k, l8, mask);
+            if (l8 == 0 && s < nv) {
+                const int b = b0 + s;
+                const float z = __fadd_rn(__fadd_rn(sf, sb), __ldg(p.bias));
+                float lv, d;
+                fmb::bce_logits_value_grad(p.loss_kind, z, y[b], b, p.B, lv, d);
+                p.lossv[b] = lv;
+                p.delta[b] = d;
+                d_s[s] = d;
+            }
+        }
     }
     __syncthreads();
+    FMB_TS(4);
 
-    // phase 4: one thread per (entry, 16-byte chunk): gradient contribution of the entry; single-hit rows are
-    // updated here from the shared-memory copy, the others stage their contribution at their sorted position
-    const int items = nv * F * p.cu;
-    for (int it = threadIdx.x; it < items; it += blockDim.x) {
-        const int ef = it / p.cu, q = it - ef * p.cu;
+    // phase 4a: rows hit once, one thread per (entry, 16-byte chunk): the gradient is the entry's contribution alone
+    // (0 + contribution, like the reference's zero-initialised grad row); the row is updated from the shared-memory
+    // copy.  Chunks no coordinate of which moved are not written back (on saturated samples the sign step is below a
+    // quarter ulp of every weight).
+    const int ns = n_single, nm = n_multi;
+    for (int it = threadIdx.x; it < ((p.dbg & 1) ? 0 : ns * p.cu); it += blockDim.x) {
+        const int li = it / p.cu, q = it - li * p.cu;
+        const int ef = single_s[li];
         const int s = ef / F;
         const float x = x_s[ef], d = d_s[s];
-        const uint32_t pf = pos_s[ef];
+        const float* Ss = S_s + s * p.kp4;
         const float4 v4 = *reinterpret_cast<const float4*>(rows_s + (size_t)ef * rp + q * 4);
         const float v[4] = {v4.x, v4.y, v4.z, v4.w};
-        float a[4];
+        float o[4];
+        bool moved = false;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const int j = q * 4 + t;
-            a[t] = 0.f;
-            if (j < k) {
-                const float ej = __fmul_rn(v[t], x);
-                a[t] = __fmul_rn(__fsub_rn(__fmul_rn(d, S_s[s * p.kp4 + j]), __fmul_rn(d, ej)), x);
-            } else if (j == k) {
-                a[t] = __fmul_rn(d, x);
+            o[t] = v[t];
+            if (j <= k) {
+                float a;
+                if (j < k) {
+                    const float ej = __fmul_rn(v[t], x);
+                    a = __fmul_rn(__fsub_rn(__fmul_rn(d, Ss[j]), __fmul_rn(d, ej)), x);
+                } else {
+                    a = __fmul_rn(d, x);
+                }
+                o[t] = fmb::apply_update_a(v[t], __fadd_rn(0.f, a), p.lr, p.astep, p.mode);
+                moved |= __float_as_int(o[t]) != __float_as_int(v[t]);
             }
         }
-        if (!(pf >> 31)) {
-            float o[4];
+        if (moved) *reinterpret_cast<float4*>(p.table + (size_t)ids_s[ef] * p.rowp + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    FMB_TS(5);
+    // phase 4b: rows hit several times: stage the entry's contribution at its sorted position (run kernel sums them)
+    for (int it = threadIdx.x; it < ((p.dbg & 2) ? 0 : nm * p.cu); it += blockDim.x) {
+        const int li = it / p.cu, q = it - li * p.cu;
+        const int ef = multi_s[li];
+        const int s = ef / F;
+        const float x = x_s[ef], d = d_s[s];
+        const size_t pos = pos_s[ef] & 0x7fffffffu;
+        const float* Ss = S_s + s * p.kp4;
+        const float4 v4 = *reinterpret_cast<const float4*>(rows_s + (size_t)ef * rp + q * 4);
+        const float v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
-            for (int t = 0; t < 4; ++t)   // sum over the row's single entry = 0 + contribution
-                o[t] = (q * 4 + t <= k) ? fmb::apply_update_a(v[t], __fadd_rn(0.f, a[t]), p.lr, p.astep, p.mode) : v[t];
-            *reinterpret_cast<float4*>(p.table + (size_t)ids_s[ef] * p.rowp + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
-        } else {
-            const size_t pos = pf & 0x7fffffffu;
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-                if (q * 4 + t <= k) p.G[(size_t)(q * 4 + t) * p.Npad + pos] = a[t];
+        for (int t = 0; t < 4; ++t) {
+            const int j = q * 4 + t;
+            if (j < k) {
+                const float ej = __fmul_rn(v[t], x);
+                p.G[(size_t)j * p.Npad + pos] = __fmul_rn(__fsub_rn(__fmul_rn(d, Ss[j]), __fmul_rn(d, ej)), x);
+            } else if (j == k) {
+                p.G[(size_t)j * p.Npad + pos] = __fmul_rn(d, x);
+            }
         }
     }
+    FMB_TS(6);
 }
 
 // posflag[perm[i]] = i | (row of sorted position i is hit more than once ? 0x80000000 : 0)
@@ -177,6 +238,12 @@ __global__ void __launch_bounds__(256) pos_flags_kernel(const int32_t* __restric
 static int ilog2_ceil(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
 
 }  // namespace
+
+static int g_step_dbg = 0;
+static long long* g_step_tdbg = nullptr;
+FMB_API void fmb_debug_set_step_timestamps(long long* dev) { g_step_tdbg = dev; }
+// debug hook (not in the public header): timing attribution of the fused kernel's phases
+FMB_API void fmb_debug_set_step_flags(int f) { g_step_dbg = f; }
 
 // host-side handle of the fused kernel, for graph-node identification in session.cu (arguments 0..3 are ids, xv, y, posflag)
 FMB_API const void* fmb_fused_kernel_fn(void) { return (const void*)fm_step_fused_kernel; }
@@ -211,11 +278,13 @@ FMB_API int fmb_fm_step_fused(const int32_t* ids, const float* xv, const float* 
     p.loss_kind = loss_kind; p.mode = mode; p.lr = lr; p.astep = -(lr / 0.1f);
     p.delta = delta; p.lossv = lossv;
     p.G = (float*)ws; p.Npad = (N + 3) / 4 * 4 + 64;
+    p.dbg = g_step_dbg;
+    p.tdbg = g_step_tdbg;
     int SB = 256 >> p.jl_log;
     if (SB < 4) SB = 4;
     if (SB > 32) SB = 32;
     auto bytes = [&](int sb) {
-        return sizeof(float) * ((size_t)sb * F * p.cu * 4 + (size_t)3 * sb * F + (size_t)sb * k + (size_t)sb * p.kp4 + sb);
+        return sizeof(float) * ((size_t)sb * F * p.cu * 4 + (size_t)4 * sb * F + (size_t)sb * k + (size_t)sb * p.kp4 + sb);
     };
     while (SB > 1 && bytes(SB) > 48 * 1024) SB >>= 1;
     FMB_CHECK_ARG(bytes(SB) <= 200 * 1024, "fmb_fm_step_fused: F*k too large for one sample tile");

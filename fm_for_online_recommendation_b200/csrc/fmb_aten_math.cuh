@@ -128,24 +128,27 @@ __device__ __forceinline__ float log_sigmoid(float x) {
 static __device__ const unsigned short fmb_rsqrt14_tab[65536] = {
 #include "rsqrt14_table.inc"
 };
-__device__ __forceinline__ float sqrt_mkl(float x) {
-    uint32_t b = (uint32_t)__float_as_int(x);
-    if (x != x || b == 0x7f800000u || x == 0.0f) return x;
-    if (b >> 31) return __int_as_float(0x7fc00000);
-    int q = 0;
-    if (b < 0x00800000u) { x = __fmul_rn(x, 18446744073709551616.0f); b = (uint32_t)__float_as_int(x); q = -32; }
-    const int E = (int)(b >> 23), p = (E + 1) & 1;
-    q += (E - 127 - p) / 2;
-    const uint32_t man = b & 0x7fffffu;
-    const float xn = __int_as_float((int)(((uint32_t)(127 + p) << 23) | man));
-    const float y = (p == 0 && man == 0)
-                        ? 1.0f
-                        : __int_as_float((int)((126u << 23) |
-                                               ((uint32_t)__ldg(&fmb_rsqrt14_tab[((uint32_t)p << 15) | (man >> 8)]) << 7)));
+// normal inputs only (0x00800000 <= bits < 0x7f800000).  An exact power of four needs no special case: the table's
+// first entry gives S = 0x1.fffap-1 and the Newton step rounds back to exactly 1.
+__device__ __forceinline__ float sqrt_mkl_normal(float x) {
+    const uint32_t b = (uint32_t)__float_as_int(x);
+    const uint32_t E = b >> 23, man = b & 0x7fffffu;
+    const uint32_t par = ~E & 1u;                                  // E - 127 = 2q + par
+    const float xn = __int_as_float((int)(((127u + par) << 23) | man));   // [1, 4)
+    const float y = __int_as_float((int)(0x3f000000u | ((uint32_t)__ldg(&fmb_rsqrt14_tab[(par << 15) | (man >> 8)]) << 7)));
     const float S = __fmul_rn(xn, y), H = __fmul_rn(0.5f, y);
     const float e = __fmaf_rn(-S, S, xn);
     const float r = __fmaf_rn(e, H, S);
-    return __int_as_float((int)((uint32_t)__float_as_int(r) + ((uint32_t)q << 23)));
+    const int q = ((int)E - 127 - (int)par) >> 1;                  // even numerator: the shift is exact
+    return __int_as_float(__float_as_int(r) + (q << 23));
+}
+__device__ __forceinline__ float sqrt_mkl(float x) {
+    uint32_t b = (uint32_t)__float_as_int(x);
+    if (b - 0x00800000u < 0x7f000000u) return sqrt_mkl_normal(x);
+    if (x != x || b == 0x7f800000u || x == 0.0f) return x;
+    if (b >> 31) return __int_as_float(0x7fc00000);
+    // denormal: MKL pre-scales by an even power of two
+    return __fmul_rn(sqrt_mkl_normal(__fmul_rn(x, 18446744073709551616.0f)), 2.3283064365386963e-10f);   // 2^64, 2^-32
 }
 
 }  // namespace fmb

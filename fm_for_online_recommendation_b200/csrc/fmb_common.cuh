@@ -124,7 +124,21 @@ __device__ __forceinline__ float adam1_a(float p, float g, float a) {
     }
     float m = __fmul_rn(0.1f, g);
     float v = __fmul_rn(__fmul_rn(0.001f, g), g);
-    float d = __fadd_rn(__fdiv_rn(sqrt_mkl(v), bc2s), 1e-8f);   // exp_avg_sq.sqrt() is MKL's vsSqrt
+    // denom = exp_avg_sq.sqrt() / bias_correction2_sqrt + eps.  Tensor.sqrt() is MKL's vsSqrt (sqrt_mkl).  For a normal
+    // v the quotient s / bc2s is formed without the division: q = RN(s * RN(1/c)), r = s - q*c exactly (one fma),
+    // RN(q + r * RN(1/c)) is the correctly rounded quotient -- checked against s / c for ALL 2^23 mantissas of every
+    // binade of s from 2^-104 to 2^122 (sqrt of a normal float lies in [2^-63, 2^64)).
+    float d1;
+    const uint32_t vb = (uint32_t)__float_as_int(v);
+    if (vb - 0x00800000u < 0x7f000000u) {
+        const float s = sqrt_mkl_normal(v);
+        const float rc = 0x1.f9f6e6p+4f;        // RN(1 / bc2s) = 31.6227779...
+        const float q = __fmul_rn(s, rc);
+        d1 = __fmaf_rn(__fmaf_rn(-q, bc2s, s), rc, q);
+    } else {
+        d1 = __fdiv_rn(sqrt_mkl(v), bc2s);
+    }
+    const float d = __fadd_rn(d1, 1e-8f);
     return __fadd_rn(p, __fdiv_rn(__fmul_rn(a, m), d));
 }
 __device__ __forceinline__ float adam1(float p, float g, float lr) { return adam1_a(p, g, adam_astep(lr)); }
@@ -182,6 +196,30 @@ __device__ __forceinline__ float aten_row_sum_small(Load ld, int n) {
         a0 = __fadd_rn(a0, a1); a0 = __fadd_rn(a0, a2); a0 = __fadd_rn(a0, a3);
         fin = __fadd_rn(fin, a0);
     }
+    return fin;
+}
+
+// The same order (n < 512) evaluated by a group of 8 consecutive lanes of a warp: lane l8 owns vector lane l8 of ATen's
+// accumulators, so the eight per-lane chains run side by side and only the final fold (scalar tail, then lanes 0..7
+// in order) is serial: ~20 dependent adds for n = 39 instead of 71.  All 8 lanes of the group must call; every lane
+// returns the result.  `mask` names the calling lanes of the warp (whole groups).
+template <typename Load>
+__device__ __forceinline__ float aten_row_sum_lanes8(Load ld, int n, int l8, unsigned mask) {
+    if (n < 8) return aten_row_sum_small(ld, n);
+    const int vec_size = n >> 3, size_ilp = vec_size >> 2;
+    float fin = 0.f;
+    for (int i = vec_size << 3; i < n; ++i) fin = __fadd_rn(fin, ld(i));
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int i = 0; i < size_ilp; ++i) {
+        a0 = __fadd_rn(a0, ld(i * 32 + l8));
+        a1 = __fadd_rn(a1, ld(i * 32 + 8 + l8));
+        a2 = __fadd_rn(a2, ld(i * 32 + 16 + l8));
+        a3 = __fadd_rn(a3, ld(i * 32 + 24 + l8));
+    }
+    for (int v = size_ilp << 2; v < vec_size; ++v) a0 = __fadd_rn(a0, ld(v * 8 + l8));
+    a0 = __fadd_rn(a0, a1); a0 = __fadd_rn(a0, a2); a0 = __fadd_rn(a0, a3);
+#pragma unroll
+    for (int l = 0; l < 8; ++l) fin = __fadd_rn(fin, __shfl_sync(mask, a0, l, 8));
     return fin;
 }
 
