@@ -53,6 +53,11 @@ struct BwdParams {
     int64_t Npad;         // row pitch of G (positions, multiple of 4, >= N + 64)
     long long* dbg;       // optional per-run timing records (debug builds of bench only), else NULL
     float astep;          // -(lr/0.1f): Adam step size, computed once on the host (same IEEE division)
+    // multi-GPU (csrc/shard2.cu): shard_G > 0 = do not update, store the run's partial gradient into the inbox of the
+    // row's owner (key % G) at slot [shard_me][position of the run's first entry]
+    float* inbox[8];
+    int shard_G, shard_me;
+    int64_t shard_N;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -294,7 +299,7 @@ __global__ void __launch_bounds__(256, 2) fm_bwd_runs_kernel(const __grid_consta
             (void)isB; (void)comp;
             // the row's old value is needed only at the very end: fetch it now, off the critical path
             float pold = 0.f;
-            if (v0 == 0 && lane < kc) pold = p.table[(size_t)key * p.rowp + lane];
+            if (v0 == 0 && lane < kc && !p.shard_G) pold = p.table[(size_t)key * p.rowp + lane];
             // direct part: up to 32 entries straight from G, all loads in flight at once
             float acc = 0.f;
             {
@@ -419,6 +424,10 @@ __global__ void __launch_bounds__(256, 2) fm_bwd_runs_kernel(const __grid_consta
             if (c < kc) {
                 float gsum = accs[c];
                 if (two && c < p.k) gsum = __fadd_rn(gsum, accs[kc + c]);
+                if (p.shard_G) {
+                    p.inbox[key % p.shard_G][((size_t)p.shard_me * p.shard_N + s) * 16 + c] = gsum;
+                    continue;
+                }
                 float* addr = p.table + (size_t)key * p.rowp + c;
                 const float old = c < 32 ? accs[accs_n + c] : *addr;
                 *addr = fmb::apply_update_a(old, gsum, p.lr, p.astep, p.mode);
@@ -521,6 +530,7 @@ FMB_API int fmb_fm_backward_update_ex(const int32_t* sorted_keys, const int32_t*
     FMB_CHECK_ARG(n_entries > 0 && n_entries < ((int64_t)1 << 31), "fmb_fm_backward_update: n_entries out of range");
     if (ws_bytes < fmb_bwd_workspace_bytes(N, k)) { fmb_set_error("fmb_fm_backward_update: workspace too small"); return FMB_ERR_WS; }
     BwdParams p;
+    memset(&p, 0, sizeof(p));
     p.skeys = sorted_keys; p.perm = perm; p.N = N; p.xv = xv; p.table = table;
     p.F = F; p.k = k; p.rowp = fmb_round_up(k + 1, 16); p.kp4 = fmb_round_up(k, 4);
     p.cu = (k + 1 + 3) / 4; p.ql_log = ilog2_ceil(p.cu);
@@ -570,6 +580,25 @@ FMB_API int fmb_fm_backward_runs(const int32_t* sorted_keys, int64_t N, float* t
     p.dbg = nullptr;
     p.Npad = bwd_npad(N);
     p.G = (float*)ws;
+    return launch_runs(p, false, stream);
+}
+
+// multi-GPU variant of fmb_fm_backward_runs (csrc/shard2.cu): the partial gradient of every run of >= 2 equal keys goes
+// to the inbox of the row's owner instead of being applied.  inbox: G peer-mapped pointers to [G][N][16] floats.
+FMB_API int fmb_shard2_runs(const int32_t* sorted_keys, int64_t N, int F, int k, void* ws, size_t ws_bytes,
+                            void* const* inbox, int G, int me, cudaStream_t stream) {
+    FMB_CHECK_ARG(sorted_keys && ws && inbox, "fmb_shard2_runs: null pointer");
+    FMB_CHECK_ARG(N > 0 && F > 0 && F < 512 && k > 0 && k <= 15 && G >= 1 && G <= 8 && me >= 0 && me < G, "fmb_shard2_runs: bad arguments");
+    if (ws_bytes < fmb_bwd_workspace_bytes(N, k)) { fmb_set_error("fmb_shard2_runs: workspace too small"); return FMB_ERR_WS; }
+    BwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.skeys = sorted_keys; p.N = N; p.table = nullptr;
+    p.F = F; p.k = k; p.rowp = fmb_round_up(k + 1, 16); p.kp4 = fmb_round_up(k, 4);
+    p.use_fm2 = 1; p.key_limit = 0x7fffffff;
+    p.Npad = bwd_npad(N);
+    p.G = (float*)ws;
+    for (int o = 0; o < G; ++o) p.inbox[o] = (float*)inbox[o];
+    p.shard_G = G; p.shard_me = me; p.shard_N = N;
     return launch_runs(p, false, stream);
 }
 

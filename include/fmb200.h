@@ -135,7 +135,28 @@ int fmb_shard_cw(int k); /* floats per sample context [S | delta | loss | z] */
 int fmb_shard_sort_max_cap(void);
 int fmb_transpose_ids(const int32_t* ids_dev /*[B,F]*/, int B, int F, int32_t* out_dev /*[F,B]*/, fmb_stream_t stream);
 int fmb_shard_partial_forward(const int32_t* idsT_all_dev /*[G,F,B]*/, const float* table_local_dev, int G, int me,
-                              int B, int F, int k, float* partial_dev /*[G*B,PW]*/, fmb_stream_t stream);
+                              int B, int F, int k, float* partial_dev /* ---- multi-GPU, second design (csrc/shard2.cu): O(B*F) work per rank ------------------------------------------
+ * Row r lives on rank r % G at local row r / G.  Every rank steps on its own batch; rows are gathered from the owners'
+ * shards through peer-mapped pointers (NVLink), each rank stores one partial gradient per distinct row of its batch into
+ * the owner's inbox (slot = [source rank][position in the source's stable sort]), the owner adds the partials in rank
+ * order and applies the update.  Pointer arrays hold G peer-mapped addresses (entry `me` = the caller's own buffer).
+ *   fmb_shard2_fused       forward + loss + contributions (rows hit once in my batch go straight to the inbox)
+ *   fmb_shard2_runs        run kernel: partial gradient of every run of >= 2 equal keys -> inbox
+ *   fmb_shard2_push_keys   my sorted keys -> slab `me` of every rank's keys_all [G][N]
+ *   fmb_shard2_owner_apply scan keys_all, count the ranks hitting each owned row, rank-ordered add, row update
+ * Exchanges are fenced with fmb_shard_signal epochs.  Reference semantics: fm_adam.py:56-69 on the concatenated batch. */
+int fmb_shard2_slot_floats(void);
+int fmb_shard2_fused(const int32_t* ids_dev, const float* xv_dev, const float* y_dev, const uint32_t* posflag_dev,
+                     void* const* tables, void* const* inbox, void* const* dl, const float* bias_dev, int G, int me, int B,
+                     int F, int k, int loss_kind, void* ws_dev, size_t ws_bytes, fmb_stream_t stream);
+int fmb_shard2_runs(const int32_t* sorted_keys_dev, int64_t N, int F, int k, void* ws_dev, size_t ws_bytes,
+                    void* const* inbox, int G, int me, fmb_stream_t stream);
+int fmb_shard2_push_keys(const int32_t* sorted_keys_dev, int64_t N, int G, int me, void* const* keys_all,
+                         fmb_stream_t stream);
+int fmb_shard2_owner_apply(const int32_t* keys_all_dev, const float* inbox_dev, float* table_dev, uint32_t* cnt_dev, int G,
+                           int me, int B, int F, int k, float lr, int mode, fmb_stream_t stream);
+
+/*[G*B,PW]*/, fmb_stream_t stream);
 int fmb_shard_combine(const float* recv_dev /*[G,B,PW]*/, const float* bias_dev, const float* y_dev, int G, int me,
                       int B, int k, int loss_kind, float* ctx_dev /*[B,CW]*/, float* z_dev /*nullable*/, fmb_stream_t stream);
 int fmb_shard_unpack_ctx(const float* ctx_all_dev, int64_t n, int k, float* delta_dev, float* lossv_dev,

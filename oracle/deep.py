@@ -23,7 +23,7 @@ class _Model(C.Structure):
                 ("R", C.c_int32), ("batch_size", C.c_int32), ("update_mode", C.c_int32),
                 ("w1", _f), ("V", _f), ("mlp", _f), ("bias", _f), ("alpha", _f),
                 ("lr", C.c_float), ("hb", C.c_float), ("hs", C.c_float),
-                ("gA", _f), ("gB", _f), ("touched", _u8), ("shard_G", C.c_int32)]
+                ("gA", _f), ("gB", _f), ("touched", _u8), ("shard_G", C.c_int32), ("rank_B", C.c_int32)]
 
 
 _lib = None
@@ -94,7 +94,12 @@ class OracleDeep:
         self.touched = np.zeros(self.R, dtype=np.uint8)
         self.m = _Model(KINDS[kind], self.F, k, self.L, self.H, self.R, batch_size, update_mode,
                         _fp(self.w1), _fp(self.V), _fp(self.mlp), _fp(self.bias), _fp(self.alpha),
-                        lr, hb, hs, _fp(self.gA), _fp(self.gB), self.touched.ctypes.data_as(_u8), 0)
+                        lr, hb, hs, _fp(self.gA), _fp(self.gB), self.touched.ctypes.data_as(_u8), 0, 0)
+
+    def set_rank_partial_order(self, rank_B):
+        """Sum duplicate rows in rank-partial order (csrc/shard2.cu): the batch is the concatenation of per-rank
+        batches of rank_B samples; 0 = reference order."""
+        self.m.rank_B = int(rank_B)
 
     def set_shard_order(self, G):
         """Evaluate forward sums in the G-way row-sharded order (csrc/sharded.cu); 0/1 = reference order."""

@@ -137,6 +137,10 @@ typedef struct {
     uint8_t* touched; /* [R] */
     int32_t shard_G;  /* > 1: forward sums in the row-sharded multi-GPU order (owner-major), see
                          fm_for_online_recommendation_b200/csrc/sharded.cu; 0/1: reference order */
+    int32_t rank_B;   /* > 0: the batch is the concatenation of per-rank batches of rank_B samples and duplicate rows
+                         are summed in RANK-PARTIAL order (csrc/shard2.cu): every rank sums its own entries of a
+                         row in sample order, the partial sums are added in rank order.  0: reference order
+                         (one chain over all samples).  Identical to the reference when a row is hit by one rank. */
 } orc_model;
 
 static size_t mlp_w_off(const orc_model* m, int l) {
@@ -338,6 +342,7 @@ API void orc_update_dense(float* p, const float* g, int64_t n, float lr, int mod
 typedef struct {
     orc_model* m; const int32_t* ids; const float* xv; int B; const float* S; const float* gs; int use_fm2;
     const float* gvec; int32_t* tl; size_t* ntf; int by_field;
+    float* tot; int32_t* cur_rank;   /* rank-partial order (m->rank_B > 0): folded partials of finished ranks, rank of ga */
 } bwd_ctx;
 /* contribution of entry (b, f) to the gradient sums of its row */
 static inline void bwd_entry(const bwd_ctx* c, int b, int f, int32_t* tl, size_t* nt) {
@@ -345,10 +350,21 @@ static inline void bwd_entry(const bwd_ctx* c, int b, int f, int32_t* tl, size_t
     const int F = m->F, k = m->k, kp = k + 1;
     const int32_t r = c->ids[(size_t)b * F + f];
     const float x = c->xv[(size_t)b * F + f];
-    if (!m->touched[r]) { m->touched[r] = 1; tl[(*nt)++] = r; }
+    if (!m->touched[r]) { m->touched[r] = 1; tl[(*nt)++] = r; if (c->cur_rank) c->cur_rank[r] = -1; }
     const float* v = m->V + (size_t)r * k;
     float* ga = m->gA + (size_t)r * kp;
     float* gb = m->gB + (size_t)r * kp;
+    if (c->cur_rank) {   /* a new rank starts on this row: fold the previous rank's partial into the total */
+        const int rk = b / m->rank_B;
+        if (c->cur_rank[r] != rk) {
+            float* tt = c->tot + (size_t)r * kp;
+            if (c->cur_rank[r] >= 0)
+                for (int j = 0; j < kp; ++j) { tt[j] = (tt[j] != tt[j]) ? ga[j] : tt[j] + ga[j]; ga[j] = 0.f; }
+            else
+                for (int j = 0; j < kp; ++j) tt[j] = NAN;   /* "no partial yet" marker */
+            c->cur_rank[r] = rk;
+        }
+    }
     ga[k] = ga[k] + (c->gs[b] * x);
     for (int j = 0; j < k; ++j) {
         float e = v[j] * x;
@@ -372,6 +388,10 @@ static void bwd_rows_update(const bwd_ctx* c, const int32_t* tl, size_t nt) {
         float* v = m->V + (size_t)r * k;
         float* ga = m->gA + (size_t)r * kp;
         float* gb = m->gB + (size_t)r * kp;
+        if (c->cur_rank) {   /* total = partial of the first rank, then + the later ranks' partials in rank order */
+            const float* tt = c->tot + (size_t)r * kp;
+            for (int j = 0; j < kp; ++j) if (!(tt[j] != tt[j])) ga[j] = tt[j] + ga[j];
+        }
         for (int j = 0; j < k; ++j) {
             float g = (c->use_fm2 && c->gvec) ? ga[j] + gb[j] : (c->gvec ? gb[j] : ga[j]);
             v[j] = upd(v[j], g, m->lr, m->update_mode);
@@ -397,7 +417,11 @@ API void orc_fm_backward_update(orc_model* m, const int32_t* ids, const float* x
                                 const float* gs, int use_fm2, const float* gvec) {
     const int F = m->F;
     int32_t* tl = (int32_t*)malloc(sizeof(int32_t) * (size_t)B * F);
-    bwd_ctx c = {m, ids, xv, B, S, gs, use_fm2, gvec, tl, NULL, 0};
+    bwd_ctx c = {m, ids, xv, B, S, gs, use_fm2, gvec, tl, NULL, 0, NULL, NULL};
+    if (m->rank_B > 0 && !gvec) {   /* FM-only step of the multi-GPU path */
+        c.tot = (float*)malloc(sizeof(float) * (size_t)m->R * (m->k + 1));
+        c.cur_rank = (int32_t*)malloc(sizeof(int32_t) * (size_t)m->R);
+    }
     /* A row's contributions must be added in sample order.  The reference walk is b-major, f-minor; when the rows
      * of different fields are disjoint (global id = field offset + local id), walking field by field with the samples
      * ascending inside gives every row the same order, and the fields become independent (one thread each).  That
@@ -425,7 +449,7 @@ API void orc_fm_backward_update(orc_model* m, const int32_t* ids, const float* x
             for (int f = 0; f < F; ++f) bwd_entry(&c, b, f, tl, &nt);
         bwd_rows_update(&c, tl, nt);
     }
-    free(tl);
+    free(tl); free(c.tot); free(c.cur_rank);
 }
 
 /* ------------------------------------------------------------------ */
