@@ -94,6 +94,12 @@ _SIGS = {
                                                  C.c_int, vp]),
     "fmb_session_presort": (C.c_int, [vp, vp, C.c_int, C.c_int]),
     "fmb_session_presort_invalidate": (None, [vp]),
+    "fmb_session_set_ftrl": (C.c_int, [vp, vp, vp, C.c_float, C.c_float, C.c_float]),
+    "fmb_fm_step_fused_ex": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp,
+                                       vp, vp, vp, C.c_size_t, vp]),
+    "fmb_fm_backward_runs_ex": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp, C.c_size_t,
+                                          vp]),
+    "fmb_finish_step_ex": (C.c_int, [vp, vp, C.c_int, vp, C.c_float, C.c_int, vp, vp, vp]),
     "fmb_session_fm_step_next": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp,
                                            vp]),
     "fmb_pos_flags": (C.c_int, [vp, vp, C.c_int64, vp, vp]),

@@ -110,7 +110,8 @@ __device__ float aten_sum_cta(const float* __restrict__ x, int64_t n, float* bs 
 __global__ void __launch_bounds__(FIN_THREADS) finish_step_kernel(const float* __restrict__ delta,
                                                                   const float* __restrict__ lossv, int B, float* bias,
                                                                   float lr, int mode, float* loss_out,
-                                                                  float* scratch /*[2][nblocks*32] or NULL*/) {
+                                                                  float* scratch /*[2][nblocks*32] or NULL*/,
+                                                                  fmb::FtrlState ftrl) {
     extern __shared__ __align__(16) float fin_sm[];
     const int half = (threadIdx.x >> 5) >= 16 ? 1 : 0;
     const float* src = half == 0 ? (bias ? delta : nullptr) : ((loss_out && lossv) ? lossv : nullptr);
@@ -127,7 +128,15 @@ __global__ void __launch_bounds__(FIN_THREADS) finish_step_kernel(const float* _
         if ((threadIdx.x >> 5) != half * 16) return;
     }
     if (lane == 0) {
-        if (half == 0) bias[0] = fmb::apply_update(bias[0], total, lr, mode);
+        if (half == 0) {
+            if (mode == 2) {
+                float z = ftrl.bias_zn[0], n = ftrl.bias_zn[1];
+                bias[0] = fmb::ftrl_update(bias[0], total, z, n, lr, ftrl.beta, ftrl.l1, ftrl.l2);
+                ftrl.bias_zn[0] = z; ftrl.bias_zn[1] = n;
+            } else {
+                bias[0] = fmb::apply_update(bias[0], total, lr, mode);
+            }
+        }
         else loss_out[0] = __fdiv_rn(total, (float)B);
     }
 }
@@ -174,8 +183,10 @@ FMB_API int fmb_update_dense(float* p, const float* g, int64_t n, float lr, int 
 // end of a training step: bias update from sum(delta) (bias nullable) and mean loss (loss_out nullable).
 // B <= 1 M samples (block sums are staged in shared memory up to 256 K samples, in `fmb_finish_scratch` above).
 static float* g_fin_scratch = nullptr;
-FMB_API int fmb_finish_step(const float* delta, const float* lossv, int B, float* bias, float lr, int mode,
-                            float* loss_out, cudaStream_t stream) {
+struct fmb_ftrl_t { float* zn; float* bias_zn; float beta, l1, l2; };   // include/fmb200.h
+
+FMB_API int fmb_finish_step_ex(const float* delta, const float* lossv, int B, float* bias, float lr, int mode,
+                               const fmb_ftrl_t* ftrl, float* loss_out, cudaStream_t stream) {
     FMB_CHECK_ARG(delta && B > 0, "fmb_finish_step: bad arguments");
     FMB_CHECK_ARG((int64_t)B <= (int64_t)FIN_MAX_BLOCKS * 16 * 32, "fmb_finish_step: B=%d too large", B);
     // block sums: 2 arrays x (B/512) blocks x 32 floats; shared memory up to 512 blocks per array (128 KB total)
@@ -193,7 +204,17 @@ FMB_API int fmb_finish_step(const float* delta, const float* lossv, int B, float
     }
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(finish_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024); attr = true; }
-    finish_step_kernel<<<1, FIN_THREADS, smem, stream>>>(delta, lossv, B, bias, lr, mode, loss_out, scratch);
+    fmb::FtrlState fs = {nullptr, nullptr, 0.f, 0.f, 0.f};
+    if (mode == 2) {
+        FMB_CHECK_ARG(ftrl && ftrl->bias_zn, "fmb_finish_step: update mode 2 needs the FTRL state");
+        fs.zn = ftrl->zn; fs.bias_zn = ftrl->bias_zn; fs.beta = ftrl->beta; fs.l1 = ftrl->l1; fs.l2 = ftrl->l2;
+    }
+    finish_step_kernel<<<1, FIN_THREADS, smem, stream>>>(delta, lossv, B, bias, lr, mode, loss_out, scratch, fs);
     FMB_CHECK_LAUNCH("finish_step_kernel");
     return FMB_OK;
+}
+
+FMB_API int fmb_finish_step(const float* delta, const float* lossv, int B, float* bias, float lr, int mode,
+                            float* loss_out, cudaStream_t stream) {
+    return fmb_finish_step_ex(delta, lossv, B, bias, lr, mode, nullptr, loss_out, stream);
 }

@@ -55,6 +55,7 @@ struct BwdParams {
     float astep;          // -(lr/0.1f): Adam step size, computed once on the host (same IEEE division)
     // multi-GPU (csrc/shard2.cu): shard_G > 0 = do not update, store the run's partial gradient into the inbox of the
     // row's owner (key % G) at slot [shard_me][position of the run's first entry]
+    fmb::FtrlState ftrl;   // mode 2 only
     float* inbox[8];
     int shard_G, shard_me;
     int64_t shard_N;
@@ -430,7 +431,14 @@ __global__ void __launch_bounds__(256, 2) fm_bwd_runs_kernel(const __grid_consta
                 }
                 float* addr = p.table + (size_t)key * p.rowp + c;
                 const float old = c < 32 ? accs[accs_n + c] : *addr;
-                *addr = fmb::apply_update_a(old, gsum, p.lr, p.astep, p.mode);
+                if (p.mode == 2) {
+                    float* zp = p.ftrl.zn + (size_t)key * 2 * p.rowp + c;
+                    float z = zp[0], n = zp[p.rowp];
+                    *addr = fmb::ftrl_update(old, gsum, z, n, p.lr, p.ftrl.beta, p.ftrl.l1, p.ftrl.l2);
+                    zp[0] = z; zp[p.rowp] = n;
+                } else {
+                    *addr = fmb::apply_update_a(old, gsum, p.lr, p.astep, p.mode);
+                }
             }
         }
         __syncwarp();
@@ -565,11 +573,13 @@ FMB_API int fmb_fm_backward_update_ex(const int32_t* sorted_keys, const int32_t*
 
 // Run kernel alone: sums the contributions staged in ws (by fmb_fm_step_fused, at sorted positions) over every run
 // of >= 2 equal keys, in sample order, and updates those rows.  Same arguments as fmb_fm_backward_update.
-FMB_API int fmb_fm_backward_runs(const int32_t* sorted_keys, int64_t N, float* table, int F, int k, float lr,
-                                 int mode, void* ws, size_t ws_bytes, cudaStream_t stream) {
+struct fmb_ftrl_t { float* zn; float* bias_zn; float beta, l1, l2; };   // include/fmb200.h
+
+FMB_API int fmb_fm_backward_runs_ex(const int32_t* sorted_keys, int64_t N, float* table, int F, int k, float lr,
+                                    int mode, const fmb_ftrl_t* ftrl, void* ws, size_t ws_bytes, cudaStream_t stream) {
     FMB_CHECK_ARG(sorted_keys && table && ws, "fmb_fm_backward_runs: null pointer");
     FMB_CHECK_ARG(N > 0 && F > 0 && F < 512 && k > 0 && k <= 124, "fmb_fm_backward_runs: bad shape");
-    FMB_CHECK_ARG(mode == 0 || mode == 1, "fmb_fm_backward_runs: unknown update mode %d", mode);
+    FMB_CHECK_ARG(mode == 0 || mode == 1 || (mode == 2 && ftrl && ftrl->zn), "fmb_fm_backward_runs: unknown update mode %d", mode);
     if (ws_bytes < fmb_bwd_workspace_bytes(N, k)) { fmb_set_error("fmb_fm_backward_runs: workspace too small"); return FMB_ERR_WS; }
     BwdParams p;
     memset(&p, 0, sizeof(p));
@@ -580,7 +590,13 @@ FMB_API int fmb_fm_backward_runs(const int32_t* sorted_keys, int64_t N, float* t
     p.dbg = nullptr;
     p.Npad = bwd_npad(N);
     p.G = (float*)ws;
+    if (mode == 2) { p.ftrl.zn = ftrl->zn; p.ftrl.bias_zn = ftrl->bias_zn; p.ftrl.beta = ftrl->beta; p.ftrl.l1 = ftrl->l1; p.ftrl.l2 = ftrl->l2; }
     return launch_runs(p, false, stream);
+}
+
+FMB_API int fmb_fm_backward_runs(const int32_t* sorted_keys, int64_t N, float* table, int F, int k, float lr,
+                                 int mode, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    return fmb_fm_backward_runs_ex(sorted_keys, N, table, F, k, lr, mode, nullptr, ws, ws_bytes, stream);
 }
 
 // multi-GPU variant of fmb_fm_backward_runs (csrc/shard2.cu): the partial gradient of every run of >= 2 equal keys goes

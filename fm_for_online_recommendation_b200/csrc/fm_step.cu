@@ -46,6 +46,7 @@ struct StepParams {
     float* lossv;              // [B] out
     float* G;                  // [k+1][Npad] staged contributions of multi-hit entries
     int64_t Npad;
+    fmb::FtrlState ftrl;       // mode 2 only
     long long* tdbg;           // debug only: per-CTA phase timestamps [grid][8] (globaltimer ns), else NULL
     int dbg;                   // debug/attribution only (fmb_debug_set_step_flags): 1 = skip phase 4a, 2 = skip phase 4b
 };
@@ -180,6 +181,14 @@ __global__ void __launch_bounds__(256) fm_step_fused_kernel(const int32_t* __res
         const float v[4] = {v4.x, v4.y, v4.z, v4.w};
         float o[4];
         bool moved = false;
+        float zz[4] = {0.f, 0.f, 0.f, 0.f}, nn[4] = {0.f, 0.f, 0.f, 0.f};
+        float* zrow = nullptr;
+        if (p.mode == 2) {   // FTRL-Proximal: the row's z and n sub-rows (read + written: 16F(k+1) more bytes per sample)
+            zrow = p.ftrl.zn + (size_t)ids_s[ef] * 2 * p.rowp + q * 4;
+            const float4 z4 = *reinterpret_cast<const float4*>(zrow), n4 = *reinterpret_cast<const float4*>(zrow + p.rowp);
+            zz[0] = z4.x; zz[1] = z4.y; zz[2] = z4.z; zz[3] = z4.w;
+            nn[0] = n4.x; nn[1] = n4.y; nn[2] = n4.z; nn[3] = n4.w;
+        }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const int j = q * 4 + t;
@@ -192,11 +201,20 @@ __global__ void __launch_bounds__(256) fm_step_fused_kernel(const int32_t* __res
                 } else {
                     a = __fmul_rn(d, x);
                 }
-                o[t] = fmb::apply_update_a(v[t], __fadd_rn(0.f, a), p.lr, p.astep, p.mode);
-                moved |= __float_as_int(o[t]) != __float_as_int(v[t]);
+                if (p.mode == 2) {
+                    o[t] = fmb::ftrl_update(v[t], __fadd_rn(0.f, a), zz[t], nn[t], p.lr, p.ftrl.beta, p.ftrl.l1, p.ftrl.l2);
+                    moved = true;
+                } else {
+                    o[t] = fmb::apply_update_a(v[t], __fadd_rn(0.f, a), p.lr, p.astep, p.mode);
+                    moved |= __float_as_int(o[t]) != __float_as_int(v[t]);
+                }
             }
         }
         if (moved) *reinterpret_cast<float4*>(p.table + (size_t)ids_s[ef] * p.rowp + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+        if (p.mode == 2) {
+            *reinterpret_cast<float4*>(zrow) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+            *reinterpret_cast<float4*>(zrow + p.rowp) = make_float4(nn[0], nn[1], nn[2], nn[3]);
+        }
     }
     FMB_TS(5);
     // phase 4b: rows hit several times: stage the entry's contribution at its sorted position (run kernel sums them)
@@ -262,13 +280,16 @@ FMB_API int fmb_pos_flags(const int32_t* sorted_keys, const int32_t* perm, int64
 //   posflag [B*F]: output of fmb_pos_flags for THIS batch's ids;  G: workspace of fmb_bwd_workspace_bytes(B*F, k)
 //   bytes, handed to fmb_fm_backward_runs afterwards;  delta/lossv [B]: per-sample gradient and loss (inputs of
 //   fmb_finish_step).  mode as in fmb_fm_backward_update.
-FMB_API int fmb_fm_step_fused(const int32_t* ids, const float* xv, const float* y, float* table, const float* bias,
-                              const uint32_t* posflag, int B, int F, int k, int loss_kind, float lr, int mode,
-                              float* delta, float* lossv, void* ws, size_t ws_bytes, cudaStream_t stream) {
+struct fmb_ftrl_t { float* zn; float* bias_zn; float beta, l1, l2; };   // include/fmb200.h
+
+FMB_API int fmb_fm_step_fused_ex(const int32_t* ids, const float* xv, const float* y, float* table, const float* bias,
+                                 const uint32_t* posflag, int B, int F, int k, int loss_kind, float lr, int mode,
+                                 const fmb_ftrl_t* ftrl, float* delta, float* lossv, void* ws, size_t ws_bytes,
+                                 cudaStream_t stream) {
     FMB_CHECK_ARG(ids && y && table && bias && posflag && delta && lossv && ws, "fmb_fm_step_fused: null pointer");
     FMB_CHECK_ARG(B > 0 && F > 0 && F < 512 && k > 0 && k <= 124, "fmb_fm_step_fused: bad shape B=%d F=%d k=%d", B, F, k);
     FMB_CHECK_ARG(loss_kind == 0 || loss_kind == 1, "fmb_fm_step_fused: unknown loss kind %d", loss_kind);
-    FMB_CHECK_ARG(mode == 0 || mode == 1, "fmb_fm_step_fused: unknown update mode %d", mode);
+    FMB_CHECK_ARG(mode == 0 || mode == 1 || (mode == 2 && ftrl && ftrl->zn), "fmb_fm_step_fused: unknown update mode %d (mode 2 needs the FTRL state)", mode);
     const int64_t N = (int64_t)B * F;
     if (ws_bytes < fmb_bwd_workspace_bytes(N, k)) { fmb_set_error("fmb_fm_step_fused: workspace too small"); return FMB_ERR_WS; }
     StepParams p;
@@ -279,6 +300,8 @@ FMB_API int fmb_fm_step_fused(const int32_t* ids, const float* xv, const float* 
     p.delta = delta; p.lossv = lossv;
     p.G = (float*)ws; p.Npad = (N + 3) / 4 * 4 + 64;
     p.dbg = g_step_dbg;
+    p.ftrl.zn = nullptr; p.ftrl.bias_zn = nullptr; p.ftrl.beta = p.ftrl.l1 = p.ftrl.l2 = 0.f;
+    if (mode == 2) { p.ftrl.zn = ftrl->zn; p.ftrl.bias_zn = ftrl->bias_zn; p.ftrl.beta = ftrl->beta; p.ftrl.l1 = ftrl->l1; p.ftrl.l2 = ftrl->l2; }
     p.tdbg = g_step_tdbg;
     int SB = 256 >> p.jl_log;
     if (SB < 4) SB = 4;
@@ -297,4 +320,11 @@ FMB_API int fmb_fm_step_fused(const int32_t* ids, const float* xv, const float* 
     fm_step_fused_kernel<<<(B + SB - 1) / SB, 256, bytes(SB), stream>>>(ids, xv, y, posflag, p);
     FMB_CHECK_LAUNCH("fm_step_fused_kernel");
     return FMB_OK;
+}
+
+FMB_API int fmb_fm_step_fused(const int32_t* ids, const float* xv, const float* y, float* table, const float* bias,
+                              const uint32_t* posflag, int B, int F, int k, int loss_kind, float lr, int mode,
+                              float* delta, float* lossv, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    return fmb_fm_step_fused_ex(ids, xv, y, table, bias, posflag, B, F, k, loss_kind, lr, mode, nullptr, delta, lossv, ws,
+                                ws_bytes, stream);
 }

@@ -143,11 +143,33 @@ __device__ __forceinline__ float adam1_a(float p, float g, float a) {
 }
 __device__ __forceinline__ float adam1(float p, float g, float lr) { return adam1_a(p, g, adam_astep(lr)); }
 __device__ __forceinline__ float apply_update(float p, float g, float lr, int mode) {
-    return mode == 0 ? adam1(p, g, lr) : __fsub_rn(p, __fmul_rn(lr, g));
+    return mode == 0 ? adam1(p, g, lr) : __fmaf_rn(g, -lr, p);   // SGD: ATen's add_(grad, alpha=-lr) is one fma
+}
+// mode 2: per-coordinate FTRL-Proximal (McMahan et al. 2013; SURVEY.md 8f.4 -- the reference's FM_FTRL is the
+// unregularised linearised form, models/models_online/FM_FTRL.py:76-80, and never keeps n): state z, n per coordinate,
+//   n' = n + g^2;  sigma = (sqrt(n') - sqrt(n)) / alpha;  z' = z + (g - sigma*w);
+//   w' = |z'| <= l1 ? 0 : -(z' - sign(z')*l1) / ((beta + sqrt(n')) / alpha + l2)
+// every operation rounded once, in this order (oracle/fm_oracle.c orc_ftrl_update is the same sequence).
+struct FtrlState {
+    float* zn;        // [R][2][rowp]: z sub-row, n sub-row of every packed table row (NULL = mode 2 unavailable)
+    float* bias_zn;   // [2]: z, n of the bias
+    float beta, l1, l2;
+};
+__device__ __forceinline__ float ftrl_update(float w, float g, float& z, float& n, float alpha, float beta, float l1,
+                                             float l2) {
+    const float nn = __fadd_rn(n, __fmul_rn(g, g));
+    const float sn = __fsqrt_rn(n), snn = __fsqrt_rn(nn);
+    const float sigma = __fdiv_rn(__fsub_rn(snn, sn), alpha);
+    const float zz = __fadd_rn(z, __fsub_rn(g, __fmul_rn(sigma, w)));
+    z = zz; n = nn;
+    if (fabsf(zz) <= l1) return 0.f;
+    const float num = __fsub_rn(zz, copysignf(l1, zz));
+    const float den = __fadd_rn(__fdiv_rn(__fadd_rn(beta, snn), alpha), l2);
+    return -__fdiv_rn(num, den);
 }
 // same with the Adam step size precomputed
 __device__ __forceinline__ float apply_update_a(float p, float g, float lr, float astep, int mode) {
-    return mode == 0 ? adam1_a(p, g, astep) : __fsub_rn(p, __fmul_rn(lr, g));
+    return mode == 0 ? adam1_a(p, g, astep) : __fmaf_rn(g, -lr, p);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -22,6 +22,12 @@ int fmb_sort_fields(const int32_t*, int, int, const int32_t*, int32_t*, int32_t*
 int fmb_fm_backward_update(const int32_t*, const int32_t*, int64_t, const float*, float*, int, int, const float*,
                            const float*, int, const float*, float, int, void*, size_t, cudaStream_t);
 int fmb_finish_step(const float*, const float*, int, float*, float, int, float*, cudaStream_t);
+struct fmb_ftrl_t { float* zn; float* bias_zn; float beta, l1, l2; };
+int fmb_finish_step_ex(const float*, const float*, int, float*, float, int, const fmb_ftrl_t*, float*, cudaStream_t);
+int fmb_fm_step_fused_ex(const int32_t*, const float*, const float*, float*, const float*, const uint32_t*, int, int, int,
+                         int, float, int, const fmb_ftrl_t*, float*, float*, void*, size_t, cudaStream_t);
+int fmb_fm_backward_runs_ex(const int32_t*, int64_t, float*, int, int, float, int, const fmb_ftrl_t*, void*, size_t,
+                            cudaStream_t);
 int fmb_pos_flags(const int32_t*, const int32_t*, int64_t, uint32_t*, cudaStream_t);
 int fmb_fm_step_fused(const int32_t*, const float*, const float*, float*, const float*, const uint32_t*, int, int, int,
                       int, float, int, float*, float*, void*, size_t, cudaStream_t);
@@ -97,6 +103,8 @@ struct fmb_session {
     int ngraphs, next_evict;
     StepVariant gvar[FMB_GRAPH_CACHE];
     cudaEvent_t ev_join2;
+    fmb_ftrl_t ftrl;       // update mode 2 (fmb_session_set_ftrl)
+    int ftrl_set;
 };
 
 #define CU(call)                                                                              \
@@ -190,6 +198,18 @@ FMB_API int fmb_session_create(fmb_session** out, int F, int k, int64_t max_batc
     return FMB_OK;
 }
 
+// update mode 2 (FTRL-Proximal): the per-coordinate state the session's steps read and write.  zn_dev [R][2][rowp]
+// (z and n sub-rows of every packed row), bias_zn_dev [2]; zero-initialised by the caller.  Step graphs captured
+// before this call are dropped.
+FMB_API int fmb_session_set_ftrl(fmb_session* s, float* zn_dev, float* bias_zn_dev, float beta, float l1, float l2) {
+    FMB_CHECK_ARG(s && zn_dev && bias_zn_dev && l1 >= 0.f && l2 >= 0.f, "fmb_session_set_ftrl: bad arguments");
+    s->ftrl.zn = zn_dev; s->ftrl.bias_zn = bias_zn_dev; s->ftrl.beta = beta; s->ftrl.l1 = l1; s->ftrl.l2 = l2;
+    s->ftrl_set = 1;
+    for (int i = 0; i < s->ngraphs; ++i) { cudaGraphExecDestroy(s->gvar[i].exec); cudaGraphDestroy(s->gvar[i].graph); }
+    s->ngraphs = 0; s->next_evict = 0;
+    return FMB_OK;
+}
+
 FMB_API int64_t fmb_session_launches(const fmb_session* s) { return s ? s->launches : 0; }
 FMB_API int fmb_session_graph_count(const fmb_session* s) { return s ? s->ngraphs : 0; }
 
@@ -237,15 +257,16 @@ static int fm_step_launch(fmb_session* s, const int32_t* ids, const float* xv, c
         rc = sort_launch(s, ids, B, key_bits, cur, s->d_sort_ws, main, nlaunch);
         if (rc) return rc;
     }
-    rc = fmb_fm_step_fused(ids, xv, y, table, bias, s->d_posflag_buf[cur], B, s->F, s->k, loss_kind, lr, mode,
-                           s->d_delta, s->d_lossv, s->d_bwd_ws, s->bwd_ws_bytes, main);
+    const fmb_ftrl_t* ft = s->ftrl_set ? &s->ftrl : nullptr;
+    rc = fmb_fm_step_fused_ex(ids, xv, y, table, bias, s->d_posflag_buf[cur], B, s->F, s->k, loss_kind, lr, mode, ft,
+                              s->d_delta, s->d_lossv, s->d_bwd_ws, s->bwd_ws_bytes, main);
     if (rc) return rc;
     cudaEventRecord(s->ev_fwd, main);
     cudaStreamWaitEvent(side, s->ev_fwd, 0);
-    rc = fmb_finish_step(s->d_delta, s->d_lossv, B, bias, lr, mode, loss_dev ? loss_dev : s->d_loss, side);
+    rc = fmb_finish_step_ex(s->d_delta, s->d_lossv, B, bias, lr, mode, ft, loss_dev ? loss_dev : s->d_loss, side);
     if (rc) return rc;
     cudaEventRecord(s->ev_join, side);
-    rc = fmb_fm_backward_runs(s->d_skeys_buf[cur], N, table, s->F, s->k, lr, mode, s->d_bwd_ws, s->bwd_ws_bytes, main);
+    rc = fmb_fm_backward_runs_ex(s->d_skeys_buf[cur], N, table, s->F, s->k, lr, mode, ft, s->d_bwd_ws, s->bwd_ws_bytes, main);
     if (rc) return rc;
     cudaStreamWaitEvent(main, s->ev_join, 0);
     if (next_ids) cudaStreamWaitEvent(main, s->ev_join2, 0);

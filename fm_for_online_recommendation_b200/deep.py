@@ -25,7 +25,7 @@ import torch.nn as nn
 from . import _lib
 from ._lib import FmbError, check, ptr
 
-UPDATE_ADAM1, UPDATE_SGD = 0, 1
+UPDATE_ADAM1, UPDATE_SGD, UPDATE_FTRL = 0, 1, 2   # 2: per-coordinate FTRL-Proximal (enable_ftrl), FM-only steps
 LOSS_LOGITS, LOSS_LOGITS_OF_SIG = 0, 1
 
 
@@ -235,6 +235,30 @@ class _DeepBase(nn.Module):
                 y = torch.from_numpy(np.asarray(Y, dtype=np.float32).reshape(-1)).to(self.device)
         return EncodedBatch(ids, xv, y)
 
+    def enable_ftrl(self, beta=1.0, l1=0.0, l2=0.0):
+        """Switch update_embedding / FMAdam.fit to per-coordinate FTRL-Proximal (z, n, w): alpha is the
+        learning rate `n`.  The state starts at n = 0 with z chosen so that the closed form reproduces the current
+        weights (warm start).  The reference's own FM_FTRL is the unregularised linearised form
+        (models/models_online/FM_FTRL.py:76-80) and lives in classical.py; this mode is the McMahan update the
+        north_star names, off by default."""
+        k, rp = self.embedding_size, self._rowp
+        self.update_mode = UPDATE_FTRL
+        self._ftrl = (float(np.float32(beta)), float(np.float32(l1)), float(np.float32(l2)))
+        c = np.float32(np.float32(beta) / np.float32(self._lr) + np.float32(l2))
+        z0 = lambda w: (-(w * c) - np.sign(w) * np.float32(l1)).astype(np.float32)
+        w = self._table.detach().cpu().numpy()
+        zn = np.zeros((self._R, 2, rp), np.float32)
+        zn[:, 0, :k + 1] = z0(w[:, :k + 1])
+        self._ftrl_zn = torch.from_numpy(zn).to(self.device)
+        self._ftrl_bias = torch.from_numpy(np.array([z0(self.bias.detach().cpu().numpy().reshape(1))[0], 0.0],
+                                                    np.float32)).to(self.device)
+        if self._session is not None:
+            self._bind_ftrl()
+
+    def _bind_ftrl(self):
+        check(self._lib.fmb_session_set_ftrl(self._session, ptr(self._ftrl_zn), ptr(self._ftrl_bias), *self._ftrl),
+              "fmb_session_set_ftrl")
+
     def _get_session(self, B):
         if self._session is None or B > self._session_cap:
             if self._session is not None:
@@ -247,6 +271,8 @@ class _DeepBase(nn.Module):
                                                off32.ctypes.data_as(C.c_void_p)), "fmb_session_create")
             self._session, self._session_cap = h, cap
             self._presorted = None
+            if self.update_mode == UPDATE_FTRL:
+                self._bind_ftrl()
         return self._session
 
     def _buf(self, name, shape, dtype=torch.float32):

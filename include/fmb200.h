@@ -102,6 +102,19 @@ int fmb_sort_fields(const int32_t* ids_dev, int B, int F, const int32_t* field_o
  *   fmb_fm_backward_runs sums every run of >= 2 equal sorted keys in sample order (torch's CPU
  *                        embedding_dense_backward order) and updates those rows
  * followed by fmb_finish_step (bias step, mean loss) on delta/lossv.  ws: fmb_bwd_workspace_bytes(B*F, k). */
+/* update mode 2: per-coordinate FTRL-Proximal (z, n, w with L1/L2; McMahan et al. 2013 -- the update BASELINE.json's
+ * north_star names; the reference's FM_FTRL.py:76-80 is the linearised form without n and lives in fmb_ftrl_fm_run).
+ * zn_dev [R][2][rowp] holds the z and n sub-rows of every packed table row, bias_zn_dev [2] those of the bias.  The _ex
+ * entry points are the plain ones plus this state (NULL unless mode == 2); algorithmic bytes grow by 16F(k+1) per sample. */
+typedef struct fmb_ftrl_t { float* zn_dev; float* bias_zn_dev; float beta, l1, l2; } fmb_ftrl_t;
+int fmb_fm_step_fused_ex(const int32_t* ids_dev, const float* xv_dev, const float* y_dev, float* table_dev,
+                         const float* bias_dev, const uint32_t* posflag_dev, int B, int F, int k, int loss_kind, float lr,
+                         int mode, const fmb_ftrl_t* ftrl, float* delta_dev, float* lossv_dev, void* ws_dev,
+                         size_t ws_bytes, fmb_stream_t stream);
+int fmb_fm_backward_runs_ex(const int32_t* sorted_keys_dev, int64_t N, float* table_dev, int F, int k, float lr, int mode,
+                            const fmb_ftrl_t* ftrl, void* ws_dev, size_t ws_bytes, fmb_stream_t stream);
+int fmb_finish_step_ex(const float* delta_dev, const float* lossv_dev, int B, float* bias_dev, float lr, int mode,
+                       const fmb_ftrl_t* ftrl, float* loss_dev, fmb_stream_t stream);
 int fmb_pos_flags(const int32_t* sorted_keys_dev, const int32_t* perm_dev, int64_t N, uint32_t* posflag_dev,
                   fmb_stream_t stream);
 int fmb_fm_step_fused(const int32_t* ids_dev, const float* xv_dev /*nullable*/, const float* y_dev, float* table_dev,
@@ -285,6 +298,8 @@ int fmb_session_fm_step_host(fmb_session* s, const int32_t* ids_host, const floa
  * stream (overlapping the step in flight); the next fmb_session_fm_step called with the same ids pointer and
  * B skips its own sort.  The ids must stay unchanged until that step has been submitted. */
 int fmb_session_presort(fmb_session* s, const int32_t* ids_dev, int B, int key_bits);
+/* FTRL-Proximal state of the session's steps (update mode 2) */
+int fmb_session_set_ftrl(fmb_session* s, float* zn_dev, float* bias_zn_dev, float beta, float l1, float l2);
 /* forget a pending pre-sort (the caller cannot vouch that the pre-sorted ids buffer still holds the same batch) */
 void fmb_session_presort_invalidate(fmb_session* s);
 /* fmb_session_fm_step with the sort of the NEXT batch riding along: next_ids_dev (nullable) are the ids the

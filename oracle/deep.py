@@ -23,7 +23,9 @@ class _Model(C.Structure):
                 ("R", C.c_int32), ("batch_size", C.c_int32), ("update_mode", C.c_int32),
                 ("w1", _f), ("V", _f), ("mlp", _f), ("bias", _f), ("alpha", _f),
                 ("lr", C.c_float), ("hb", C.c_float), ("hs", C.c_float),
-                ("gA", _f), ("gB", _f), ("touched", _u8), ("shard_G", C.c_int32), ("rank_B", C.c_int32)]
+                ("gA", _f), ("gB", _f), ("touched", _u8), ("shard_G", C.c_int32), ("rank_B", C.c_int32),
+                ("fz_V", _f), ("fn_V", _f), ("fz_w1", _f), ("fn_w1", _f), ("f_bias", _f),
+                ("f_beta", C.c_float), ("f_l1", C.c_float), ("f_l2", C.c_float)]
 
 
 _lib = None
@@ -94,7 +96,22 @@ class OracleDeep:
         self.touched = np.zeros(self.R, dtype=np.uint8)
         self.m = _Model(KINDS[kind], self.F, k, self.L, self.H, self.R, batch_size, update_mode,
                         _fp(self.w1), _fp(self.V), _fp(self.mlp), _fp(self.bias), _fp(self.alpha),
-                        lr, hb, hs, _fp(self.gA), _fp(self.gB), self.touched.ctypes.data_as(_u8), 0, 0)
+                        lr, hb, hs, _fp(self.gA), _fp(self.gB), self.touched.ctypes.data_as(_u8), 0, 0,
+                        None, None, None, None, None, 1.0, 0.0, 0.0)
+
+    def enable_ftrl(self, beta=1.0, l1=0.0, l2=0.0):
+        """update_mode 2: per-coordinate FTRL-Proximal with zero-initialised z/n state (FM-only steps)."""
+        # n = 0 and z chosen so that the closed form w(z, n) reproduces the current weights (warm start)
+        z0 = lambda w: (-(w * np.float32(np.float32(beta) / np.float32(self.m.lr) + np.float32(l2)))
+                        - np.sign(w) * np.float32(l1)).astype(np.float32)
+        self.fz_V = z0(self.V); self.fn_V = np.zeros_like(self.V)
+        self.fz_w1 = z0(self.w1); self.fn_w1 = np.zeros_like(self.w1)
+        self.f_bias = np.array([z0(self.bias)[0], 0.0], np.float32)
+        m = self.m
+        m.update_mode = 2
+        m.fz_V, m.fn_V, m.fz_w1, m.fn_w1, m.f_bias = (_fp(self.fz_V), _fp(self.fn_V), _fp(self.fz_w1), _fp(self.fn_w1),
+                                                      _fp(self.f_bias))
+        m.f_beta, m.f_l1, m.f_l2 = beta, l1, l2
 
     def set_rank_partial_order(self, rank_B):
         """Sum duplicate rows in rank-partial order (csrc/shard2.cu): the batch is the concatenation of per-rank

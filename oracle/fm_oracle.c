@@ -141,6 +141,11 @@ typedef struct {
                          are summed in RANK-PARTIAL order (csrc/shard2.cu): every rank sums its own entries of a
                          row in sample order, the partial sums are added in rank order.  0: reference order
                          (one chain over all samples).  Identical to the reference when a row is hit by one rank. */
+    /* update_mode 2 (per-coordinate FTRL-Proximal): state, zero-initialised by the caller */
+    float *fz_V, *fn_V;   /* [R*k] */
+    float *fz_w1, *fn_w1; /* [R]   */
+    float* f_bias;        /* [2] z, n of the bias */
+    float f_beta, f_l1, f_l2;
 } orc_model;
 
 static size_t mlp_w_off(const orc_model* m, int l) {
@@ -324,14 +329,32 @@ static inline float adam1(float p, float g, float lr) {
     float a = -(lr / 0.1f);                  /* -(lr / bias_correction1) */
     return p + ((a * m) / d);
 }
+/* mode 1: torch.optim.SGD.  param.add_(grad, alpha=-lr) is ONE fused multiply-add in ATen's CPU add kernel
+ * (BinaryOpsKernel.cpp: vec::fmadd(b, alpha, a)); pinned in tests/test_oracle_math.py. */
 static inline float upd(float p, float g, float lr, int mode) {
-    return mode == 0 ? adam1(p, g, lr) : p - lr * g;
+    return mode == 0 ? adam1(p, g, lr) : fmaf(g, -lr, p);
 }
 /* element-wise exports for tests/test_oracle_math.py */
 API void orc_vec_sqrt_mkl(const float* x, float* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = orc_sqrt_mkl(x[i]); }
 API void orc_vec_sigmoid(const float* x, float* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = orc_sigmoid_at(x[i], i, n); }
 API void orc_vec_log_sigmoid(const float* x, float* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = orc_log_sigmoid(x[i]); }
 API void orc_vec_expf_glibc(const float* x, float* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = orc_expf_glibc(x[i]); }
+/* per-coordinate FTRL-Proximal (McMahan et al. 2013), every operation rounded once in this order; the CUDA side is
+ * fmb::ftrl_update (csrc/fmb_common.cuh).  alpha = the learning rate. */
+static inline float orc_ftrl_update(float w, float g, float* z, float* n, float alpha, float beta, float l1, float l2) {
+    const float nn = *n + (g * g);
+    const float sn = sqrtf(*n), snn = sqrtf(nn);
+    const float sigma = (snn - sn) / alpha;
+    const float zz = *z + (g - (sigma * w));
+    *z = zz; *n = nn;
+    if (fabsf(zz) <= l1) return 0.f;
+    const float num = zz - copysignf(l1, zz);
+    const float den = ((beta + snn) / alpha) + l2;
+    return -(num / den);
+}
+API void orc_vec_ftrl(float* w, const float* g, float* z, float* nacc, int64_t n, float alpha, float beta, float l1, float l2) {
+    for (int64_t i = 0; i < n; ++i) w[i] = orc_ftrl_update(w[i], g[i], z + i, nacc + i, alpha, beta, l1, l2);
+}
 API void orc_update_dense(float* p, const float* g, int64_t n, float lr, int mode) {
     for (int64_t i = 0; i < n; ++i) p[i] = upd(p[i], g[i], lr, mode);
 }
@@ -394,10 +417,17 @@ static void bwd_rows_update(const bwd_ctx* c, const int32_t* tl, size_t nt) {
         }
         for (int j = 0; j < k; ++j) {
             float g = (c->use_fm2 && c->gvec) ? ga[j] + gb[j] : (c->gvec ? gb[j] : ga[j]);
-            v[j] = upd(v[j], g, m->lr, m->update_mode);
+            if (m->update_mode == 2)
+                v[j] = orc_ftrl_update(v[j], g, m->fz_V + (size_t)r * k + j, m->fn_V + (size_t)r * k + j, m->lr, m->f_beta,
+                                       m->f_l1, m->f_l2);
+            else
+                v[j] = upd(v[j], g, m->lr, m->update_mode);
             ga[j] = 0.f; gb[j] = 0.f;
         }
-        m->w1[r] = upd(m->w1[r], ga[k], m->lr, m->update_mode);
+        if (m->update_mode == 2)
+            m->w1[r] = orc_ftrl_update(m->w1[r], ga[k], m->fz_w1 + r, m->fn_w1 + r, m->lr, m->f_beta, m->f_l1, m->f_l2);
+        else
+            m->w1[r] = upd(m->w1[r], ga[k], m->lr, m->update_mode);
         ga[k] = 0.f;
         m->touched[r] = 0;
     }
@@ -522,7 +552,10 @@ API float orc_update_embedding(orc_model* m, const int32_t* ids, const float* xv
     float loss = orc_loss_delta(kind, w.zfm, y, B, delta);
     float gbias = orc_sum_aten(delta, B);
     orc_fm_backward_update(m, ids, xv, B, w.S, delta, 1, NULL);
-    m->bias[0] = upd(m->bias[0], gbias, m->lr, m->update_mode);
+    if (m->update_mode == 2)
+        m->bias[0] = orc_ftrl_update(m->bias[0], gbias, m->f_bias, m->f_bias + 1, m->lr, m->f_beta, m->f_l1, m->f_l2);
+    else
+        m->bias[0] = upd(m->bias[0], gbias, m->lr, m->update_mode);
     free(delta); fb_free(&w);
     return loss;
 }

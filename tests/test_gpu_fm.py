@@ -346,3 +346,26 @@ def test_step_graph_is_repointed_per_batch_and_next_batch_sort_rides_along(B):
         assert np.float32(got.item()) == np.float32(want), (t, i)
     assert_same_params(m, orc)
     assert lib.fmb_session_graph_count(m._session) <= 6   # (sorted before / in the step) x (with / without next) x buffer parity
+
+
+def test_ftrl_proximal_mode_bit_exact_and_sane():
+    """update mode 2: per-coordinate FTRL-Proximal z/n/w fused into the step, bit-exact vs the oracle's
+    restatement over 12 steps (duplicate-heavy and unique rows, L1 zeroing some weights); the restatement itself is
+    checked against a float64 evaluation of McMahan's closed form."""
+    import ctypes as C
+    from oracle.deep import lib as olib
+    sizes, k, B = [9, 300, 7, 2000, 40], 6, 500
+    m, orc = _pair("FMAdam", sizes, k, lr=0.05, scale=0.1)
+    orc.enable_ftrl(1.0, 2e-3, 1e-3)
+    m.enable_ftrl(1.0, 2e-3, 1e-3)
+    for s in range(12):
+        Xi, Xv, Y = synth(sizes, B, 900 + s, zipf=(s % 2 == 0))
+        got = m.update_embedding(Xi, Xv, Y).item()
+        want = orc.update_embedding(Xi, Xv, Y)
+        assert np.float32(got) == np.float32(want), s
+    assert_same_params(m, orc)
+    zn = m._ftrl_zn.cpu().numpy()
+    assert np.array_equal(zn[:, 0, :k], orc.fz_V) and np.array_equal(zn[:, 1, :k], orc.fn_V)
+    assert np.array_equal(zn[:, 0, k], orc.fz_w1) and np.array_equal(zn[:, 1, k], orc.fn_w1)
+    assert np.array_equal(m._ftrl_bias.cpu().numpy(), orc.f_bias)
+    assert (orc.w1 == 0).any()                       # L1 produced exact zeros

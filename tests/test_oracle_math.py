@@ -109,3 +109,51 @@ def test_adam_first_step_equals_torch_optimizer_on_small_parameters():
         L.orc_update_dense(mine.ctypes.data_as(C.POINTER(C.c_float)), g.ctypes.data_as(C.POINTER(C.c_float)), n,
                            C.c_float(np.float32(lr)), 0)
         assert np.array_equal(bits(mine), bits(p.detach().numpy())), lr
+
+
+def test_sgd_mode_equals_torch_optim_sgd():
+    """update mode 1 pinned on torch: torch.optim.SGD's param.add_(grad, alpha=-lr) is one fused multiply-add (vector
+    body and scalar tail alike); legacy notebooks, .ipynb_checkpoints/Online FM-checkpoint.ipynb cell 1."""
+    rng = np.random.RandomState(0)
+    for n in (7, 4096, 4099):
+        p0 = rng.standard_normal(n).astype(np.float32)
+        g = (rng.standard_normal(n) * np.exp(rng.uniform(-20, 2, n))).astype(np.float32)
+        for lr in (0.01, 0.003):
+            p = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+            p.grad = torch.from_numpy(g.copy())
+            torch.optim.SGD([p], lr=lr).step()
+            mine = p0.copy()
+            lib().orc_update_dense(mine.ctypes.data_as(C.POINTER(C.c_float)), g.ctypes.data_as(C.POINTER(C.c_float)), n,
+                                   C.c_float(np.float32(lr)), 1)
+            assert np.array_equal(bits(mine), bits(p.detach().numpy())), (n, lr)
+
+
+def test_ftrl_proximal_restatement_follows_mcmahans_closed_form():
+    """update mode 2: the fp32 restatement against a float64 evaluation of the per-coordinate
+    FTRL-Proximal update over 50 steps of random gradients (the reference never exercises it: no torch oracle exists)."""
+    rng = np.random.RandomState(1)
+    n = 2000
+    alpha, beta, l1, l2 = 0.05, 1.0, 0.02, 0.01
+    w = (rng.standard_normal(n) * 0.1).astype(np.float32)
+    z = (-(w.astype(np.float64) * (beta / alpha + l2)) - np.sign(w) * l1).astype(np.float32)
+    nacc = np.zeros(n, np.float32)
+    w64, z64, n64 = w.astype(np.float64), z.astype(np.float64), nacc.astype(np.float64)
+    L = lib()
+    fp = C.POINTER(C.c_float)
+    L.orc_vec_ftrl.restype = None
+    L.orc_vec_ftrl.argtypes = [fp, fp, fp, fp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float]
+    for _ in range(50):
+        g = (rng.standard_normal(n) * np.exp(rng.uniform(-6, 0, n))).astype(np.float32)
+        L.orc_vec_ftrl(w.ctypes.data_as(fp), g.ctypes.data_as(fp), z.ctypes.data_as(fp), nacc.ctypes.data_as(fp), n,
+                       alpha, beta, l1, l2)
+        g64 = g.astype(np.float64)
+        nn = n64 + g64 * g64
+        sigma = (np.sqrt(nn) - np.sqrt(n64)) / alpha
+        z64 = z64 + g64 - sigma * w64
+        n64 = nn
+        w64 = np.where(np.abs(z64) <= l1, 0.0, -(z64 - np.sign(z64) * l1) / ((beta + np.sqrt(n64)) / alpha + l2))
+    # coordinates sitting on the L1 threshold may differ in the zero / non-zero decision; everything else agrees
+    both = (w != 0) & (w64 != 0)
+    assert both.mean() > 0.5 and (w == 0).any()
+    np.testing.assert_allclose(w[both], w64[both], rtol=2e-3, atol=2e-5)
+    assert ((w == 0) != (w64 == 0)).mean() < 0.01
