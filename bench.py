@@ -174,8 +174,12 @@ def run_ours(args):
     lib = pkg.require_cuda()
 
     if world > 1:
-        from fm_for_online_recommendation_b200 import sharded
-        return sharded.bench_main(args, sizes, workload_config(args, sizes))
+        # FMB_SHARD_V1=1 selects the round-1 design (owner-side pooled partials + global owner sort: sharded.py)
+        if os.environ.get("FMB_SHARD_V1", "0") == "1":
+            from fm_for_online_recommendation_b200 import sharded
+            return sharded.bench_main(args, sizes, workload_config(args, sizes))
+        from fm_for_online_recommendation_b200 import sharded2
+        return sharded2.bench_main(args, sizes, workload_config(args, sizes))
 
     torch.manual_seed(0)
     model = pkg.DeepFMAdam(sizes, embedding_size=k, num_hidden_layers=3, neuron_per_hidden_layer=400, n=1e-4)

@@ -19,6 +19,7 @@
 // Work per rank per step: B*F entries forward and backward, G*B*F sorted KEYS scanned (10 MB at G = 8), <= B*F inbox
 // slots applied -- nothing grows with the global batch except that key scan.
 #include "fmb_common.cuh"
+#include <cstring>
 
 extern "C" size_t fmb_bwd_workspace_bytes(int64_t, int);
 
@@ -36,7 +37,11 @@ __device__ __forceinline__ void cp_async_wait_all() {
 constexpr int SLOTW = 16;   // floats per inbox slot (64 bytes: k + 1 <= 16 on this path)
 
 struct S2Params {
-    float* tables[8];      // peer-mapped table shards
+    float* tables[8];      // peer-mapped table shards (only tables[me] is read: remote rows arrive in rowbox)
+    const float* rowbox;   // [N][SLOTW] rows the owners pushed for MY entries, at my sorted positions
+    const float* hot;      // [R_hot][SLOTW] replica of the rows of the small ("hot") fields, kept current by the owners
+    const int32_t* hot_base;   // [F] first hot-table row of field f, or -1 (device array)
+    const int32_t* field_off;  // [F+1]
     float* inbox[8];       // peer-mapped inboxes [G sources][N slots][SLOTW]
     float* dl[8];          // peer-mapped [2][G*B]: delta | per-sample loss of the global batch
     const float* bias;
@@ -69,15 +74,21 @@ __global__ void __launch_bounds__(256) shard2_fused_kernel(const int32_t* __rest
         pos_s[e] = __ldg(posflag + (size_t)b0 * F + e);
     }
     __syncthreads();
-    // gather: row r from its owner's shard (peer-mapped pointer: a 64-byte read over NVLink unless r % G == me)
+    // gather: every row read is LOCAL -- hot-field replica, my own shard, or the slot its owner pushed it to (64-byte
+    // reads over NVLink are round trips with few requests in flight: 90 us for 10 MB measured; posted writes stream)
     {
         const int q = threadIdx.x & ((1 << p.ql_log) - 1);
         const int estep = blockDim.x >> p.ql_log;
         if (q < p.cu)
             for (int ef = threadIdx.x >> p.ql_log; ef < nv * F; ef += estep) {
                 const int r = ids_s[ef];
-                const int o = r % G;
-                cp_async16(rows_s + (size_t)ef * rp + q * 4, p.tables[o] + (size_t)(r / G) * p.rowp + q * 4);
+                const int f = ef % F;
+                const int hb = __ldg(p.hot_base + f);
+                const float* src;
+                if (hb >= 0) src = p.hot + (size_t)(hb + r - __ldg(p.field_off + f)) * SLOTW;            // replicated hot row
+                else if (r % G == p.me) src = p.tables[p.me] + (size_t)(r / G) * p.rowp;                 // my own shard
+                else src = p.rowbox + (size_t)(pos_s[ef] & 0x7fffffffu) * SLOTW;                         // pushed by its owner
+                cp_async16(rows_s + (size_t)ef * rp + q * 4, src + q * 4);
             }
     }
     cp_async_wait_all();
@@ -181,77 +192,126 @@ struct OwnerParams {
     const float* inbox;        // [G][N][SLOTW] partial gradients at run-start positions
     float* table;              // my shard
     uint32_t* cnt;             // [R_local] ranks that hit each owned row this step (zero between steps)
-    int64_t N;
-    int B, F, k, rowp, G, me, mode;
+    float* rowbox[8];          // peer-mapped rowboxes (push_rows)
+    float* hot[8];             // peer-mapped hot-row replicas
+    const int32_t* hot_base;   // [F]
+    const int32_t* field_off;  // [F+1]
+    int N, B, F, k, rowp, G, me, mode, gshift;   // gshift: log2(G) when G is a power of two, else -1
     float lr, astep;
 };
 
-// is sorted position i of source s the first entry of a run of a row I own?  (key returned through *key)
-__device__ __forceinline__ bool owned_run_start(const OwnerParams& p, int s, int64_t i, int32_t* key) {
+__device__ __forceinline__ int own_mod(const OwnerParams& p, int key) { return p.gshift >= 0 ? (key & (p.G - 1)) : key % p.G; }
+__device__ __forceinline__ int own_div(const OwnerParams& p, int key) { return p.gshift >= 0 ? (key >> p.gshift) : key / p.G; }
+
+// grid: x over sorted positions (a block never straddles a field when B % 256 == 0, else the test below is per thread),
+// y = source rank.  Is position i of source s the first entry of a run of a row I own?
+__device__ __forceinline__ bool owned_run_start(const OwnerParams& p, int s, int i, int* key, int* field) {
     const int32_t kk = __ldg(p.keys_all + (size_t)s * p.N + i);
-    if (kk % p.G != p.me) return false;
-    const int64_t i0 = (i / p.B) * p.B;   // fields are sorted independently: a run never crosses a field boundary
-    if (i > i0 && __ldg(p.keys_all + (size_t)s * p.N + i - 1) == kk) return false;
-    *key = kk;
+    if (own_mod(p, kk) != p.me) return false;
+    const int f = i / p.B;
+    if (i > f * p.B && __ldg(p.keys_all + (size_t)s * p.N + i - 1) == kk) return false;
+    *key = kk; *field = f;
     return true;
 }
 
 __global__ void __launch_bounds__(256) owner_count_kernel(OwnerParams p) {
-    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= (int64_t)p.G * p.N) return;
-    const int s = (int)(idx / p.N);
-    const int64_t i = idx - (int64_t)s * p.N;
-    int32_t key;
-    if (owned_run_start(p, s, i, &key)) atomicAdd(p.cnt + key / p.G, 1u);   // integer: order-independent
+    const int i = blockIdx.x * 256 + threadIdx.x, s = blockIdx.y;
+    if (i >= p.N) return;
+    int key, f;
+    if (owned_run_start(p, s, i, &key, &f)) atomicAdd(p.cnt + own_div(p, key), 1u);   // integer: order-independent
 }
 
 // first position of `key` in source s's sorted field segment [lo, lo+B), or -1
-__device__ __forceinline__ int64_t find_key(const OwnerParams& p, int s, int64_t lo, int32_t key) {
+__device__ __forceinline__ int find_key(const OwnerParams& p, int s, int lo, int32_t key) {
     const int32_t* a = p.keys_all + (size_t)s * p.N + lo;
     int l = 0, h = p.B;
     while (l < h) { const int m = (l + h) >> 1; if (__ldg(a + m) < key) l = m + 1; else h = m; }
     return (l < p.B && __ldg(a + l) == key) ? lo + l : -1;
 }
 
+// four lanes per (source, sorted position): lane q applies 16-byte chunk q of the row (the key tests and, for the rare
+// rows several ranks hit, the searches are done by all four lanes -- same addresses, one transaction)
 __global__ void __launch_bounds__(256) owner_apply_kernel(OwnerParams p) {
-    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= (int64_t)p.G * p.N) return;
-    const int s = (int)(idx / p.N);
-    const int64_t i = idx - (int64_t)s * p.N;
-    int32_t key;
-    if (!owned_run_start(p, s, i, &key)) return;
-    const int lrow = key / p.G;
+    const int t = blockIdx.x * 256 + threadIdx.x, s = blockIdx.y;
+    const int i = t >> 2, q = t & 3;
+    if (i >= p.N) return;
+    int key, f;
+    if (!owned_run_start(p, s, i, &key, &f)) return;
+    const int lrow = own_div(p, key);
     const uint32_t c = p.cnt[lrow];
-    const int64_t lo = (i / p.B) * p.B;
-    int64_t src_pos[8];
+    const int lo = f * p.B;
+    size_t src_pos[8];
     int nsrc = 1;
-    src_pos[0] = (int64_t)s * p.N + i;
+    src_pos[0] = (size_t)s * p.N + i;
     if (c > 1) {
         // several ranks hit this row: the lowest rank among them adds the partials in rank order
-        for (int t = 0; t < s; ++t)
-            if (find_key(p, t, lo, key) >= 0) return;
-        for (int t = s + 1; t < p.G; ++t) {
-            const int64_t q = find_key(p, t, lo, key);
-            if (q >= 0) src_pos[nsrc++] = (int64_t)t * p.N + q;
+        for (int r = 0; r < s; ++r)
+            if (find_key(p, r, lo, key) >= 0) return;
+        for (int r = s + 1; r < p.G; ++r) {
+            const int pos = find_key(p, r, lo, key);
+            if (pos >= 0) src_pos[nsrc++] = (size_t)r * p.N + pos;
         }
     }
-    float* row = p.table + (size_t)lrow * p.rowp;
     const int cu = (p.k + 1 + 3) / 4;
-    for (int q = 0; q < cu; ++q) {
-        float4 g = __ldg(reinterpret_cast<const float4*>(p.inbox + (size_t)src_pos[0] * SLOTW + q * 4));
-        for (int t = 1; t < nsrc; ++t) {
-            const float4 h = __ldg(reinterpret_cast<const float4*>(p.inbox + (size_t)src_pos[t] * SLOTW + q * 4));
-            g.x = __fadd_rn(g.x, h.x); g.y = __fadd_rn(g.y, h.y); g.z = __fadd_rn(g.z, h.z); g.w = __fadd_rn(g.w, h.w);
-        }
-        const float4 v = *reinterpret_cast<const float4*>(row + q * 4);
-        float4 o = v;
-        if (q * 4 + 0 <= p.k) o.x = fmb::apply_update_a(v.x, g.x, p.lr, p.astep, p.mode);
-        if (q * 4 + 1 <= p.k) o.y = fmb::apply_update_a(v.y, g.y, p.lr, p.astep, p.mode);
-        if (q * 4 + 2 <= p.k) o.z = fmb::apply_update_a(v.z, g.z, p.lr, p.astep, p.mode);
-        if (q * 4 + 3 <= p.k) o.w = fmb::apply_update_a(v.w, g.w, p.lr, p.astep, p.mode);
-        *reinterpret_cast<float4*>(row + q * 4) = o;
+    if (q >= cu) return;
+    float* row = p.table + (size_t)lrow * p.rowp;
+    float4 g = __ldg(reinterpret_cast<const float4*>(p.inbox + src_pos[0] * SLOTW + q * 4));
+    for (int r = 1; r < nsrc; ++r) {
+        const float4 h = __ldg(reinterpret_cast<const float4*>(p.inbox + src_pos[r] * SLOTW + q * 4));
+        g.x = __fadd_rn(g.x, h.x); g.y = __fadd_rn(g.y, h.y); g.z = __fadd_rn(g.z, h.z); g.w = __fadd_rn(g.w, h.w);
     }
-    p.cnt[lrow] = 0;   // ready for the next step (only this thread touches the row's counter now)
+    const float4 v = *reinterpret_cast<const float4*>(row + q * 4);
+    float4 o = v;
+    if (q * 4 + 0 <= p.k) o.x = fmb::apply_update_a(v.x, g.x, p.lr, p.astep, p.mode);
+    if (q * 4 + 1 <= p.k) o.y = fmb::apply_update_a(v.y, g.y, p.lr, p.astep, p.mode);
+    if (q * 4 + 2 <= p.k) o.z = fmb::apply_update_a(v.z, g.z, p.lr, p.astep, p.mode);
+    if (q * 4 + 3 <= p.k) o.w = fmb::apply_update_a(v.w, g.w, p.lr, p.astep, p.mode);
+    const bool moved = __float_as_int(o.x) != __float_as_int(v.x) || __float_as_int(o.y) != __float_as_int(v.y) ||
+                       __float_as_int(o.z) != __float_as_int(v.z) || __float_as_int(o.w) != __float_as_int(v.w);
+    if (moved) {
+        *reinterpret_cast<float4*>(row + q * 4) = o;
+        const int hb = __ldg(p.hot_base + f);
+        if (hb >= 0) {   // a hot-field row: keep every rank's replica current
+            const size_t h = (size_t)(hb + key - __ldg(p.field_off + f)) * SLOTW + q * 4;
+            for (int r = 0; r < p.G; ++r) *reinterpret_cast<float4*>(p.hot[r] + h) = o;
+        }
+    }
+}
+
+// the counters go back to zero for the next step (after every apply thread has read them)
+__global__ void __launch_bounds__(256) owner_reset_kernel(OwnerParams p) {
+    const int i = blockIdx.x * 256 + threadIdx.x, s = blockIdx.y;
+    if (i >= p.N) return;
+    int key, f;
+    if (owned_run_start(p, s, i, &key, &f)) p.cnt[own_div(p, key)] = 0;
+}
+
+// Row service for the NEXT forward pass: every entry of every other rank's sorted list that names a row I own (outside
+// the replicated hot fields) gets that row stored into the requester's rowbox at the entry's sorted position.  Posted
+// 16-byte stores over NVLink; four lanes per entry.
+__global__ void __launch_bounds__(256) push_rows_kernel(OwnerParams p) {
+    const int t = blockIdx.x * 256 + threadIdx.x, s = blockIdx.y;
+    const int i = t >> 2, q = t & 3;
+    if (i >= p.N || s == p.me || q >= (p.k + 1 + 3) / 4) return;
+    const int32_t key = __ldg(p.keys_all + (size_t)s * p.N + i);
+    if (own_mod(p, key) != p.me) return;
+    if (__ldg(p.hot_base + i / p.B) >= 0) return;
+    const float4 v = *reinterpret_cast<const float4*>(p.table + (size_t)own_div(p, key) * p.rowp + q * 4);
+    *reinterpret_cast<float4*>(p.rowbox[s] + (size_t)i * SLOTW + q * 4) = v;
+}
+
+// my owned rows of the hot fields -> every rank's replica (initialisation / after loading parameters)
+__global__ void __launch_bounds__(256) push_hot_kernel(OwnerParams p, int R_hot) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int h = t >> 2, q = t & 3;
+    if (h >= R_hot || q >= (p.k + 1 + 3) / 4) return;
+    // field of hot row h
+    int f = 0;
+    for (int g = 0; g < p.F; ++g) { const int hb = __ldg(p.hot_base + g); if (hb >= 0 && hb <= h) f = g; }
+    const int key = __ldg(p.field_off + f) + (h - __ldg(p.hot_base + f));
+    if (own_mod(p, key) != p.me) return;
+    const float4 v = *reinterpret_cast<const float4*>(p.table + (size_t)own_div(p, key) * p.rowp + q * 4);
+    for (int r = 0; r < p.G; ++r) *reinterpret_cast<float4*>(p.hot[r] + (size_t)h * SLOTW + q * 4) = v;
 }
 
 static int ilog2_ceil(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
@@ -264,9 +324,12 @@ FMB_API int fmb_shard2_slot_floats(void) { return SLOTW; }
 // (entry `me` = my own buffers).  posflag: fmb_pos_flags of MY ids.  ws: fmb_bwd_workspace_bytes(B*F, k) bytes, handed
 // to fmb_shard2_runs afterwards.  dl[o]: [2][G*B] floats (delta | loss) of the step's parity.
 FMB_API int fmb_shard2_fused(const int32_t* ids, const float* xv, const float* y, const uint32_t* posflag,
-                             void* const* tables, void* const* inbox, void* const* dl, const float* bias, int G, int me,
-                             int B, int F, int k, int loss_kind, void* ws, size_t ws_bytes, cudaStream_t stream) {
-    FMB_CHECK_ARG(ids && y && posflag && tables && inbox && dl && bias && ws, "fmb_shard2_fused: null pointer");
+                             void* const* tables, void* const* inbox, void* const* dl, const float* rowbox,
+                             const float* hot, const int32_t* hot_base, const int32_t* field_off, const float* bias,
+                             int G, int me, int B, int F, int k, int loss_kind, void* ws, size_t ws_bytes,
+                             cudaStream_t stream) {
+    FMB_CHECK_ARG(ids && y && posflag && tables && inbox && dl && rowbox && hot && hot_base && field_off && bias && ws,
+                  "fmb_shard2_fused: null pointer");
     FMB_CHECK_ARG(G >= 1 && G <= 8 && me >= 0 && me < G, "fmb_shard2_fused: bad rank %d of %d", me, G);
     FMB_CHECK_ARG(B > 0 && F > 0 && F < 512 && k > 0 && k + 1 <= SLOTW, "fmb_shard2_fused: bad shape B=%d F=%d k=%d (k <= 15)", B, F, k);
     const int64_t N = (int64_t)B * F;
@@ -277,6 +340,7 @@ FMB_API int fmb_shard2_fused(const int32_t* ids, const float* xv, const float* y
         p.inbox[o] = o < G ? (float*)inbox[o] : nullptr;
         p.dl[o] = o < G ? (float*)dl[o] : nullptr;
     }
+    p.rowbox = rowbox; p.hot = hot; p.hot_base = hot_base; p.field_off = field_off;
     p.bias = bias; p.B = B; p.F = F; p.k = k; p.rowp = fmb_round_up(k + 1, 16); p.kp4 = fmb_round_up(k, 4);
     p.cu = (k + 1 + 3) / 4; p.ql_log = ilog2_ceil(p.cu); p.jl_log = ilog2_ceil(p.kp4);
     p.loss_kind = loss_kind; p.G = G; p.me = me;
@@ -310,21 +374,62 @@ FMB_API int fmb_shard2_push_keys(const int32_t* sorted_keys, int64_t N, int G, i
     return FMB_OK;
 }
 
-// Owner side: count the ranks that hit each owned row, then add their partials in rank order and update the row.
-// keys_all [G][N], inbox [G][N][16] and cnt [R_local] (zero on entry, zero on return) are MY buffers.
-FMB_API int fmb_shard2_owner_apply(const int32_t* keys_all, const float* inbox, float* table, uint32_t* cnt, int G, int me,
+static int fill_owner(OwnerParams& p, const int32_t* keys_all, const float* inbox, float* table, uint32_t* cnt,
+                      void* const* rowbox, void* const* hot, const int32_t* hot_base, const int32_t* field_off, int G, int me,
+                      int B, int F, int k, float lr, int mode) {
+    FMB_CHECK_ARG(keys_all && table && hot && hot_base && field_off, "fmb_shard2 owner: null pointer");
+    FMB_CHECK_ARG(G >= 1 && G <= 8 && me >= 0 && me < G && B > 0 && F > 0 && k > 0 && k + 1 <= SLOTW, "fmb_shard2 owner: bad arguments");
+    FMB_CHECK_ARG((int64_t)B * F < ((int64_t)1 << 29), "fmb_shard2 owner: B*F too large");
+    memset(&p, 0, sizeof(p));
+    p.keys_all = keys_all; p.inbox = inbox; p.table = table; p.cnt = cnt; p.N = B * F;
+    for (int o = 0; o < G; ++o) { p.rowbox[o] = rowbox ? (float*)rowbox[o] : nullptr; p.hot[o] = (float*)hot[o]; }
+    p.hot_base = hot_base; p.field_off = field_off;
+    p.B = B; p.F = F; p.k = k; p.rowp = fmb_round_up(k + 1, 16); p.G = G; p.me = me; p.mode = mode;
+    p.gshift = -1;
+    for (int l = 0; l < 4; ++l) if ((1 << l) == G) p.gshift = l;
+    p.lr = lr; p.astep = -(lr / 0.1f);
+    return FMB_OK;
+}
+
+// Owner side: count the ranks that hit each owned row, add their partials in rank order, update the row (and every
+// rank's replica of it when the row belongs to a hot field).  keys_all [G][N], inbox [G][N][16], cnt [R_local] (zero on
+// entry, zero on return) are MY buffers; hot: G peer-mapped replicas.
+FMB_API int fmb_shard2_owner_apply(const int32_t* keys_all, const float* inbox, float* table, uint32_t* cnt,
+                                   void* const* hot, const int32_t* hot_base, const int32_t* field_off, int G, int me,
                                    int B, int F, int k, float lr, int mode, cudaStream_t stream) {
-    FMB_CHECK_ARG(keys_all && inbox && table && cnt, "fmb_shard2_owner_apply: null pointer");
-    FMB_CHECK_ARG(G >= 1 && G <= 8 && me >= 0 && me < G && B > 0 && F > 0 && k > 0 && k + 1 <= SLOTW, "fmb_shard2_owner_apply: bad arguments");
+    FMB_CHECK_ARG(inbox && cnt, "fmb_shard2_owner_apply: null pointer");
     FMB_CHECK_ARG(mode == 0 || mode == 1, "fmb_shard2_owner_apply: unknown update mode %d", mode);
     OwnerParams p;
-    p.keys_all = keys_all; p.inbox = inbox; p.table = table; p.cnt = cnt; p.N = (int64_t)B * F;
-    p.B = B; p.F = F; p.k = k; p.rowp = fmb_round_up(k + 1, 16); p.G = G; p.me = me; p.mode = mode;
-    p.lr = lr; p.astep = -(lr / 0.1f);
-    const unsigned grid = (unsigned)(((int64_t)G * p.N + 255) / 256);
-    owner_count_kernel<<<grid, 256, 0, stream>>>(p);
-    FMB_CHECK_LAUNCH("owner_count_kernel");
-    owner_apply_kernel<<<grid, 256, 0, stream>>>(p);
-    FMB_CHECK_LAUNCH("owner_apply_kernel");
+    if (int rc = fill_owner(p, keys_all, inbox, table, cnt, nullptr, hot, hot_base, field_off, G, me, B, F, k, lr, mode)) return rc;
+    const dim3 g1((p.N + 255) / 256, G), g4((p.N * 4 + 255) / 256, G);
+    owner_count_kernel<<<g1, 256, 0, stream>>>(p);
+    owner_apply_kernel<<<g4, 256, 0, stream>>>(p);
+    owner_reset_kernel<<<g1, 256, 0, stream>>>(p);
+    FMB_CHECK_LAUNCH("owner kernels");
+    return FMB_OK;
+}
+
+// Row service: store the rows I own that the other ranks' batches (keys_all of the NEXT step) name into their rowboxes.
+FMB_API int fmb_shard2_push_rows(const int32_t* keys_all, float* table, void* const* rowbox, void* const* hot,
+                                 const int32_t* hot_base, const int32_t* field_off, int G, int me, int B, int F, int k,
+                                 cudaStream_t stream) {
+    FMB_CHECK_ARG(rowbox, "fmb_shard2_push_rows: null pointer");
+    OwnerParams p;
+    if (int rc = fill_owner(p, keys_all, nullptr, table, nullptr, rowbox, hot, hot_base, field_off, G, me, B, F, k, 0.f, 0)) return rc;
+    if (G == 1) return FMB_OK;
+    push_rows_kernel<<<dim3((p.N * 4 + 255) / 256, G), 256, 0, stream>>>(p);
+    FMB_CHECK_LAUNCH("push_rows_kernel");
+    return FMB_OK;
+}
+
+// my owned rows of the hot fields -> every rank's replica [R_hot][16] (after initialising / loading parameters)
+FMB_API int fmb_shard2_push_hot(float* table, void* const* hot, const int32_t* hot_base, const int32_t* field_off, int R_hot,
+                                int G, int me, int F, int k, cudaStream_t stream) {
+    OwnerParams p;
+    static const int32_t dummy = 0;
+    if (int rc = fill_owner(p, &dummy, nullptr, table, nullptr, nullptr, hot, hot_base, field_off, G, me, 1, F, k, 0.f, 0)) return rc;
+    if (R_hot <= 0) return FMB_OK;
+    push_hot_kernel<<<(R_hot * 4 + 255) / 256, 256, 0, stream>>>(p, R_hot);
+    FMB_CHECK_LAUNCH("push_hot_kernel");
     return FMB_OK;
 }

@@ -23,7 +23,7 @@ from . import _lib
 from ._lib import check, ptr
 from .sharded import full_from_shards, local_rows_count, shard_from_full  # noqa: F401  (re-exported helpers)
 
-CH_KEYS, CH_PUSH, CH_DONE = 0, 1, 2
+CH_KEYS, CH_PUSH, CH_ROWS = 0, 1, 2
 
 
 def _stream():
@@ -39,7 +39,7 @@ class ShardedFM2:
     of ShardedFM2 objects living in ONE process (tests: the ranks' phases are called in lock step, no flags)."""
 
     def __init__(self, feature_sizes, embedding_size, B, n=1e-4, b=0.99, update_mode=0, group=None, seed=0,
-                 init="normal", world=None, rank=None):
+                 init="normal", world=None, rank=None, hot_max=4096):
         self._lib = _lib.require_cuda()
         self.group = group
         self.emulated = world is not None
@@ -60,9 +60,20 @@ class ShardedFM2:
         G, N = self.G, B * self.F
         self.N = N
         slotw = self._lib.fmb_shard2_slot_floats()
+        # "hot" fields (few rows, every batch hits every row): replicated on every rank, the owners keep the replicas
+        # current; rows of the other fields reach a requester through its rowbox (pushed by the owners)
+        hot_base, nh = [], 0
+        for fs in feature_sizes:
+            if fs <= hot_max:
+                hot_base.append(nh)
+                nh += int(fs)
+            else:
+                hot_base.append(-1)
+        self.R_hot = nh
+        self.hot_base_dev = torch.tensor(hot_base, dtype=torch.int32, device=self.device)
         # ---- buffers the peers read or write: one arena (symmetric memory when the ranks are processes)
         words = {"table": (self.R_local + 1) * self.rowp, "keys0": G * N, "keys1": G * N, "inbox": G * N * slotw,
-                 "dl0": 2 * G * B, "dl1": 2 * G * B, "flags": 64}
+                 "dl0": 2 * G * B, "dl1": 2 * G * B, "rowbox": N * slotw, "hot": max(nh, 1) * slotw, "flags": 64}
         # every rank must lay its arena out identically: the table size differs by at most one row between ranks
         words["table"] = (local_rows_count(self.R, G, 0) + 1) * self.rowp
         off, total = {}, 0
@@ -87,6 +98,8 @@ class ShardedFM2:
         self.inbox = view["inbox"].view(torch.float32)
         self.dl = [view["dl0"].view(torch.float32), view["dl1"].view(torch.float32)]
         self.flags = view["flags"]
+        self.rowbox = view["rowbox"].view(torch.float32)
+        self.hot = view["hot"].view(torch.float32)
         self._peer_ptrs = None
         if not self.emulated:
             self._bind([int(self._hdl.buffer_ptrs[r]) for r in range(G)])
@@ -95,6 +108,8 @@ class ShardedFM2:
             g.manual_seed(seed * 1000 + self.rank)
             self.table[:self.R_local, :self.k + 1].normal_(generator=g)
         self.bias = torch.full((1,), float(np.float32(b)), device=self.device)
+        if not self.emulated:
+            self.sync_hot()
         # ---- private buffers
         self.skeys = [torch.empty(N, dtype=torch.int32, device=self.device) for _ in range(2)]
         self.perm = [torch.empty(N, dtype=torch.int32, device=self.device) for _ in range(2)]
@@ -105,6 +120,7 @@ class ShardedFM2:
         self.epoch = torch.zeros(16, dtype=torch.int32, device=self.device)
         self.error = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._pre = torch.cuda.Stream()
+        self._side = torch.cuda.Stream()
         self._slot = 0
         self.launches = 0
 
@@ -112,7 +128,7 @@ class ShardedFM2:
         """peer pointer tables from the base address of every rank's arena"""
         o = self._off
         self._peer_ptrs = {name: _pp([p + 4 * o[name] for p in arena_ptrs])
-                           for name in ("table", "keys0", "keys1", "inbox", "dl0", "dl1", "flags")}
+                           for name in ("table", "keys0", "keys1", "inbox", "dl0", "dl1", "rowbox", "hot", "flags")}
 
     @staticmethod
     def bind_emulated(ranks):
@@ -127,6 +143,16 @@ class ShardedFM2:
         t[:self.R_local, self.k] = shard_from_full(np.asarray(w1, np.float32), self.G, self.rank)
         self.table.copy_(torch.from_numpy(t))
         self.bias.fill_(float(np.asarray(bias).reshape(-1)[0]))
+
+    def sync_hot(self):
+        """(re)build every rank's replica of the hot-field rows from the owners' shards (collective: every rank calls it
+        after initialising or loading parameters; emulated ranks: call it on every rank, then synchronize)"""
+        check(self._lib.fmb_shard2_push_hot(ptr(self.table), self._peer_ptrs["hot"], ptr(self.hot_base_dev),
+                                            ptr(self.field_off_dev), self.R_hot, self.G, self.rank, self.F, self.k,
+                                            _stream()), "fmb_shard2_push_hot")
+        if not self.emulated:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group if self.group is not None else dist.group.WORLD)
 
     def local_params(self):
         t = self.table[:self.R_local].cpu().numpy()
@@ -146,23 +172,35 @@ class ShardedFM2:
                                          self.rank, mode, ptr(self.error), _stream()), "fmb_shard_signal")
         self.launches += 1
 
-    def phase_sort(self, ids, slot):
-        """stable sort of MY batch's ids + position words; my sorted keys go to every rank (current stream)."""
+    def phase_sort(self, ids, slot, push_after=None):
+        """stable sort of MY batch's ids + position words (current stream); then -- once `push_after` (an event: the
+        peers have finished with this key slot) has fired -- my sorted keys go to every rank"""
         lib, st = self._lib, _stream()
         check(lib.fmb_sort_fields(ptr(ids), self.B, self.F, ptr(self.field_off_dev), ptr(self.skeys[slot]),
                                   ptr(self.perm[slot]), st), "fmb_sort_fields")
         check(lib.fmb_pos_flags(ptr(self.skeys[slot]), ptr(self.perm[slot]), self.N, ptr(self.posflag[slot]), st),
               "fmb_pos_flags")
+        if push_after is not None:
+            torch.cuda.current_stream().wait_event(push_after)
         check(lib.fmb_shard2_push_keys(ptr(self.skeys[slot]), self.N, self.G, self.rank,
                                        self._peer_ptrs[f"keys{slot}"], st), "fmb_shard2_push_keys")
         self.launches += 3
         self._signal(CH_KEYS, 3)     # every rank's keys of this batch have landed here
 
+    def phase_rows(self, slot):
+        """row service: the rows I own that the other ranks' batches name go to their rowboxes (posted NVLink stores)"""
+        check(self._lib.fmb_shard2_push_rows(ptr(self.keys_all[slot]), ptr(self.table), self._peer_ptrs["rowbox"],
+                                             self._peer_ptrs["hot"], ptr(self.hot_base_dev), ptr(self.field_off_dev),
+                                             self.G, self.rank, self.B, self.F, self.k, _stream()), "fmb_shard2_push_rows")
+        self.launches += 1
+        self._signal(CH_ROWS, 3)     # my rowbox is complete; every owner has applied the previous step's updates
+
     def phase_forward(self, ids, y, slot, loss_kind=0):
-        """gather (remote rows over NVLink), logits, loss, contributions: singles -> owners' inboxes, multis -> run kernel"""
+        """gather (all local), logits, loss, contributions: singles -> owners' inboxes, multis -> run kernel -> inboxes"""
         lib, st = self._lib, _stream()
         check(lib.fmb_shard2_fused(ptr(ids), None, ptr(y), ptr(self.posflag[slot]), self._peer_ptrs["table"],
-                                   self._peer_ptrs["inbox"], self._peer_ptrs[f"dl{slot}"], ptr(self.bias), self.G,
+                                   self._peer_ptrs["inbox"], self._peer_ptrs[f"dl{slot}"], ptr(self.rowbox), ptr(self.hot),
+                                   ptr(self.hot_base_dev), ptr(self.field_off_dev), ptr(self.bias), self.G,
                                    self.rank, self.B, self.F, self.k, loss_kind, ptr(self.ws), self.ws_bytes, st),
               "fmb_shard2_fused")
         check(lib.fmb_shard2_runs(ptr(self.skeys[slot]), self.N, self.F, self.k, ptr(self.ws), self.ws_bytes,
@@ -171,17 +209,22 @@ class ShardedFM2:
         self._signal(CH_PUSH, 3)     # every rank's partials (and deltas) of this step have landed here
 
     def phase_owner(self, slot):
-        """owner side: rank-ordered add of the partials + row update; bias step and mean loss over the global batch"""
-        lib, st = self._lib, _stream()
-        check(lib.fmb_shard2_owner_apply(ptr(self.keys_all[slot]), ptr(self.inbox), ptr(self.table), ptr(self.cnt),
-                                         self.G, self.rank, self.B, self.F, self.k, self.lr, self.update_mode, st),
-              "fmb_shard2_owner_apply")
+        """owner side: rank-ordered add of the partials + row update; bias step and mean loss over the global batch
+        (they need the deltas only: side stream, beside the row updates)"""
+        lib = self._lib
+        main = torch.cuda.current_stream()
         Bt = self.G * self.B
         loss = torch.empty((), device=self.device)
-        check(lib.fmb_finish_step(ptr(self.dl[slot]), ptr(self.dl[slot][Bt:]), Bt, ptr(self.bias), self.lr,
-                                  self.update_mode, ptr(loss), st), "fmb_finish_step")
-        self.launches += 3
-        self._signal(CH_DONE, 3)     # every rank has applied its updates: the next forward may gather
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            check(lib.fmb_finish_step(ptr(self.dl[slot]), ptr(self.dl[slot][Bt:]), Bt, ptr(self.bias), self.lr,
+                                      self.update_mode, ptr(loss), _stream()), "fmb_finish_step")
+        check(lib.fmb_shard2_owner_apply(ptr(self.keys_all[slot]), ptr(self.inbox), ptr(self.table), ptr(self.cnt),
+                                         self._peer_ptrs["hot"], ptr(self.hot_base_dev), ptr(self.field_off_dev),
+                                         self.G, self.rank, self.B, self.F, self.k, self.lr, self.update_mode, _stream()),
+              "fmb_shard2_owner_apply")
+        self.launches += 4
+        main.wait_stream(self._side)
         return loss
 
     # ---------------------------------------------------------------- the step
@@ -196,13 +239,19 @@ class ShardedFM2:
 
     def step(self, ids, y, ids_next, loss_kind=0):
         """train on (ids, y) -- the batch given as `ids_next` to the previous call (or to prepare()) -- while the next
-        batch's ids are sorted and their keys exchanged on a side stream.  Returns the mean loss over the G*B samples."""
+        batch's ids are sorted and their keys exchanged on a side stream.  Returns the mean loss over the G*B samples.
+        Order on the main stream: row service -> ROWS barrier -> forward + runs -> PUSH barrier -> owner updates."""
         p = self._slot
         main = torch.cuda.current_stream()
+        self.phase_rows(p)
         if ids_next is not None:
-            self._pre.wait_stream(main)          # the previous step's owner phase has finished with keys_all[1 - p]
+            # the ROWS barrier means every rank has finished the previous step's owner phase, the last reader of key
+            # slot 1 - p: from here on the next batch's keys may land there
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self._pre.wait_stream(main)
             with torch.cuda.stream(self._pre):
-                self.phase_sort(ids_next, 1 - p)
+                self.phase_sort(ids_next, 1 - p, push_after=ev)
         self.phase_forward(ids, y, p, loss_kind)
         loss = self.phase_owner(p)
         main.wait_stream(self._pre)

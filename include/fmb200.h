@@ -159,15 +159,26 @@ int fmb_shard_partial_forward(const int32_t* idsT_all_dev /*[G,F,B]*/, const flo
  *   fmb_shard2_owner_apply scan keys_all, count the ranks hitting each owned row, rank-ordered add, row update
  * Exchanges are fenced with fmb_shard_signal epochs.  Reference semantics: fm_adam.py:56-69 on the concatenated batch. */
 int fmb_shard2_slot_floats(void);
+/* every row read of the forward pass is local: hot-field replica (hot_dev [R_hot][16], hot_base_dev [F] = first replica row
+ * of a field or -1), own shard, or rowbox_dev [N][16] (filled by the owners: fmb_shard2_push_rows) */
 int fmb_shard2_fused(const int32_t* ids_dev, const float* xv_dev, const float* y_dev, const uint32_t* posflag_dev,
-                     void* const* tables, void* const* inbox, void* const* dl, const float* bias_dev, int G, int me, int B,
+                     void* const* tables, void* const* inbox, void* const* dl, const float* rowbox_dev, const float* hot_dev,
+                     const int32_t* hot_base_dev, const int32_t* field_off_dev, const float* bias_dev, int G, int me, int B,
                      int F, int k, int loss_kind, void* ws_dev, size_t ws_bytes, fmb_stream_t stream);
 int fmb_shard2_runs(const int32_t* sorted_keys_dev, int64_t N, int F, int k, void* ws_dev, size_t ws_bytes,
                     void* const* inbox, int G, int me, fmb_stream_t stream);
 int fmb_shard2_push_keys(const int32_t* sorted_keys_dev, int64_t N, int G, int me, void* const* keys_all,
                          fmb_stream_t stream);
-int fmb_shard2_owner_apply(const int32_t* keys_all_dev, const float* inbox_dev, float* table_dev, uint32_t* cnt_dev, int G,
-                           int me, int B, int F, int k, float lr, int mode, fmb_stream_t stream);
+/* row service for the next forward pass: rows I own that the other ranks' sorted lists name -> their rowboxes */
+int fmb_shard2_push_rows(const int32_t* keys_all_dev, float* table_dev, void* const* rowbox, void* const* hot,
+                         const int32_t* hot_base_dev, const int32_t* field_off_dev, int G, int me, int B, int F, int k,
+                         fmb_stream_t stream);
+/* my rows of the hot fields -> every rank's replica (after initialising / loading parameters) */
+int fmb_shard2_push_hot(float* table_dev, void* const* hot, const int32_t* hot_base_dev, const int32_t* field_off_dev,
+                        int R_hot, int G, int me, int F, int k, fmb_stream_t stream);
+int fmb_shard2_owner_apply(const int32_t* keys_all_dev, const float* inbox_dev, float* table_dev, uint32_t* cnt_dev,
+                           void* const* hot, const int32_t* hot_base_dev, const int32_t* field_off_dev, int G, int me, int B,
+                           int F, int k, float lr, int mode, fmb_stream_t stream);
 
 /*[G*B,PW]*/, fmb_stream_t stream);
 int fmb_shard_combine(const float* recv_dev /*[G,B,PW]*/, const float* bias_dev, const float* y_dev, int G, int me,

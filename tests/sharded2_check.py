@@ -45,8 +45,9 @@ def main():
     orc = OracleDeep("FMAdam", SIZES, K, lr=0.01, seed=3)
     orc.V *= np.float32(0.3)
     orc.set_rank_partial_order(B)
-    m = s2.ShardedFM2(SIZES, K, B, n=0.01, init="zeros")
+    m = s2.ShardedFM2(SIZES, K, B, n=0.01, init="zeros", hot_max=100)
     m.load_full(orc.V, orc.w1, orc.bias)
+    m.sync_hot()
     torch.cuda.synchronize()
     dist.barrier()
     mine = lambda s: m.encode(batches[s][0][rank * B:(rank + 1) * B], batches[s][1][rank * B:(rank + 1) * B])

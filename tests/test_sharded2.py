@@ -48,21 +48,28 @@ def test_rank_partial_order_is_the_reference_order_for_one_rank_and_close_to_it_
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("G,B", [(1, 64), (2, 48), (4, 33), (8, 16), (3, 20), (8, 128)])
-def test_emulated_ranks_bit_exact_vs_oracle(G, B):
+@pytest.mark.parametrize("G,B,hot_max", [(1, 64, 4096), (2, 48, 50), (4, 33, 0), (8, 16, 50), (3, 20, 4096), (8, 128, 50),
+                                          (8, 256, 0)])
+def test_emulated_ranks_bit_exact_vs_oracle(G, B, hot_max):
     import torch
     from fm_for_online_recommendation_b200 import sharded2 as s2
     steps = 4
     orc, (V0, w0, b0), batches, want = _oracle(G, B, steps)
-    ranks = [s2.ShardedFM2(SIZES, K, B, n=0.01, init="zeros", world=G, rank=r) for r in range(G)]
+    ranks = [s2.ShardedFM2(SIZES, K, B, n=0.01, init="zeros", world=G, rank=r, hot_max=hot_max) for r in range(G)]
     s2.ShardedFM2.bind_emulated(ranks)
     for m in ranks:
         m.load_full(V0, w0, b0)
+    for m in ranks:
+        m.sync_hot()
+    torch.cuda.synchronize()
     for t, ((Xi, Y), w) in enumerate(zip(batches, want)):
         slot = t & 1
         enc = [m.encode(Xi[r * B:(r + 1) * B], Y[r * B:(r + 1) * B]) for r, m in enumerate(ranks)]
         for m, e in zip(ranks, enc):
             m.phase_sort(e[0], slot)
+        torch.cuda.synchronize()
+        for m in ranks:
+            m.phase_rows(slot)
         torch.cuda.synchronize()
         for m, e in zip(ranks, enc):
             m.phase_forward(e[0], e[1], slot)
