@@ -67,13 +67,13 @@ _SIGS = {
     "fmb_shard_partial_forward": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "fmb_shard2_slot_floats": (C.c_int, []),
     "fmb_shard2_fused": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int,
-                                   C.c_int, C.c_int, vp, C.c_size_t, vp]),
+                                   C.c_int, C.c_int, vp, C.c_size_t, vp, vp, C.c_int, vp, vp]),
     "fmb_shard2_push_rows": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "fmb_shard2_push_hot": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "fmb_shard2_runs": (C.c_int, [vp, C.c_int64, C.c_int, C.c_int, vp, C.c_size_t, vp, C.c_int, C.c_int, vp]),
     "fmb_shard2_push_keys": (C.c_int, [vp, C.c_int64, C.c_int, C.c_int, vp, vp]),
-    "fmb_shard2_owner_apply": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
-                                         C.c_int, vp]),
+    "fmb_shard2_owner_apply": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_float, C.c_int, vp, vp, C.c_int, vp, vp]),
     "fmb_shard_combine": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     "fmb_shard_unpack_ctx": (C.c_int, [vp, C.c_int64, C.c_int, vp, vp, vp]),
     "fmb_shard_sort_fields": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp]),

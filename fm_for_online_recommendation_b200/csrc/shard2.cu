@@ -34,6 +34,27 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
+// Consumer-side wait of an exchange: returns once all G peers have published (fmb_shard_signal, mode 1) the epoch this
+// rank itself has reached on `channel`.  flags: uint32 [8 channels][8 ranks] written by the peers; epoch: my own counters.
+// Called by every thread of a block; bounded spin, *error = 1 + channel on a time-out (the step's results are then void:
+// ShardedFM2 polls the word).
+struct WaitSpec { const uint32_t* flags; const uint32_t* epoch; int* error; int channel, G; };
+__device__ __forceinline__ void wait_epoch(const WaitSpec& w) {
+    if (w.channel < 0) return;
+    if ((int)threadIdx.x < w.G) {
+        const uint32_t e = w.epoch[w.channel];
+        const uint32_t* f = w.flags + w.channel * 8 + threadIdx.x;
+        bool ok = false;
+        for (long long spin = 0; spin < (1ll << 26) && !ok; ++spin) {
+            uint32_t v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(f) : "memory");
+            ok = (int32_t)(v - e) >= 0;
+        }
+        if (!ok && w.error) *w.error = 1 + w.channel;
+    }
+    __syncthreads();
+}
+
 constexpr int SLOTW = 16;   // floats per inbox slot (64 bytes: k + 1 <= 16 on this path)
 
 struct S2Params {
@@ -49,6 +70,7 @@ struct S2Params {
     int G, me;
     float* Gst;            // local component-major staging of multi-hit entries (run kernel input)
     int64_t Npad, N;
+    WaitSpec wait;         // the rowbox must be complete (ROWS channel) before the gather
 };
 
 //   ids [B,F] global row ids of MY batch;  xv [B,F] or NULL;  y [B];  posflag [B*F]: sorted position | multi-hit flag
@@ -68,6 +90,7 @@ __global__ void __launch_bounds__(256) shard2_fused_kernel(const int32_t* __rest
     const int b0 = blockIdx.x * SB;
     const int nv = min(SB, p.B - b0);
 
+    wait_epoch(p.wait);
     for (int e = threadIdx.x; e < nv * F; e += blockDim.x) {
         ids_s[e] = __ldg(ids + (size_t)b0 * F + e);
         x_s[e] = xv ? __ldg(xv + (size_t)b0 * F + e) : 1.0f;
@@ -198,6 +221,10 @@ struct OwnerParams {
     const int32_t* field_off;  // [F+1]
     int N, B, F, k, rowp, G, me, mode, gshift;   // gshift: log2(G) when G is a power of two, else -1
     float lr, astep;
+    uint32_t* list;            // [G*N] compact list of the owned run starts (s*N + i), any order
+    uint32_t* nlist;           // [2] list length of this step (index `par`) / of the next one (zeroed here)
+    int par;
+    WaitSpec wait;             // the partials must have landed (PUSH channel) before they are counted
 };
 
 __device__ __forceinline__ int own_mod(const OwnerParams& p, int key) { return p.gshift >= 0 ? (key & (p.G - 1)) : key % p.G; }
@@ -214,11 +241,23 @@ __device__ __forceinline__ bool owned_run_start(const OwnerParams& p, int s, int
     return true;
 }
 
+// pass 1: count the ranks hitting every owned row and build the compact list of owned run starts, so that the apply
+// pass runs full warps (ownership r % G interleaves: 1 lane in G would be active otherwise)
 __global__ void __launch_bounds__(256) owner_count_kernel(OwnerParams p) {
+    wait_epoch(p.wait);
     const int i = blockIdx.x * 256 + threadIdx.x, s = blockIdx.y;
-    if (i >= p.N) return;
-    int key, f;
-    if (owned_run_start(p, s, i, &key, &f)) atomicAdd(p.cnt + own_div(p, key), 1u);   // integer: order-independent
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.nlist[1 - p.par] = 0;   // next step's counter
+    int key = 0, f = 0;
+    const bool mine = i < p.N && owned_run_start(p, s, i, &key, &f);
+    if (mine) atomicAdd(p.cnt + own_div(p, key), 1u);   // integer: order-independent
+    const unsigned m = __ballot_sync(0xffffffffu, mine);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        uint32_t base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(p.nlist + p.par, (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (mine) p.list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)s * (uint32_t)p.N + (uint32_t)i;
+    }
 }
 
 // first position of `key` in source s's sorted field segment [lo, lo+B), or -1
@@ -229,61 +268,65 @@ __device__ __forceinline__ int find_key(const OwnerParams& p, int s, int lo, int
     return (l < p.B && __ldg(a + l) == key) ? lo + l : -1;
 }
 
-// four lanes per (source, sorted position): lane q applies 16-byte chunk q of the row (the key tests and, for the rare
-// rows several ranks hit, the searches are done by all four lanes -- same addresses, one transaction)
+// pass 2: four lanes per listed run start: lane q applies 16-byte chunk q of the row (for the rare rows several ranks
+// hit, the searches are done by all four lanes -- same addresses, one transaction).  Grid-stride over the list.
 __global__ void __launch_bounds__(256) owner_apply_kernel(OwnerParams p) {
-    const int t = blockIdx.x * 256 + threadIdx.x, s = blockIdx.y;
-    const int i = t >> 2, q = t & 3;
-    if (i >= p.N) return;
-    int key, f;
-    if (!owned_run_start(p, s, i, &key, &f)) return;
-    const int lrow = own_div(p, key);
-    const uint32_t c = p.cnt[lrow];
-    const int lo = f * p.B;
-    size_t src_pos[8];
-    int nsrc = 1;
-    src_pos[0] = (size_t)s * p.N + i;
-    if (c > 1) {
-        // several ranks hit this row: the lowest rank among them adds the partials in rank order
-        for (int r = 0; r < s; ++r)
-            if (find_key(p, r, lo, key) >= 0) return;
-        for (int r = s + 1; r < p.G; ++r) {
-            const int pos = find_key(p, r, lo, key);
-            if (pos >= 0) src_pos[nsrc++] = (size_t)r * p.N + pos;
-        }
-    }
+    const uint32_t n = p.nlist[p.par];
     const int cu = (p.k + 1 + 3) / 4;
-    if (q >= cu) return;
-    float* row = p.table + (size_t)lrow * p.rowp;
-    float4 g = __ldg(reinterpret_cast<const float4*>(p.inbox + src_pos[0] * SLOTW + q * 4));
-    for (int r = 1; r < nsrc; ++r) {
-        const float4 h = __ldg(reinterpret_cast<const float4*>(p.inbox + src_pos[r] * SLOTW + q * 4));
-        g.x = __fadd_rn(g.x, h.x); g.y = __fadd_rn(g.y, h.y); g.z = __fadd_rn(g.z, h.z); g.w = __fadd_rn(g.w, h.w);
-    }
-    const float4 v = *reinterpret_cast<const float4*>(row + q * 4);
-    float4 o = v;
-    if (q * 4 + 0 <= p.k) o.x = fmb::apply_update_a(v.x, g.x, p.lr, p.astep, p.mode);
-    if (q * 4 + 1 <= p.k) o.y = fmb::apply_update_a(v.y, g.y, p.lr, p.astep, p.mode);
-    if (q * 4 + 2 <= p.k) o.z = fmb::apply_update_a(v.z, g.z, p.lr, p.astep, p.mode);
-    if (q * 4 + 3 <= p.k) o.w = fmb::apply_update_a(v.w, g.w, p.lr, p.astep, p.mode);
-    const bool moved = __float_as_int(o.x) != __float_as_int(v.x) || __float_as_int(o.y) != __float_as_int(v.y) ||
-                       __float_as_int(o.z) != __float_as_int(v.z) || __float_as_int(o.w) != __float_as_int(v.w);
-    if (moved) {
-        *reinterpret_cast<float4*>(row + q * 4) = o;
-        const int hb = __ldg(p.hot_base + f);
-        if (hb >= 0) {   // a hot-field row: keep every rank's replica current
-            const size_t h = (size_t)(hb + key - __ldg(p.field_off + f)) * SLOTW + q * 4;
-            for (int r = 0; r < p.G; ++r) *reinterpret_cast<float4*>(p.hot[r] + h) = o;
+    for (uint32_t t = blockIdx.x * 256 + threadIdx.x; t < n * 4; t += gridDim.x * 256) {
+        const uint32_t li = t >> 2;
+        const int q = (int)(t & 3);
+        const uint32_t sp = p.list[li];
+        const int s = (int)(sp / (uint32_t)p.N), i = (int)(sp - (uint32_t)s * (uint32_t)p.N);
+        const int32_t key = __ldg(p.keys_all + sp);
+        const int f = i / p.B;
+        const int lrow = own_div(p, key);
+        const uint32_t c = p.cnt[lrow];
+        const int lo = f * p.B;
+        size_t src_pos[8];
+        int nsrc = 1;
+        src_pos[0] = sp;
+        bool leader = true;
+        if (c > 1) {
+            // several ranks hit this row: the lowest rank among them adds the partials in rank order
+            for (int r = 0; r < s && leader; ++r)
+                if (find_key(p, r, lo, key) >= 0) leader = false;
+            for (int r = s + 1; r < p.G && leader; ++r) {
+                const int pos = find_key(p, r, lo, key);
+                if (pos >= 0) src_pos[nsrc++] = (size_t)r * p.N + pos;
+            }
+        }
+        if (!leader || q >= cu) continue;
+        float* row = p.table + (size_t)lrow * p.rowp;
+        float4 g = __ldg(reinterpret_cast<const float4*>(p.inbox + src_pos[0] * SLOTW + q * 4));
+        for (int r = 1; r < nsrc; ++r) {
+            const float4 h = __ldg(reinterpret_cast<const float4*>(p.inbox + src_pos[r] * SLOTW + q * 4));
+            g.x = __fadd_rn(g.x, h.x); g.y = __fadd_rn(g.y, h.y); g.z = __fadd_rn(g.z, h.z); g.w = __fadd_rn(g.w, h.w);
+        }
+        const float4 v = *reinterpret_cast<const float4*>(row + q * 4);
+        float4 o = v;
+        if (q * 4 + 0 <= p.k) o.x = fmb::apply_update_a(v.x, g.x, p.lr, p.astep, p.mode);
+        if (q * 4 + 1 <= p.k) o.y = fmb::apply_update_a(v.y, g.y, p.lr, p.astep, p.mode);
+        if (q * 4 + 2 <= p.k) o.z = fmb::apply_update_a(v.z, g.z, p.lr, p.astep, p.mode);
+        if (q * 4 + 3 <= p.k) o.w = fmb::apply_update_a(v.w, g.w, p.lr, p.astep, p.mode);
+        const bool moved = __float_as_int(o.x) != __float_as_int(v.x) || __float_as_int(o.y) != __float_as_int(v.y) ||
+                           __float_as_int(o.z) != __float_as_int(v.z) || __float_as_int(o.w) != __float_as_int(v.w);
+        if (moved) {
+            *reinterpret_cast<float4*>(row + q * 4) = o;
+            const int hb = __ldg(p.hot_base + f);
+            if (hb >= 0) {   // a hot-field row: keep every rank's replica current
+                const size_t h = (size_t)(hb + key - __ldg(p.field_off + f)) * SLOTW + q * 4;
+                for (int r = 0; r < p.G; ++r) *reinterpret_cast<float4*>(p.hot[r] + h) = o;
+            }
         }
     }
 }
 
-// the counters go back to zero for the next step (after every apply thread has read them)
+// pass 3: the counters go back to zero for the next step (after every apply thread has read them)
 __global__ void __launch_bounds__(256) owner_reset_kernel(OwnerParams p) {
-    const int i = blockIdx.x * 256 + threadIdx.x, s = blockIdx.y;
-    if (i >= p.N) return;
-    int key, f;
-    if (owned_run_start(p, s, i, &key, &f)) p.cnt[own_div(p, key)] = 0;
+    const uint32_t n = p.nlist[p.par];
+    for (uint32_t t = blockIdx.x * 256 + threadIdx.x; t < n; t += gridDim.x * 256)
+        p.cnt[own_div(p, __ldg(p.keys_all + p.list[t]))] = 0;
 }
 
 // Row service for the NEXT forward pass: every entry of every other rank's sorted list that names a row I own (outside
@@ -327,6 +370,7 @@ FMB_API int fmb_shard2_fused(const int32_t* ids, const float* xv, const float* y
                              void* const* tables, void* const* inbox, void* const* dl, const float* rowbox,
                              const float* hot, const int32_t* hot_base, const int32_t* field_off, const float* bias,
                              int G, int me, int B, int F, int k, int loss_kind, void* ws, size_t ws_bytes,
+                             const uint32_t* wait_flags, const uint32_t* wait_epoch_words, int wait_channel, int* error,
                              cudaStream_t stream) {
     FMB_CHECK_ARG(ids && y && posflag && tables && inbox && dl && rowbox && hot && hot_base && field_off && bias && ws,
                   "fmb_shard2_fused: null pointer");
@@ -345,6 +389,8 @@ FMB_API int fmb_shard2_fused(const int32_t* ids, const float* xv, const float* y
     p.cu = (k + 1 + 3) / 4; p.ql_log = ilog2_ceil(p.cu); p.jl_log = ilog2_ceil(p.kp4);
     p.loss_kind = loss_kind; p.G = G; p.me = me;
     p.Gst = (float*)ws; p.Npad = (N + 3) / 4 * 4 + 64; p.N = N;
+    p.wait.flags = wait_flags; p.wait.epoch = wait_epoch_words; p.wait.error = error; p.wait.G = G;
+    p.wait.channel = (wait_flags && wait_epoch_words) ? wait_channel : -1;
     int SB = 256 >> p.jl_log;
     if (SB < 4) SB = 4;
     if (SB > 32) SB = 32;
@@ -395,16 +441,21 @@ static int fill_owner(OwnerParams& p, const int32_t* keys_all, const float* inbo
 // rank's replica of it when the row belongs to a hot field).  keys_all [G][N], inbox [G][N][16], cnt [R_local] (zero on
 // entry, zero on return) are MY buffers; hot: G peer-mapped replicas.
 FMB_API int fmb_shard2_owner_apply(const int32_t* keys_all, const float* inbox, float* table, uint32_t* cnt,
-                                   void* const* hot, const int32_t* hot_base, const int32_t* field_off, int G, int me,
-                                   int B, int F, int k, float lr, int mode, cudaStream_t stream) {
-    FMB_CHECK_ARG(inbox && cnt, "fmb_shard2_owner_apply: null pointer");
+                                   uint32_t* list, uint32_t* nlist, int parity, void* const* hot, const int32_t* hot_base,
+                                   const int32_t* field_off, int G, int me, int B, int F, int k, float lr, int mode,
+                                   const uint32_t* wait_flags, const uint32_t* wait_epoch_words, int wait_channel,
+                                   int* error, cudaStream_t stream) {
+    FMB_CHECK_ARG(inbox && cnt && list && nlist && (parity == 0 || parity == 1), "fmb_shard2_owner_apply: null pointer");
     FMB_CHECK_ARG(mode == 0 || mode == 1, "fmb_shard2_owner_apply: unknown update mode %d", mode);
     OwnerParams p;
     if (int rc = fill_owner(p, keys_all, inbox, table, cnt, nullptr, hot, hot_base, field_off, G, me, B, F, k, lr, mode)) return rc;
-    const dim3 g1((p.N + 255) / 256, G), g4((p.N * 4 + 255) / 256, G);
+    p.list = list; p.nlist = nlist; p.par = parity;
+    p.wait.flags = wait_flags; p.wait.epoch = wait_epoch_words; p.wait.error = error; p.wait.G = G;
+    p.wait.channel = (wait_flags && wait_epoch_words) ? wait_channel : -1;
+    const dim3 g1((p.N + 255) / 256, G);
     owner_count_kernel<<<g1, 256, 0, stream>>>(p);
-    owner_apply_kernel<<<g4, 256, 0, stream>>>(p);
-    owner_reset_kernel<<<g1, 256, 0, stream>>>(p);
+    owner_apply_kernel<<<148 * 8, 256, 0, stream>>>(p);
+    owner_reset_kernel<<<148 * 2, 256, 0, stream>>>(p);
     FMB_CHECK_LAUNCH("owner kernels");
     return FMB_OK;
 }

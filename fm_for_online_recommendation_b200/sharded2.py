@@ -115,6 +115,8 @@ class ShardedFM2:
         self.perm = [torch.empty(N, dtype=torch.int32, device=self.device) for _ in range(2)]
         self.posflag = [torch.empty(N, dtype=torch.int32, device=self.device) for _ in range(2)]
         self.cnt = torch.zeros(self.R_local + 1, dtype=torch.int32, device=self.device)
+        self.olist = torch.empty(G * N, dtype=torch.int32, device=self.device)    # owner phase: compact run-start list
+        self.nlist = torch.zeros(2, dtype=torch.int32, device=self.device)
         self.ws_bytes = self._lib.fmb_bwd_workspace_bytes(N, self.k)
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
         self.epoch = torch.zeros(16, dtype=torch.int32, device=self.device)
@@ -172,6 +174,12 @@ class ShardedFM2:
                                          self.rank, mode, ptr(self.error), _stream()), "fmb_shard_signal")
         self.launches += 1
 
+    def _wait(self, channel):
+        """(flags, epoch words, channel, error) of an in-kernel wait; nothing to wait for when the ranks are emulated"""
+        if self.emulated:
+            return None, None, -1, None
+        return ptr(self.flags), ptr(self.epoch), channel, ptr(self.error)
+
     def phase_sort(self, ids, slot, push_after=None):
         """stable sort of MY batch's ids + position words (current stream); then -- once `push_after` (an event: the
         peers have finished with this key slot) has fired -- my sorted keys go to every rank"""
@@ -193,7 +201,7 @@ class ShardedFM2:
                                              self._peer_ptrs["hot"], ptr(self.hot_base_dev), ptr(self.field_off_dev),
                                              self.G, self.rank, self.B, self.F, self.k, _stream()), "fmb_shard2_push_rows")
         self.launches += 1
-        self._signal(CH_ROWS, 3)     # my rowbox is complete; every owner has applied the previous step's updates
+        self._signal(CH_ROWS, 1)     # published; the forward kernel itself waits for every owner's ROWS epoch
 
     def phase_forward(self, ids, y, slot, loss_kind=0):
         """gather (all local), logits, loss, contributions: singles -> owners' inboxes, multis -> run kernel -> inboxes"""
@@ -201,12 +209,12 @@ class ShardedFM2:
         check(lib.fmb_shard2_fused(ptr(ids), None, ptr(y), ptr(self.posflag[slot]), self._peer_ptrs["table"],
                                    self._peer_ptrs["inbox"], self._peer_ptrs[f"dl{slot}"], ptr(self.rowbox), ptr(self.hot),
                                    ptr(self.hot_base_dev), ptr(self.field_off_dev), ptr(self.bias), self.G,
-                                   self.rank, self.B, self.F, self.k, loss_kind, ptr(self.ws), self.ws_bytes, st),
-              "fmb_shard2_fused")
+                                   self.rank, self.B, self.F, self.k, loss_kind, ptr(self.ws), self.ws_bytes,
+                                   *self._wait(CH_ROWS), st), "fmb_shard2_fused")
         check(lib.fmb_shard2_runs(ptr(self.skeys[slot]), self.N, self.F, self.k, ptr(self.ws), self.ws_bytes,
                                   self._peer_ptrs["inbox"], self.G, self.rank, st), "fmb_shard2_runs")
         self.launches += 3
-        self._signal(CH_PUSH, 3)     # every rank's partials (and deltas) of this step have landed here
+        self._signal(CH_PUSH, 1)     # published; the owner phase waits for every rank's PUSH epoch
 
     def phase_owner(self, slot):
         """owner side: rank-ordered add of the partials + row update; bias step and mean loss over the global batch
@@ -217,11 +225,13 @@ class ShardedFM2:
         loss = torch.empty((), device=self.device)
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side):
+            self._signal(CH_PUSH, 2)     # every rank's deltas have landed
             check(lib.fmb_finish_step(ptr(self.dl[slot]), ptr(self.dl[slot][Bt:]), Bt, ptr(self.bias), self.lr,
                                       self.update_mode, ptr(loss), _stream()), "fmb_finish_step")
         check(lib.fmb_shard2_owner_apply(ptr(self.keys_all[slot]), ptr(self.inbox), ptr(self.table), ptr(self.cnt),
-                                         self._peer_ptrs["hot"], ptr(self.hot_base_dev), ptr(self.field_off_dev),
-                                         self.G, self.rank, self.B, self.F, self.k, self.lr, self.update_mode, _stream()),
+                                         ptr(self.olist), ptr(self.nlist), slot, self._peer_ptrs["hot"],
+                                         ptr(self.hot_base_dev), ptr(self.field_off_dev), self.G, self.rank, self.B, self.F,
+                                         self.k, self.lr, self.update_mode, *self._wait(CH_PUSH), _stream()),
               "fmb_shard2_owner_apply")
         self.launches += 4
         main.wait_stream(self._side)

@@ -164,7 +164,8 @@ int fmb_shard2_slot_floats(void);
 int fmb_shard2_fused(const int32_t* ids_dev, const float* xv_dev, const float* y_dev, const uint32_t* posflag_dev,
                      void* const* tables, void* const* inbox, void* const* dl, const float* rowbox_dev, const float* hot_dev,
                      const int32_t* hot_base_dev, const int32_t* field_off_dev, const float* bias_dev, int G, int me, int B,
-                     int F, int k, int loss_kind, void* ws_dev, size_t ws_bytes, fmb_stream_t stream);
+                     int F, int k, int loss_kind, void* ws_dev, size_t ws_bytes, const uint32_t* wait_flags_dev,
+                     const uint32_t* wait_epoch_dev, int wait_channel, int* error_dev, fmb_stream_t stream);
 int fmb_shard2_runs(const int32_t* sorted_keys_dev, int64_t N, int F, int k, void* ws_dev, size_t ws_bytes,
                     void* const* inbox, int G, int me, fmb_stream_t stream);
 int fmb_shard2_push_keys(const int32_t* sorted_keys_dev, int64_t N, int G, int me, void* const* keys_all,
@@ -176,9 +177,13 @@ int fmb_shard2_push_rows(const int32_t* keys_all_dev, float* table_dev, void* co
 /* my rows of the hot fields -> every rank's replica (after initialising / loading parameters) */
 int fmb_shard2_push_hot(float* table_dev, void* const* hot, const int32_t* hot_base_dev, const int32_t* field_off_dev,
                         int R_hot, int G, int me, int F, int k, fmb_stream_t stream);
+/* list_dev [G*N] / nlist_dev [2] / parity: compact list of the owned run starts (built by the count pass so that the
+ * apply pass runs full warps).  wait_*: the kernels themselves wait for the peers' epoch on wait_channel (NULL = no wait). */
 int fmb_shard2_owner_apply(const int32_t* keys_all_dev, const float* inbox_dev, float* table_dev, uint32_t* cnt_dev,
-                           void* const* hot, const int32_t* hot_base_dev, const int32_t* field_off_dev, int G, int me, int B,
-                           int F, int k, float lr, int mode, fmb_stream_t stream);
+                           uint32_t* list_dev, uint32_t* nlist_dev, int parity, void* const* hot,
+                           const int32_t* hot_base_dev, const int32_t* field_off_dev, int G, int me, int B, int F, int k,
+                           float lr, int mode, const uint32_t* wait_flags_dev, const uint32_t* wait_epoch_dev,
+                           int wait_channel, int* error_dev, fmb_stream_t stream);
 
 /*[G*B,PW]*/, fmb_stream_t stream);
 int fmb_shard_combine(const float* recv_dev /*[G,B,PW]*/, const float* bias_dev, const float* y_dev, int G, int me,

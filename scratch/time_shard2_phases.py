@@ -38,14 +38,15 @@ for t in range(14, 28):
     e[0].record()
     lib.fmb_shard2_fused(ptr(ids), None, ptr(y), ptr(m.posflag[p]), m._peer_ptrs["table"], m._peer_ptrs["inbox"],
                          m._peer_ptrs[f"dl{p}"], ptr(m.rowbox), ptr(m.hot), ptr(m.hot_base_dev), ptr(m.field_off_dev),
-                         ptr(m.bias), m.G, m.rank, m.B, m.F, m.k, 0, ptr(m.ws), m.ws_bytes, st())
+                         ptr(m.bias), m.G, m.rank, m.B, m.F, m.k, 0, ptr(m.ws), m.ws_bytes, *m._wait(s2.CH_ROWS), st())
     e[1].record()
     lib.fmb_shard2_runs(ptr(m.skeys[p]), m.N, m.F, m.k, ptr(m.ws), m.ws_bytes, m._peer_ptrs["inbox"], m.G, m.rank, st())
     e[2].record()
-    m._signal(s2.CH_PUSH, 3)
+    m._signal(s2.CH_PUSH, 1)
     e[3].record()
-    lib.fmb_shard2_owner_apply(ptr(m.keys_all[p]), ptr(m.inbox), ptr(m.table), ptr(m.cnt), m._peer_ptrs["hot"],
-                               ptr(m.hot_base_dev), ptr(m.field_off_dev), m.G, m.rank, m.B, m.F, m.k, m.lr, 0, st())
+    lib.fmb_shard2_owner_apply(ptr(m.keys_all[p]), ptr(m.inbox), ptr(m.table), ptr(m.cnt), ptr(m.olist), ptr(m.nlist), p,
+                               m._peer_ptrs["hot"], ptr(m.hot_base_dev), ptr(m.field_off_dev), m.G, m.rank, m.B, m.F, m.k,
+                               m.lr, 0, *m._wait(s2.CH_PUSH), st())
     e[4].record()
     loss = torch.empty((), device="cuda")
     lib.fmb_finish_step(ptr(m.dl[p]), ptr(m.dl[p][m.G * m.B:]), m.G * m.B, ptr(m.bias), m.lr, 0, ptr(loss), st())
@@ -53,8 +54,8 @@ for t in range(14, 28):
     e[6].record()
     torch.cuda.synchronize()
     if t >= 18:
-        for n, a, b in (("  fused (remote gathers)", 0, 1), ("  runs (push partials)", 1, 2), ("  PUSH barrier", 2, 3),
-                        ("  owner count+apply+reset", 3, 4), ("  finish", 4, 5), ("  push_rows + ROWS barrier", 7, 0)):
+        for n, a, b in (("  fused (waits ROWS; local gathers)", 0, 1), ("  runs (push partials)", 1, 2), ("  PUSH publish", 2, 3),
+                        ("  owner (wait PUSH)+count+apply+reset", 3, 4), ("  finish", 4, 5), ("  push_rows + ROWS publish", 7, 0)):
             acc.setdefault(n, []).append(e[a].elapsed_time(e[b]) * 1e3)
 dist.barrier()
 if rank == 0:
