@@ -174,12 +174,14 @@ def run_ours(args):
     lib = pkg.require_cuda()
 
     if world > 1:
-        # FMB_SHARD_V1=1 selects the round-1 design (owner-side pooled partials + global owner sort: sharded.py)
-        if os.environ.get("FMB_SHARD_V1", "0") == "1":
-            from fm_for_online_recommendation_b200 import sharded
-            return sharded.bench_main(args, sizes, workload_config(args, sizes))
-        from fm_for_online_recommendation_b200 import sharded2
-        return sharded2.bench_main(args, sizes, workload_config(args, sizes))
+        # two multi-GPU designs: FMB_SHARD=1 = owner-side pooled partials + owner sort of the global
+        # batch (sharded.py; the faster one today), FMB_SHARD=2 = per-rank partial gradients, O(B*F) work per rank,
+        # reference-order forward (sharded2.py)
+        if os.environ.get("FMB_SHARD", "1") == "2":
+            from fm_for_online_recommendation_b200 import sharded2
+            return sharded2.bench_main(args, sizes, workload_config(args, sizes))
+        from fm_for_online_recommendation_b200 import sharded
+        return sharded.bench_main(args, sizes, workload_config(args, sizes))
 
     torch.manual_seed(0)
     model = pkg.DeepFMAdam(sizes, embedding_size=k, num_hidden_layers=3, neuron_per_hidden_layer=400, n=1e-4)

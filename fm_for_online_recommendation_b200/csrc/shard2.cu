@@ -67,7 +67,7 @@ struct S2Params {
     float* dl[8];          // peer-mapped [2][G*B]: delta | per-sample loss of the global batch
     const float* bias;
     int B, F, k, rowp, kp4, SB, cu, ql_log, jl_log, loss_kind;
-    int G, me;
+    int G, me, gshift;     // gshift = log2(G) when G is a power of two, else -1
     float* Gst;            // local component-major staging of multi-hit entries (run kernel input)
     int64_t Npad, N;
     WaitSpec wait;         // the rowbox must be complete (ROWS channel) before the gather
@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(256) shard2_fused_kernel(const int32_t* __rest
                 const int hb = __ldg(p.hot_base + f);
                 const float* src;
                 if (hb >= 0) src = p.hot + (size_t)(hb + r - __ldg(p.field_off + f)) * SLOTW;            // replicated hot row
-                else if (r % G == p.me) src = p.tables[p.me] + (size_t)(r / G) * p.rowp;                 // my own shard
+                else if ((p.gshift >= 0 ? (r & (G - 1)) : r % G) == p.me)
+                    src = p.tables[p.me] + (size_t)(p.gshift >= 0 ? (r >> p.gshift) : r / G) * p.rowp;  // my own shard
                 else src = p.rowbox + (size_t)(pos_s[ef] & 0x7fffffffu) * SLOTW;                         // pushed by its owner
                 cp_async16(rows_s + (size_t)ef * rp + q * 4, src + q * 4);
             }
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(256) shard2_fused_kernel(const int32_t* __rest
             }
         }
         if (!(pf >> 31)) {
-            const int o = ids_s[ef] % G;   // partial of a single entry = 0 + contribution
+            const int o = p.gshift >= 0 ? (ids_s[ef] & (G - 1)) : ids_s[ef] % G;   // partial of a single entry = 0 + contribution
             *reinterpret_cast<float4*>(p.inbox[o] + ((size_t)p.me * p.N + pos) * SLOTW + q * 4) =
                 make_float4(__fadd_rn(0.f, a[0]), __fadd_rn(0.f, a[1]), __fadd_rn(0.f, a[2]), __fadd_rn(0.f, a[3]));
         } else {
@@ -250,14 +251,19 @@ __global__ void __launch_bounds__(256) owner_count_kernel(OwnerParams p) {
     int key = 0, f = 0;
     const bool mine = i < p.N && owned_run_start(p, s, i, &key, &f);
     if (mine) atomicAdd(p.cnt + own_div(p, key), 1u);   // integer: order-independent
+    // block-aggregated append: one atomic on the list length per block
+    __shared__ uint32_t wcount[8], bbase;
     const unsigned m = __ballot_sync(0xffffffffu, mine);
-    if (m) {
-        const int lane = threadIdx.x & 31;
-        uint32_t base = 0;
-        if (lane == __ffs(m) - 1) base = atomicAdd(p.nlist + p.par, (uint32_t)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-        if (mine) p.list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)s * (uint32_t)p.N + (uint32_t)i;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) wcount[warp] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < 8; ++w) { const uint32_t c = wcount[w]; wcount[w] = tot; tot += c; }
+        bbase = tot ? atomicAdd(p.nlist + p.par, tot) : 0u;
     }
+    __syncthreads();
+    if (mine) p.list[bbase + wcount[warp] + __popc(m & ((1u << lane) - 1u))] = (uint32_t)s * (uint32_t)p.N + (uint32_t)i;
 }
 
 // first position of `key` in source s's sorted field segment [lo, lo+B), or -1
@@ -273,7 +279,7 @@ __device__ __forceinline__ int find_key(const OwnerParams& p, int s, int lo, int
 __global__ void __launch_bounds__(256) owner_apply_kernel(OwnerParams p) {
     const uint32_t n = p.nlist[p.par];
     const int cu = (p.k + 1 + 3) / 4;
-    for (uint32_t t = blockIdx.x * 256 + threadIdx.x; t < n * 4; t += gridDim.x * 256) {
+    for (uint32_t t = blockIdx.x * 256 + threadIdx.x; t < n * 4; t += gridDim.x * 256) {   // one item per thread (grid covers G*N*4)
         const uint32_t li = t >> 2;
         const int q = (int)(t & 3);
         const uint32_t sp = p.list[li];
@@ -333,6 +339,7 @@ __global__ void __launch_bounds__(256) owner_reset_kernel(OwnerParams p) {
 // the replicated hot fields) gets that row stored into the requester's rowbox at the entry's sorted position.  Posted
 // 16-byte stores over NVLink; four lanes per entry.
 __global__ void __launch_bounds__(256) push_rows_kernel(OwnerParams p) {
+    // four lanes per key (one per 16-byte chunk): a thread per key copying 48 bytes was slower (44 vs 32 us at G = 2)
     const int t = blockIdx.x * 256 + threadIdx.x, s = blockIdx.y;
     const int i = t >> 2, q = t & 3;
     if (i >= p.N || s == p.me || q >= (p.k + 1 + 3) / 4) return;
@@ -388,6 +395,8 @@ FMB_API int fmb_shard2_fused(const int32_t* ids, const float* xv, const float* y
     p.bias = bias; p.B = B; p.F = F; p.k = k; p.rowp = fmb_round_up(k + 1, 16); p.kp4 = fmb_round_up(k, 4);
     p.cu = (k + 1 + 3) / 4; p.ql_log = ilog2_ceil(p.cu); p.jl_log = ilog2_ceil(p.kp4);
     p.loss_kind = loss_kind; p.G = G; p.me = me;
+    p.gshift = -1;
+    for (int l = 0; l < 4; ++l) if ((1 << l) == G) p.gshift = l;
     p.Gst = (float*)ws; p.Npad = (N + 3) / 4 * 4 + 64; p.N = N;
     p.wait.flags = wait_flags; p.wait.epoch = wait_epoch_words; p.wait.error = error; p.wait.G = G;
     p.wait.channel = (wait_flags && wait_epoch_words) ? wait_channel : -1;
@@ -454,8 +463,8 @@ FMB_API int fmb_shard2_owner_apply(const int32_t* keys_all, const float* inbox, 
     p.wait.channel = (wait_flags && wait_epoch_words) ? wait_channel : -1;
     const dim3 g1((p.N + 255) / 256, G);
     owner_count_kernel<<<g1, 256, 0, stream>>>(p);
-    owner_apply_kernel<<<148 * 8, 256, 0, stream>>>(p);
-    owner_reset_kernel<<<148 * 2, 256, 0, stream>>>(p);
+    owner_apply_kernel<<<(unsigned)(((int64_t)p.N * 4 * (G > 1 ? 2 : 1) + 255) / 256), 256, 0, stream>>>(p);   // the list holds ~N entries
+    owner_reset_kernel<<<(unsigned)(((int64_t)p.N * (G > 1 ? 2 : 1) + 255) / 256), 256, 0, stream>>>(p);
     FMB_CHECK_LAUNCH("owner kernels");
     return FMB_OK;
 }
