@@ -28,6 +28,11 @@ _SIGS = {
                                  vp]),
     "fmb_loss_delta": (C.c_int, [C.c_int, vp, vp, C.c_int, vp, vp, vp]),
     "fmb_sum_aten": (C.c_int, [vp, C.c_int64, vp, vp]),
+    "fmb_metric_regression": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
+    "fmb_metric_classification": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp]),
+    "fmb_confusion": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
+    "fmb_auc_pairs": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
+    "fmb_sigmoid": (C.c_int, [vp, C.c_int, vp, vp]),
     "fmb_math_eval": (C.c_int, [C.c_int, vp, vp, C.c_int64, vp]),
     "fmb_update_dense": (C.c_int, [vp, vp, C.c_int64, C.c_float, C.c_int, vp]),
     "fmb_finish_step": (C.c_int, [vp, vp, C.c_int, vp, C.c_float, C.c_int, vp, vp]),

@@ -471,6 +471,16 @@ class _DeepBase(nn.Module):
         self.eval()
         return self._predict_dev(self.encode(Xi, Xv)).cpu().numpy().astype(bool)
 
+    def predict_proba(self, Xi, Xv):
+        """torch.sigmoid(forward(...)) as a device tensor (extension, SURVEY.md 8f.2: scores for AUC / RMSE checks; the
+        ONN classes return sigmoid of the last head's probability, exactly what their predict thresholds)."""
+        self.eval()
+        o = self._full_forward(self.encode(Xi, Xv))
+        z = o["z"].contiguous()
+        p = torch.empty_like(z)
+        check(self._lib.fmb_sigmoid(ptr(z), z.numel(), ptr(p), _stream()), "fmb_sigmoid")
+        return p
+
     _KIND_ID = 0
 
     def run_experiment(self, data_Xi, data_Xv, data_Y):
@@ -492,25 +502,15 @@ class _DeepBase(nn.Module):
                                             ptr(self.bias), ptr(self._mlp), ptr(getattr(self, "alpha", None)),
                                             ptr(acc), self._lr, self._hb, self._hs, self.update_mode, ptr(preds_dev),
                                             ptr(conf_dev), _stream()), "fmb_online_deep_run")
+        # bookkeeping of fm_adam.py:101-116: the kernel counted tp/fp/tn/fn as it went; the reference returns only the
+        # LAST accuracy / roc entry, which are functions of the final counts (one 32-byte read, no per-sample host loop)
+        tp, fp, tn, fn = (int(v) for v in conf_dev.cpu())
+        confusion_matrix = {"tp": tp, "fp": fp, "tn": tn, "fn": fn}
+        tpr = tp / (tp + fn + 1e-16)
+        fpr = fp / (fp + tn + 1e-16)
+        roc = [{'tpr': tpr, 'fpr': fpr}]
+        accuracy = [(tp + tn) / data_size * 100]
         preds = preds_dev.cpu().numpy().astype(bool)
-        labels = np.asarray(data_Y).reshape(-1)
-        for i in range(data_size):
-            pred = preds[i]
-            if pred == labels[i]:
-                if labels[i] == 1:
-                    confusion_matrix["tp"] += 1
-                else:
-                    confusion_matrix["tn"] += 1
-            else:
-                if labels[i] == 1:
-                    confusion_matrix["fn"] += 1
-                else:
-                    confusion_matrix["fp"] += 1
-            if i % 1000 == 0 or i == data_size - 1:
-                tpr = confusion_matrix['tp'] / (confusion_matrix['tp'] + confusion_matrix['fn'] + 1e-16)
-                fpr = confusion_matrix['fp'] / (confusion_matrix['fp'] + confusion_matrix['tn'] + 1e-16)
-                roc.append({'tpr': tpr, 'fpr': fpr})
-                accuracy.append(((confusion_matrix['tp'] + confusion_matrix['tn']) / (i + 1) * 100))
         time_elapsed = time() - start
         self._last_online_preds = preds
         return time_elapsed, accuracy[-1], roc[-1], confusion_matrix

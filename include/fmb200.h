@@ -67,6 +67,20 @@ int fmb_fm_forward(const int32_t* ids_dev, const float* xv_dev, const float* tab
 /* ---- A6: loss + gradient on the logit (fm_adam.py:63-67, :77-81) ------------------------------- */
 int fmb_loss_delta(int loss_kind, const float* z_dev, const float* y_dev, int B, float* delta_dev,
                    float* lossv_dev, fmb_stream_t stream);
+/* ---- metrics on the device (csrc/metrics.cu) -------------------------------------------------
+ * running curves of utils/metric_manager.py:7-29 (fp64, sequential accumulation like the Python loops), confusion
+ * counts of fm_adam.py:101-111 for a batch of predictions, exact ROC AUC ingredients (pair counts), torch.sigmoid of
+ * a logit vector (predict_proba). */
+int fmb_metric_regression(const double* pred_dev, const double* real_dev, int64_t n, double* out_dev /*[n+1]*/,
+                          fmb_stream_t stream);
+int fmb_metric_classification(const double* pred_dev, const double* real_dev, int64_t n, double* metric_dev,
+                              double* acc_dev, fmb_stream_t stream);
+int fmb_confusion(const uint8_t* pred_dev, const float* y_dev, int64_t n, unsigned long long* conf_dev /*tp,fp,tn,fn*/,
+                  fmb_stream_t stream);
+int fmb_auc_pairs(const float* scores_dev, const float* labels_dev, int64_t n, unsigned long long* counts_dev,
+                  fmb_stream_t stream);
+int fmb_sigmoid(const float* z_dev, int n, float* p_dev, fmb_stream_t stream);
+
 /* element-wise ATen mirrors (torch 2.11 CPU arithmetic restated on the device, csrc/fmb_aten_math.cuh):
  * op 0 torch.sigmoid of element i of a contiguous [n] tensor (fm_adam.py:80,86), 1 at::log_sigmoid (inside
  * F.binary_cross_entropy_with_logits, fm_adam.py:65), 2 Tensor.sqrt as torch.optim.Adam calls it (fm_adam.py:68),
