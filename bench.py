@@ -116,6 +116,78 @@ def cpu_port_rate(sizes, k, B, budget_s, seed=0, threads=None):
     return n * B / dt, n, dt
 
 
+def reference_classes_rate(B=8192, steps=5, threads=None):
+    """The reference's OWN classes (baseline/_ref, copied there unmodified by __graft_entry__.build()) on this box's host
+    cores: DeepFMAdam(use_cuda=False).update_embedding at BASELINE.json configs[3]'s shape (the Criteo-tiny tables of
+    main_experiment.py:56-58; the 33 M-row tables of configs[4] would need minutes per step: the reference's Adam step is
+    dense over every row).  ndarray inputs (the reference converts them per call)."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "models")):
+        return {"unavailable": "baseline/_ref not populated (run __graft_entry__.build() where /root/reference exists)"}
+    import types
+    import torch
+    if "matplotlib" not in sys.modules:
+        mpl = types.ModuleType("matplotlib"); mpl.use = lambda *a, **k: None
+        plt = types.ModuleType("matplotlib.pyplot"); mpl.pyplot = plt
+        sys.modules["matplotlib"] = mpl; sys.modules["matplotlib.pyplot"] = plt
+    sys.path.insert(0, ref)
+    try:
+        from models.models_online_deep.deepfm_adam import DeepFMAdam as RefDeepFMAdam
+        threads = threads or os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        torch.manual_seed(0)
+        sizes = list(CRITEO_TINY)
+        m = RefDeepFMAdam(sizes, embedding_size=10, num_hidden_layers=3, neuron_per_hidden_layer=400, n=1e-4, use_cuda=False)
+        batches = synth_batches(sizes, B, 2, 99)
+        ones = np.ones((B, len(sizes)), np.float32)
+        m.update_embedding(batches[0][0], ones, batches[0][1])   # warm-up
+        t0 = time.perf_counter()
+        for i in range(steps):
+            m.update_embedding(batches[i % 2][0], ones, batches[i % 2][1])
+        dt = time.perf_counter() - t0
+        return {"value": steps * B / dt, "unit": "samples/s", "cores": threads, "kind": "reference",
+                "sample": f"{steps} DeepFMAdam(use_cuda=False).update_embedding steps of B={B} at configs[3]'s shape "
+                          f"(F=39, R=1006628, k=10) in {dt:.1f}s, torch {torch.__version__} CPU, {threads} threads"}
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+    finally:
+        sys.path.remove(ref)
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]
+
+
+def cfg4_fit_record(lib, steps=30):
+    """BASELINE.json configs[3]: DeepFMAdam.fit (forward + tower backward + table / tower / bias updates) at B = 8192 with
+    the tcgen05 3xTF32 tower: a second, tensor-bound record carried inside the bench line."""
+    import torch
+    import fm_for_online_recommendation_b200 as pkg
+    B, k, L, H = 8192, 10, 3, 400
+    torch.manual_seed(0)
+    m = pkg.DeepFMAdam(CRITEO_TINY, embedding_size=k, num_hidden_layers=L, neuron_per_hidden_layer=H, n=1e-4)
+    enc = [m.encode(Xi, None, Y) for Xi, Y in synth_batches(CRITEO_TINY, B, 4, 7)]
+    for i in range(4):
+        m._deep_fit(enc[i % 4])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        m._deep_fit(enc[i % 4])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    flop = 2 * B * (k * H + (L - 1) * H * H) * 3          # forward + dX + dW products of the tower
+    peaks, _ = measured_peaks()
+    tf32x3_peak = 1100.0 / 3                                # nominal dense TF32 (1.1 PFLOP/s) / 3 products per fp32-grade product
+    return {"workload": "cfg4: DeepFMAdam.fit, B=8192, k=10, tower 10-400-400-400, F=39, R=1006628", "steps": steps,
+            "ms_per_step": ms, "value": B / (ms * 1e-3), "unit": "samples/s",
+            "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "peak": tf32x3_peak, "unit": "TFLOP/s",
+                         "frac": flop / (ms * 1e-3) / 1e12 / tf32x3_peak,
+                         "note": "tower flops (1.944 MFLOP/sample) over the WHOLE fit step (gather, sort and row updates "
+                                 "included); peak = nominal dense TF32 / 3 (3xTF32 split); measured bf16 peak for scale: "
+                                 f"{peaks.get('bf16_tflops')} TFLOP/s"},
+            "tensor_core_error_flag": int(lib.fmb_gemm_tc_error())}
+
+
 def run_reference(args):
     """--impl reference: the reference is pure Python/PyTorch and cannot travel to the GPU box, so this
     arm times the CPU oracle port of the same step (oracle/fm_oracle.c) on all the host cores (ORC_THREADS)."""
@@ -146,7 +218,8 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
                              "sample": f"{K} update_embedding steps of B={B} (oracle/fm_oracle.c, {threads} host threads: "
                                        "samples in parallel forward, fields in parallel backward)"},
-            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "cpu_baseline_reference": reference_classes_rate()}
     print(json.dumps(line))
 
 
@@ -347,11 +420,17 @@ def run_ours(args):
                      "phase_ms": phases,
                      "whole_step_GBps": step_bytes / (ms / K * 1e-3) / 1e9},
     }
+    if not args.no_extra:
+        try:
+            line["cfg4_fit"] = cfg4_fit_record(lib)
+        except Exception as exc:  # noqa: BLE001 -- the headline line must not die with the extra record
+            line["cfg4_fit"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
     if not args.no_cpu_baseline:
         v, n, dt = cpu_port_rate(sizes, k, B, args.cpu_budget)
         line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
                                 "sample": f"{n} update_embedding steps of B={B} in {dt:.1f}s "
                                           f"(oracle/fm_oracle.c, all {os.cpu_count()} host threads)"}
+        line["cpu_baseline_reference"] = reference_classes_rate()
     print(json.dumps(line))
 
 
@@ -365,6 +444,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8192)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the cfg4 DeepFMAdam.fit record")
     ap.add_argument("--no-presort", action="store_true", help="sort each batch inside its own step")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -106,6 +106,7 @@ class _DeepBase(nn.Module):
             raise ValueError("total rows must fit int32")
         self._key_bits = max(1, int(self._R - 1).bit_length())
         self._offsets_dev = torch.from_numpy(self._offsets_np[:-1].copy()).to(self.device)
+        self._sizes_dev = torch.from_numpy(sizes.copy()).to(self.device)
         self._field_off_dev = torch.from_numpy(self._offsets_np.astype(np.int32)).to(self.device)
 
         # parameters are drawn on the CPU in the reference's order so torch.manual_seed(s) gives the
@@ -173,6 +174,12 @@ class _DeepBase(nn.Module):
             mods.append(_ViewLinear(w, c))
         self.hidden_layers = nn.ModuleList(mods)
 
+    def _apply(self, fn, recurse=True):
+        """nn.Module.to()/.cpu()/.double()/.half() would re-create the Parameters away from the packed table the kernels
+        train (the views would silently stop being the model): the classes live on the device they were built on."""
+        raise RuntimeError("fm_for_online_recommendation_b200 models are bound to their CUDA device and to fp32: "
+                           ".to()/.cpu()/.cuda()/.double() are not supported (pickle the model to move it)")
+
     # ------------------------------------------------------------------ persistence
     def _ctor_kwargs(self):
         raise NotImplementedError
@@ -212,7 +219,11 @@ class _DeepBase(nn.Module):
             return Xi
         F = self.field_size
         if torch.is_tensor(Xi):
-            ids = (Xi.to(self.device).reshape(-1, F).to(torch.int64) + self._offsets_dev).to(torch.int32)
+            loc = Xi.to(self.device).reshape(-1, F).to(torch.int64)
+            # same failure as nn.Embedding in the reference: an out-of-range id must raise, never gather out of bounds
+            if loc.numel() and bool(((loc < 0) | (loc >= self._sizes_dev)).any()):
+                raise IndexError("index out of range in self")
+            ids = (loc + self._offsets_dev).to(torch.int32)
         else:
             a = np.asarray(Xi, dtype=np.int64).reshape(-1, F)
             if a.size and (a.min() < 0 or (a >= (self._offsets_np[1:] - self._offsets_np[:-1])[None, :]).any()):
