@@ -2,7 +2,7 @@
 
 Public surface mirrors haan6/fm-for-online-recommendation:
   deep family      : FMAdam, DeepFMAdam, NFMAdam, DeepFMOnn, NFMOnn   (models/models_online_deep/*.py)
-  classical family : FM_FTRL, SFTRL_CCFM, SFTRL_Vanila                (models/models_online/*.py)
+  classical family : FM_FTRL, SFTRL_CCFM, SFTRL_Vanila, RRF_Online    (models/models_online/*.py)
 All arithmetic runs in lib/libfmb200.so (hand-written CUDA, include/fmb200.h); there is no CPU path.
 """
 from ._lib import FmbError, load, require_cuda  # noqa: F401
@@ -14,7 +14,7 @@ def __getattr__(name):  # lazy: importing the package must not need torch.cuda
     if name in ("FMAdam", "DeepFMAdam", "NFMAdam", "DeepFMOnn", "NFMOnn", "EncodedBatch"):
         from . import deep
         return getattr(deep, name)
-    if name in ("FM_FTRL", "SFTRL_CCFM", "SFTRL_Vanila"):
+    if name in ("FM_FTRL", "SFTRL_CCFM", "SFTRL_Vanila", "RRF_Online"):
         from . import classical
         return getattr(classical, name)
     raise AttributeError(name)

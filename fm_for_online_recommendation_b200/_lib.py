@@ -28,6 +28,7 @@ _SIGS = {
                                  vp]),
     "fmb_loss_delta": (C.c_int, [C.c_int, vp, vp, C.c_int, vp, vp, vp]),
     "fmb_sum_aten": (C.c_int, [vp, C.c_int64, vp, vp]),
+    "fmb_rrf_run": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, vp, vp, vp, vp]),
     "fmb_metric_regression": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
     "fmb_metric_classification": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp]),
     "fmb_confusion": (C.c_int, [vp, vp, C.c_int64, vp, vp]),

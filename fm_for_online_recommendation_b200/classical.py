@@ -140,3 +140,72 @@ class SFTRL_Vanila(_SFTRL):
     def __init__(self, inputs_matrix, outputs, task, learning_rate, num_feature):
         super().__init__(inputs_matrix, outputs, task, learning_rate, num_feature)
         self.model_name = "SFTRL_Vanila"
+
+
+class RRF_Online(torch.nn.Module):
+    """RRF_Online.py:18-187: online reparameterised random Fourier features.  Same constructor and state
+    attributes (`gamma` log-scale [d,1], `w` [2D], `eps` [d,D]), same RNG draws on the CPU in the same order
+    (np.random.rand for gamma, torch.randn for w, torch.randn for eps), `online_learning()` -> (preds, reals, seconds)
+    with only the non-NaN samples appended.  The stream runs as one persistent fp64 kernel (csrc/rrf.cu)."""
+
+    def __init__(self, inputs_matrix, outputs, task, loss_type=None, gamma=None, w=None, num_sampled_spectral=10,
+                 random_seed=100, lr_RRF_w=0.05, lr_RRF_gamma=0.05):
+        super().__init__()
+        self._lib = _lib.require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.X = torch.as_tensor(inputs_matrix, dtype=torch.float64).to(self.device).contiguous()
+        self.Y = torch.as_tensor(outputs, dtype=torch.float64).reshape(-1).to(self.device).contiguous()
+        self.loss_type = loss_type
+        self.num_feature = self.X.shape[1]
+        self.model_name = "RRF_Online"
+        self.task = task
+        self.num_sampled_spectral = num_sampled_spectral
+        self.lr_RRF_w = lr_RRF_w
+        self.lr_RRF_gamma = lr_RRF_gamma
+        self.random_seed = random_seed
+        self._init_param(gamma, w, loss_type)
+
+    def _init_param(self, gamma, w, loss_type):   # RRF_Online.py:46-67
+        if self.task == 'cls':
+            self.loss_type = 'logit' if loss_type is None else 'hinge'
+        elif self.task == 'reg':
+            self.loss_type = 'l2' if loss_type is None else 'l1'
+        else:
+            raise NotImplementedError('wrong task assigned')
+        if gamma is None:
+            g = Tensor_type(np.log(np.random.rand(self.num_feature, 1)))
+        else:
+            g = Tensor_type(np.log(gamma) * np.ones((self.num_feature, 1)))
+        self.gamma = g.to(self.device)
+        if w is None:
+            self.w = (0.1 * torch.randn(2 * self.num_sampled_spectral).type(Tensor_type)).to(self.device)
+        else:
+            self.w = torch.as_tensor(w, dtype=torch.float64).to(self.device).clone()
+        self.eps = torch.randn(self.num_feature, self.num_sampled_spectral).type(Tensor_type).to(self.device)
+
+    def online_learning(self):
+        if self.loss_type in ('hinge', 'l1'):
+            raise NotImplementedError('wrong loss type in get_grad')   # RRF_Online.py:115-122
+        start = time.time()
+        print("==" * 20)
+        N = self.X.shape[0]
+        preds = torch.empty(N, dtype=torch.float64, device=self.device)
+        nvalid = torch.zeros(1, dtype=torch.int32, device=self.device)
+        gam = self.gamma.reshape(-1).contiguous()
+        wv = self.w.contiguous()
+        eps = self.eps.contiguous()
+        check(self._lib.fmb_rrf_run(ptr(self.X), ptr(self.Y), N, self.num_feature, self.num_sampled_spectral,
+                                    1 if self.task == 'cls' else 0, float(self.lr_RRF_w), float(self.lr_RRF_gamma), ptr(gam),
+                                    ptr(wv), ptr(eps), ptr(preds), ptr(nvalid), _stream()), "fmb_rrf_run")
+        self.gamma = gam.reshape(-1, 1)
+        self.w = wv
+        n = int(nvalid.item())
+        p = preds[:n].cpu().numpy()
+        real = self.Y.cpu().numpy()
+        # the reference appends the label of every non-NaN sample; with no NaN that is the whole stream
+        reals = real if n == N else real[:n]
+        for t in range(0, min(n, N), 1000):
+            print(' %d th : pred %f , real %f ' % (t, p[t], real[t]))
+        end = time.time()
+        print('learning time : %f ' % (end - start))
+        return p, reals, (end - start)

@@ -67,6 +67,13 @@ int fmb_fm_forward(const int32_t* ids_dev, const float* xv_dev, const float* tab
 /* ---- A6: loss + gradient on the logit (fm_adam.py:63-67, :77-81) ------------------------------- */
 int fmb_loss_delta(int loss_kind, const float* z_dev, const float* y_dev, int B, float* delta_dev,
                    float* lossv_dev, fmb_stream_t stream);
+/* ---- RRF_Online (RRF_Online.py:70-187): persistent fp64 kernel, one CTA walks the stream in order.
+ * gamma_dev [d] (log scale) and w_dev [2D] are updated in place; preds_dev [N] / nvalid_dev: predictions of the samples whose
+ * score was not NaN (the reference skips the others).  task 0 = 'reg' (l2 loss), 1 = 'cls' (logit loss). */
+int fmb_rrf_run(const double* X_dev, const double* Y_dev, int N, int d, int D, int task, double lr_w, double lr_gamma,
+                double* gamma_dev, double* w_dev, const double* eps_dev, double* preds_dev, int* nvalid_dev,
+                fmb_stream_t stream);
+
 /* ---- metrics on the device (csrc/metrics.cu) -------------------------------------------------
  * running curves of utils/metric_manager.py:7-29 (fp64, sequential accumulation like the Python loops), confusion
  * counts of fm_adam.py:101-111 for a batch of predictions, exact ROC AUC ingredients (pair counts), torch.sigmoid of
