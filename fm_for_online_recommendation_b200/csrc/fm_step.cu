@@ -17,6 +17,7 @@
 // written 4F(k+1) + delta/loss 8 = 3 752 B (SURVEY.md 8d's figure; the sorted-position words replace the
 // sorted-key reads of the entry kernel).
 #include "fmb_common.cuh"
+#include <cstdlib>
 
 extern "C" size_t fmb_bwd_workspace_bytes(int64_t, int);
 
@@ -310,6 +311,15 @@ FMB_API int fmb_fm_step_fused_ex(const int32_t* ids, const float* xv, const floa
         return sizeof(float) * ((size_t)sb * F * p.cu * 4 + (size_t)4 * sb * F + (size_t)sb * k + (size_t)sb * p.kp4 + sb);
     };
     while (SB > 1 && bytes(SB) > 48 * 1024) SB >>= 1;
+    // at least ~6 tiles per SM when the batch allows it: the tiles of an SM are then in different phases (gather, reduce,
+    // update) at any time and the 148 SMs finish together (8 192 samples: 1 024 tiles of 8 instead of 512 of 16, measured
+    // 64 instead of 75 us per step, profiles/r2_sweep_tile.txt)
+    while (SB > 8 && (B + SB - 1) / SB < 6 * 148) SB >>= 1;
+    {   // experiment knob: FMB_STEP_SB caps the samples per tile
+        static int cap = -1;
+        if (cap < 0) { const char* e = getenv("FMB_STEP_SB"); cap = e ? atoi(e) : 0; }
+        if (cap > 0 && SB > cap) SB = cap;
+    }
     FMB_CHECK_ARG(bytes(SB) <= 200 * 1024, "fmb_fm_step_fused: F*k too large for one sample tile");
     p.SB = SB;
     static bool attr_set = false;

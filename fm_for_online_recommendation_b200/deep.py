@@ -27,6 +27,7 @@ from ._lib import FmbError, check, ptr
 
 UPDATE_ADAM1, UPDATE_SGD, UPDATE_FTRL = 0, 1, 2   # 2: per-coordinate FTRL-Proximal (enable_ftrl), FM-only steps
 LOSS_LOGITS, LOSS_LOGITS_OF_SIG = 0, 1
+_PRESORT_STANDALONE = __import__("os").environ.get("FMB_PRESORT_STANDALONE", "0") == "1"
 
 
 def _stream():
@@ -371,10 +372,15 @@ class _DeepBase(nn.Module):
             self._lib.fmb_session_presort_invalidate(s)   # a pre-sort is only ever honoured for the very same batch object
         nxt = next_batch if (next_batch is not None and next_batch.B == e.B) else None
         loss = torch.empty((), device=self.device)
+        inside = nxt is not None and not _PRESORT_STANDALONE
         check(self._lib.fmb_session_fm_step_next(s, ptr(e.ids), ptr(e.xv), ptr(e.y), e.B, ptr(self._table),
                                                  ptr(self.bias), self._key_bits, loss_kind, self._lr, self.update_mode,
-                                                 ptr(nxt.ids) if nxt is not None else None, ptr(loss), _stream()),
+                                                 ptr(nxt.ids) if inside else None, ptr(loss), _stream()),
               "fmb_session_fm_step_next")
+        if nxt is not None and not inside:
+            # the next batch's sort as a stand-alone launch on the session's side stream: it may still be running when this
+            # step's graph has finished (the step after waits for it), instead of being joined at the end of this graph
+            check(self._lib.fmb_session_presort(s, ptr(nxt.ids), nxt.B, self._key_bits), "fmb_session_presort")
         self._presorted = nxt
         return loss
 
