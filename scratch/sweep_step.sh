@@ -1,5 +1,5 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
-for sb in 16 8 4; do for ps in 0 1; do
+for sb in 8; do for ps in 0 1; do
 FMB_STEP_SB=$sb FMB_PRESORT_STANDALONE=$ps python bench.py --steps 100 --warmup 10 --no-cpu-baseline --no-extra 2>/dev/null > /tmp/o.json
 SB=$sb PS=$ps python - <<'PY'
 import json, os
