@@ -28,6 +28,11 @@ _SIGS = {
                                  vp]),
     "fmb_loss_delta": (C.c_int, [C.c_int, vp, vp, C.c_int, vp, vp, vp]),
     "fmb_sum_aten": (C.c_int, [vp, C.c_int64, vp, vp]),
+    "fmb_afm_dense_floats": (C.c_size_t, [C.c_int, C.c_int]),
+    "fmb_afm_step": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp,
+                               vp, vp, vp, vp, C.c_size_t, vp]),
+    "fmb_afm_dense_update": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_float, C.c_int, vp, vp]),
+    "fmb_fm_backward_runs_all": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, C.c_size_t, vp]),
     "fmb_rrf_run": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, vp, vp, vp, vp]),
     "fmb_metric_regression": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
     "fmb_metric_classification": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp]),

@@ -56,6 +56,7 @@ struct BwdParams {
     // multi-GPU (csrc/shard2.cu): shard_G > 0 = do not update, store the run's partial gradient into the inbox of the
     // row's owner (key % G) at slot [shard_me][position of the run's first entry]
     fmb::FtrlState ftrl;   // mode 2 only
+    int min_run1;          // 1: rows hit once are summed (0 + g) and updated here too (AFM path: nothing updates them earlier)
     float* inbox[8];
     int shard_G, shard_me;
     int64_t shard_N;
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(256, 2) fm_bwd_runs_kernel(const __grid_consta
     if (lane == 0) prev = P0 > 0 ? __ldg(p.skeys + P0 - 1) : -1;
     if (lane == 31) next = k1_0;
     // runs (>= 2 entries) that START inside these 32 positions
-    unsigned todo = __ballot_sync(0xffffffffu, pos < p.N && k0 >= 0 && k0 < p.key_limit && k0 != prev && k0 == next);
+    unsigned todo = __ballot_sync(0xffffffffu, pos < p.N && k0 >= 0 && k0 < p.key_limit && k0 != prev && (k0 == next || p.min_run1));
     bool bars_ready = false;
     unsigned phase = 0;  // bit st = parity to wait for on bars[st]
 
@@ -597,6 +598,21 @@ FMB_API int fmb_fm_backward_runs_ex(const int32_t* sorted_keys, int64_t N, float
 FMB_API int fmb_fm_backward_runs(const int32_t* sorted_keys, int64_t N, float* table, int F, int k, float lr,
                                  int mode, void* ws, size_t ws_bytes, cudaStream_t stream) {
     return fmb_fm_backward_runs_ex(sorted_keys, N, table, F, k, lr, mode, nullptr, ws, ws_bytes, stream);
+}
+
+// every run, rows hit once included (the AFM step stages ALL its per-entry gradients: csrc/afm.cu)
+FMB_API int fmb_fm_backward_runs_all(const int32_t* sorted_keys, int64_t N, float* table, int F, int k, float lr,
+                                     int mode, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    FMB_CHECK_ARG(sorted_keys && table && ws, "fmb_fm_backward_runs_all: null pointer");
+    FMB_CHECK_ARG(N > 0 && F > 0 && F < 512 && k > 0 && k <= 124 && (mode == 0 || mode == 1), "fmb_fm_backward_runs_all: bad arguments");
+    if (ws_bytes < fmb_bwd_workspace_bytes(N, k)) { fmb_set_error("fmb_fm_backward_runs_all: workspace too small"); return FMB_ERR_WS; }
+    BwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.skeys = sorted_keys; p.N = N; p.table = table;
+    p.F = F; p.k = k; p.rowp = fmb_round_up(k + 1, 16); p.kp4 = fmb_round_up(k, 4);
+    p.use_fm2 = 1; p.lr = lr; p.mode = mode; p.key_limit = 0x7fffffff; p.astep = -(lr / 0.1f);
+    p.Npad = bwd_npad(N); p.G = (float*)ws; p.min_run1 = 1;
+    return launch_runs(p, false, stream);
 }
 
 // multi-GPU variant of fmb_fm_backward_runs (csrc/shard2.cu): the partial gradient of every run of >= 2 equal keys goes

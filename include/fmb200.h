@@ -67,6 +67,22 @@ int fmb_fm_forward(const int32_t* ids_dev, const float* xv_dev, const float* tab
 /* ---- A6: loss + gradient on the logit (fm_adam.py:63-67, :77-81) ------------------------------- */
 int fmb_loss_delta(int loss_kind, const float* z_dev, const float* y_dev, int B, float* delta_dev,
                    float* lossv_dev, fmb_stream_t stream);
+/* ---- AFM (csrc/afm.cu): the reference's afm_adam.py cannot run (afm_adam.py:67,69,121-123), so the model
+ * is the AFM paper's (Xiao et al. 2017, eq. 8) with the reference's parameter set (afm_adam.py:34-41); checked against
+ * oracle/afm.py.  fmb_afm_step: forward (+ backward when delta_dev != NULL: loss gradient, per-sample dense gradients, per-entry
+ * embedding gradients staged in ws at their sorted positions); fmb_afm_dense_update: batch sum + update of W | c | H | P;
+ * fmb_fm_backward_runs_all: the FM run kernel over every run (rows hit once included) sums and applies the staged gradients. */
+size_t fmb_afm_dense_floats(int k, int A);
+int fmb_afm_step(const int32_t* ids_dev, const float* xv_dev, const float* y_dev, const uint32_t* posflag_dev,
+                 const float* table_dev, const float* bias_dev, const float* W_dev, const float* c_dev, const float* H_dev,
+                 const float* P_dev, const unsigned char* pair_i_dev, const unsigned char* pair_j_dev, int B, int F, int k,
+                 int A, int loss_kind, float* z_dev, float* delta_dev, float* lossv_dev, float* dense_g_dev, void* ws_dev,
+                 size_t ws_bytes, fmb_stream_t stream);
+int fmb_afm_dense_update(const float* dense_g_dev, int B, int k, int A, float* W_dev, float* c_dev, float* H_dev,
+                         float* P_dev, float lr, int mode, float* grads_out_dev, fmb_stream_t stream);
+int fmb_fm_backward_runs_all(const int32_t* sorted_keys_dev, int64_t N, float* table_dev, int F, int k, float lr, int mode,
+                             void* ws_dev, size_t ws_bytes, fmb_stream_t stream);
+
 /* ---- RRF_Online (RRF_Online.py:70-187): persistent fp64 kernel, one CTA walks the stream in order.
  * gamma_dev [d] (log scale) and w_dev [2D] are updated in place; preds_dev [N] / nvalid_dev: predictions of the samples whose
  * score was not NaN (the reference skips the others).  task 0 = 'reg' (l2 loss), 1 = 'cls' (logit loss). */
