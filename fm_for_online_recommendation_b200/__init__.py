@@ -1,7 +1,7 @@
 """B200-native (sm_100a) FM-family training hot path behind the reference's Python model classes.
 
 Public surface mirrors haan6/fm-for-online-recommendation:
-  deep family      : FMAdam, DeepFMAdam, NFMAdam, DeepFMOnn, NFMOnn   (models/models_online_deep/*.py)
+  deep family      : FMAdam, DeepFMAdam, NFMAdam, DeepFMOnn, NFMOnn, AFMAdam   (models/models_online_deep/*.py)
   classical family : FM_FTRL, SFTRL_CCFM, SFTRL_Vanila, RRF_Online    (models/models_online/*.py)
 All arithmetic runs in lib/libfmb200.so (hand-written CUDA, include/fmb200.h); there is no CPU path.
 """
@@ -11,7 +11,7 @@ __all__ = ["FmbError", "load", "require_cuda"]
 
 
 def __getattr__(name):  # lazy: importing the package must not need torch.cuda
-    if name in ("FMAdam", "DeepFMAdam", "NFMAdam", "DeepFMOnn", "NFMOnn", "EncodedBatch"):
+    if name in ("FMAdam", "DeepFMAdam", "NFMAdam", "DeepFMOnn", "NFMOnn", "AFMAdam", "EncodedBatch"):
         from . import deep
         return getattr(deep, name)
     if name in ("FM_FTRL", "SFTRL_CCFM", "SFTRL_Vanila", "RRF_Online"):

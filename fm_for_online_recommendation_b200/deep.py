@@ -648,3 +648,167 @@ class NFMOnn(_DeepBase):
         return f"NFMOnn-Feature_Sizes{self.feature_sizes}-Embedding_Sizes{self.embedding_size}-" \
                f"Num_Hidden_Layers{self.num_hidden_layers}-Neuron_Per_Hidden_Layer{self.neuron_per_hidden_layer}-" \
                f"Num_Classes{self.num_classes}-N{self.n}"
+
+
+class AFMAdam(nn.Module):
+    """Attentional FM with the reference's constructor and parameter set (models/models_online_deep/afm_adam.py:13-41).
+    The reference class cannot run (afm_adam.py:67,69 pass a float to .view; :121-123,167 use undefined attributes --
+    SURVEY.md fact 7), so `forward` is the AFM paper's model (Xiao et al. 2017, eq. 8; definition: oracle/afm.py) and the
+    training step is the family's per-call fresh-state Adam step on every parameter (`update_embedding`, and `fit` as the
+    reference's epoch / mini-batch loop around it).  F <= 64, embedding_size <= 15, attention_size <= 8."""
+
+    def __init__(self, feature_sizes, embedding_size=4, attention_size=4, n_epochs=64, batch_size=256, num_classes=1,
+                 b=0.99, n=0.003, use_cuda=True):
+        super().__init__()
+        self._lib = _lib.require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.field_size, self.feature_sizes = len(feature_sizes), feature_sizes
+        self.embedding_size, self.attention_size = embedding_size, attention_size
+        self.n_epochs, self.batch_size, self.num_classes, self.use_cuda = n_epochs, batch_size, num_classes, use_cuda
+        F, k, A = self.field_size, embedding_size, attention_size
+        if not (2 <= F <= 64 and k <= 15 and A <= 8):
+            raise ValueError("AFMAdam: need 2 <= fields <= 64, embedding_size <= 15, attention_size <= 8")
+        self._kw = dict(feature_sizes=feature_sizes, embedding_size=embedding_size, attention_size=attention_size,
+                        n_epochs=n_epochs, batch_size=batch_size, num_classes=num_classes, b=b, n=n, use_cuda=use_cuda)
+        self._rowp = self._lib.fmb_rowp(k)
+        sizes = np.asarray(list(feature_sizes), dtype=np.int64)
+        self._offsets_np = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        self._R = int(self._offsets_np[-1])
+        self._field_off_dev = torch.from_numpy(self._offsets_np.astype(np.int32)).to(self.device)
+        # parameters drawn on the CPU in the reference's order (afm_adam.py:30-41)
+        self.bias = nn.Parameter(torch.tensor(b).to(self.device))
+        self.n = nn.Parameter(torch.tensor(n).to(self.device), requires_grad=False)
+        self._lr = float(np.float32(n))
+        table = torch.zeros(self._R, self._rowp)
+        fo = [nn.Embedding(int(fs), 1) for fs in sizes]
+        so = [nn.Embedding(int(fs), k) for fs in sizes]
+        with torch.no_grad():
+            for f in range(F):
+                lo, hi = int(self._offsets_np[f]), int(self._offsets_np[f + 1])
+                table[lo:hi, :k] = so[f].weight
+                table[lo:hi, k] = fo[f].weight[:, 0]
+        self._table = table.to(self.device)
+        fo_m, so_m = [], []
+        for f in range(F):
+            lo, hi = int(self._offsets_np[f]), int(self._offsets_np[f + 1])
+            so_m.append(_ViewEmbedding(self._table[lo:hi, :k]))
+            fo_m.append(_ViewEmbedding(self._table[lo:hi, k:k + 1]))
+        self.first_order_embeddings, self.second_order_embeddings = nn.ModuleList(fo_m), nn.ModuleList(so_m)
+        lin = nn.Linear(k, A)
+        flat = torch.cat([lin.weight.detach().reshape(-1), lin.bias.detach(), torch.randn(A), torch.randn(k)])
+        self._att = flat.to(self.device).contiguous()          # W [A,k] | c [A] | H [A] | P [k]
+        self.attention_linear = _ViewLinear(self._att[:A * k].view(A, k), self._att[A * k:A * k + A])
+        self.H = nn.Parameter(self._att[A * k + A:A * k + 2 * A])
+        self.P = nn.Parameter(self._att[A * k + 2 * A:])
+        pi, pj = np.triu_indices(F, 1)
+        self._pair_i = torch.from_numpy(pi.astype(np.uint8)).to(self.device)
+        self._pair_j = torch.from_numpy(pj.astype(np.uint8)).to(self.device)
+        self._ws = {}
+
+    def _apply(self, fn, recurse=True):
+        raise RuntimeError("fm_for_online_recommendation_b200 models are bound to their CUDA device and to fp32")
+
+    def __reduce__(self):
+        return (_rebuild_afm, (self._kw, self._table.detach().cpu(), self.bias.detach().cpu(), self._att.detach().cpu()))
+
+    def __str__(self):
+        return f"AFMAdam-Feature_Sizes{self.feature_sizes}-Embedding_Sizes{self.embedding_size}-" \
+               f"Num_Classes{self.num_classes}"
+
+    def _buf(self, name, shape, dtype=torch.float32):
+        n = int(np.prod(shape))
+        t = self._ws.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._ws[name] = t
+        return t[:n].view(*shape)
+
+    def _encode(self, Xi, Xv, Y=None):
+        F = self.field_size
+        a = np.asarray(Xi.cpu() if torch.is_tensor(Xi) else Xi, dtype=np.int64).reshape(-1, F)
+        if a.size and (a.min() < 0 or (a >= (self._offsets_np[1:] - self._offsets_np[:-1])[None, :]).any()):
+            raise IndexError("index out of range in self")
+        ids = torch.from_numpy((a + self._offsets_np[:-1][None, :]).astype(np.int32)).to(self.device).contiguous()
+        xv = torch.from_numpy(np.ascontiguousarray(np.asarray(Xv.cpu() if torch.is_tensor(Xv) else Xv, dtype=np.float32)
+                                                   .reshape(-1, F))).to(self.device)
+        y = None if Y is None else torch.from_numpy(np.asarray(Y.cpu() if torch.is_tensor(Y) else Y, dtype=np.float32)
+                                                    .reshape(-1)).to(self.device)
+        return ids, xv, y
+
+    def _att_ptrs(self):
+        k, A = self.embedding_size, self.attention_size
+        base = self._att.data_ptr()
+        return [C.c_void_p(base + 4 * o) for o in (0, A * k, A * k + A, A * k + 2 * A)]
+
+    def forward(self, Xi, Xv):
+        ids, xv, _ = self._encode(Xi, Xv)
+        B = ids.shape[0]
+        z = torch.empty(B, device=self.device)
+        check(self._lib.fmb_afm_step(ptr(ids), ptr(xv), None, None, ptr(self._table), ptr(self.bias), *self._att_ptrs(),
+                                     ptr(self._pair_i), ptr(self._pair_j), B, self.field_size, self.embedding_size,
+                                     self.attention_size, 0, ptr(z), None, None, None, None, 0, _stream()), "fmb_afm_step")
+        return z
+
+    def predict(self, Xi, Xv):
+        self.eval()
+        z = self.forward(Xi, Xv)
+        out = torch.empty(z.numel(), dtype=torch.uint8, device=self.device)
+        check(self._lib.fmb_predict(ptr(z), z.numel(), ptr(out), _stream()), "fmb_predict")
+        return out.cpu().numpy().astype(bool)
+
+    def update_embedding(self, Xi, Xv, Y, _grads_out=None):
+        """one batch: BCE-with-logits on the AFM logit, fresh-state Adam step on every parameter; returns the loss"""
+        self.train()
+        lib, st = self._lib, _stream()
+        ids, xv, y = self._encode(Xi, Xv, Y)
+        B, F, k, A = ids.shape[0], self.field_size, self.embedding_size, self.attention_size
+        N = B * F
+        sk = self._buf("skeys", (N,), torch.int32); pm = self._buf("perm", (N,), torch.int32)
+        pf = self._buf("posflag", (N,), torch.int32)
+        if B <= lib.fmb_sort_fields_max_batch():
+            check(lib.fmb_sort_fields(ptr(ids), B, F, ptr(self._field_off_dev), ptr(sk), ptr(pm), st), "fmb_sort_fields")
+        else:
+            wsb = lib.fmb_sort_workspace_bytes(N)
+            sws = self._buf("sort_ws", (wsb,), torch.uint8)
+            kb = max(1, int(self._R - 1).bit_length())
+            check(lib.fmb_sort_segment(ptr(ids), N, kb, ptr(sws), wsb, ptr(sk), ptr(pm), None, None, st), "fmb_sort_segment")
+        check(lib.fmb_pos_flags(ptr(sk), ptr(pm), N, ptr(pf), st), "fmb_pos_flags")
+        delta = self._buf("delta", (B,)); lossv = self._buf("lossv", (B,))
+        PD = int(lib.fmb_afm_dense_floats(k, A))
+        dg = self._buf("dense_g", (B, PD))
+        wsb = lib.fmb_bwd_workspace_bytes(N, k)
+        ws = self._buf("bwd_ws", (wsb,), torch.uint8)
+        check(lib.fmb_afm_step(ptr(ids), ptr(xv), ptr(y), ptr(pf), ptr(self._table), ptr(self.bias), *self._att_ptrs(),
+                               ptr(self._pair_i), ptr(self._pair_j), B, F, k, A, 0, None, ptr(delta), ptr(lossv), ptr(dg),
+                               ptr(ws), wsb, st), "fmb_afm_step")
+        check(lib.fmb_fm_backward_runs_all(ptr(sk), N, ptr(self._table), F, k, self._lr, 0, ptr(ws), wsb, st),
+              "fmb_fm_backward_runs_all")
+        check(lib.fmb_afm_dense_update(ptr(dg), B, k, A, *self._att_ptrs(), self._lr, 0, ptr(_grads_out), st),
+              "fmb_afm_dense_update")
+        loss = torch.empty((), device=self.device)
+        check(lib.fmb_finish_step(ptr(delta), ptr(lossv), B, ptr(self.bias), self._lr, 0, ptr(loss), st), "fmb_finish_step")
+        return loss
+
+    def fit(self, Xi_train, Xv_train, y_train, Xi_valid=None, Xv_valid=None, y_valid=None):
+        """afm_adam.py:76-135's loop: n_epochs passes over the training set in mini-batches of batch_size"""
+        Xi = np.asarray(Xi_train).reshape(-1, self.field_size)
+        Xv = np.asarray(Xv_train, dtype=np.float32).reshape(-1, self.field_size)
+        y = np.asarray(y_train, dtype=np.float32).reshape(-1)
+        losses = []
+        for _ in range(self.n_epochs):
+            tot, nb = 0.0, 0
+            for off in range(0, len(y), self.batch_size):
+                end = min(len(y), off + self.batch_size)
+                tot += float(self.update_embedding(Xi[off:end], Xv[off:end], y[off:end]).item())
+                nb += 1
+            losses.append(tot / max(nb, 1))
+        return losses
+
+
+def _rebuild_afm(kw, table, bias, att):
+    m = AFMAdam(**kw)
+    with torch.no_grad():
+        m._table.copy_(table)
+        m.bias.copy_(bias)
+        m._att.copy_(att)
+    return m
