@@ -354,28 +354,42 @@ def run_ours(args):
     bwsb = lib.fmb_bwd_workspace_bytes(N, k); bws = torch.empty(bwsb, dtype=torch.uint8, device="cuda")
     lossd = torch.empty(1, device="cuda")
     st = C.c_void_p(stream.cuda_stream)
-    phases = {"sort": 0.0, "pos_flags": 0.0, "fm_step_fused": 0.0, "fm_bwd_runs": 0.0, "finish": 0.0}
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+    # the kernels of the step as the session launches them: the per-field sort (its tail writes the position words and the
+    # run list), the fused kernel, the run kernel over the run list, the bias step
+    phases = {"sort": 0.0, "fm_step_fused": 0.0, "fm_bwd_runs": 0.0, "finish": 0.0}
+    from fm_for_online_recommendation_b200._lib import RunList
+    by_field = B <= lib.fmb_sort_fields_max_batch()
+    nseg_, cap_ = C.c_int(1), C.c_int(N // 2 + 1)
+    if by_field:
+        lib.fmb_runlist_shape(B, F, C.byref(nseg_), C.byref(cap_))
+    rl = torch.empty((nseg_.value * cap_.value, 4), dtype=torch.int32, device="cuda")
+    rcnt = torch.zeros(2 * nseg_.value, dtype=torch.int32, device="cuda")
+    rld = RunList(rl.data_ptr(), rcnt.data_ptr(), nseg_.value, cap_.value)
+    sparse_ok = 0 if os.environ.get("FMB_SPARSE") == "0" else 1
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     reps = max(5, min(K, 50))
     for i in range(reps + 2):
         e = enc[i % NB]
+        rcnt.zero_()
         evs[0].record(stream)
-        if B <= lib.fmb_sort_fields_max_batch():
-            rc = lib.fmb_sort_fields(p(e.ids), B, F, p(model._field_off_dev), p(sk), p(pm), st)
+        if sparse_ok:
+            pf.zero_()      # contract of FMB_SORT_SPARSE_OK: position words of rows hit once are not written
+        if by_field:
+            rc = lib.fmb_sort_fields_ex(p(e.ids), B, F, p(model._field_off_dev), p(sk), p(pm), p(pf), C.byref(rld), sparse_ok, st)
         else:
             rc = lib.fmb_sort_segment(p(e.ids), N, model._key_bits, p(ws), wsb, p(sk), p(pm), None, None, st)
+            assert rc == 0, lib.fmb_last_error()
+            rc = lib.fmb_pos_flags_ex(p(sk), p(pm), N, p(pf), C.byref(rld), st)
         assert rc == 0, lib.fmb_last_error()
         evs[1].record(stream)
-        assert lib.fmb_pos_flags(p(sk), p(pm), N, p(pf), st) == 0
-        evs[2].record(stream)
         rc = lib.fmb_fm_step_fused(p(e.ids), None, p(e.y), tptr, bptr, p(pf), B, F, k, 0, model._lr, 0, p(delta), p(lossv),
                                    p(bws), bwsb, st)
         assert rc == 0, lib.fmb_last_error()
+        evs[2].record(stream)
+        assert lib.fmb_fm_backward_runs_list(p(sk), N, tptr, F, k, model._lr, 0, None, C.byref(rld), p(bws), bwsb, st) == 0
         evs[3].record(stream)
-        assert lib.fmb_fm_backward_runs(p(sk), N, tptr, F, k, model._lr, 0, p(bws), bwsb, st) == 0
-        evs[4].record(stream)
         assert lib.fmb_finish_step(p(delta), p(lossv), B, bptr, model._lr, 0, p(lossd), st) == 0
-        evs[5].record(stream)
+        evs[4].record(stream)
         torch.cuda.synchronize()
         if i >= 2:
             for j, name in enumerate(phases):

@@ -99,6 +99,9 @@ _SIGS = {
     "fmb_session_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int64, vp]),
     "fmb_sort_fields_max_batch": (C.c_int, []),
     "fmb_sort_fields": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "fmb_runlist_shape": (None, [C.c_int, C.c_int, vp, vp]),
+    "fmb_sort_fields_sparse_min_rows": (C.c_int64, [C.c_int]),
+    "fmb_sort_fields_ex": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp]),
     "fmb_session_destroy": (None, [vp]),
     "fmb_session_launches": (C.c_int64, [vp]),
     "fmb_session_graph_count": (C.c_int, [vp]),
@@ -116,6 +119,9 @@ _SIGS = {
     "fmb_session_fm_step_next": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp,
                                            vp]),
     "fmb_pos_flags": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
+    "fmb_pos_flags_ex": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp]),
+    "fmb_fm_backward_runs_list": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp, vp,
+                                            C.c_size_t, vp]),
     "fmb_fm_step_fused": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp,
                                     vp, C.c_size_t, vp]),
     "fmb_fm_backward_runs": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, C.c_size_t, vp]),
@@ -125,6 +131,11 @@ _SIGS = {
 }
 
 _lib = None
+
+
+class RunList(C.Structure):
+    """fmb_runlist_t (include/fmb200.h): the runs of >= 2 equal sorted keys, one segment per producer CTA."""
+    _fields_ = [("entries", C.c_void_p), ("seg_count", C.c_void_p), ("nseg", C.c_int), ("seg_cap", C.c_int)]
 
 
 def load():

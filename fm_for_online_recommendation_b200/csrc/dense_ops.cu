@@ -214,6 +214,9 @@ FMB_API int fmb_finish_step_ex(const float* delta, const float* lossv, int B, fl
     return FMB_OK;
 }
 
+// host-side handle of the kernel, for graph-node identification in session.cu (argument 6 of 9 = loss_out)
+FMB_API const void* fmb_finish_kernel_fn(void) { return (const void*)finish_step_kernel; }
+
 FMB_API int fmb_finish_step(const float* delta, const float* lossv, int B, float* bias, float lr, int mode,
                             float* loss_out, cudaStream_t stream) {
     return fmb_finish_step_ex(delta, lossv, B, bias, lr, mode, nullptr, loss_out, stream);

@@ -60,6 +60,12 @@ struct BwdParams {
     float* inbox[8];
     int shard_G, shard_me;
     int64_t shard_N;
+    // run-list mode (fm_bwd_runs_kernel<true>): the runs of >= 2 entries as {first sorted position, key, entries among
+    // the first 32 positions that belong to the run (2..32), 0}, in any order, in one segment per producer CTA (no global
+    // counter, nothing to zero) -- written one step ahead by the sort (radix_sort.cu / fm_step.cu pos_flags_kernel)
+    const int4* run_list;          // [run_nseg][run_cap] entries, segment g holds run_segc[g] of them
+    const uint32_t* run_segc;
+    int run_nseg, run_cap;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -203,9 +209,12 @@ __global__ void __launch_bounds__(256) fm_bwd_entry1_kernel(BwdParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-constexpr int RING_SE = 64;            // entries per ring stage
-constexpr int RING_NS = 4;             // stages
-constexpr int RING_SEP = RING_SE + 4;  // floats per lane row of a stage = inner box of the tensor-map copy.  TMA needs
+// Ring geometry (template parameters of the run kernel): RING_SE entries per stage, RING_NS stages.  The short-run
+// launches use 64 x 4; the launch that takes the LONG runs of the run list (>= 128 entries: the hot rows of the small
+// fields, ~180 of a Criteo-shaped batch's 1 900 runs but its whole critical path) uses 128 x 4 and starts the ring at the
+// run's first entry: the per-stage costs (mbarrier wait, TMA issue by lane 0, loop control: ~460 cycles) were 7 of the 16
+// cycles per entry with 64-entry stages, and the 32-entry direct part in front of the ring cost another 3 600 cycles.
+// RING_SEP = RING_SE + 4 floats per lane row of a stage = inner box of the tensor-map copy.  TMA needs
                                        // 16-byte aligned row starts, so a stage starts up to 3 entries early (`mis`);
                                        // the pitch of 4 banks per lane also makes the LDS.128 conflict-free
 
@@ -236,12 +245,21 @@ __device__ __forceinline__ void tma_g2s_2d(void* smem_dst, const CUtensorMap* tm
         : "memory");
 }
 
-__global__ void __launch_bounds__(256, 2) fm_bwd_runs_kernel(const __grid_constant__ CUtensorMap gmap, BwdParams p, int warps_per_block, int warp_f, int accs_n,
-                                                             int ring_comps) {
+// LIST = false: one warp per 32 sorted positions, handling the runs that start there (the tower `fit` path, the AFM path and
+// the sharded paths: the run list does not exist there).  LIST = true: one warp per entry of the run list, grid-strided:
+// the ~2 000 runs of a Criteo-shaped batch are then all in flight at once, where the position-major mapping packed them
+// into the first third of the grid (the small fields sort first) and needed two waves of CTAs for them (17 -> 9 us).
+// bid / nblocks: this CTA's index among the CTAs running this body, and their number (the run-list launch runs two bodies:
+// its first CTAs take the long runs, the others the short ones).  segb_off: offset (floats) of the segment-count prefix in
+// dynamic shared memory.  warps_per_block: working warps (the CTA's other warps only help with the prefix).
+template <bool LIST, int RING_SE, int RING_NS, bool LONGM>
+__device__ __forceinline__ void runs_body(const CUtensorMap& gmap, const BwdParams& p, int warps_per_block, int warp_f, int accs_n,
+                                          int ring_comps, unsigned bid, unsigned nblocks, int segb_off) {
+    constexpr int RING_SEP = RING_SE + 4;
     extern __shared__ __align__(128) float smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t P0 = ((int64_t)blockIdx.x * warps_per_block + wib) * 32;
-    if (P0 >= p.N) return;
+    const int64_t P0 = ((int64_t)bid * warps_per_block + wib) * 32;
+    if (!LIST && P0 >= p.N) return;
     const bool two = p.use_fm2 && p.gvec;
     const int kc = p.k + 1;
     const int nv = kc + (two ? p.k : 0);          // virtual lanes: chain A comps, then chain B comps
@@ -250,39 +268,85 @@ __global__ void __launch_bounds__(256, 2) fm_bwd_runs_kernel(const __grid_consta
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + RING_NS * stage_f);   // [NS] mbarriers
     float* accs = reinterpret_cast<float*>(bars + RING_NS);                   // [accs_n + 32]
 
-    // keys of this warp's 32 positions and of the 32 after them (one memory latency for both)
-    const int64_t pos = P0 + lane;
-    const int32_t k0 = pos < p.N ? __ldg(p.skeys + pos) : -2;
-    const int32_t k1 = pos + 32 < p.N ? __ldg(p.skeys + pos + 32) : -2;
-    int32_t prev = __shfl_up_sync(0xffffffffu, k0, 1);
-    int32_t next = __shfl_down_sync(0xffffffffu, k0, 1);
-    const int32_t k1_0 = __shfl_sync(0xffffffffu, k1, 0);
-    if (lane == 0) prev = P0 > 0 ? __ldg(p.skeys + P0 - 1) : -1;
-    if (lane == 31) next = k1_0;
-    // runs (>= 2 entries) that START inside these 32 positions
-    unsigned todo = __ballot_sync(0xffffffffu, pos < p.N && k0 >= 0 && k0 < p.key_limit && k0 != prev && (k0 == next || p.min_run1));
+    int32_t k0 = -2, k1 = -2;
+    unsigned todo = 0;
+    uint32_t lr = 0, ln = 0, lstep = 0;           // LIST: next run of this warp, number of runs, stride
+    // exclusive prefix of the segment counts, behind the warps' rings in dynamic shared memory: [run_nseg + 1]
+    uint32_t* seg_base = reinterpret_cast<uint32_t*>(smem + segb_off);
+    if (LIST) {
+        lr = bid * warps_per_block + wib;
+        lstep = nblocks * warps_per_block;
+        // every CTA scans the segment counts itself (a few hundred words, one L2 round trip -- the same latency as the
+        // single global counter it replaces, but no atomics in the producers and no memset in front of them)
+        // (the long runs' counts follow the short runs' in run_segc; their entries grow downwards from each segment's end)
+        for (int g = threadIdx.x; g < p.run_nseg; g += blockDim.x) seg_base[g] = __ldg(p.run_segc + (LONGM ? p.run_nseg : 0) + g);
+        __syncthreads();
+        if (wib == 0) {
+            uint32_t carry = 0;
+            for (int b0 = 0; b0 < p.run_nseg; b0 += 32) {
+                const uint32_t v = b0 + lane < p.run_nseg ? seg_base[b0 + lane] : 0u;
+                uint32_t inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                if (b0 + lane < p.run_nseg) seg_base[b0 + lane] = carry + inc - v;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) seg_base[p.run_nseg] = carry;
+        }
+        __syncthreads();
+        const uint32_t total = seg_base[p.run_nseg];
+        ln = total;
+        if (wib >= warps_per_block) return;
+    } else {
+        // keys of this warp's 32 positions and of the 32 after them (one memory latency for both)
+        const int64_t pos = P0 + lane;
+        k0 = pos < p.N ? __ldg(p.skeys + pos) : -2;
+        k1 = pos + 32 < p.N ? __ldg(p.skeys + pos + 32) : -2;
+        int32_t prev = __shfl_up_sync(0xffffffffu, k0, 1);
+        int32_t next = __shfl_down_sync(0xffffffffu, k0, 1);
+        const int32_t k1_0 = __shfl_sync(0xffffffffu, k1, 0);
+        if (lane == 0) prev = P0 > 0 ? __ldg(p.skeys + P0 - 1) : -1;
+        if (lane == 31) next = k1_0;
+        // runs (>= 2 entries) that START inside these 32 positions
+        todo = __ballot_sync(0xffffffffu, pos < p.N && k0 >= 0 && k0 < p.key_limit && k0 != prev && (k0 == next || p.min_run1));
+    }
     bool bars_ready = false;
     unsigned phase = 0;  // bit st = parity to wait for on bars[st]
 
-    while (todo) {
-        const int bit = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int64_t s = P0 + bit;
-        const int32_t key = __shfl_sync(0xffffffffu, k0, bit);
+    while (LIST ? lr < ln : todo != 0) {
+        int64_t s;
+        int32_t key;
+        int n0;
+        if (LIST) {
+            int lo = 0, hi = p.run_nseg;              // largest segment with seg_base[seg] <= lr
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (seg_base[mid] <= lr) lo = mid; else hi = mid; }
+            const uint32_t idx = lr - seg_base[lo];
+            const int4 e = __ldg(p.run_list + (size_t)lo * p.run_cap + (LONGM ? (uint32_t)p.run_cap - 1u - idx : idx));
+            lr += lstep;
+            s = e.x; key = e.y; n0 = e.z;
+        } else {
+            const int bit = __ffs(todo) - 1;
+            todo &= todo - 1;
+            s = P0 + bit;
+            key = __shfl_sync(0xffffffffu, k0, bit);
+            // leading matches among the first 32 entries of the run (keys are already in registers)
+            const int t = bit + lane;
+            const int32_t ka = __shfl_sync(0xffffffffu, k0, t & 31);
+            const int32_t kb = __shfl_sync(0xffffffffu, k1, t & 31);
+            const unsigned mm = __ballot_sync(0xffffffffu, (t < 32 ? ka : kb) == key);
+            n0 = (mm == 0xffffffffu) ? 32 : __ffs(~mm) - 1;
+        }
         long long t_start = 0, t_direct = 0, t_ring = 0, c_wait = 0, c_cons = 0, c_issue = 0;
         if (p.dbg) t_start = clock64();
         int run_len = 0;
-        // leading matches among the first 32 entries of the run (keys are already in registers)
-        const int t = bit + lane;
-        const int32_t ka = __shfl_sync(0xffffffffu, k0, t & 31);
-        const int32_t kb = __shfl_sync(0xffffffffu, k1, t & 31);
-        const unsigned mm = __ballot_sync(0xffffffffu, (t < 32 ? ka : kb) == key);
-        const int n0 = (mm == 0xffffffffu) ? 32 : __ffs(~mm) - 1;
         // long run: probe its extent.  Keys are sorted, so "key at the end of 32-entry block b still matches"
         // is a prefix property: one load per lane covers the next 1024 entries.
         int32_t probe = -2;
-        if (n0 == 32) { const int64_t q = s + 32 + 32 * (int64_t)(lane + 1) - 1; probe = q < p.N ? __ldg(p.skeys + q) : -2; }
-        if (n0 == 32 && !bars_ready) {
+        const int64_t ring0 = LONGM ? s : s + 32;     // first entry that goes through the ring
+        if (LONGM) n0 = 0;                            // no direct part
+        const bool ringed = LONGM || n0 == 32;
+        if (ringed) { const int64_t q = ring0 + 32 * (int64_t)(lane + 1) - 1; probe = q < p.N ? __ldg(p.skeys + q) : -2; }
+        if (ringed && !bars_ready) {
             if (lane == 0) {
                 for (int st = 0; st < RING_NS; ++st) mbar_init(bars + st, 1);
                 asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -320,10 +384,10 @@ __global__ void __launch_bounds__(256, 2) fm_bwd_runs_kernel(const __grid_consta
             }
             if (p.dbg) t_direct = clock64();
             run_len = n0;
-            if (n0 == 32) {
+            if (ringed) {
                 // stream the rest in windows of up to 1024 entries: [c0, c0 + wlen); every stage's copy starts `mis`
                 // entries early (windows and stages are multiples of 4 entries, so `mis` is the same for all of them)
-                int64_t c0 = s + 32;
+                int64_t c0 = ring0;
                 const int mis = (int)(c0 & 3);
                 int32_t pr = probe;
                 bool ok = true;
@@ -362,23 +426,36 @@ __global__ void __launch_bounds__(256, 2) fm_bwd_runs_kernel(const __grid_consta
                         const int n = min(RING_SE, wlen - RING_SE * ts);
                         if (active) {
                             const float4* b4 = reinterpret_cast<const float4*>(ring + (size_t)st * stage_f + lane * RING_SEP);
-                            if (n == RING_SE) {        // full stage: 17 LDS.128 in flight, then the bare 64-add chain
-                                float4 tv[RING_SE / 4 + 1];
-#pragma unroll
-                                for (int u = 0; u <= RING_SE / 4; ++u) tv[u] = b4[u];
-                                // entries [mis, mis + 64): part of quad 0, quads 1..15, part of quad 16
-                                if (mis == 0) acc = __fadd_rn(acc, tv[0].x);
-                                if (mis <= 1) acc = __fadd_rn(acc, tv[0].y);
-                                if (mis <= 2) acc = __fadd_rn(acc, tv[0].z);
-                                acc = __fadd_rn(acc, tv[0].w);
-#pragma unroll
-                                for (int u = 1; u < RING_SE / 4; ++u) {
-                                    acc = __fadd_rn(acc, tv[u].x); acc = __fadd_rn(acc, tv[u].y);
-                                    acc = __fadd_rn(acc, tv[u].z); acc = __fadd_rn(acc, tv[u].w);
+                            if (n == RING_SE) {        // full stage: entries [mis, mis + SE) of the lane's row = part of quad
+                                                       // 0, quads 1 .. SE/4-1, part of quad SE/4; 16 LDS.128 in flight at a
+                                                       // time, then the bare add chain
+                                {
+                                    const float4 q = b4[0];
+                                    if (mis == 0) acc = __fadd_rn(acc, q.x);
+                                    if (mis <= 1) acc = __fadd_rn(acc, q.y);
+                                    if (mis <= 2) acc = __fadd_rn(acc, q.z);
+                                    acc = __fadd_rn(acc, q.w);
                                 }
-                                if (mis >= 1) acc = __fadd_rn(acc, tv[RING_SE / 4].x);
-                                if (mis >= 2) acc = __fadd_rn(acc, tv[RING_SE / 4].y);
-                                if (mis >= 3) acc = __fadd_rn(acc, tv[RING_SE / 4].z);
+#pragma unroll
+                                for (int c = 0; c < RING_SE / 64; ++c) {
+                                    constexpr int last = RING_SE / 64 - 1;
+                                    const int nq = c == last ? 15 : 16;
+                                    float4 tv[16];
+#pragma unroll
+                                    for (int u = 0; u < 16; ++u) if (u < nq) tv[u] = b4[1 + 16 * c + u];
+#pragma unroll
+                                    for (int u = 0; u < 16; ++u)
+                                        if (u < nq) {
+                                            acc = __fadd_rn(acc, tv[u].x); acc = __fadd_rn(acc, tv[u].y);
+                                            acc = __fadd_rn(acc, tv[u].z); acc = __fadd_rn(acc, tv[u].w);
+                                        }
+                                }
+                                {
+                                    const float4 q = b4[RING_SE / 4];
+                                    if (mis >= 1) acc = __fadd_rn(acc, q.x);
+                                    if (mis >= 2) acc = __fadd_rn(acc, q.y);
+                                    if (mis >= 3) acc = __fadd_rn(acc, q.z);
+                                }
                             } else {
                                 const int end = mis + n;   // entries [mis, end) of this lane's row
                                 int e = 0;
@@ -447,11 +524,29 @@ __global__ void __launch_bounds__(256, 2) fm_bwd_runs_kernel(const __grid_consta
             const unsigned long long slot = atomicAdd((unsigned long long*)p.dbg, 1ULL);
             if (slot < 4000) {
                 long long* r = p.dbg + 8 + slot * 8;
-                r[0] = run_len; r[1] = t_start; r[2] = t_direct - t_start; r[3] = t_ring - t_direct;
+                unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+                r[0] = run_len; r[1] = (long long)gt - (clock64() - t_start) * 1000 / 1965; r[2] = t_direct - t_start; r[3] = t_ring - t_direct;
                 r[4] = clock64() - t_ring; r[5] = c_issue; r[6] = c_wait; r[7] = c_cons;
             }
         }
     }
+}
+
+// position-major launch (tower fit, AFM, sharded paths)
+__global__ void __launch_bounds__(256, 2) fm_bwd_runs_kernel(const __grid_constant__ CUtensorMap gmap, BwdParams p, int warps_per_block, int warp_f,
+                                                             int accs_n, int ring_comps) {
+    runs_body<false, 64, 4, false>(gmap, p, warps_per_block, warp_f, accs_n, ring_comps, blockIdx.x, gridDim.x, 0);
+}
+
+// run-list launch: CTAs [0, nlong) take the long runs (>= 128 entries: 128-entry stages, ring from the first entry, wpl
+// working warps), the others the short runs.  The long runs are the step's longest dependent chain, so their CTAs come
+// first in the grid and are placed first; as two launches the second one waited for shared memory behind the first.
+constexpr int LONG_SE = 128, LONG_NS = 4;
+__global__ void __launch_bounds__(256, 2) fm_bwd_runs_list_kernel(const __grid_constant__ CUtensorMap gmap_s, const __grid_constant__ CUtensorMap gmap_l,
+                                                                  BwdParams p, int wps, int warp_f_s, int wpl, int warp_f_l, int accs_n,
+                                                                  int ring_comps, unsigned nlong, int segb_off) {
+    if (blockIdx.x < nlong) runs_body<true, LONG_SE, LONG_NS, true>(gmap_l, p, wpl, warp_f_l, accs_n, ring_comps, blockIdx.x, nlong, segb_off);
+    else runs_body<true, 64, 4, false>(gmap_s, p, wps, warp_f_s, accs_n, ring_comps, blockIdx.x - nlong, gridDim.x - nlong, segb_off);
 }
 
 static int ilog2_ceil(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
@@ -471,51 +566,90 @@ static long long* g_runs_dbg = nullptr;
 FMB_API void fmb_debug_set_runs_buffer(long long* dev) { g_runs_dbg = dev; }
 
 // launches fm_bwd_runs_kernel over the staged contributions p.G (per-warp shared memory = ring + mbarriers + accumulators)
+typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiled tensor_map_encoder() {
+    static EncodeTiled encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn) encode = (EncodeTiled)fn;
+    }
+    return encode;
+}
+
+static int ring_warp_floats(int ring_comps, int accs_n, int SE, int NS, int* stage_f_out) {
+    // ring (multiple of 128 B per warp) + NS mbarriers (8 B each) + accumulators + prefetched old row
+    const int stage_f = fmb_round_up(ring_comps * (SE + 4), 32);
+    if (stage_f_out) *stage_f_out = stage_f;
+    return fmb_round_up(NS * stage_f + 2 * NS + accs_n + 32, 32);
+}
+// tensor map of the staging buffer: [nv rows][Npad] fp32, box = [ring_comps rows][SE + 4 entries]
+static int ring_tensor_map(CUtensorMap* gmap, const BwdParams& p, int nv, int ring_comps, int SE) {
+    EncodeTiled encode = tensor_map_encoder();
+    if (!encode) { fmb_set_error("fmb_fm_backward_update: cuTensorMapEncodeTiled not available from the driver"); return FMB_ERR_CUDA; }
+    const cuuint64_t gdim[2] = {(cuuint64_t)p.Npad, (cuuint64_t)nv};
+    const cuuint64_t gstride[1] = {(cuuint64_t)p.Npad * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)(SE + 4), (cuuint32_t)ring_comps};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = encode(gmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, p.G, gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { fmb_set_error("fmb_fm_backward_update: cuTensorMapEncodeTiled failed (%d)", (int)cr); return FMB_ERR_CUDA; }
+    return FMB_OK;
+}
+
 static int launch_runs(BwdParams& p, bool two, cudaStream_t stream) {
     const int k = p.k;
     const int64_t N = p.N;
     const int nv = k + 1 + (two ? k : 0);
     const int accs_n = (nv + 3) / 4 * 4;
     const int ring_comps = nv < 32 ? nv : 32;
-    // ring (multiple of 128 B per warp) + NS mbarriers (8 B each) + accumulators + prefetched old row
-    const int stage_f = fmb_round_up(ring_comps * RING_SEP, 32);
-    const int warp_f = fmb_round_up(RING_NS * stage_f + 2 * RING_NS + accs_n + 32, 32);
+    const int warp_f = ring_warp_floats(ring_comps, accs_n, 64, 4, nullptr);
     int wpb = 8;
     while (wpb > 1 && (size_t)wpb * warp_f * 4 > 56 * 1024) wpb >>= 1;
     const size_t sm = (size_t)wpb * warp_f * 4;
     FMB_CHECK_ARG(sm <= 200 * 1024, "fmb_fm_backward_update: k too large for the run ring");
     const int64_t nwarps = (N + 31) / 32;
     const unsigned grid = (unsigned)((nwarps + wpb - 1) / wpb);
-    {
-        // tensor map of the staging buffer: [nv rows][Npad] fp32, box = [ring_comps rows][RING_SEP entries]
-        typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        static EncodeTiled encode = nullptr;
-        static bool attr = false;
-        if (!attr) {
-            void* fn = nullptr;
-            cudaDriverEntryPointQueryResult qres;
-            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
-                fmb_set_error("fmb_fm_backward_update: cuTensorMapEncodeTiled not available from the driver");
-                return FMB_ERR_CUDA;
-            }
-            encode = (EncodeTiled)fn;
-            cudaFuncSetAttribute(fm_bwd_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr = true;
-        }
-        CUtensorMap gmap;
-        const cuuint64_t gdim[2] = {(cuuint64_t)p.Npad, (cuuint64_t)nv};
-        const cuuint64_t gstride[1] = {(cuuint64_t)p.Npad * 4};
-        const cuuint32_t box[2] = {(cuuint32_t)RING_SEP, (cuuint32_t)ring_comps};
-        const cuuint32_t estr[2] = {1, 1};
-        const CUresult cr = encode(&gmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, p.G, gdim, gstride, box, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) { fmb_set_error("fmb_fm_backward_update: cuTensorMapEncodeTiled failed (%d)", (int)cr); return FMB_ERR_CUDA; }
-        fm_bwd_runs_kernel<<<grid, 32 * wpb, sm, stream>>>(gmap, p, wpb, warp_f, accs_n, ring_comps);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(fm_bwd_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(fm_bwd_runs_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr = true;
     }
-    FMB_CHECK_LAUNCH("fm_bwd_runs_kernel");
+    CUtensorMap gmap;
+    int rc = ring_tensor_map(&gmap, p, nv, ring_comps, 64);
+    if (rc) return rc;
+    if (!p.run_list) {
+        fm_bwd_runs_kernel<<<grid, 32 * wpb, sm, stream>>>(gmap, p, wpb, warp_f, accs_n, ring_comps);
+        FMB_CHECK_LAUNCH("fm_bwd_runs_kernel");
+        return FMB_OK;
+    }
+    // run-list launch.  Long-run CTAs: as many working warps as the short CTAs' shared memory holds with the deeper ring.
+    CUtensorMap gmap_l;
+    rc = ring_tensor_map(&gmap_l, p, nv, ring_comps, LONG_SE);
+    if (rc) return rc;
+    const int warp_f_l = ring_warp_floats(ring_comps, accs_n, LONG_SE, LONG_NS, nullptr);
+    int wpl = (int)(sm / ((size_t)warp_f_l * 4));
+    size_t smd = sm;
+    if (wpl < 1) { wpl = 1; smd = (size_t)warp_f_l * 4; }
+    if (wpl > wpb) wpl = wpb;
+    FMB_CHECK_ARG(smd <= 200 * 1024, "fmb_fm_backward_update: k too large for the long-run ring");
+    const size_t segb = (size_t)(p.run_nseg + 1 + 31) / 32 * 128;
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    // short runs: as many CTAs as are resident at once beside the long-run CTAs, grid-strided over the list
+    int per_sm = (int)((size_t)224 * 1024 / (smd + segb + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm * wpb > 32) per_sm = 32 / wpb;
+    const unsigned nlong = (unsigned)sms;                                   // one long-run CTA per SM
+    unsigned nshort = (unsigned)(sms * (per_sm > 1 ? per_sm - 1 : 1));
+    if (nshort > grid) nshort = grid;
+    fm_bwd_runs_list_kernel<<<nlong + nshort, 32 * wpb, smd + segb, stream>>>(gmap, gmap_l, p, wpb, warp_f, wpl, warp_f_l, accs_n,
+                                                                             ring_comps, nlong, (int)(smd / 4));
+    FMB_CHECK_LAUNCH("fm_bwd_runs_list_kernel");
     return FMB_OK;
 }
 
@@ -576,9 +710,16 @@ FMB_API int fmb_fm_backward_update_ex(const int32_t* sorted_keys, const int32_t*
 // of >= 2 equal keys, in sample order, and updates those rows.  Same arguments as fmb_fm_backward_update.
 struct fmb_ftrl_t { float* zn; float* bias_zn; float beta, l1, l2; };   // include/fmb200.h
 
-FMB_API int fmb_fm_backward_runs_ex(const int32_t* sorted_keys, int64_t N, float* table, int F, int k, float lr,
-                                    int mode, const fmb_ftrl_t* ftrl, void* ws, size_t ws_bytes, cudaStream_t stream) {
+// rl (nullable): the runs of >= 2 entries found by the sort one step ahead (fmb_sort_fields_ex / fmb_pos_flags_ex); with it
+// one warp is started per RUN instead of per 32 sorted positions.
+struct fmb_runlist_t { int32_t* entries; uint32_t* seg_count; int nseg, seg_cap; };   // include/fmb200.h
+
+FMB_API int fmb_fm_backward_runs_list(const int32_t* sorted_keys, int64_t N, float* table, int F, int k, float lr,
+                                      int mode, const fmb_ftrl_t* ftrl, const fmb_runlist_t* rl,
+                                      void* ws, size_t ws_bytes, cudaStream_t stream) {
     FMB_CHECK_ARG(sorted_keys && table && ws, "fmb_fm_backward_runs: null pointer");
+    FMB_CHECK_ARG(!rl || (rl->entries && rl->seg_count && rl->nseg >= 1 && rl->nseg <= 2048 && rl->seg_cap >= 1),
+                  "fmb_fm_backward_runs: bad run list");
     FMB_CHECK_ARG(N > 0 && F > 0 && F < 512 && k > 0 && k <= 124, "fmb_fm_backward_runs: bad shape");
     FMB_CHECK_ARG(mode == 0 || mode == 1 || (mode == 2 && ftrl && ftrl->zn), "fmb_fm_backward_runs: unknown update mode %d", mode);
     if (ws_bytes < fmb_bwd_workspace_bytes(N, k)) { fmb_set_error("fmb_fm_backward_runs: workspace too small"); return FMB_ERR_WS; }
@@ -592,7 +733,14 @@ FMB_API int fmb_fm_backward_runs_ex(const int32_t* sorted_keys, int64_t N, float
     p.Npad = bwd_npad(N);
     p.G = (float*)ws;
     if (mode == 2) { p.ftrl.zn = ftrl->zn; p.ftrl.bias_zn = ftrl->bias_zn; p.ftrl.beta = ftrl->beta; p.ftrl.l1 = ftrl->l1; p.ftrl.l2 = ftrl->l2; }
+    if (rl) { p.run_list = reinterpret_cast<const int4*>(rl->entries); p.run_segc = rl->seg_count; p.run_nseg = rl->nseg; p.run_cap = rl->seg_cap; }
+    p.dbg = g_runs_dbg;
     return launch_runs(p, false, stream);
+}
+
+FMB_API int fmb_fm_backward_runs_ex(const int32_t* sorted_keys, int64_t N, float* table, int F, int k, float lr,
+                                    int mode, const fmb_ftrl_t* ftrl, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    return fmb_fm_backward_runs_list(sorted_keys, N, table, F, k, lr, mode, ftrl, nullptr, ws, ws_bytes, stream);
 }
 
 FMB_API int fmb_fm_backward_runs(const int32_t* sorted_keys, int64_t N, float* table, int F, int k, float lr,

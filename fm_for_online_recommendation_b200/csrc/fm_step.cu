@@ -41,6 +41,7 @@ struct StepParams {
     int cu;                    // 16-byte chunks of a row that hold data: ceil((k+1)/4)
     int ql_log;                // log2 of lanes per (sample, field) in the gather phase (pow2 >= cu)
     int jl_log;                // log2 of lanes per sample in the reduce phase (pow2 >= kp4)
+    uint32_t mF, mcu;          // ceil(2^32 / F), ceil(2^32 / cu): x / F == __umulhi(x, mF) for x < 2^16 * ... (see magic_div)
     int loss_kind, mode;
     float lr, astep;
     float* delta;              // [B] out
@@ -54,17 +55,23 @@ struct StepParams {
 
 //   ids [B,F] global row ids;  xv [B,F] or NULL (all ones);  y [B];
 //   posflag [B*F] entry-major: sorted position of the entry | 0x80000000 if its row is hit more than once
+// Template parameters: CU = 16-byte chunks per row when known at compile time (3 for k = 8..11: the row pitch in shared
+// memory is then a constant and the field loop addresses with immediates), 0 = read it from the parameters;
+// XV = the batch carries real feature values (else all ones: no loads, no multiplications by x -- a product with 1.0f
+// is exact, so skipping it changes no bit); MODE = update rule (0 fresh-Adam sign step, 1 SGD, 2 FTRL-Proximal).
+template <int CU, bool XV, int MODE>
 __global__ void __launch_bounds__(256) fm_step_fused_kernel(const int32_t* __restrict__ ids, const float* __restrict__ xv,
                                                             const float* __restrict__ y, const uint32_t* __restrict__ posflag,
                                                             StepParams p) {
     extern __shared__ __align__(16) float smem[];
     const int F = p.F, k = p.k, SB = p.SB;
-    const int rp = p.cu * 4;                       // shared-memory row pitch (floats)
+    const int cu = CU ? CU : p.cu;
+    const int rp = cu * 4;                         // shared-memory row pitch (floats)
     float* rows_s = smem;                          // [SB][F][rp]
-    float* x_s = rows_s + (size_t)SB * F * rp;     // [SB][F]
-    float* bi_s = x_s + SB * F;                    // [SB][k]
-    float* S_s = bi_s + SB * k;                    // [SB][kp4]
-    float* d_s = S_s + SB * p.kp4;                 // [SB]
+    float* S_s = rows_s + (size_t)SB * F * rp;     // [SB][rp]  (16-byte aligned: read as float4)
+    float* x_s = S_s + SB * rp;                    // [SB][F]   (XV only)
+    float* bi_s = x_s + (XV ? SB * F : 0);         // [SB][k]
+    float* d_s = bi_s + SB * k;                    // [SB]
     int32_t* ids_s = reinterpret_cast<int32_t*>(d_s + SB);            // [SB][F]
     uint32_t* pos_s = reinterpret_cast<uint32_t*>(ids_s + SB * F);    // [SB][F]
     uint16_t* single_s = reinterpret_cast<uint16_t*>(pos_s + SB * F); // [SB*F] entries whose row is hit once
@@ -85,7 +92,7 @@ __global__ void __launch_bounds__(256) fm_step_fused_kernel(const int32_t* __res
         uint32_t pf = 0;
         if (valid) {
             ids_s[e] = __ldg(ids + (size_t)b0 * F + e);
-            x_s[e] = xv ? __ldg(xv + (size_t)b0 * F + e) : 1.0f;
+            if (XV) x_s[e] = __ldg(xv + (size_t)b0 * F + e);
             pf = __ldg(posflag + (size_t)b0 * F + e);
             pos_s[e] = pf;
         }
@@ -107,7 +114,7 @@ __global__ void __launch_bounds__(256) fm_step_fused_kernel(const int32_t* __res
     {
         const int q = threadIdx.x & ((1 << p.ql_log) - 1);
         const int estep = blockDim.x >> p.ql_log;
-        if (q < p.cu)
+        if (q < cu)
             for (int ef = threadIdx.x >> p.ql_log; ef < nv * F; ef += estep)
                 cp_async16(rows_s + (size_t)ef * rp + q * 4, p.table + (size_t)ids_s[ef] * p.rowp + q * 4);
     }
@@ -126,15 +133,15 @@ __global__ void __launch_bounds__(256) fm_step_fused_kernel(const int32_t* __res
                     float Qj = 0.f;
                     const float* r = rows_s + (size_t)s * F * rp + j;
                     const float* xs = x_s + s * F;
-#pragma unroll 4
+#pragma unroll 8
                     for (int f = 0; f < F; ++f) {
-                        const float e = __fmul_rn(r[(size_t)f * rp], xs[f]);
+                        const float e = XV ? __fmul_rn(r[(size_t)f * rp], xs[f]) : r[(size_t)f * rp];
                         Sj = __fadd_rn(Sj, e);
                         Qj = __fadd_rn(Qj, __fmul_rn(e, e));
                     }
                     bi_s[s * k + j] = __fmul_rn(__fsub_rn(__fmul_rn(Sj, Sj), Qj), 0.5f);
                 }
-                S_s[s * p.kp4 + j] = Sj;
+                S_s[s * rp + j] = Sj;
             }
     }
     __syncthreads();
@@ -150,7 +157,8 @@ __global__ void __launch_bounds__(256) fm_step_fused_kernel(const int32_t* __res
             const int sc = min(s, nv - 1);                    // padding groups recompute the last sample (discarded)
             const float* r = rows_s + (size_t)sc * F * rp + k;
             const float* xs = x_s + sc * F;
-            const float sf = fmb::aten_row_sum_lanes8([&](int f) { return __fmul_rn(r[(size_t)f * rp], xs[f]); }, F, l8, mask);
+            const float sf = fmb::aten_row_sum_lanes8(
+                [&](int f) { return XV ? __fmul_rn(r[(size_t)f * rp], xs[f]) : r[(size_t)f * rp]; }, F, l8, mask);
             const float* bs = bi_s + sc * k;
             const float sb = fmb::aten_row_sum_lanes8([&](int j) { return bs[j]; }, k, l8, mask);
             if (l8 == 0 && s < nv) {
@@ -170,21 +178,23 @@ __global__ void __launch_bounds__(256) fm_step_fused_kernel(const int32_t* __res
     // phase 4a: rows hit once, one thread per (entry, 16-byte chunk): the gradient is the entry's contribution alone
     // (0 + contribution, like the reference's zero-initialised grad row); the row is updated from the shared-memory
     // copy.  Chunks no coordinate of which moved are not written back (on saturated samples the sign step is below a
-    // quarter ulp of every weight).
+    // quarter ulp of every weight).  Item -> (entry, chunk) and entry -> sample by multiplication with the
+    // precomputed reciprocals (a runtime integer division is ~20 instructions, and there were two per item).
     const int ns = n_single, nm = n_multi;
-    for (int it = threadIdx.x; it < ((p.dbg & 1) ? 0 : ns * p.cu); it += blockDim.x) {
-        const int li = it / p.cu, q = it - li * p.cu;
+    for (int it = threadIdx.x; it < ((p.dbg & 1) ? 0 : ns * cu); it += blockDim.x) {
+        const int li = (int)__umulhi((unsigned)it, p.mcu), q = it - li * cu;
         const int ef = single_s[li];
-        const int s = ef / F;
-        const float x = x_s[ef], d = d_s[s];
-        const float* Ss = S_s + s * p.kp4;
+        const int s = (int)__umulhi((unsigned)ef, p.mF);
+        const float x = XV ? x_s[ef] : 1.0f, d = d_s[s];
+        const float4 S4 = *reinterpret_cast<const float4*>(S_s + s * rp + q * 4);
         const float4 v4 = *reinterpret_cast<const float4*>(rows_s + (size_t)ef * rp + q * 4);
+        const float Sq[4] = {S4.x, S4.y, S4.z, S4.w};
         const float v[4] = {v4.x, v4.y, v4.z, v4.w};
         float o[4];
         bool moved = false;
         float zz[4] = {0.f, 0.f, 0.f, 0.f}, nn[4] = {0.f, 0.f, 0.f, 0.f};
         float* zrow = nullptr;
-        if (p.mode == 2) {   // FTRL-Proximal: the row's z and n sub-rows (read + written: 16F(k+1) more bytes per sample)
+        if (MODE == 2) {   // FTRL-Proximal: the row's z and n sub-rows (read + written: 16F(k+1) more bytes per sample)
             zrow = p.ftrl.zn + (size_t)ids_s[ef] * 2 * p.rowp + q * 4;
             const float4 z4 = *reinterpret_cast<const float4*>(zrow), n4 = *reinterpret_cast<const float4*>(zrow + p.rowp);
             zz[0] = z4.x; zz[1] = z4.y; zz[2] = z4.z; zz[3] = z4.w;
@@ -197,61 +207,100 @@ __global__ void __launch_bounds__(256) fm_step_fused_kernel(const int32_t* __res
             if (j <= k) {
                 float a;
                 if (j < k) {
-                    const float ej = __fmul_rn(v[t], x);
-                    a = __fmul_rn(__fsub_rn(__fmul_rn(d, Ss[j]), __fmul_rn(d, ej)), x);
+                    const float ej = XV ? __fmul_rn(v[t], x) : v[t];
+                    a = __fsub_rn(__fmul_rn(d, Sq[t]), __fmul_rn(d, ej));
+                    if (XV) a = __fmul_rn(a, x);
                 } else {
-                    a = __fmul_rn(d, x);
+                    a = XV ? __fmul_rn(d, x) : d;
                 }
-                if (p.mode == 2) {
+                if (MODE == 2) {
                     o[t] = fmb::ftrl_update(v[t], __fadd_rn(0.f, a), zz[t], nn[t], p.lr, p.ftrl.beta, p.ftrl.l1, p.ftrl.l2);
                     moved = true;
                 } else {
-                    o[t] = fmb::apply_update_a(v[t], __fadd_rn(0.f, a), p.lr, p.astep, p.mode);
+                    o[t] = fmb::apply_update_a(v[t], __fadd_rn(0.f, a), p.lr, p.astep, MODE);
                     moved |= __float_as_int(o[t]) != __float_as_int(v[t]);
                 }
             }
         }
         if (moved) *reinterpret_cast<float4*>(p.table + (size_t)ids_s[ef] * p.rowp + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
-        if (p.mode == 2) {
+        if (MODE == 2) {
             *reinterpret_cast<float4*>(zrow) = make_float4(zz[0], zz[1], zz[2], zz[3]);
             *reinterpret_cast<float4*>(zrow + p.rowp) = make_float4(nn[0], nn[1], nn[2], nn[3]);
         }
     }
     FMB_TS(5);
     // phase 4b: rows hit several times: stage the entry's contribution at its sorted position (run kernel sums them)
-    for (int it = threadIdx.x; it < ((p.dbg & 2) ? 0 : nm * p.cu); it += blockDim.x) {
-        const int li = it / p.cu, q = it - li * p.cu;
+    for (int it = threadIdx.x; it < ((p.dbg & 2) ? 0 : nm * cu); it += blockDim.x) {
+        const int li = (int)__umulhi((unsigned)it, p.mcu), q = it - li * cu;
         const int ef = multi_s[li];
-        const int s = ef / F;
-        const float x = x_s[ef], d = d_s[s];
-        const size_t pos = pos_s[ef] & 0x7fffffffu;
-        const float* Ss = S_s + s * p.kp4;
+        const int s = (int)__umulhi((unsigned)ef, p.mF);
+        const float x = XV ? x_s[ef] : 1.0f, d = d_s[s];
+        const float4 S4 = *reinterpret_cast<const float4*>(S_s + s * rp + q * 4);
         const float4 v4 = *reinterpret_cast<const float4*>(rows_s + (size_t)ef * rp + q * 4);
+        const float Sq[4] = {S4.x, S4.y, S4.z, S4.w};
         const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+        float* g = p.G + (size_t)(q * 4) * p.Npad + (pos_s[ef] & 0x7fffffffu);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const int j = q * 4 + t;
             if (j < k) {
-                const float ej = __fmul_rn(v[t], x);
-                p.G[(size_t)j * p.Npad + pos] = __fmul_rn(__fsub_rn(__fmul_rn(d, Ss[j]), __fmul_rn(d, ej)), x);
+                const float ej = XV ? __fmul_rn(v[t], x) : v[t];
+                float a = __fsub_rn(__fmul_rn(d, Sq[t]), __fmul_rn(d, ej));
+                if (XV) a = __fmul_rn(a, x);
+                g[(size_t)t * p.Npad] = a;
             } else if (j == k) {
-                p.G[(size_t)j * p.Npad + pos] = __fmul_rn(d, x);
+                g[(size_t)t * p.Npad] = XV ? __fmul_rn(d, x) : d;
             }
         }
     }
     FMB_TS(6);
 }
 
-// posflag[perm[i]] = i | (row of sorted position i is hit more than once ? 0x80000000 : 0)
+// posflag[perm[i]] = i | (row of sorted position i is hit more than once ? 0x80000000 : 0); optionally the list of the
+// runs of >= 2 entries {first position, key, entries of the run among its first 32 positions, 0} and their number
+// (*run_count zeroed by the caller).  Used behind the generic sort; the per-field sorts do this in their own tail
+// (radix_sort.cu sort_tail).
 __global__ void __launch_bounds__(256) pos_flags_kernel(const int32_t* __restrict__ skeys, const int32_t* __restrict__ perm,
-                                                        int64_t N, uint32_t* __restrict__ posflag) {
+                                                        int64_t N, uint32_t* __restrict__ posflag, int4* __restrict__ run_list,
+                                                        uint32_t* __restrict__ run_count, int cap) {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= N) return;
-    const int32_t key = __ldg(skeys + i);
-    const int32_t kprev = i > 0 ? __ldg(skeys + i - 1) : -1;
-    const int32_t knext = i + 1 < N ? __ldg(skeys + i + 1) : -1;
-    const bool multi = key == kprev || key == knext;
-    posflag[__ldg(perm + i)] = (uint32_t)i | (multi ? 0x80000000u : 0u);
+    int32_t key = -1;
+    bool start = false;
+    if (i < N) {
+        key = __ldg(skeys + i);
+        const int32_t kprev = i > 0 ? __ldg(skeys + i - 1) : -1;
+        const int32_t knext = i + 1 < N ? __ldg(skeys + i + 1) : -1;
+        const bool multi = key == kprev || key == knext;
+        start = multi && key != kprev;
+        posflag[__ldg(perm + i)] = (uint32_t)i | (multi ? 0x80000000u : 0u);
+    }
+    if (!run_list) return;
+    const unsigned m = __ballot_sync(0xffffffffu, start);
+    if (!m) return;
+    // long runs (>= 128 entries) are listed downwards from the end of the segment and counted in run_count[1]
+    const bool lng = start && i + 127 < N && __ldg(skeys + i + 127) == key;
+    const unsigned ml = __ballot_sync(0xffffffffu, lng), ms = m & ~ml;
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0, basel = 0;
+    if (ms) { const int leader = __ffs(ms) - 1; if (lane == leader) base = atomicAdd(run_count, (uint32_t)__popc(ms)); base = __shfl_sync(0xffffffffu, base, leader); }
+    if (ml) { const int leader = __ffs(ml) - 1; if (lane == leader) basel = atomicAdd(run_count + 1, (uint32_t)__popc(ml)); basel = __shfl_sync(0xffffffffu, basel, leader); }
+    if (start) {
+        int n0 = 1;
+        bool more = true;
+        for (int c = 0; c < 4 && more; ++c) {          // eight keys per round trip
+            int32_t kk[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int64_t q = i + 1 + c * 8 + u; kk[u] = q < N ? __ldg(skeys + q) : -1; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (more && c * 8 + u < 31 && kk[u] == key) ++n0; else more = false;
+            }
+        }
+        const uint32_t lt = (1u << lane) - 1u;
+        const int4 e4 = make_int4((int)i, key, n0, lng ? 1 : 0);
+        if (lng) run_list[(size_t)cap - 1 - (basel + __popc(ml & lt))] = e4;
+        else run_list[base + __popc(ms & lt)] = e4;
+    }
 }
 
 static int ilog2_ceil(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
@@ -265,16 +314,44 @@ FMB_API void fmb_debug_set_step_timestamps(long long* dev) { g_step_tdbg = dev; 
 FMB_API void fmb_debug_set_step_flags(int f) { g_step_dbg = f; }
 
 // host-side handle of the fused kernel, for graph-node identification in session.cu (arguments 0..3 are ids, xv, y, posflag)
-FMB_API const void* fmb_fused_kernel_fn(void) { return (const void*)fm_step_fused_kernel; }
+typedef void (*fused_fn_t)(const int32_t*, const float*, const float*, const uint32_t*, StepParams);
+static fused_fn_t fused_fn(int cu, bool xv, int mode) {
+#define FMB_FUSED_ROW(C, X) {fm_step_fused_kernel<C, X, 0>, fm_step_fused_kernel<C, X, 1>, fm_step_fused_kernel<C, X, 2>}
+    static const fused_fn_t tab[2][2][3] = {{FMB_FUSED_ROW(0, false), FMB_FUSED_ROW(0, true)},
+                                            {FMB_FUSED_ROW(3, false), FMB_FUSED_ROW(3, true)}};
+#undef FMB_FUSED_ROW
+    return tab[cu == 3][xv][mode];
+}
+// is `fn` one of the fused kernel's instantiations?  (graph-node identification in session.cu)
+FMB_API int fmb_is_fused_kernel_fn(const void* fn) {
+    for (int c = 0; c < 2; ++c)
+        for (int x = 0; x < 2; ++x)
+            for (int m = 0; m < 3; ++m)
+                if (fn == (const void*)fused_fn(c ? 3 : 0, x != 0, m)) return 1;
+    return 0;
+}
 FMB_API const void* fmb_pos_flags_kernel_fn(void) { return (const void*)pos_flags_kernel; }
 
-// per-entry sorted position + multi-hit flag from the stable sort's output (fmb_sort_fields / fmb_sort_segment)
-FMB_API int fmb_pos_flags(const int32_t* sorted_keys, const int32_t* perm, int64_t N, uint32_t* posflag,
-                          cudaStream_t stream) {
+// per-entry sorted position + multi-hit flag from the stable sort's output (fmb_sort_fields / fmb_sort_segment);
+// _ex: also the run list for fmb_fm_backward_runs_list, as ONE segment (rl->nseg == 1, seg_cap >= N/2) whose counters
+// rl->seg_count[0..1] (short, long runs) the caller zeroes beforehand (this kernel appends with atomics; the per-field
+// sorts need neither)
+struct fmb_runlist_t { int32_t* entries; uint32_t* seg_count; int nseg, seg_cap; };   // include/fmb200.h
+FMB_API int fmb_pos_flags_ex(const int32_t* sorted_keys, const int32_t* perm, int64_t N, uint32_t* posflag,
+                             const fmb_runlist_t* rl, cudaStream_t stream) {
     FMB_CHECK_ARG(sorted_keys && perm && posflag && N > 0 && N < ((int64_t)1 << 31), "fmb_pos_flags: bad arguments");
-    pos_flags_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(sorted_keys, perm, N, posflag);
+    FMB_CHECK_ARG(!rl || (rl->entries && rl->seg_count && rl->nseg == 1 && rl->seg_cap >= N / 2),
+                  "fmb_pos_flags: the run list must be one segment of at least N/2 entries");
+    int32_t* run_list = rl ? rl->entries : nullptr;
+    uint32_t* run_count = rl ? rl->seg_count : nullptr;
+    pos_flags_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(sorted_keys, perm, N, posflag,
+                                                                      reinterpret_cast<int4*>(run_list), run_count, rl ? rl->seg_cap : 0);
     FMB_CHECK_LAUNCH("pos_flags_kernel");
     return FMB_OK;
+}
+FMB_API int fmb_pos_flags(const int32_t* sorted_keys, const int32_t* perm, int64_t N, uint32_t* posflag,
+                          cudaStream_t stream) {
+    return fmb_pos_flags_ex(sorted_keys, perm, N, posflag, nullptr, stream);
 }
 
 // Forward + loss + single-hit row updates + staging of multi-hit contributions (see file header).
@@ -297,6 +374,7 @@ FMB_API int fmb_fm_step_fused_ex(const int32_t* ids, const float* xv, const floa
     p.table = table; p.bias = bias;
     p.B = B; p.F = F; p.k = k; p.rowp = fmb_round_up(k + 1, 16); p.kp4 = fmb_round_up(k, 4);
     p.cu = (k + 1 + 3) / 4; p.ql_log = ilog2_ceil(p.cu); p.jl_log = ilog2_ceil(p.kp4);
+    p.mF = (uint32_t)(0x100000000ull / (unsigned)F) + 1u; p.mcu = (uint32_t)(0x100000000ull / (unsigned)p.cu) + 1u;
     p.loss_kind = loss_kind; p.mode = mode; p.lr = lr; p.astep = -(lr / 0.1f);
     p.delta = delta; p.lossv = lossv;
     p.G = (float*)ws; p.Npad = (N + 3) / 4 * 4 + 64;
@@ -308,7 +386,7 @@ FMB_API int fmb_fm_step_fused_ex(const int32_t* ids, const float* xv, const floa
     if (SB < 4) SB = 4;
     if (SB > 32) SB = 32;
     auto bytes = [&](int sb) {
-        return sizeof(float) * ((size_t)sb * F * p.cu * 4 + (size_t)4 * sb * F + (size_t)sb * k + (size_t)sb * p.kp4 + sb);
+        return sizeof(float) * ((size_t)sb * F * p.cu * 4 + (size_t)4 * sb * F + (size_t)sb * k + (size_t)sb * p.cu * 4 + sb);
     };
     while (SB > 1 && bytes(SB) > 48 * 1024) SB >>= 1;
     // at least ~6 tiles per SM when the batch allows it: the tiles of an SM are then in different phases (gather, reduce,
@@ -322,12 +400,9 @@ FMB_API int fmb_fm_step_fused_ex(const int32_t* ids, const float* xv, const floa
     }
     FMB_CHECK_ARG(bytes(SB) <= 200 * 1024, "fmb_fm_step_fused: F*k too large for one sample tile");
     p.SB = SB;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(fm_step_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
-    fm_step_fused_kernel<<<(B + SB - 1) / SB, 256, bytes(SB), stream>>>(ids, xv, y, posflag, p);
+    const fused_fn_t fn = fused_fn(p.cu, xv != nullptr, mode);
+    if (bytes(SB) > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    fn<<<(B + SB - 1) / SB, 256, bytes(SB), stream>>>(ids, xv, y, posflag, p);
     FMB_CHECK_LAUNCH("fm_step_fused_kernel");
     return FMB_OK;
 }

@@ -15,6 +15,11 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int RADIX_BITS = 8;
+constexpr int CL_SEGS = 4;   // run-list segments per field = CTAs of a sort cluster
+__device__ long long* g_sort_dbg = nullptr;   // debug: per-phase cycle counts of one CTA + per-field globaltimer stamps
+__device__ __forceinline__ void sort_stamp(int slot) {
+    if (g_sort_dbg && threadIdx.x == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); g_sort_dbg[slot] = (long long)gt; }
+}
 constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
@@ -165,6 +170,338 @@ __global__ void __launch_bounds__(1024) segment_starts_kernel(const int32_t* __r
 }
 
 
+
+// ---------------------------------------------------------------------------------------------
+// Tail of the per-field sorts: the CTA holds positions [g0, g0 + n) of field f's sorted order in shared memory (kc = row
+// ids relative to the field, pc = sample index).  Besides sorted_keys / perm it writes what the FM step needs one step
+// later (fm_step.cu, fm_backward.cu) -- this used to be a separate kernel (pos_flags_kernel, 7-8 us behind the sort):
+//   posflag[entry] = sorted position | 0x80000000 if the entry's row is hit more than once in the batch
+//   run list       = {first sorted position, key, number of the run's entries among its first 32 positions, 0} for every
+//                    run of >= 2 entries that STARTS in this CTA, appended in any order to the CTA's own segment
+//                    (rl_entries + seg * rl_cap); rl_segc[seg] = their number.  No global counter, nothing to zero.
+// key_at(gi) returns the key at field position gi when it is held by another CTA of the cluster.
+// ---------------------------------------------------------------------------------------------
+template <int THREADS, typename KeyAt>
+__device__ __forceinline__ void sort_tail(const uint32_t* kc, const uint16_t* pc, int n, int g0, int B, int F, int f,
+                                          int32_t off, int32_t* __restrict__ skeys, int32_t* __restrict__ perm,
+                                          uint32_t* __restrict__ posflag, int4* __restrict__ rl_entries,
+                                          uint32_t* __restrict__ rl_segc, int rl_cap, int rl_nseg, int seg, int seg_long, KeyAt key_at) {
+    __shared__ uint32_t wcount_s[32], wcountl_s[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int nr = (n + 31) & ~31;
+    int4* mine = rl_entries ? rl_entries + (size_t)seg * rl_cap : nullptr;
+    int4* minel = rl_entries ? rl_entries + (size_t)seg_long * rl_cap : nullptr;   // long runs: downwards from this segment's end
+    // long run (>= 128 entries) starting at local position i?  (its own launch of the run kernel)
+    auto is_long = [&](int i, uint32_t key) {
+        const int g2 = g0 + i + 127, j2 = i + 127;
+        return g2 < B && (j2 < n ? kc[j2] : key_at(g2)) == key;
+    };
+    // pass 1: outputs per position; run starts are only counted (per warp, in registers)
+    uint32_t wc = 0, wcl = 0;
+    for (int i = threadIdx.x; i < nr; i += THREADS) {     // a warp covers 32 consecutive sorted positions per iteration
+        bool start = false, lng = false;
+        if (i < n) {
+            const int gi = g0 + i;
+            const uint32_t key = kc[i];
+            const uint32_t prev = gi > 0 ? (i > 0 ? kc[i - 1] : key_at(gi - 1)) : 0xffffffffu;
+            const uint32_t next = gi + 1 < B ? (i + 1 < n ? kc[i + 1] : key_at(gi + 1)) : 0xffffffffu;
+            const bool cont = key == prev, multi = cont || key == next;
+            start = multi && !cont;
+            if (start && mine) lng = is_long(i, key);
+            const size_t o = (size_t)f * B + gi;
+            const int32_t e = (int32_t)pc[i] * F + f;
+            skeys[o] = (int32_t)key + off;
+            perm[o] = e;
+            if (posflag) posflag[e] = (uint32_t)o | (multi ? 0x80000000u : 0u);
+        }
+        if (mine) {
+            wc += __popc(__ballot_sync(0xffffffffu, start && !lng));
+            wcl += __popc(__ballot_sync(0xffffffffu, lng));
+        }
+    }
+    if (!mine) return;
+    if (lane == 0) { wcount_s[warp] = wc; wcountl_s[warp] = wcl; }
+    __syncthreads();
+    uint32_t base = 0, total = 0, basel = 0, totall = 0;
+    for (int w = 0; w < THREADS / 32; ++w) {
+        const uint32_t t = wcount_s[w], tl = wcountl_s[w];
+        if (w < warp) { base += t; basel += tl; }
+        total += t; totall += tl;
+    }
+    if (threadIdx.x == 0) { rl_segc[seg] = total; rl_segc[rl_nseg + seg_long] = totall; }
+    if (wc + wcl == 0) return;
+    // pass 2 (warps that hold run starts): the entries -- short runs from the segment's start upwards, long runs from its
+    // end downwards.  No counter in shared memory: same-address ATOMS.ADD with a return value retire one at a time.
+    for (int i = threadIdx.x; i < nr; i += THREADS) {
+        uint32_t key = 0xfffffffeu;
+        bool cont = false, start = false, lng = false;
+        const int gi = g0 + i;
+        if (i < n) {
+            key = kc[i];
+            const uint32_t prev = gi > 0 ? (i > 0 ? kc[i - 1] : key_at(gi - 1)) : 0xffffffffu;
+            const uint32_t next = gi + 1 < B ? (i + 1 < n ? kc[i + 1] : key_at(gi + 1)) : 0xffffffffu;
+            cont = key == prev;
+            start = !cont && key == next;
+            if (start) lng = is_long(i, key);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, start);
+        if (m) {
+            // entries of each run among its first 32 positions, without a loop: inside this warp's window the run of a
+            // start at lane l continues over the lanes whose key equals their predecessor's; only the LAST run of the
+            // window can leave it, and the next 32 keys tell how far (a per-start scan of up to 31 shared-memory reads
+            // cost 4-20 us per field here)
+            const unsigned ml = __ballot_sync(0xffffffffu, lng);
+            const unsigned cm = __ballot_sync(0xffffffffu, cont);
+            const uint32_t klast = __shfl_sync(0xffffffffu, key, 31);
+            const int i2 = i + 32, gi2 = gi + 32;
+            const uint32_t k2 = gi2 < B ? (i2 < n ? kc[i2] : key_at(gi2)) : 0xffffffffu;
+            const unsigned em = __ballot_sync(0xffffffffu, k2 == klast);
+            const int ext = em == 0xffffffffu ? 32 : __ffs(~em) - 1;            // run of the last lane, beyond the window
+            if (start) {
+                const unsigned after = lane == 31 ? 0u : (cm >> (lane + 1));     // continuation flags of the lanes after me
+                const int inw = lane == 31 ? 0 : __ffs(~after) - 1;              // consecutive ones (bit 31 - lane is 0)
+                int n0 = 1 + inw;
+                if (lane + inw == 31) n0 += ext;                                 // my run reaches the window's last lane
+                if (n0 > 32) n0 = 32;
+                const int4 e4 = make_int4((int)((size_t)f * B + gi), (int32_t)key + off, n0, lng ? 1 : 0);
+                if (lng) minel[rl_cap - 1 - (int)(basel + __popc(ml & lt))] = e4;
+                else mine[base + __popc((m & ~ml) & lt)] = e4;
+            }
+            base += __popc(m & ~ml);
+            basel += __popc(ml);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sparse fields (far more rows than the batch has samples: Criteo's large categorical fields, 1.27 M rows against 8 192
+// samples) need no sort at all for the FM step: what the step consumes is (a) per entry, whether its row is hit more than
+// once, and (b) for those entries only, a position such that the entries of one row are contiguous and in sample order.
+// Rows hit once are updated inside the fused kernel and their position is never used.  One CTA per sparse field:
+//   1. the field's keys go into a shared-memory hash table (open addressing, rounds of plain stores and barriers, no
+//      atomics); an entry that finds its key already present marks itself and the slot's owner as multi-hit -- the SET of
+//      marked entries does not depend on who won a slot;
+//   2. the marked entries are compacted in sample order (block scan) -- ~50 of 8 192 on uniform ids;
+//   3. their rank by (key, sample) is counted directly (n^2 comparisons, n <= 256) or, on skewed ids where many entries
+//      share rows, found by the shared-memory radix sort of smem_sort.cuh over the compacted list;
+//   4. outputs: posflag of the multi-hit entries (the caller cleared the buffer), sorted_keys / perm of the multi-hit
+//      entries at the head of the field's range [f*B, f*B + nm), sorted_keys = -1 behind them (the run kernel probes keys
+//      behind a run's end), the run list.
+// Result for the consumers = that of the full sort restricted to multi-hit entries, at 1/5 of its time and without the
+// register footprint that kept the fused kernel's tiles off the SMs.
+// ---------------------------------------------------------------------------------------------
+constexpr int SPARSE_THREADS = 1024;
+constexpr int SPARSE_DIRECT = 256;     // largest multi-hit count ranked by direct comparison
+
+__host__ __device__ inline int sparse_table_slots(int B) { int t = 1024; while (t < 2 * B) t <<= 1; return t; }
+// keys [B] u32 | flag [B] u8 | compacted keys [B] u32 | compacted samples [B] u16 | region shared by the hash table (step 1)
+// and the second key/sample buffers + radix counters (step 3)
+__host__ __device__ inline size_t sparse_region_bytes(int B) {
+    const size_t a = (size_t)sparse_table_slots(B) * 4, b = (size_t)B * 4 + (size_t)(B + (B & 1)) * 2 + 32 * 256 * 2;
+    return a > b ? a : b;
+}
+// (the two compacted buffers also hold the per-warp lists of unsettled entries during the insertion: sized for >= 2 048)
+__host__ __device__ inline int sparse_bp(int B) { return B < 2048 ? 2048 : B; }
+__host__ __device__ inline size_t sparse_smem_bytes(int B) {
+    return (size_t)B * 4 + (size_t)((B + 3) & ~3) + (size_t)sparse_bp(B) * 4 + (size_t)((sparse_bp(B) + 1) & ~1) * 2 + sparse_region_bytes(B) + 16;
+}
+
+__global__ void __launch_bounds__(SPARSE_THREADS) sparse_fields_kernel(const int32_t* __restrict__ ids, int B, int F,
+                                                                      const int32_t* __restrict__ field_off,
+                                                                      int64_t min_rows, int32_t* __restrict__ skeys,
+                                                                      int32_t* __restrict__ perm, uint32_t* __restrict__ posflag,
+                                                                      int4* __restrict__ rl_entries, uint32_t* __restrict__ rl_segc,
+                                                                      int rl_cap) {
+    const int f = blockIdx.x;
+    const int32_t off = field_off[f];
+    const uint32_t nrows = (uint32_t)(field_off[f + 1] - off);
+    if ((int64_t)nrows < min_rows) return;                 // dense field: the radix kernels own it
+    extern __shared__ __align__(16) unsigned char sp_smem[];
+    const int slots = sparse_table_slots(B);
+    uint32_t* keys = reinterpret_cast<uint32_t*>(sp_smem);             // [B]
+    uint8_t* flag = reinterpret_cast<uint8_t*>(keys + B);              // [B]
+    const int Bp = sparse_bp(B);
+    uint32_t* kbuf0 = reinterpret_cast<uint32_t*>(flag + ((B + 3) & ~3));   // compacted multi-hit keys (sample order)
+    uint16_t* pbuf0 = reinterpret_cast<uint16_t*>(kbuf0 + Bp);         // their samples
+    uint32_t* tab = reinterpret_cast<uint32_t*>(pbuf0 + ((Bp + 1) & ~1));   // [slots] owner entry + 1, 0 = empty (step 1)
+    uint32_t* kbuf1 = tab;                                             // step 3 reuses the table's memory
+    uint16_t* pbuf1 = reinterpret_cast<uint16_t*>(kbuf1 + B);
+    uint16_t* cnt = pbuf1 + B + (B & 1);                               // radix counters (fallback only)
+    __shared__ uint32_t tot[256];
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t nm_s, t_fill, t_filll;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    sort_stamp(16 + 2 * F + 2 * f);
+    for (int i0 = threadIdx.x; i0 < B; i0 += 8 * SPARSE_THREADS) {   // eight strided loads in flight per thread
+        int32_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int i = i0 + u * SPARSE_THREADS; v[u] = i < B ? __ldg(ids + (size_t)i * F + f) : 0; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * SPARSE_THREADS;
+            if (i < B) { keys[i] = (uint32_t)(v[u] - off); flag[i] = 0; }
+        }
+    }
+    for (int i = threadIdx.x; i < slots; i += SPARSE_THREADS) tab[i] = 0;
+    if (threadIdx.x == 0) { t_fill = 0; t_filll = 0; }
+    __syncthreads();
+    sort_stamp(16 + 6 * F + f);   // keys loaded, table cleared
+    // 1. insert, without atomics (8 192 ATOMS.CAS on one SM took 9 us: shared-memory atomics retire a few lanes per
+    //    clock).  Rounds of "store, barrier, look": an unresolved entry whose probe slot is empty stores its own index
+    //    there (plain store; among racing writers one survives), and after the barrier reads the slot back: its own
+    //    index = it owns the slot; an entry with the same key = both are multi-hit; another key = next probe slot.
+    //    Entries with equal keys walk the same probe sequence in the same rounds and see the same table, so they always
+    //    meet in one slot; the set of marked entries does not depend on who wins a race.
+    {
+        constexpr int PER = 8;                     // B <= 8 * SPARSE_THREADS is guaranteed by sparse_smem_bytes
+        const uint32_t mask = (uint32_t)slots - 1u;
+        const int hshift = 32 - (31 - __clz(slots));
+        uint32_t key[PER], slot[PER], step[PER];
+        unsigned open = 0;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int i = threadIdx.x + u * SPARSE_THREADS;
+            key[u] = 0; slot[u] = 0; step[u] = 1;
+            if (i < B) {
+                key[u] = keys[i];
+                slot[u] = (key[u] * 2654435761u) >> hshift;
+                step[u] = ((key[u] * 0x85ebca6bu) >> 17) | 1u;     // odd: the probe sequence visits every slot
+                open |= 1u << u;
+            }
+        }
+        // round 0: every entry (three quarters are settled here at load factor 1/2)
+#pragma unroll
+        for (int u = 0; u < PER; ++u)
+            if ((open >> u) & 1u) { if (tab[slot[u]] == 0u) tab[slot[u]] = (uint32_t)(threadIdx.x + u * SPARSE_THREADS) + 1u; }
+        __syncthreads();
+        // unsettled entries and their current probe slot, one private list per warp (a warp owns 8 x 32 entries): no
+        // counter in shared memory -- 256 ATOMS.ADD on one address took 12 us here
+        const int perb = (B + SPARSE_THREADS - 1) / SPARSE_THREADS;   // entries per thread: a warp owns 32 * perb
+        uint16_t* ulist = reinterpret_cast<uint16_t*>(kbuf0) + warp * (perb * 32);
+        uint16_t* uslot = ulist + SPARSE_THREADS * perb;           // (kbuf0 | pbuf0 are free until the compaction of step 2:
+                                                                   //  3 * Bp halfwords >= 2 * (B + 1023))
+        int wn = 0;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            bool unsettled = false;
+            const uint32_t me = (uint32_t)(threadIdx.x + u * SPARSE_THREADS) + 1u;
+            if ((open >> u) & 1u) {
+                const uint32_t cur = tab[slot[u]];
+                if (cur == me) { }
+                else if (keys[cur - 1] == key[u]) { flag[cur - 1] = 1; flag[me - 1] = 1; }
+                else unsettled = true;
+            }
+            const unsigned um = __ballot_sync(0xffffffffu, unsettled);
+            if (unsettled) {
+                const int j = wn + __popc(um & lt);
+                ulist[j] = (uint16_t)(me - 1u);
+                uslot[j] = (uint16_t)((slot[u] + step[u]) & mask);
+            }
+            wn += __popc(um);
+        }
+        __syncthreads();
+        // the unsettled quarter: classic atomicCAS probing from their next slot (equal keys walk the same sequence, so
+        // the second one meets the first).  Doing ALL entries this way took 9.5 us (ATOMS retire ~1 per ns per SM),
+        // doing all later rounds with plain stores and two barriers each took 12.
+        for (int j = lane; j < wn; j += 32) {
+            const uint32_t i = ulist[j], k = keys[i];
+            const uint32_t st = ((k * 0x85ebca6bu) >> 17) | 1u;
+            uint32_t sl = uslot[j];
+            for (;;) {
+                const uint32_t old = atomicCAS(&tab[sl], 0u, i + 1u);
+                if (old == 0u) break;
+                if (keys[old - 1] == k) { flag[old - 1] = 1; flag[i] = 1; break; }
+                sl = (sl + st) & mask;
+            }
+        }
+    }
+    __syncthreads();
+    sort_stamp(16 + 7 * F + f);   // inserted
+    // 2. compact the marked entries in sample order: thread t owns entries [t*per, (t+1)*per)
+    const int per = (B + SPARSE_THREADS - 1) / SPARSE_THREADS;
+    const int i0 = threadIdx.x * per;
+    uint32_t mine = 0;
+    for (int u = 0; u < per; ++u) if (i0 + u < B) mine += flag[i0 + u];
+    uint32_t inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = wsum[lane];
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+        wsum[lane] = winc - w;
+        if (lane == 31) nm_s = winc;
+    }
+    __syncthreads();
+    {
+        uint32_t o = wsum[warp] + inc - mine;
+        for (int u = 0; u < per; ++u)
+            if (i0 + u < B && flag[i0 + u]) { kbuf0[o] = keys[i0 + u]; pbuf0[o] = (uint16_t)(i0 + u); ++o; }
+    }
+    __syncthreads();
+    const int nm = (int)nm_s;
+    sort_stamp(16 + 5 * F + f);   // hash + compaction done
+    // 3. order by (key, sample).  The compacted list is in sample order, so a stable sort by key is what is needed.
+    uint32_t* ks = kbuf1;     // sorted keys
+    uint16_t* ps = pbuf1;     // their samples
+    if (nm <= SPARSE_DIRECT) {
+        for (int a = threadIdx.x; a < nm; a += SPARSE_THREADS) {
+            const uint32_t key = kbuf0[a];
+            int r = 0;
+            for (int b2 = 0; b2 < nm; ++b2) { const uint32_t kb = kbuf0[b2]; r += (kb < key) || (kb == key && b2 < a); }
+            kbuf1[r] = key;
+            pbuf1[r] = pbuf0[a];
+        }
+        __syncthreads();
+    } else {
+        const int bits = nrows <= 1 ? 0 : 32 - __clz(nrows - 1);
+        fmb::smem_sort_passes(kbuf0, kbuf1, pbuf0, pbuf1, cnt, tot, nm, (bits + RADIX_BITS - 1) / RADIX_BITS, &ks, &ps);
+    }
+    // 4. outputs
+    sort_stamp(16 + 8 * F + f);   // ranked
+    const size_t fb = (size_t)f * B;
+    // posflag of the rows hit once stays 0 (the caller cleared the buffer: 8 192 scattered 4-byte stores per field from
+    // one SM took 4 us, a 1.3 MB memset takes 1); perm is only defined for the placed entries
+    for (int i = nm + threadIdx.x; i < B; i += SPARSE_THREADS) skeys[fb + i] = -1;
+    int4* seg = rl_entries ? rl_entries + (size_t)(f * CL_SEGS) * rl_cap : nullptr;
+    const int nr = (nm + 31) & ~31;
+    for (int a = threadIdx.x; a < nr; a += SPARSE_THREADS) {
+        bool start = false;
+        uint32_t key = 0;
+        if (a < nm) {
+            key = ks[a];
+            const int32_t e = (int32_t)ps[a] * F + f;
+            skeys[fb + a] = (int32_t)key + off;
+            perm[fb + a] = e;
+            posflag[e] = (uint32_t)(fb + a) | 0x80000000u;
+            start = a == 0 || ks[a - 1] != key;
+        }
+        if (seg && start) {        // a few dozen runs per field: plain shared-memory counters
+            int n0 = 1;
+            while (n0 < 32 && a + n0 < nm && ks[a + n0] == key) ++n0;
+            const bool lng = a + 127 < nm && ks[a + 127] == key;
+            const int4 e4 = make_int4((int)(fb + a), (int32_t)key + off, n0, lng ? 1 : 0);
+            if (lng) seg[CL_SEGS * rl_cap - 1 - (int)atomicAdd(&t_filll, 1u)] = e4;   // the field's four segments are contiguous
+            else seg[atomicAdd(&t_fill, 1u)] = e4;
+        }
+    }
+    if (seg) {
+        __syncthreads();
+        // short runs counted in the field's first segment, long ones (stored downwards from the end of the field's
+        // four contiguous segments) in its last
+        if (threadIdx.x < CL_SEGS) {
+            rl_segc[f * CL_SEGS + threadIdx.x] = threadIdx.x == 0 ? t_fill : 0u;
+            rl_segc[F * CL_SEGS + f * CL_SEGS + threadIdx.x] = threadIdx.x == CL_SEGS - 1 ? t_filll : 0u;
+        }
+    }
+    sort_stamp(17 + 2 * F + 2 * f);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Fast path: ids come as a [B,F] matrix whose column f holds ids of field f only, so the global
 // stable sort factors into F independent stable sorts of B keys each.  One CTA per field sorts its
@@ -179,7 +516,9 @@ constexpr int FS_MAX_SLOTS = 16;  // B <= 32 warps * 16 slots * 32 lanes = 16384
 __global__ void __launch_bounds__(FS_THREADS) sort_fields_kernel(const int32_t* __restrict__ ids, int B, int F,
                                                                  const int32_t* __restrict__ field_off,
                                                                  int32_t* __restrict__ skeys,
-                                                                 int32_t* __restrict__ perm) {
+                                                                 int32_t* __restrict__ perm, uint32_t* __restrict__ posflag,
+                                                                 int4* __restrict__ rl_entries, uint32_t* __restrict__ rl_segc,
+                                                                 int rl_cap, int64_t max_rows) {
     extern __shared__ __align__(16) unsigned char fs_smem[];
     uint32_t* kbuf0 = reinterpret_cast<uint32_t*>(fs_smem);
     uint32_t* kbuf1 = kbuf0 + B;
@@ -190,8 +529,10 @@ __global__ void __launch_bounds__(FS_THREADS) sort_fields_kernel(const int32_t* 
     const int f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int32_t off = field_off[f];
     const uint32_t nrows = (uint32_t)(field_off[f + 1] - off);
+    if ((int64_t)nrows >= max_rows) return;      // sparse field: sparse_fields_kernel owns it
     const int bits = nrows <= 1 ? 0 : 32 - __clz(nrows - 1);
     const int passes = (bits + RADIX_BITS - 1) / RADIX_BITS;
+    (void)lane; (void)warp;
     for (int i = threadIdx.x; i < B; i += FS_THREADS) {
         kbuf0[i] = (uint32_t)(ids[(size_t)i * F + f] - off);
         pbuf0[i] = (uint16_t)i;
@@ -199,9 +540,13 @@ __global__ void __launch_bounds__(FS_THREADS) sort_fields_kernel(const int32_t* 
     __syncthreads();
     uint32_t* kc; uint16_t* pc;
     fmb::smem_sort_passes(kbuf0, kbuf1, pbuf0, pbuf1, cnt, tot, B, passes, &kc, &pc);
-    for (int i = threadIdx.x; i < B; i += FS_THREADS) {
-        skeys[(size_t)f * B + i] = (int32_t)kc[i] + off;
-        perm[(size_t)f * B + i] = (int32_t)pc[i] * F + f;
+    // one CTA owns the field's four (contiguous) segments: short runs upwards from the first, long runs downwards from
+    // the end of the last
+    sort_tail<FS_THREADS>(kc, pc, B, 0, B, F, f, off, skeys, perm, posflag, rl_entries, rl_segc, rl_cap, F * CL_SEGS, f * CL_SEGS,
+                          f * CL_SEGS + CL_SEGS - 1, [](int) { return 0xffffffffu; });
+    if (rl_entries && threadIdx.x >= 1 && threadIdx.x < CL_SEGS) {
+        rl_segc[f * CL_SEGS + threadIdx.x] = 0u;
+        rl_segc[F * CL_SEGS + f * CL_SEGS + threadIdx.x - 1] = 0u;
     }
 }
 
@@ -214,8 +559,7 @@ __global__ void __launch_bounds__(FS_THREADS) sort_fields_kernel(const int32_t* 
 // Same result as sort_fields_kernel on 4x the SMs (39 CTAs of 1024 threads left 109 SMs idle and
 // were issue-bound: profiles/r1c), and batches up to 65536.
 // ---------------------------------------------------------------------------------------------
-constexpr int CL = 4;
-__device__ long long* g_sort_dbg = nullptr;   // debug: per-phase cycle counts of one CTA
+constexpr int CL = CL_SEGS;
 #define SORT_PROBE(slot) do { if (dbg && threadIdx.x == 0) { long long t_ = clock64(); dbg[slot] += t_ - tlast; tlast = t_; } } while (0)
 
 // THREADS = 256 for batches up to 16384 (8 warps x <= 16 slots per CTA: the per-pass fixed work -- counter
@@ -227,7 +571,8 @@ __device__ long long* g_sort_dbg = nullptr;   // debug: per-phase cycle counts o
 template <int THREADS, bool STAGED>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS)
 sort_fields_cluster_kernel(const int32_t* __restrict__ ids, int B, int F, const int32_t* __restrict__ field_off,
-                           int32_t* __restrict__ skeys, int32_t* __restrict__ perm, int Bq) {
+                           int32_t* __restrict__ skeys, int32_t* __restrict__ perm, int Bq, uint32_t* __restrict__ posflag,
+                           int4* __restrict__ rl_entries, uint32_t* __restrict__ rl_segc, int rl_cap, int64_t max_rows) {
     constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(16) unsigned char fs_smem[];
     uint32_t* kbuf0 = reinterpret_cast<uint32_t*>(fs_smem);
@@ -246,15 +591,27 @@ sort_fields_cluster_kernel(const int32_t* __restrict__ ids, int B, int F, const 
     const int f = blockIdx.x / CL, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int32_t off = field_off[f];
     const uint32_t nrows = (uint32_t)(field_off[f + 1] - off);
+    if ((int64_t)nrows >= max_rows) return;               // sparse field (the whole cluster leaves): sparse_fields_kernel owns it
     const int bits = nrows <= 1 ? 0 : 32 - __clz(nrows - 1);
     const int passes = (bits + RADIX_BITS - 1) / RADIX_BITS;
     const int g0 = crank * Bq;                            // first field position held by this CTA
     const int n = max(0, min(Bq, B - g0));                // entries held by this CTA
     long long* dbg = (g_sort_dbg && blockIdx.x == (unsigned)(F - 1) * CL) ? g_sort_dbg : nullptr;
     long long tlast = clock64();
-    for (int i = threadIdx.x; i < n; i += THREADS) {
-        kbuf0[i] = (uint32_t)(ids[(size_t)(g0 + i) * F + f] - off);
-        pbuf0[i] = (uint16_t)(g0 + i);
+    if (crank == 0) sort_stamp(16 + 2 * f);
+    if (g_sort_dbg && threadIdx.x == 0) {   // debug: earliest CTA start / latest CTA end of the launch (globaltimer ns)
+        unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        atomicMin(reinterpret_cast<unsigned long long*>(g_sort_dbg) + 14, gt);
+    }
+    for (int i0 = threadIdx.x; i0 < n; i0 += 8 * THREADS) {   // eight strided loads in flight per thread
+        int32_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int i = i0 + u * THREADS; v[u] = i < n ? __ldg(ids + (size_t)(g0 + i) * F + f) : 0; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * THREADS;
+            if (i < n) { kbuf0[i] = (uint32_t)(v[u] - off); pbuf0[i] = (uint16_t)(g0 + i); }
+        }
     }
     __syncthreads();
     SORT_PROBE(0);
@@ -396,11 +753,22 @@ sort_fields_cluster_kernel(const int32_t* __restrict__ ids, int B, int F, const 
         uint32_t* tk = kc; kc = kn; kn = tk;
         uint16_t* tp = pc; pc = pn; pn = tp;
     }
-    for (int i = threadIdx.x; i < n; i += THREADS) {
-        skeys[(size_t)f * B + g0 + i] = (int32_t)kc[i] + off;
-        perm[(size_t)f * B + g0 + i] = (int32_t)pc[i] * F + f;
-    }
+    if (crank == 0) sort_stamp(16 + 4 * F + f);   // passes done
+    if (passes == 0) cluster.sync();   // the neighbours' keys are read below: their initial loads must have landed
+    // every CTA holds the same buffer parity (same number of passes), so kc names the sorted keys in all of them
+    sort_tail<THREADS>(kc, pc, n, g0, B, F, f, off, skeys, perm, posflag, rl_entries, rl_segc, rl_cap, F * CL_SEGS, f * CL_SEGS + crank, f * CL_SEGS + crank, [&](int gi) {
+        const int dest = (gi >= Bq) + (gi >= 2 * Bq) + (gi >= 3 * Bq);
+        return cluster.map_shared_rank(kc, dest)[gi - dest * Bq];
+    });
     SORT_PROBE(8);
+    cluster.sync();                    // no CTA leaves while a neighbour may still read its keys
+    if (crank == 0) sort_stamp(17 + 2 * f);
+    if (g_sort_dbg && threadIdx.x == 0) {
+        unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        atomicMax(reinterpret_cast<unsigned long long*>(g_sort_dbg) + 15, gt);
+        if (nrows > 100000u && crank == 0) atomicMin(reinterpret_cast<unsigned long long*>(g_sort_dbg) + 13, gt);   // first large field done
+        if (nrows <= 256u) atomicMax(reinterpret_cast<unsigned long long*>(g_sort_dbg) + 12, gt);                    // last small field done
+    }
 }
 
 }  // namespace
@@ -456,13 +824,14 @@ FMB_API int fmb_sort_segment(const int32_t* keys, int64_t N, int key_bits, void*
     return FMB_OK;
 }
 
-// host-side handles of the three per-field sort kernels (argument 0 = ids, 4 = sorted_keys, 5 = perm; 6 or 7 arguments),
+// host-side handles of the per-field sort kernels (argument 0 = ids; sorted_keys = argument 4, or 5 for the sparse-field kernel),
 // for graph-node identification in session.cu
-FMB_API int fmb_sort_fields_kernel_fns(const void** fns, int* nparams) {
-    fns[0] = (const void*)sort_fields_kernel; nparams[0] = 6;
-    fns[1] = (const void*)sort_fields_cluster_kernel<256, true>; nparams[1] = 7;
-    fns[2] = (const void*)sort_fields_cluster_kernel<1024, false>; nparams[2] = 7;
-    return 3;
+FMB_API int fmb_sort_fields_kernel_fns(const void** fns, int* nparams, int* skeys_arg) {
+    fns[0] = (const void*)sort_fields_kernel; nparams[0] = 11; skeys_arg[0] = 4;
+    fns[1] = (const void*)sort_fields_cluster_kernel<256, true>; nparams[1] = 12; skeys_arg[1] = 4;
+    fns[2] = (const void*)sort_fields_cluster_kernel<1024, false>; nparams[2] = 12; skeys_arg[2] = 4;
+    fns[3] = (const void*)sparse_fields_kernel; nparams[3] = 11; skeys_arg[3] = 5;
+    return 4;
 }
 
 // Largest batch the per-field shared-memory sort accepts (cluster of 4 CTAs, 16-bit sample payload).
@@ -472,30 +841,76 @@ FMB_API int fmb_sort_fields_max_batch(void) { return 65536; }
 // field offsets) -> sorted_keys[B*F], perm[B*F] (original entry index b*F+f), identical to
 // fmb_sort_segment over the flattened matrix.  Everything stays in shared memory: one CTA per field for
 // B <= 2048, otherwise a 4-CTA thread-block cluster per field exchanging through distributed shared memory.
-FMB_API int fmb_sort_fields(const int32_t* ids, int B, int F, const int32_t* field_off, int32_t* sorted_keys,
-                            int32_t* perm, cudaStream_t stream) {
+// _ex: optional outputs for the FM step of fm_step.cu / fm_backward.cu (see sort_tail): posflag[B*F] and the run list rl
+// (shape from fmb_runlist_shape; nothing to zero: every segment's count is written).  flags & FMB_SORT_SPARSE_OK: fields
+// with at least 16*B rows may skip the sort (sparse_fields_kernel): sorted_keys / perm then hold only the entries of
+// rows hit more than once, at the head of the field's range, and -1 behind them -- all the FM step reads.
+struct fmb_runlist_t { int32_t* entries; uint32_t* seg_count; int nseg, seg_cap; };   // include/fmb200.h
+#define FMB_SORT_SPARSE_OK 1
+
+FMB_API void fmb_runlist_shape(int B, int F, int* nseg, int* seg_cap) {
+    int Bq = (B + CL - 1) / CL;
+    Bq = (Bq + 31) / 32 * 32;
+    *nseg = F * CL_SEGS;
+    *seg_cap = Bq;
+}
+
+// rows a field must have for FMB_SORT_SPARSE_OK to skip its sort at batch size B; 0 = never at this batch size
+FMB_API int64_t fmb_sort_fields_sparse_min_rows(int B) {
+    return (B > 0 && sparse_smem_bytes(B) <= 200 * 1024) ? (int64_t)16 * B : 0;
+}
+
+// flags & FMB_SORT_PART_DENSE / FMB_SORT_PART_SPARSE (internal, with FMB_SORT_SPARSE_OK): launch only the radix kernel of
+// the dense fields / only the hash kernel of the sparse fields -- the two are independent, so a caller with two streams
+// (session.cu) runs them side by side; neither bit = both, one after the other on `stream`.
+#define FMB_SORT_PART_DENSE 2
+#define FMB_SORT_PART_SPARSE 4
+FMB_API int fmb_sort_fields_ex(const int32_t* ids, int B, int F, const int32_t* field_off, int32_t* sorted_keys,
+                               int32_t* perm, uint32_t* posflag, const fmb_runlist_t* rl, int flags, cudaStream_t stream) {
     FMB_CHECK_ARG(ids && field_off && sorted_keys && perm, "fmb_sort_fields: null pointer");
     FMB_CHECK_ARG(B > 0 && B <= fmb_sort_fields_max_batch() && F > 0, "fmb_sort_fields: B=%d out of range", B);
+    int Bq = (B + CL - 1) / CL;
+    Bq = (Bq + 31) / 32 * 32;
+    FMB_CHECK_ARG(!rl || (rl->entries && rl->seg_count && rl->nseg == F * CL_SEGS && rl->seg_cap >= Bq && F * CL_SEGS <= 2048),
+                  "fmb_sort_fields: run list shape must be that of fmb_runlist_shape");
+    int4* rle = rl ? reinterpret_cast<int4*>(rl->entries) : nullptr;
+    uint32_t* rlc = rl ? rl->seg_count : nullptr;
+    const int rcap = rl ? rl->seg_cap : 0;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(sort_fields_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(sort_fields_cluster_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(sort_fields_cluster_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(sparse_fields_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         attr = true;
     }
-    if (B <= 2048) {
-        sort_fields_kernel<<<F, FS_THREADS, fmb::smem_sort_bytes(B), stream>>>(ids, B, F, field_off, sorted_keys, perm);
+    // sparse fields: the hash kernel, when the caller allows the reduced contract and the batch fits its shared memory
+    const bool sparse = (flags & FMB_SORT_SPARSE_OK) && posflag && fmb_sort_fields_sparse_min_rows(B) > 0;
+    const int64_t split = sparse ? fmb_sort_fields_sparse_min_rows(B) : ((int64_t)1 << 40);   // fields with >= split rows are sparse
+    const bool do_dense = !(flags & FMB_SORT_PART_SPARSE), do_sparse = sparse && !(flags & FMB_SORT_PART_DENSE);
+    if (!do_dense) {
+    } else if (B <= 2048) {
+        sort_fields_kernel<<<F, FS_THREADS, fmb::smem_sort_bytes(B), stream>>>(ids, B, F, field_off, sorted_keys, perm, posflag,
+                                                                               rle, rlc, rcap, split);
         FMB_CHECK_LAUNCH("sort_fields_kernel");
     } else {
-        int Bq = (B + CL - 1) / CL;
-        Bq = (Bq + 31) / 32 * 32;
         if (Bq <= 256 * FS_MAX_SLOTS)
-            sort_fields_cluster_kernel<256, true><<<F * CL, 256, fmb::smem_sort_bytes(Bq) + (size_t)Bq * 6 + 16, stream>>>(ids, B, F, field_off,
-                                                                                             sorted_keys, perm, Bq);
+            sort_fields_cluster_kernel<256, true><<<F * CL, 256, fmb::smem_sort_bytes(Bq) + (size_t)Bq * 6 + 16, stream>>>(
+                ids, B, F, field_off, sorted_keys, perm, Bq, posflag, rle, rlc, rcap, split);
         else
-            sort_fields_cluster_kernel<1024, false><<<F * CL, 1024, fmb::smem_sort_bytes(Bq), stream>>>(ids, B, F, field_off,
-                                                                                               sorted_keys, perm, Bq);
+            sort_fields_cluster_kernel<1024, false><<<F * CL, 1024, fmb::smem_sort_bytes(Bq), stream>>>(
+                ids, B, F, field_off, sorted_keys, perm, Bq, posflag, rle, rlc, rcap, split);
         FMB_CHECK_LAUNCH("sort_fields_cluster_kernel");
     }
+    if (do_sparse) {
+        sparse_fields_kernel<<<F, SPARSE_THREADS, sparse_smem_bytes(B), stream>>>(ids, B, F, field_off, split, sorted_keys, perm,
+                                                                                   posflag, rle, rlc, rcap);
+        FMB_CHECK_LAUNCH("sparse_fields_kernel");
+    }
     return FMB_OK;
+}
+
+FMB_API int fmb_sort_fields(const int32_t* ids, int B, int F, const int32_t* field_off, int32_t* sorted_keys,
+                            int32_t* perm, cudaStream_t stream) {
+    return fmb_sort_fields_ex(ids, B, F, field_off, sorted_keys, perm, nullptr, nullptr, 0, stream);
 }

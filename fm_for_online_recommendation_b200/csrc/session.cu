@@ -18,11 +18,16 @@ int fmb_sort_segment(const int32_t*, int64_t, int, void*, size_t, int32_t*, int3
                      cudaStream_t);
 size_t fmb_bwd_workspace_bytes(int64_t, int);
 int fmb_sort_fields_max_batch(void);
-int fmb_sort_fields(const int32_t*, int, int, const int32_t*, int32_t*, int32_t*, cudaStream_t);
+struct fmb_runlist_t { int32_t* entries; uint32_t* seg_count; int nseg, seg_cap; };
+void fmb_runlist_shape(int, int, int*, int*);
+int fmb_sort_fields_ex(const int32_t*, int, int, const int32_t*, int32_t*, int32_t*, uint32_t*, const fmb_runlist_t*, int, cudaStream_t);
+int fmb_pos_flags_ex(const int32_t*, const int32_t*, int64_t, uint32_t*, const fmb_runlist_t*, cudaStream_t);
 int fmb_fm_backward_update(const int32_t*, const int32_t*, int64_t, const float*, float*, int, int, const float*,
                            const float*, int, const float*, float, int, void*, size_t, cudaStream_t);
 int fmb_finish_step(const float*, const float*, int, float*, float, int, float*, cudaStream_t);
 struct fmb_ftrl_t { float* zn; float* bias_zn; float beta, l1, l2; };
+int fmb_fm_backward_runs_list(const int32_t*, int64_t, float*, int, int, float, int, const fmb_ftrl_t*, const fmb_runlist_t*,
+                              void*, size_t, cudaStream_t);
 int fmb_finish_step_ex(const float*, const float*, int, float*, float, int, const fmb_ftrl_t*, float*, cudaStream_t);
 int fmb_fm_step_fused_ex(const int32_t*, const float*, const float*, float*, const float*, const uint32_t*, int, int, int,
                          int, float, int, const fmb_ftrl_t*, float*, float*, void*, size_t, cudaStream_t);
@@ -32,8 +37,9 @@ int fmb_pos_flags(const int32_t*, const int32_t*, int64_t, uint32_t*, cudaStream
 int fmb_fm_step_fused(const int32_t*, const float*, const float*, float*, const float*, const uint32_t*, int, int, int,
                       int, float, int, float*, float*, void*, size_t, cudaStream_t);
 int fmb_fm_backward_runs(const int32_t*, int64_t, float*, int, int, float, int, void*, size_t, cudaStream_t);
-const void* fmb_fused_kernel_fn(void);
-int fmb_sort_fields_kernel_fns(const void**, int*);
+int fmb_is_fused_kernel_fn(const void*);
+const void* fmb_finish_kernel_fn(void);
+int fmb_sort_fields_kernel_fns(const void**, int*, int*);
 }
 
 // One captured step graph per CONFIGURATION (batch size, loss, update mode, with/without xv, sorted in the step or
@@ -47,8 +53,8 @@ struct StepVariant {
     float lr;
     cudaGraph_t graph;        // kept alive: its nodes own the argument storage the patches start from
     cudaGraphExec_t exec;
-    cudaGraphNode_t n_fused, n_sort_cur, n_sort_next;
-    int np_sort_cur, np_sort_next;
+    cudaGraphNode_t n_fused, n_finish, n_sort_cur[2], n_sort_next[2];   // a per-field sort is up to two kernels (radix + sparse fields)
+    int np_sort_cur[2], np_sort_next[2];
     int nlaunch;
 };
 
@@ -69,6 +75,9 @@ struct fmb_session {
     int32_t* d_skeys_buf[2];
     int32_t* d_perm_buf[2];
     uint32_t* d_posflag_buf[2];   // per entry: sorted position | multi-hit flag (fmb_pos_flags), one per sorted buffer
+    int32_t* d_runlist_buf[2];    // runs of >= 2 entries {position, key, n0, 0} found by the sort: [rl_nseg][rl_cap][4]
+    uint32_t* d_runcount_buf[2];  // entries per segment [rl_nseg]
+    int rl_nseg, rl_cap;          // shape for the largest batch (fmb_runlist_shape)
     void* d_sort_ws2;             // radix workspace of the pre-sort (the in-step sort may be using d_sort_ws)
     // pre-sort: the sort depends on the ids only, so the sort of batch t+1 may run (on st1) while step t is
     // still in its backward kernels.  presort_ids names the batch whose sorted form sits in presort_buf.
@@ -96,10 +105,14 @@ struct fmb_session {
     int slot_used[2];
     int64_t launches;  // kernels launched through this session (bench.py's gpu_launches)
     // CUDA-graph cache of whole steps, keyed by every argument that is baked into the kernels
-    cudaStream_t st0, st1, st2;   // st0/st1: graph capture (main / side branch); st2: pre-sorts
+    cudaStream_t st0, st1, st2, st3, st4;   // st0/st1: graph capture (main / side branch); st2: pre-sorts; st3: sparse-field
+                                            // part of a sort; st4: long runs of the run kernel
+    cudaEvent_t ev_sp_fork, ev_sp_join, ev_join4;
     int64_t steps_done;
     cudaEvent_t ev_fork, ev_fwd, ev_sort, ev_join;
-    int use_graph;
+    int use_graph, use_prio;
+    int sort_after;        // FMB_SORT_AFTER=1 (experiment; default 0): the next batch's sort waits for the fused kernel
+    int sparse_ok;         // FMB_SORT_SPARSE_OK unless FMB_SPARSE=0: fields with >= 16*B rows skip the sort (radix_sort.cu)
     int ngraphs, next_evict;
     StepVariant gvar[FMB_GRAPH_CACHE];
     cudaEvent_t ev_join2;
@@ -117,9 +130,14 @@ FMB_API void fmb_session_destroy(fmb_session* s) {
     if (!s) return;
     cudaFree(s->d_ids); cudaFree(s->d_xv); cudaFree(s->d_y); cudaFree(s->d_S); cudaFree(s->d_z);
     cudaFree(s->d_delta); cudaFree(s->d_lossv); cudaFree(s->d_loss);
-    for (int i = 0; i < 2; ++i) { cudaFree(s->d_skeys_buf[i]); cudaFree(s->d_perm_buf[i]); cudaFree(s->d_posflag_buf[i]); if (s->ev_buf_free[i]) cudaEventDestroy(s->ev_buf_free[i]); }
+    for (int i = 0; i < 2; ++i) { cudaFree(s->d_skeys_buf[i]); cudaFree(s->d_perm_buf[i]); cudaFree(s->d_posflag_buf[i]); cudaFree(s->d_runlist_buf[i]); cudaFree(s->d_runcount_buf[i]); if (s->ev_buf_free[i]) cudaEventDestroy(s->ev_buf_free[i]); }
     cudaFree(s->d_sort_ws2);
     if (s->ev_join2) cudaEventDestroy(s->ev_join2);
+    if (s->ev_sp_fork) cudaEventDestroy(s->ev_sp_fork);
+    if (s->ev_sp_join) cudaEventDestroy(s->ev_sp_join);
+    if (s->st3) cudaStreamDestroy(s->st3);
+    if (s->st4) cudaStreamDestroy(s->st4);
+    if (s->ev_join4) cudaEventDestroy(s->ev_join4);
     if (s->ev_presort) cudaEventDestroy(s->ev_presort);
     cudaFree(s->d_sort_ws); cudaFree(s->d_bwd_ws); cudaFree(s->d_field_off);
     cudaFreeHost(s->h_ids); cudaFreeHost(s->h_xv); cudaFreeHost(s->h_y); cudaFreeHost(s->h_loss);
@@ -149,6 +167,8 @@ FMB_API int fmb_session_create(fmb_session** out, int F, int k, int64_t max_batc
     memset(s, 0, sizeof(*s));
     s->F = F; s->k = k; s->rowp = fmb_round_up(k + 1, 16); s->kp4 = fmb_round_up(k, 4); s->maxB = max_batch;
     const int64_t N = max_batch * F;
+    fmb_runlist_shape((int)(max_batch < 65536 ? max_batch : 65536), F, &s->rl_nseg, &s->rl_cap);
+    if ((int64_t)s->rl_nseg * s->rl_cap < N / 2 + 64) s->rl_cap = (int)((N / 2 + 64 + s->rl_nseg - 1) / s->rl_nseg);   // generic path: one segment of N/2
     s->sort_ws_bytes = fmb_sort_workspace_bytes(N);
     s->bwd_ws_bytes = fmb_bwd_workspace_bytes(N, k);
     cudaError_t e = cudaSuccess;
@@ -157,7 +177,7 @@ FMB_API int fmb_session_create(fmb_session** out, int F, int k, int64_t max_batc
     dm((void**)&s->d_ids, N * 4); dm((void**)&s->d_xv, N * 4); dm((void**)&s->d_y, max_batch * 4);
     dm((void**)&s->d_S, max_batch * s->kp4 * 4); dm((void**)&s->d_z, max_batch * 4);
     dm((void**)&s->d_delta, max_batch * 4); dm((void**)&s->d_lossv, max_batch * 4); dm((void**)&s->d_loss, 256);
-    for (int i = 0; i < 2; ++i) { dm((void**)&s->d_skeys_buf[i], N * 4); dm((void**)&s->d_perm_buf[i], N * 4); dm((void**)&s->d_posflag_buf[i], N * 4); }
+    for (int i = 0; i < 2; ++i) { dm((void**)&s->d_skeys_buf[i], N * 4); dm((void**)&s->d_perm_buf[i], N * 4); dm((void**)&s->d_posflag_buf[i], N * 4); dm((void**)&s->d_runlist_buf[i], (size_t)s->rl_nseg * s->rl_cap * 16); dm((void**)&s->d_runcount_buf[i], (size_t)s->rl_nseg * 8 + 256); }
     if (!(field_off_host && max_batch <= fmb_sort_fields_max_batch())) dm(&s->d_sort_ws2, s->sort_ws_bytes);
     s->d_skeys = s->d_skeys_buf[0]; s->d_perm = s->d_perm_buf[0];
     dm(&s->d_sort_ws, s->sort_ws_bytes); dm(&s->d_bwd_ws, s->bwd_ws_bytes);
@@ -175,9 +195,28 @@ FMB_API int fmb_session_create(fmb_session** out, int F, int k, int64_t max_batc
         dm((void**)&s->d_field_off, (size_t)(F + 1) * 4);
         if (e == cudaSuccess) e = cudaMemcpy(s->d_field_off, field_off_host, (size_t)(F + 1) * 4, cudaMemcpyHostToDevice);
     }
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st0, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st1, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st2, cudaStreamNonBlocking);
+    {
+        // The sort of the NEXT batch is captured on the HIGH-priority stream, the step's own kernels on the low-priority
+        // one (graphs are instantiated with cudaGraphInstantiateFlagUseNodePriority).  The fused kernel's 1 024 CTAs fill
+        // every thread slot of the GPU; launched first they kept the sort's 156 clustered CTAs waiting until the first
+        // tiles retired (~20 us: the step took sort + 20 us whatever the fused kernel cost).  With priority the sort's
+        // CTAs are placed first (one per SM), the tiles take the remaining seven slots, and both chains start together.
+        // FMB_PRIO=0: no priorities; FMB_PRIO=2: the other way round (for comparison).
+        int least = 0, greatest = 0;
+        const char* pe = getenv("FMB_PRIO");
+        s->use_prio = pe ? atoi(pe) : 1;
+        if (s->use_prio && cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) s->use_prio = 0;
+        if (!s->use_prio) least = greatest = 0;
+        if (s->use_prio == 1) { const int t = least; least = greatest; greatest = t; }   // st0/st1 low, st2 high
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s->st0, cudaStreamNonBlocking, greatest);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s->st1, cudaStreamNonBlocking, greatest);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s->st2, cudaStreamNonBlocking, least);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s->st3, cudaStreamNonBlocking, least);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s->st4, cudaStreamNonBlocking, greatest);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_join4, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_sp_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_sp_join, cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_fwd, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_sort, cudaEventDisableTiming);
@@ -188,6 +227,10 @@ FMB_API int fmb_session_create(fmb_session** out, int F, int k, int64_t max_batc
     {
         const char* ng = getenv("FMB_NO_GRAPH");
         s->use_graph = !(ng && ng[0] == '1');
+        const char* sp = getenv("FMB_SPARSE");
+        s->sparse_ok = !(sp && sp[0] == '0');
+        const char* sa = getenv("FMB_SORT_AFTER");
+        s->sort_after = sa && sa[0] == '1';
     }
     if (e != cudaSuccess) {
         fmb_set_error("fmb_session_create: %s", cudaGetErrorString(e));
@@ -220,16 +263,38 @@ static int sort_launch(fmb_session* s, const int32_t* ids, int B, int key_bits, 
                        cudaStream_t st, int* nlaunch) {
     const int64_t N = (int64_t)B * s->F;
     int rc;
-    if (by_field_sort(s, B)) {
-        rc = fmb_sort_fields(ids, B, s->F, s->d_field_off, s->d_skeys_buf[buf], s->d_perm_buf[buf], st);
-        *nlaunch += 1;
+    fmb_runlist_t rl;
+    rl.entries = s->d_runlist_buf[buf]; rl.seg_count = s->d_runcount_buf[buf];
+    if (by_field_sort(s, B)) {   // posflag and the run list come out of the sort kernels themselves; sparse fields skip the sort
+        fmb_runlist_shape(B, s->F, &rl.nseg, &rl.seg_cap);
+        if (!s->sparse_ok) {
+            *nlaunch += 1;
+            return fmb_sort_fields_ex(ids, B, s->F, s->d_field_off, s->d_skeys_buf[buf], s->d_perm_buf[buf],
+                                      s->d_posflag_buf[buf], &rl, 0, st);
+        }
+        // dense fields: radix kernel on `st`; sparse fields: hash kernel beside it on st3 (independent outputs).  The
+        // sparse kernel only writes the position words of multi-hit entries: the others must read 0.
+        cudaMemsetAsync(s->d_posflag_buf[buf], 0, (size_t)N * 4, st);
+        cudaEventRecord(s->ev_sp_fork, st);
+        cudaStreamWaitEvent(s->st3, s->ev_sp_fork, 0);
+        rc = fmb_sort_fields_ex(ids, B, s->F, s->d_field_off, s->d_skeys_buf[buf], s->d_perm_buf[buf], s->d_posflag_buf[buf],
+                                &rl, 1 | 2, st);
+        if (rc) return rc;
+        rc = fmb_sort_fields_ex(ids, B, s->F, s->d_field_off, s->d_skeys_buf[buf], s->d_perm_buf[buf], s->d_posflag_buf[buf],
+                                &rl, 1 | 4, s->st3);
+        cudaEventRecord(s->ev_sp_join, s->st3);
+        cudaStreamWaitEvent(st, s->ev_sp_join, 0);
+        *nlaunch += 2;
+        return rc;
     } else {
         rc = fmb_sort_segment(ids, N, key_bits, radix_ws, s->sort_ws_bytes, s->d_skeys_buf[buf], s->d_perm_buf[buf],
                               nullptr, nullptr, st);
         *nlaunch += 3 * ((key_bits + 7) / 8);
     }
     if (rc) return rc;
-    rc = fmb_pos_flags(s->d_skeys_buf[buf], s->d_perm_buf[buf], N, s->d_posflag_buf[buf], st);
+    rl.nseg = 1; rl.seg_cap = (int)(N / 2 + 1);
+    cudaMemsetAsync(s->d_runcount_buf[buf], 0, 8, st);
+    rc = fmb_pos_flags_ex(s->d_skeys_buf[buf], s->d_perm_buf[buf], N, s->d_posflag_buf[buf], &rl, st);
     *nlaunch += 1;
     return rc;
 }
@@ -247,7 +312,7 @@ static int fm_step_launch(fmb_session* s, const int32_t* ids, const float* xv, c
     *nlaunch = 0;
     cudaEventRecord(s->ev_fork, main);
     cudaStreamWaitEvent(side, s->ev_fork, 0);
-    if (next_ids) {
+    if (next_ids && !s->sort_after) {
         cudaStreamWaitEvent(side2, s->ev_fork, 0);
         rc = sort_launch(s, next_ids, B, key_bits, 1 - cur, s->d_sort_ws2, side2, nlaunch);
         if (rc) return rc;
@@ -263,10 +328,24 @@ static int fm_step_launch(fmb_session* s, const int32_t* ids, const float* xv, c
     if (rc) return rc;
     cudaEventRecord(s->ev_fwd, main);
     cudaStreamWaitEvent(side, s->ev_fwd, 0);
+    if (next_ids && s->sort_after) {
+        // Experiment (FMB_SORT_AFTER=1): the sort of the NEXT batch starts when the fused kernel is done and runs beside
+        // the run kernel and the bias step.  The fused kernel then takes 19 us instead of 26-33 (the sort's CTAs no longer
+        // keep its 1 024 tiles from being resident at once), but the sort chain (~20 us) ends after the run kernel:
+        // 51.8 us per step against 42.7 with the sort started at the top of the graph.
+        cudaStreamWaitEvent(side2, s->ev_fwd, 0);
+        rc = sort_launch(s, next_ids, B, key_bits, 1 - cur, s->d_sort_ws2, side2, nlaunch);
+        if (rc) return rc;
+        cudaEventRecord(s->ev_join2, side2);
+    }
     rc = fmb_finish_step_ex(s->d_delta, s->d_lossv, B, bias, lr, mode, ft, loss_dev ? loss_dev : s->d_loss, side);
     if (rc) return rc;
     cudaEventRecord(s->ev_join, side);
-    rc = fmb_fm_backward_runs_ex(s->d_skeys_buf[cur], N, table, s->F, s->k, lr, mode, ft, s->d_bwd_ws, s->bwd_ws_bytes, main);
+    fmb_runlist_t rl;
+    rl.entries = s->d_runlist_buf[cur]; rl.seg_count = s->d_runcount_buf[cur];
+    if (by_field_sort(s, B)) fmb_runlist_shape(B, s->F, &rl.nseg, &rl.seg_cap);
+    else { rl.nseg = 1; rl.seg_cap = (int)(N / 2 + 1); }
+    rc = fmb_fm_backward_runs_list(s->d_skeys_buf[cur], N, table, s->F, s->k, lr, mode, ft, &rl, s->d_bwd_ws, s->bwd_ws_bytes, main);
     if (rc) return rc;
     cudaStreamWaitEvent(main, s->ev_join, 0);
     if (next_ids) cudaStreamWaitEvent(main, s->ev_join2, 0);
@@ -301,31 +380,36 @@ static int capture_variant(fmb_session* s, StepVariant* v, const int32_t* ids, c
     cudaGraphNode_t nodes[64];
     size_t nn = 64;
     CU(cudaGraphGetNodes(graph, nodes, &nn));
-    const void* sort_fns[3];
-    int sort_np[3];
-    const int nsort = fmb_sort_fields_kernel_fns(sort_fns, sort_np);
-    v->n_fused = v->n_sort_cur = v->n_sort_next = nullptr;
+    const void* sort_fns[8];
+    int sort_np[8], sort_ska[8];
+    const int nsort = fmb_sort_fields_kernel_fns(sort_fns, sort_np, sort_ska);
+    v->n_fused = v->n_finish = nullptr;
+    for (int j = 0; j < 2; ++j) v->n_sort_cur[j] = v->n_sort_next[j] = nullptr;
     for (size_t i = 0; i < nn; ++i) {
         cudaGraphNodeType ty;
         CU(cudaGraphNodeGetType(nodes[i], &ty));
         if (ty != cudaGraphNodeTypeKernel) continue;
         cudaKernelNodeParams kp;
         CU(cudaGraphKernelNodeGetParams(nodes[i], &kp));
-        if (kp.func == fmb_fused_kernel_fn()) { v->n_fused = nodes[i]; continue; }
+        if (fmb_is_fused_kernel_fn(kp.func)) { v->n_fused = nodes[i]; continue; }
+        if (kp.func == fmb_finish_kernel_fn()) { v->n_finish = nodes[i]; continue; }
         for (int t = 0; t < nsort; ++t)
             if (kp.func == sort_fns[t]) {
-                const int32_t* out = *static_cast<int32_t**>(kp.kernelParams[4]);   // sorted_keys argument
-                if (out == s->d_skeys_buf[v->cur]) { v->n_sort_cur = nodes[i]; v->np_sort_cur = sort_np[t]; }
-                else { v->n_sort_next = nodes[i]; v->np_sort_next = sort_np[t]; }
+                const int32_t* out = *static_cast<int32_t**>(kp.kernelParams[sort_ska[t]]);   // sorted_keys argument
+                const bool is_cur = out == s->d_skeys_buf[v->cur];
+                cudaGraphNode_t* dst = is_cur ? v->n_sort_cur : v->n_sort_next;
+                int* dnp = is_cur ? v->np_sort_cur : v->np_sort_next;
+                const int j = dst[0] ? 1 : 0;
+                dst[j] = nodes[i]; dnp[j] = sort_np[t];
             }
     }
-    if (!v->n_fused || (!v->pre && !v->n_sort_cur) || (v->has_next && !v->n_sort_next)) {
+    if (!v->n_fused || !v->n_finish || (!v->pre && !v->n_sort_cur[0]) || (v->has_next && !v->n_sort_next[0])) {
         cudaGraphDestroy(graph);
         fmb_set_error("step graph: kernel nodes not found");
         return FMB_ERR_CUDA;
     }
     cudaGraphExec_t exec = nullptr;
-    e = cudaGraphInstantiate(&exec, graph, 0);
+    e = cudaGraphInstantiate(&exec, graph, s->use_prio ? cudaGraphInstantiateFlagUseNodePriority : 0);
     if (e != cudaSuccess) { cudaGraphDestroy(graph); fmb_set_error("graph instantiate: %s", cudaGetErrorString(e)); return FMB_ERR_CUDA; }
     v->graph = graph; v->exec = exec; v->nlaunch = nl;
     return FMB_OK;
@@ -397,17 +481,28 @@ FMB_API int fmb_session_fm_step_next(fmb_session* s, const int32_t* ids, const f
         if (!pre) {
             const void* repl[16] = {nullptr};
             repl[0] = &ids;
-            rc = patch_node(v->exec, v->n_sort_cur, v->np_sort_cur, repl);
-            if (rc) return rc;
+            for (int j = 0; j < 2 && v->n_sort_cur[j]; ++j) {
+                rc = patch_node(v->exec, v->n_sort_cur[j], v->np_sort_cur[j], repl);
+                if (rc) return rc;
+            }
         }
         if (next_ids) {
             const void* repl[16] = {nullptr};
             repl[0] = &next_ids;
-            rc = patch_node(v->exec, v->n_sort_next, v->np_sort_next, repl);
+            for (int j = 0; j < 2 && v->n_sort_next[j]; ++j) {
+                rc = patch_node(v->exec, v->n_sort_next[j], v->np_sort_next[j], repl);
+                if (rc) return rc;
+            }
+        }
+        {   // the bias-step kernel writes the mean loss straight to the caller's scalar (a 4-byte copy behind every graph
+            // launch was a stream operation of its own: ~4 us of bubble per step)
+            float* lo = loss_dev ? loss_dev : s->d_loss;
+            const void* repl[16] = {nullptr};
+            repl[6] = &lo;
+            rc = patch_node(v->exec, v->n_finish, 9, repl);
             if (rc) return rc;
         }
         CU(cudaGraphLaunch(v->exec, stream));
-        if (loss_dev && loss_dev != s->d_loss) CU(cudaMemcpyAsync(loss_dev, s->d_loss, 4, cudaMemcpyDeviceToDevice, stream));
         s->launches += v->nlaunch;
     }
     CU(cudaEventRecord(s->ev_buf_free[cur], stream));

@@ -129,6 +129,25 @@ int fmb_sort_segment(const int32_t* keys_dev, int64_t N, int key_bits, void* ws_
 int fmb_sort_fields_max_batch(void);
 int fmb_sort_fields(const int32_t* ids_dev, int B, int F, const int32_t* field_off_dev, int32_t* sorted_keys_dev,
                     int32_t* perm_dev, fmb_stream_t stream);
+/* Run list: what the sort hands to the run kernel of the FM step (round 2).  One entry of 4 int32 per run of >= 2 equal
+ * sorted keys: {first sorted position, key, entries of the run among its first 32 positions (2..32), 1 if the run has
+ * at least 128 entries else 0}; entries_dev is
+ * [nseg][seg_cap][4], seg_count_dev [2*nseg]: segment g holds seg_count_dev[g] runs of fewer than 128 entries from its
+ * start upwards and seg_count_dev[nseg + g] longer runs from its end downwards, in any order (one segment per producer
+ * CTA: no global counter, nothing to zero).  fmb_runlist_shape gives the shape fmb_sort_fields_ex fills for a batch. */
+typedef struct fmb_runlist_t { int32_t* entries_dev; uint32_t* seg_count_dev; int nseg, seg_cap; } fmb_runlist_t;
+void fmb_runlist_shape(int B, int F, int* nseg, int* seg_cap);
+/* _ex: the sort kernels also write what the FM step of the NEXT section consumes, saving a kernel behind the sort:
+ * posflag_dev [B*F] (as fmb_pos_flags, nullable) and the run list rl (nullable).  flags & FMB_SORT_SPARSE_OK (needs
+ * posflag_dev): fields with >= 16*B rows are not sorted at all -- a shared-memory hash pass finds the entries whose row is
+ * hit more than once; sorted_keys_dev / perm_dev then hold only those entries, in (key, sample) order at the head of the
+ * field's range [f*B, (f+1)*B), sorted_keys_dev is -1 behind them, perm_dev undefined there; posflag_dev of the other
+ * entries of those fields is NOT written: the caller clears posflag_dev (cudaMemsetAsync) in front of the call.  That is
+ * all the FM step reads (rows hit once are updated inside fmb_fm_step_fused and their position is never used). */
+#define FMB_SORT_SPARSE_OK 1
+int64_t fmb_sort_fields_sparse_min_rows(int B);   /* rows a field needs to skip its sort at batch B; 0 = never at this B */
+int fmb_sort_fields_ex(const int32_t* ids_dev, int B, int F, const int32_t* field_off_dev, int32_t* sorted_keys_dev,
+                       int32_t* perm_dev, uint32_t* posflag_dev, const fmb_runlist_t* rl, int flags, fmb_stream_t stream);
 
 /* ---- A1-A3 + A6 fused: the FM-only step with every row read once (csrc/fm_step.cu) ----------------
  * replaces forward_fm + F.binary_cross_entropy_with_logits + loss.backward() + optimizer.step() of
@@ -154,6 +173,16 @@ int fmb_finish_step_ex(const float* delta_dev, const float* lossv_dev, int B, fl
                        const fmb_ftrl_t* ftrl, float* loss_dev, fmb_stream_t stream);
 int fmb_pos_flags(const int32_t* sorted_keys_dev, const int32_t* perm_dev, int64_t N, uint32_t* posflag_dev,
                   fmb_stream_t stream);
+/* run-list forms (round 2): fmb_pos_flags_ex also appends the runs of >= 2 equal keys to rl, which must be ONE segment
+ * (nseg == 1, seg_cap >= N/2) whose counters seg_count_dev[0..1] the caller zeroes beforehand (used behind fmb_sort_segment;
+ * fmb_sort_fields_ex needs neither).  fmb_fm_backward_runs_list starts one warp per listed run instead of one per 32
+ * sorted positions (all runs of a Criteo-shaped batch in flight at once; the first CTAs of the grid take the runs of
+ * >= 128 entries with a deeper ring started at the run's first entry).  rl == NULL: the plain forms. */
+int fmb_pos_flags_ex(const int32_t* sorted_keys_dev, const int32_t* perm_dev, int64_t N, uint32_t* posflag_dev,
+                     const fmb_runlist_t* rl, fmb_stream_t stream);
+int fmb_fm_backward_runs_list(const int32_t* sorted_keys_dev, int64_t N, float* table_dev, int F, int k, float lr, int mode,
+                              const fmb_ftrl_t* ftrl, const fmb_runlist_t* rl, void* ws_dev, size_t ws_bytes,
+                              fmb_stream_t stream);
 int fmb_fm_step_fused(const int32_t* ids_dev, const float* xv_dev /*nullable*/, const float* y_dev, float* table_dev,
                       const float* bias_dev, const uint32_t* posflag_dev, int B, int F, int k, int loss_kind, float lr,
                       int mode, float* delta_dev, float* lossv_dev, void* ws_dev, size_t ws_bytes, fmb_stream_t stream);

@@ -7,6 +7,9 @@
  *     /tmp/verify_math divc      # s / c == fma(fma(-q, c, s), rc, q), q = s*rc, for all mantissas, binades 2^-104 .. 2^122
  *     /tmp/verify_math window    # the Adam window test never disagrees with the full pipeline (4e8 random triples,
  *                                # reciprocal perturbed by +-1 ulp)
+ *     /tmp/verify_math qbound    # the invariant behind the window test: the pipeline's step q lies within 2^-19 (relative)
+ *                                # of the cheap estimate U = (A*|g|) * rcp(|g| + c0) for EVERY binade of |g| in
+ *                                # [1e-25, 1e15) (2^18 random mantissas per binade x 6 learning rates x rcp +-1 ulp)
  * Results recorded in DESIGN.md section 4 (round 2, build container: glibc 2.39, x86-64 with FMA).
  */
 #include "oracle_math.h"
@@ -56,20 +59,69 @@ static int adam_window(float p, float g, float lr, int pert, float* out) {
     if (ra == rb) { *out = ra; return 1; }
     return 0;
 }
+/* general window (round 2, second form): one reciprocal of (|g| + c0), valid for every tau */
+static float adam_U(float g, float lr, int pert) {
+    const float a = -(lr / 0.1f), ag = fabsf(g);
+    const float den = ag + 9.99999905e-09f;
+    float rc = 1.0f / den;
+    rc = orc_bits2f(orc_f2bits(rc) + pert);
+    const float A = a * 0.099999994f;
+    float U = (A * ag) * rc;
+    return g < 0.f ? -U : U;
+}
+static int adam_window2(float p, float g, float lr, int pert, float* out) {
+    const float ag = fabsf(g);
+    if (!(ag >= 1e-25f && ag < 1e15f)) return 0;
+    const float U = adam_U(g, lr, pert);
+    const float ra = p + fmaf(U, 1.9073486328125e-06f, U), rb = p + fmaf(-U, 1.9073486328125e-06f, U);
+    if (ra == rb) { *out = ra; return 1; }
+    return 0;
+}
+static int check_qbound(void) {
+    const float lrs[] = {1e-5f, 1e-4f, 1e-3f, 1e-2f, 0.05f, 3e-3f};
+    const float bc2s = 0.03162277660168381f;
+    double worst = 0; long n = 0, bad = 0;
+    srand48(7);
+    for (int e = -84; e < 50; ++e) {          /* 2^-84 = 5e-26 .. 2^50 = 1.1e15 */
+        double wb = 0;
+        for (int it = 0; it < (1 << 18); ++it) {
+            float g = (float)ldexp(1.0 + drand48(), e);
+            if (!(g >= 1e-25f && g < 1e15f)) continue;
+            if (it & 1) g = -g;
+            for (int l = 0; l < 6; ++l) {
+                const float lr = lrs[l], a = -(lr / 0.1f);
+                const float m = 0.1f * g, v = (0.001f * g) * g, d = (orc_sqrt_mkl(v) / bc2s) + 1e-8f;
+                const float q = (a * m) / d;
+                for (int pert = -1; pert <= 1; ++pert) {
+                    const float U = adam_U(g, lr, pert);
+                    const double rel = fabs((double)q - (double)U) / fabs((double)U) * 16777216.0;   /* units of 2^-24 */
+                    if (rel > wb) wb = rel;
+                    ++n;
+                    if (!(rel < 32.0)) ++bad;
+                }
+            }
+        }
+        if (wb > worst) worst = wb;
+        if (wb > 14.0) printf("binade 2^%d: worst |q-U|/|U| = %.2f * 2^-24\n", e, wb);
+    }
+    printf("qbound: %ld cases, worst %.2f * 2^-24 (window half-width 32 * 2^-24), %ld outside\n", n, worst, bad);
+    return bad != 0;
+}
+
 static int check_window(void) {
     const float lrs[] = {1e-4f, 1e-3f, 1e-2f, 0.05f, 3e-3f};
     long n = 0, fast = 0, bad = 0;
     srand48(1);
     for (long it = 0; it < 400000000L; ++it) {
         const float lr = lrs[it % 5];
-        float g = (float)(exp((drand48() * 24 - 17) * 0.6931471805599453) * (0.5 + drand48()));
+        float g = (float)(exp((drand48() * (it & 1 ? 60 : 24) - (it & 1 ? 53 : 17)) * 0.6931471805599453) * (0.5 + drand48()));
         if (lrand48() & 1) g = -g;
         const float p = (float)((drand48() * 2 - 1) * exp((drand48() * 12 - 10) * 0.6931471805599453) * 4);
         const float ex = adam_exact(p, g, lr);
         ++n;
         for (int pert = -1; pert <= 1; ++pert) {
             float o;
-            if (adam_window(p, g, lr, pert, &o)) {
+            if ((it & 1 ? adam_window2 : adam_window)(p, g, lr, pert, &o)) {
                 if (pert == 0) ++fast;
                 if (orc_f2bits(o) != orc_f2bits(ex)) { if (++bad < 10) printf("BAD p=%a g=%a lr=%g\n", p, g, lr); }
             }
@@ -80,8 +132,9 @@ static int check_window(void) {
 }
 
 int main(int argc, char** argv) {
-    if (argc < 2) { fprintf(stderr, "usage: verify_math expf|divc|window\n"); return 2; }
+    if (argc < 2) { fprintf(stderr, "usage: verify_math expf|divc|window|qbound\n"); return 2; }
     if (argv[1][0] == 'e') return check_expf();
     if (argv[1][0] == 'd') return check_divc();
+    if (argv[1][0] == 'q') return check_qbound();
     return check_window();
 }

@@ -137,6 +137,83 @@ def test_sort_fields_matches_global_stable_sort(B):
     order = np.argsort(flat, kind="stable").astype(np.int32)
     assert np.array_equal(pm.cpu().numpy(), order)
     assert np.array_equal(sk.cpu().numpy(), flat[order])
+    # the sort's tail (posflag + run list), the stand-alone kernel behind the generic sort, and the sparse-field hash
+    # pass (fields with >= 16*B rows are not sorted: only their multi-hit entries are placed) give what numpy gives
+    from fm_for_online_recommendation_b200._lib import RunList
+    exp_pf, exp_runs = _posflag_and_runs(flat, order)
+    N = B * F
+    nseg, cap = C.c_int(), C.c_int()
+    lib.fmb_runlist_shape(B, F, C.byref(nseg), C.byref(cap))
+    nseg, cap = nseg.value, cap.value
+    skn, multi = flat[order], (exp_pf >> 31).astype(bool)
+    for producer in ("sort_tail", "pos_flags", "sparse"):
+        pf = torch.zeros(N, dtype=torch.int32, device="cuda")
+        one = producer == "pos_flags"
+        rl = torch.full((max(nseg * cap, N // 2 + 1), 4), -1, dtype=torch.int32, device="cuda")
+        rc_ = torch.zeros(2 * nseg, dtype=torch.int32, device="cuda")
+        desc = RunList(rl.data_ptr(), rc_.data_ptr(), 1 if one else nseg, N // 2 + 1 if one else cap)
+        sk.zero_(); pm.zero_()
+        if producer == "pos_flags":
+            assert lib.fmb_sort_fields(p(d), B, F, p(doff), p(sk), p(pm), None) == 0
+            assert lib.fmb_pos_flags_ex(p(sk), p(pm), N, p(pf), C.byref(desc), None) == 0, lib.fmb_last_error()
+        else:
+            assert lib.fmb_sort_fields_ex(p(d), B, F, p(doff), p(sk), p(pm), p(pf), C.byref(desc),
+                                          1 if producer == "sparse" else 0, None) == 0, lib.fmb_last_error()
+        torch.cuda.synchronize()
+        counts = rc_.cpu().numpy()
+        rln, cp_ = rl.cpu().numpy(), desc.seg_cap
+        short = [rln[g * cp_: g * cp_ + counts[g]] for g in range(desc.nseg)]                                   # upwards from the start
+        long_ = [rln[(g + 1) * cp_ - counts[desc.nseg + g]: (g + 1) * cp_] for g in range(desc.nseg)]            # downwards from the end
+        got = np.concatenate(short + long_ + [np.zeros((0, 4), np.int32)])
+        assert all(np.all(a[:, 3] == 0) for a in short) and all(np.all(a[:, 3] == 1) for a in long_)
+        gpf = pf.cpu().numpy().view(np.uint32)
+        gsk, gpm = sk.cpu().numpy(), pm.cpu().numpy()
+        if producer != "sparse":
+            assert np.array_equal(gpm, order) and np.array_equal(gsk, skn)
+            assert np.array_equal(gpf, exp_pf), producer
+            assert len(got) == len(exp_runs), producer
+            assert np.array_equal(got[np.argsort(got[:, 0])], exp_runs), producer
+            continue
+        # sparse contract: same multi-hit flags; per field the multi-hit entries in (key, sample) order at the head of the
+        # field's range, -1 behind them; every listed run is a run of the placed keys; dense fields as before
+        assert np.array_equal(gpf >> 31, exp_pf >> 31)
+        min_rows = lib.fmb_sort_fields_sparse_min_rows(B) or (1 << 40)
+        for f in range(F):
+            lo, hi = f * B, (f + 1) * B
+            if sizes[f] < min_rows:
+                assert np.array_equal(gsk[lo:hi], skn[lo:hi]) and np.array_equal(gpm[lo:hi], order[lo:hi])
+                ent = order[lo:hi]
+                assert np.array_equal(gpf[ent], exp_pf[ent])
+                continue
+            ms = multi[order[lo:hi]]                  # sorted positions of the field whose entry is multi-hit
+            nm = int(ms.sum())
+            assert np.array_equal(gsk[lo:lo + nm], skn[lo:hi][ms]) and np.all(gsk[lo + nm:hi] == -1)
+            assert np.array_equal(gpm[lo:lo + nm], order[lo:hi][ms])
+            assert np.array_equal(gpf[gpm[lo:lo + nm]] & 0x7fffffff, np.arange(lo, lo + nm, dtype=np.uint32))
+        # run list == the runs of the placed keys
+        placed = gsk.copy()
+        same_prev = np.concatenate([[False], (placed[1:] == placed[:-1]) & (placed[1:] >= 0)])
+        same_next = np.concatenate([(placed[:-1] == placed[1:]) & (placed[:-1] >= 0), [False]])
+        starts = np.flatnonzero(same_next & ~same_prev)
+        ends = np.flatnonzero(same_prev & ~same_next)
+        exp2 = np.stack([starts, placed[starts], np.minimum(ends - starts + 1, 32), ends - starts + 1 >= 128], 1).astype(np.int32)
+        assert len(got) == len(exp2)
+        assert np.array_equal(got[np.argsort(got[:, 0])], exp2)
+
+
+def _posflag_and_runs(flat, order):
+    """numpy statement of radix_sort.cu sort_tail / fm_step.cu pos_flags_kernel"""
+    sk = flat[order]
+    N = len(sk)
+    same_prev = np.concatenate([[False], sk[1:] == sk[:-1]])
+    same_next = np.concatenate([sk[:-1] == sk[1:], [False]])
+    multi = same_prev | same_next
+    pf = np.zeros(N, np.uint32)
+    pf[order] = np.arange(N, dtype=np.uint32) | (multi.astype(np.uint32) << 31)
+    starts = np.flatnonzero(multi & ~same_prev)
+    ends = np.flatnonzero(multi & ~same_next)
+    n0 = np.minimum(ends - starts + 1, 32)
+    return pf, np.stack([starts, sk[starts], n0, ends - starts + 1 >= 128], 1).astype(np.int32)   # last: "long run" flag
 
 
 @pytest.mark.parametrize("n", [1, 5, 7, 8, 39, 511, 512, 513, 2500, 4096, 8192, 20000, 100003, 600001])
