@@ -66,6 +66,7 @@ struct BwdParams {
     const int4* run_list;          // [run_nseg][run_cap] entries, segment g holds run_segc[g] of them
     const uint32_t* run_segc;
     int run_nseg, run_cap;
+    int pdl;                       // 1: launched as a programmatic dependent of the kernel that stages G
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -297,6 +298,9 @@ __device__ __forceinline__ void runs_body(const CUtensorMap& gmap, const BwdPara
         const uint32_t total = seg_base[p.run_nseg];
         ln = total;
         if (wib >= warps_per_block) return;
+        // launched with programmatic stream serialization behind the fused kernel (session.cu): everything above only
+        // reads the sort's outputs; the staged contributions and the rows are complete once the fused grid has finished
+        if (p.pdl) asm volatile("griddepcontrol.wait;\n" ::: "memory");
     } else {
         // keys of this warp's 32 positions and of the 32 after them (one memory latency for both)
         const int64_t pos = P0 + lane;
@@ -647,8 +651,21 @@ static int launch_runs(BwdParams& p, bool two, cudaStream_t stream) {
     const unsigned nlong = (unsigned)sms;                                   // one long-run CTA per SM
     unsigned nshort = (unsigned)(sms * (per_sm > 1 ? per_sm - 1 : 1));
     if (nshort > grid) nshort = grid;
-    fm_bwd_runs_list_kernel<<<nlong + nshort, 32 * wpb, smd + segb, stream>>>(gmap, gmap_l, p, wpb, warp_f, wpl, warp_f_l, accs_n,
-                                                                             ring_comps, nlong, (int)(smd / 4));
+    if (p.pdl) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(nlong + nshort); cfg.blockDim = dim3(32 * wpb); cfg.dynamicSmemBytes = smd + segb; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const cudaError_t le = cudaLaunchKernelEx(&cfg, fm_bwd_runs_list_kernel, gmap, gmap_l, p, wpb, warp_f, wpl, warp_f_l, accs_n,
+                                                  ring_comps, nlong, (int)(smd / 4));
+        if (le != cudaSuccess) { fmb_set_error("fm_bwd_runs_list_kernel (programmatic launch): %s", cudaGetErrorString(le)); return FMB_ERR_CUDA; }
+    } else {
+        fm_bwd_runs_list_kernel<<<nlong + nshort, 32 * wpb, smd + segb, stream>>>(gmap, gmap_l, p, wpb, warp_f, wpl, warp_f_l, accs_n,
+                                                                                 ring_comps, nlong, (int)(smd / 4));
+    }
     FMB_CHECK_LAUNCH("fm_bwd_runs_list_kernel");
     return FMB_OK;
 }
@@ -714,6 +731,11 @@ struct fmb_ftrl_t { float* zn; float* bias_zn; float beta, l1, l2; };   // inclu
 // one warp is started per RUN instead of per 32 sorted positions.
 struct fmb_runlist_t { int32_t* entries; uint32_t* seg_count; int nseg, seg_cap; };   // include/fmb200.h
 
+static int g_runs_pdl = 0;
+// internal (session.cu): the NEXT fmb_fm_backward_runs_list call is launched as a programmatic dependent of the kernel
+// in front of it on its stream (the fused kernel, which executes griddepcontrol.launch_dependents)
+FMB_API void fmb_runs_list_next_is_dependent(int on) { g_runs_pdl = on; }
+
 FMB_API int fmb_fm_backward_runs_list(const int32_t* sorted_keys, int64_t N, float* table, int F, int k, float lr,
                                       int mode, const fmb_ftrl_t* ftrl, const fmb_runlist_t* rl,
                                       void* ws, size_t ws_bytes, cudaStream_t stream) {
@@ -734,6 +756,8 @@ FMB_API int fmb_fm_backward_runs_list(const int32_t* sorted_keys, int64_t N, flo
     p.G = (float*)ws;
     if (mode == 2) { p.ftrl.zn = ftrl->zn; p.ftrl.bias_zn = ftrl->bias_zn; p.ftrl.beta = ftrl->beta; p.ftrl.l1 = ftrl->l1; p.ftrl.l2 = ftrl->l2; }
     if (rl) { p.run_list = reinterpret_cast<const int4*>(rl->entries); p.run_segc = rl->seg_count; p.run_nseg = rl->nseg; p.run_cap = rl->seg_cap; }
+    p.pdl = rl ? g_runs_pdl : 0;
+    g_runs_pdl = 0;
     p.dbg = g_runs_dbg;
     return launch_runs(p, false, stream);
 }

@@ -81,6 +81,10 @@ __global__ void __launch_bounds__(256) fm_step_fused_kernel(const int32_t* __res
     __syncthreads();
     const int b0 = blockIdx.x * SB;
     const int nv = min(SB, p.B - b0);
+    // programmatic dependent launch: the run kernel behind this one may be launched (and run its prologue: segment
+    // counts, list entry, mbarriers) as soon as every CTA of this grid has started; it waits for this grid's completion
+    // (griddepcontrol.wait) before it reads the staged contributions.  No effect without the launch attribute.
+    asm volatile("griddepcontrol.launch_dependents;\n" ::);
 #define FMB_TS(i) do { if (p.tdbg && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); p.tdbg[(size_t)blockIdx.x * 8 + (i)] = (long long)t_; } } while (0)
     FMB_TS(0);
 

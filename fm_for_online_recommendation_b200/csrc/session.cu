@@ -38,6 +38,7 @@ int fmb_fm_step_fused(const int32_t*, const float*, const float*, float*, const 
                       int, float, int, float*, float*, void*, size_t, cudaStream_t);
 int fmb_fm_backward_runs(const int32_t*, int64_t, float*, int, int, float, int, void*, size_t, cudaStream_t);
 int fmb_is_fused_kernel_fn(const void*);
+void fmb_runs_list_next_is_dependent(int);
 const void* fmb_finish_kernel_fn(void);
 int fmb_sort_fields_kernel_fns(const void**, int*, int*);
 }
@@ -111,11 +112,15 @@ struct fmb_session {
     int64_t steps_done;
     cudaEvent_t ev_fork, ev_fwd, ev_sort, ev_join;
     int use_graph, use_prio;
+    int use_pdl;           // FMB_PDL=0 switches the programmatic dependent launch of the run kernel off
     int sort_after;        // FMB_SORT_AFTER=1 (experiment; default 0): the next batch's sort waits for the fused kernel
     int sparse_ok;         // FMB_SORT_SPARSE_OK unless FMB_SPARSE=0: fields with >= 16*B rows skip the sort (radix_sort.cu)
     int ngraphs, next_evict;
     StepVariant gvar[FMB_GRAPH_CACHE];
     cudaEvent_t ev_join2;
+    // graphs of stand-alone pre-sorts (host entry point: one per input slot and sorted buffer), keyed by ids pointer
+    struct { const int32_t* ids; int B, key_bits, buf, nl; cudaGraphExec_t exec; cudaGraph_t graph; } psg[8];
+    int npsg, presort_warm;
     fmb_ftrl_t ftrl;       // update mode 2 (fmb_session_set_ftrl)
     int ftrl_set;
 };
@@ -133,6 +138,7 @@ FMB_API void fmb_session_destroy(fmb_session* s) {
     for (int i = 0; i < 2; ++i) { cudaFree(s->d_skeys_buf[i]); cudaFree(s->d_perm_buf[i]); cudaFree(s->d_posflag_buf[i]); cudaFree(s->d_runlist_buf[i]); cudaFree(s->d_runcount_buf[i]); if (s->ev_buf_free[i]) cudaEventDestroy(s->ev_buf_free[i]); }
     cudaFree(s->d_sort_ws2);
     if (s->ev_join2) cudaEventDestroy(s->ev_join2);
+    for (int i = 0; i < s->npsg; ++i) if (s->psg[i].exec) { cudaGraphExecDestroy(s->psg[i].exec); cudaGraphDestroy(s->psg[i].graph); }
     if (s->ev_sp_fork) cudaEventDestroy(s->ev_sp_fork);
     if (s->ev_sp_join) cudaEventDestroy(s->ev_sp_join);
     if (s->st3) cudaStreamDestroy(s->st3);
@@ -229,6 +235,8 @@ FMB_API int fmb_session_create(fmb_session** out, int F, int k, int64_t max_batc
         s->use_graph = !(ng && ng[0] == '1');
         const char* sp = getenv("FMB_SPARSE");
         s->sparse_ok = !(sp && sp[0] == '0');
+        const char* pd = getenv("FMB_PDL");
+        s->use_pdl = !(pd && pd[0] == '0');
         const char* sa = getenv("FMB_SORT_AFTER");
         s->sort_after = sa && sa[0] == '1';
     }
@@ -345,6 +353,7 @@ static int fm_step_launch(fmb_session* s, const int32_t* ids, const float* xv, c
     rl.entries = s->d_runlist_buf[cur]; rl.seg_count = s->d_runcount_buf[cur];
     if (by_field_sort(s, B)) fmb_runlist_shape(B, s->F, &rl.nseg, &rl.seg_cap);
     else { rl.nseg = 1; rl.seg_cap = (int)(N / 2 + 1); }
+    fmb_runs_list_next_is_dependent(s->use_pdl);
     rc = fmb_fm_backward_runs_list(s->d_skeys_buf[cur], N, table, s->F, s->k, lr, mode, ft, &rl, s->d_bwd_ws, s->bwd_ws_bytes, main);
     if (rc) return rc;
     cudaStreamWaitEvent(main, s->ev_join, 0);
@@ -531,8 +540,33 @@ static int presort_impl(fmb_session* s, const int32_t* ids, int B, int key_bits,
     if (s->buf_used[buf]) CU(cudaStreamWaitEvent(s->st2, s->ev_buf_free[buf], 0));
     if (ready) CU(cudaStreamWaitEvent(s->st2, ready, 0));
     int nl = 0;
-    const int rc = sort_launch(s, ids, B, key_bits, buf, s->d_sort_ws2 ? s->d_sort_ws2 : s->d_sort_ws, s->st2, &nl);
-    if (rc) return rc;
+    if (s->use_graph && s->presort_warm && by_field_sort(s, B)) {
+        // memset + radix kernel + sparse-field kernel on two streams with their events: one graph launch instead of
+        // nine stream operations (the host entry point is bound by the host's submission time)
+        int g = -1;
+        for (int i = 0; i < s->npsg; ++i)
+            if (s->psg[i].ids == ids && s->psg[i].B == B && s->psg[i].key_bits == key_bits && s->psg[i].buf == buf) g = i;
+        if (g < 0) {
+            cudaGraph_t graph = nullptr;
+            CU(cudaStreamBeginCapture(s->st2, cudaStreamCaptureModeThreadLocal));
+            const int rc = sort_launch(s, ids, B, key_bits, buf, s->d_sort_ws2 ? s->d_sort_ws2 : s->d_sort_ws, s->st2, &nl);
+            const cudaError_t e = cudaStreamEndCapture(s->st2, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) { fmb_set_error("pre-sort graph capture: %s", cudaGetErrorString(e)); return FMB_ERR_CUDA; }
+            cudaGraphExec_t exec = nullptr;
+            if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGraphDestroy(graph); fmb_set_error("pre-sort graph instantiate failed"); return FMB_ERR_CUDA; }
+            g = s->npsg < 8 ? s->npsg++ : 0;
+            if (s->psg[g].exec) { cudaGraphExecDestroy(s->psg[g].exec); cudaGraphDestroy(s->psg[g].graph); }
+            s->psg[g].ids = ids; s->psg[g].B = B; s->psg[g].key_bits = key_bits; s->psg[g].buf = buf; s->psg[g].nl = nl;
+            s->psg[g].exec = exec; s->psg[g].graph = graph;
+        }
+        nl = s->psg[g].nl;
+        CU(cudaGraphLaunch(s->psg[g].exec, s->st2));
+    } else {
+        const int rc = sort_launch(s, ids, B, key_bits, buf, s->d_sort_ws2 ? s->d_sort_ws2 : s->d_sort_ws, s->st2, &nl);
+        if (rc) return rc;
+        s->presort_warm = 1;
+    }
     CU(cudaEventRecord(s->ev_presort, s->st2));
     s->launches += nl;
     s->presort_ids = ids; s->presort_B = B; s->presort_buf = buf; s->presort_ext = 1;
@@ -553,11 +587,19 @@ FMB_API void fmb_session_presort_invalidate(fmb_session* s) {
 
 // true when `p` is page-locked host memory the copy engine can read directly (no staging copy needed)
 static bool host_ptr_is_pinned(const void* p) {
+    // the answer for the last few pointers is remembered (a training loop passes the same pinned buffers again and again;
+    // cudaPointerGetAttributes is a driver call)
+    static thread_local const void* seen[16];
+    static thread_local bool pinned[16];
+    static thread_local int nseen = 0, nextw = 0;
+    for (int i = 0; i < nseen; ++i) if (seen[i] == p) return pinned[i];
     cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost;
+    bool r = false;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) cudaGetLastError();
+    else r = a.type == cudaMemoryTypeHost;
+    seen[nextw] = p; pinned[nextw] = r; nextw = (nextw + 1) % 16; if (nseen < 16) ++nseen;
+    return r;
 }
-
 // Pipelined step with HOST inputs.  `slot` (0 or 1) selects one of two device input buffers: the copies of
 // step t+1 (on the session's copy stream) overlap the kernels of step t (on `stream`).  Pinned / registered
 // host buffers are read in place, pageable ones go through the session's pinned staging area.  The loss
@@ -593,10 +635,12 @@ FMB_API int fmb_session_fm_step_host_async(fmb_session* s, int slot, const int32
     // the sort of this batch starts as soon as its ids have landed: it overlaps the step still in flight
     int rc = presort_impl(s, d_ids, B, key_bits, s->ev_h2d[slot]);
     if (rc) return rc;
+    // the bias-step kernel writes the mean loss straight into the pinned result word (4 bytes over PCIe: the D2H of the
+    // step, without a copy operation of its own)
+    (void)d_loss;
     rc = fmb_session_fm_step(s, d_ids, xv_host ? d_xv : nullptr, d_y, B, table, bias, key_bits, loss_kind, lr,
-                                 mode, d_loss, stream);
+                                 mode, s->h_loss + 8 * slot, stream);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(s->h_loss + 8 * slot, d_loss, 4, cudaMemcpyDeviceToHost, stream));
     CU(cudaEventRecord(s->ev_done[slot], stream));
     s->slot_used[slot] = 1;
     return FMB_OK;

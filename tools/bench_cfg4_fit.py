@@ -1,6 +1,6 @@
 """BASELINE configs[3]: one DeepFMAdam.fit (fwd + tower bwd + table/tower/bias updates) at B = 8192, k = 10,
 400-400-400 tower, 1 006 628-row tables; tensor-core tower vs the exact SIMT tower.  Prints one JSON line.
-    python scratch/bench_cfg4_fit.py [--steps 50] [--tc-only]"""
+    python tools/bench_cfg4_fit.py [--steps 50] [--tc-only]"""
 import sys, os, json, argparse, ctypes as C
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

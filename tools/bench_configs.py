@@ -1,5 +1,5 @@
 """Timings of the other BASELINE.json configs on one B200 (CUDA events / wall clock for the persistent online kernels).
-Prints one JSON object.  python scratch/bench_configs.py"""
+Prints one JSON object.  python tools/bench_configs.py"""
 import sys, os, io, json, time, contextlib
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,4 +1,4 @@
-# usage: bash scratch/job_ncu_list.sh <tag>  -- bench line + ncu launch list (per-kernel durations, serialised, cold cache)
+# usage: bash tools/job_ncu_list.sh <tag>  -- bench line + ncu launch list (per-kernel durations, serialised, cold cache)
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 tag=$1
 A="--no-cpu-baseline --no-extra"

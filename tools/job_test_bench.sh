@@ -1,4 +1,4 @@
-# usage: bash scratch/job_test_bench.sh <tag> [pytest args...]   -- GPU suite, then the bench line under the driver's arguments
+# usage: bash tools/job_test_bench.sh <tag> [pytest args...]   -- GPU suite, then the bench line under the driver's arguments
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 tag=$1; shift
 timeout 900 python -m pytest tests -m gpu -x -q "$@" > gpurun_out/${tag}_gputest.log 2>&1; tail -4 gpurun_out/${tag}_gputest.log

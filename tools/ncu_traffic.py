@@ -1,5 +1,5 @@
 """ncu raw CSV (ncu -i X.ncu-rep --page raw --csv) -> {kernel: {dram_read_bytes, dram_write_bytes, duration_us}} (first launch
-of each kernel name).  usage: python scratch/ncu_traffic.py raw.csv out.json"""
+of each kernel name).  usage: python tools/ncu_traffic.py raw.csv out.json"""
 import csv, json, sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units = rows[0], rows[1]

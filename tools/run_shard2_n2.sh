@@ -1,7 +1,7 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 N=${1:-2}
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 tests/sharded2_check.py --graph 2>&1 | grep -E "SHARD2|Error|error" | head -5
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29536 scratch/time_shard2_phases.py 2>&1 | grep "G=" 
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29536 tools/time_shard2_phases.py 2>&1 | grep "G=" 
 FMB_SHARD=2 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29535 bench.py --gpus $N --steps 50 --warmup 10 2>&1 | grep '^{' | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print('N', d['n_gpus'], 'ms/step', d['ms_per_step'], 'value', d['value'], 'e2e', d['e2e']['value'], 'timeouts', d['config']['exchange_timeouts'])"
