@@ -54,6 +54,7 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.p = None
+        self.gpu = gpu_index
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
                                        "--format=csv,noheader,nounits", "-lms", "50"],
@@ -83,6 +84,15 @@ class ClockSampler:
             for nme, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nme)
+        if not sm:   # the sampler never got a line out (very short run): one synchronous query, flagged as such
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout
+                f = [x.strip() for x in out.strip().splitlines()[0].split(",")]
+                sm.append(float(f[0])); mx.append(float(f[1]))
+                reasons.add("sampled after the timed region")
+            except Exception:
+                pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
 

@@ -678,11 +678,16 @@ static int launch_runs(BwdParams& p, bool two, cudaStream_t stream) {
 // _ex adds: n_entries = 1 + the largest entry index stored in perm (B*F; the sharded path passes
 //   world*B*F), s_pitch / gs_stride (S, gvec and gs may live inside a gathered per-sample context),
 //   key_limit (sorted keys >= key_limit are padding and are skipped).
-FMB_API int fmb_fm_backward_update_ex(const int32_t* sorted_keys, const int32_t* perm, int64_t N, int64_t n_entries,
+// _rl: with the run list of the sorted keys (nullable; fmb_shard_sort_fields_rl / fmb_sort_fields_ex) the run kernel starts
+// one warp per run, the long runs first (the owner-side chains of the sharded step are G*B/rows long)
+struct fmb_runlist_t { int32_t* entries; uint32_t* seg_count; int nseg, seg_cap; };   // include/fmb200.h
+FMB_API int fmb_fm_backward_update_rl(const int32_t* sorted_keys, const int32_t* perm, int64_t N, int64_t n_entries,
                                       const float* xv, float* table, int F, int k, const float* S, int s_pitch,
                                       const float* gs, int gs_stride, int use_fm2, const float* gvec,
-                                      int32_t key_limit, float lr, int mode, void* ws, size_t ws_bytes,
+                                      int32_t key_limit, float lr, int mode, const fmb_runlist_t* rl, void* ws, size_t ws_bytes,
                                       cudaStream_t stream) {
+    FMB_CHECK_ARG(!rl || (rl->entries && rl->seg_count && rl->nseg >= 1 && rl->nseg <= 2048 && rl->seg_cap >= 1),
+                  "fmb_fm_backward_update: bad run list");
     FMB_CHECK_ARG(sorted_keys && perm && table && S && gs && ws, "fmb_fm_backward_update: null pointer");
     FMB_CHECK_ARG(N > 0 && F > 0 && F < 512 && k > 0 && k <= 124, "fmb_fm_backward_update: bad shape");
     FMB_CHECK_ARG(mode == 0 || mode == 1, "fmb_fm_backward_update: unknown update mode %d", mode);
@@ -720,7 +725,17 @@ FMB_API int fmb_fm_backward_update_ex(const int32_t* sorted_keys, const int32_t*
         }
     }
     FMB_CHECK_LAUNCH("fm_bwd_entry_kernel");
+    if (rl) { p.run_list = reinterpret_cast<const int4*>(rl->entries); p.run_segc = rl->seg_count; p.run_nseg = rl->nseg; p.run_cap = rl->seg_cap; }
     return launch_runs(p, two, stream);
+}
+
+FMB_API int fmb_fm_backward_update_ex(const int32_t* sorted_keys, const int32_t* perm, int64_t N, int64_t n_entries,
+                                      const float* xv, float* table, int F, int k, const float* S, int s_pitch,
+                                      const float* gs, int gs_stride, int use_fm2, const float* gvec,
+                                      int32_t key_limit, float lr, int mode, void* ws, size_t ws_bytes,
+                                      cudaStream_t stream) {
+    return fmb_fm_backward_update_rl(sorted_keys, perm, N, n_entries, xv, table, F, k, S, s_pitch, gs, gs_stride, use_fm2, gvec,
+                                     key_limit, lr, mode, nullptr, ws, ws_bytes, stream);
 }
 
 // Run kernel alone: sums the contributions staged in ws (by fmb_fm_step_fused, at sorted positions) over every run
@@ -729,7 +744,6 @@ struct fmb_ftrl_t { float* zn; float* bias_zn; float beta, l1, l2; };   // inclu
 
 // rl (nullable): the runs of >= 2 entries found by the sort one step ahead (fmb_sort_fields_ex / fmb_pos_flags_ex); with it
 // one warp is started per RUN instead of per 32 sorted positions.
-struct fmb_runlist_t { int32_t* entries; uint32_t* seg_count; int nseg, seg_cap; };   // include/fmb200.h
 
 static int g_runs_pdl = 0;
 // internal (session.cu): the NEXT fmb_fm_backward_runs_list call is launched as a programmatic dependent of the kernel

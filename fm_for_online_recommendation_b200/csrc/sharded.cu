@@ -143,7 +143,8 @@ __global__ void shard_unpack_ctx_kernel(const float* __restrict__ ctx_all, int64
 __global__ void __launch_bounds__(fmb::SS_THREADS) shard_sort_fields_kernel(
     const int32_t* __restrict__ idsT_all, int G, int glog, int me, int B, int F,
     const int32_t* __restrict__ field_off, int cap, int32_t* __restrict__ skeys, int32_t* __restrict__ perm,
-    int32_t* __restrict__ counts, int32_t* __restrict__ overflow) {
+    int32_t* __restrict__ counts, int32_t* __restrict__ overflow, int4* __restrict__ rl_entries,
+    uint32_t* __restrict__ rl_segc, int rl_cap) {
     extern __shared__ __align__(16) unsigned char fs_smem[];
     uint32_t* kbuf0 = reinterpret_cast<uint32_t*>(fs_smem);
     uint32_t* kbuf1 = kbuf0 + cap;
@@ -203,6 +204,10 @@ __global__ void __launch_bounds__(fmb::SS_THREADS) shard_sort_fields_kernel(
         skeys[(size_t)f * cap + i] = i < n ? (int32_t)kc[i] + base : 0x7fffffff;
         perm[(size_t)f * cap + i] = i < n ? (int32_t)pc[i] * F + f : 0;
     }
+    // run list for the backward's run kernel (one segment per field; rl_segc = [F short counts | F long counts])
+    if (rl_entries)
+        fmb::runlist_from_sorted<fmb::SS_THREADS>(kc, n, f * cap, base, rl_entries + (size_t)f * rl_cap, rl_cap, rl_segc + f,
+                                                  rl_segc + F + f);
 }
 
 
@@ -568,18 +573,30 @@ FMB_API int fmb_shard_unpack_ctx(const float* ctx_all, int64_t n, int k, float* 
 
 // step 2b: per-field sorted list of the entries rank `me` owns.  skeys/perm [F][cap] (padding key
 // INT_MAX), counts [F], overflow [1] (max count seen when a field exceeded cap, else untouched).
-FMB_API int fmb_shard_sort_fields(const int32_t* idsT_all, int G, int me, int B, int F, const int32_t* field_off,
-                                  int cap, int32_t* skeys, int32_t* perm, int32_t* counts, int32_t* overflow,
-                                  cudaStream_t stream) {
+// _rl: also the run list of every field's sorted owned entries (rl: nseg == F, seg_cap >= cap / 2 + 1; nullable), for
+// fmb_fm_backward_update_rl
+struct fmb_runlist_t { int32_t* entries; uint32_t* seg_count; int nseg, seg_cap; };   // include/fmb200.h
+FMB_API int fmb_shard_sort_fields_rl(const int32_t* idsT_all, int G, int me, int B, int F, const int32_t* field_off,
+                                     int cap, int32_t* skeys, int32_t* perm, int32_t* counts, int32_t* overflow,
+                                     const fmb_runlist_t* rl, cudaStream_t stream) {
     FMB_CHECK_ARG(idsT_all && field_off && skeys && perm && counts && overflow, "fmb_shard_sort_fields: null pointer");
+    FMB_CHECK_ARG(!rl || (rl->entries && rl->seg_count && rl->nseg == F && rl->seg_cap >= cap / 2 + 1 && F <= 2048),
+                  "fmb_shard_sort_fields: run list must have F segments of at least cap/2 + 1 entries");
     FMB_CHECK_ARG(cap > 0 && cap <= fmb_shard_sort_max_cap(), "fmb_shard_sort_fields: cap=%d out of range", cap);
     FMB_CHECK_ARG((int64_t)G * B <= 65536, "fmb_shard_sort_fields: G*B must be <= 65536 (16-bit sample payload)");
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(shard_sort_fields_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr = true; }
     shard_sort_fields_kernel<<<F, fmb::SS_THREADS, fmb::smem_sort_bytes(cap), stream>>>(
-        idsT_all, G, ilog2_exact(G), me, B, F, field_off, cap, skeys, perm, counts, overflow);
+        idsT_all, G, ilog2_exact(G), me, B, F, field_off, cap, skeys, perm, counts, overflow,
+        rl ? reinterpret_cast<int4*>(rl->entries) : nullptr, rl ? rl->seg_count : nullptr, rl ? rl->seg_cap : 0);
     FMB_CHECK_LAUNCH("shard_sort_fields_kernel");
     return FMB_OK;
+}
+
+FMB_API int fmb_shard_sort_fields(const int32_t* idsT_all, int G, int me, int B, int F, const int32_t* field_off,
+                                  int cap, int32_t* skeys, int32_t* perm, int32_t* counts, int32_t* overflow,
+                                  cudaStream_t stream) {
+    return fmb_shard_sort_fields_rl(idsT_all, G, me, B, F, field_off, cap, skeys, perm, counts, overflow, nullptr, stream);
 }
 
 // ---------------------------------------------------------------------------------------------- peer-memory exchange

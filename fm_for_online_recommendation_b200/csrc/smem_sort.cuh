@@ -108,4 +108,70 @@ __device__ __forceinline__ void smem_sort_passes(uint32_t* kbuf0, uint32_t* kbuf
     *pout = pc;
 }
 
+// Run list of a sorted key array held in shared memory (what fm_bwd_runs_list_kernel consumes; see fmb_runlist_t in
+// include/fmb200.h): kc[0..n) sorted keys, position of entry i = pos0 + i, listed key = kc[i] + key_add.  Runs of >= 2 equal
+// keys are written to `seg` (a segment of seg_cap entries): those shorter than 128 entries upwards from its start, the longer
+// ones downwards from its end; *n_short / *n_long receive their numbers.  Counts per warp in registers, two passes, no
+// atomics.  All THREADS threads of the CTA must call (one __syncthreads inside).
+template <int THREADS>
+__device__ __forceinline__ void runlist_from_sorted(const uint32_t* kc, int n, int pos0, int32_t key_add, int4* seg, int seg_cap,
+                                                    uint32_t* n_short, uint32_t* n_long) {
+    __shared__ uint32_t rl_ws[32], rl_wl[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int nr = (n + 31) & ~31;
+    uint32_t wc = 0, wcl = 0;
+    for (int i = threadIdx.x; i < nr; i += THREADS) {
+        bool start = false, lng = false;
+        if (i < n) {
+            const uint32_t key = kc[i];
+            start = (i == 0 || kc[i - 1] != key) && i + 1 < n && kc[i + 1] == key;
+            lng = start && i + 127 < n && kc[i + 127] == key;
+        }
+        wc += __popc(__ballot_sync(0xffffffffu, start && !lng));
+        wcl += __popc(__ballot_sync(0xffffffffu, lng));
+    }
+    if (lane == 0) { rl_ws[warp] = wc; rl_wl[warp] = wcl; }
+    __syncthreads();
+    uint32_t base = 0, total = 0, basel = 0, totall = 0;
+    for (int w = 0; w < THREADS / 32; ++w) {
+        const uint32_t t = rl_ws[w], tl = rl_wl[w];
+        if (w < warp) { base += t; basel += tl; }
+        total += t; totall += tl;
+    }
+    if (threadIdx.x == 0) { *n_short = total; *n_long = totall; }
+    if (wc + wcl == 0) return;
+    for (int i = threadIdx.x; i < nr; i += THREADS) {
+        uint32_t key = 0xfffffffeu;
+        bool cont = false, start = false, lng = false;
+        if (i < n) {
+            key = kc[i];
+            cont = i > 0 && kc[i - 1] == key;
+            start = !cont && i + 1 < n && kc[i + 1] == key;
+            lng = start && i + 127 < n && kc[i + 127] == key;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, start);
+        if (m) {
+            const unsigned ml = __ballot_sync(0xffffffffu, lng);
+            const unsigned cm = __ballot_sync(0xffffffffu, cont);
+            const uint32_t klast = __shfl_sync(0xffffffffu, key, 31);
+            const uint32_t k2 = i + 32 < n ? kc[i + 32] : 0xffffffffu;
+            const unsigned em = __ballot_sync(0xffffffffu, k2 == klast);
+            const int ext = em == 0xffffffffu ? 32 : __ffs(~em) - 1;
+            if (start) {
+                const unsigned after = lane == 31 ? 0u : (cm >> (lane + 1));
+                const int inw = lane == 31 ? 0 : __ffs(~after) - 1;
+                int n0 = 1 + inw;
+                if (lane + inw == 31) n0 += ext;
+                if (n0 > 32) n0 = 32;
+                const int4 e4 = make_int4(pos0 + i, (int32_t)key + key_add, n0, lng ? 1 : 0);
+                if (lng) seg[seg_cap - 1 - (int)(basel + __popc(ml & lt))] = e4;
+                else seg[base + __popc((m & ~ml) & lt)] = e4;
+            }
+            base += __popc(m & ~ml);
+            basel += __popc(ml);
+        }
+    }
+}
+
 }  // namespace fmb

@@ -206,6 +206,12 @@ int fmb_fm_backward_update_ex(const int32_t* sorted_keys_dev, const int32_t* per
                               const float* gs_dev, int gs_stride, int use_fm2, const float* gvec_dev,
                               int32_t key_limit, float lr, int mode, void* ws_dev, size_t ws_bytes,
                               fmb_stream_t stream);
+/* _rl: with the run list of the sorted keys (nullable) the run kernel starts one warp per run, the long runs first */
+int fmb_fm_backward_update_rl(const int32_t* sorted_keys_dev, const int32_t* perm_dev, int64_t N, int64_t n_entries,
+                              const float* xv_dev, float* table_dev, int F, int k, const float* S_dev, int s_pitch,
+                              const float* gs_dev, int gs_stride, int use_fm2, const float* gvec_dev, int32_t key_limit,
+                              float lr, int mode, const fmb_runlist_t* rl, void* ws_dev, size_t ws_bytes,
+                              fmb_stream_t stream);
 
 /* ---- row-sharded multi-GPU step (BASELINE.json configs[4]; no counterpart in the reference, which is
  * single-device: SURVEY.md 8e).  Row r lives on rank r % G at local row r / G.  See csrc/sharded.cu. */
@@ -259,6 +265,10 @@ int fmb_shard_unpack_ctx(const float* ctx_all_dev, int64_t n, int k, float* delt
 int fmb_shard_sort_fields(const int32_t* idsT_all_dev, int G, int me, int B, int F, const int32_t* field_off_dev,
                           int cap, int32_t* sorted_keys_dev /*[F,cap]*/, int32_t* perm_dev /*[F,cap]*/,
                           int32_t* counts_dev /*[F]*/, int32_t* overflow_dev /*[1]*/, fmb_stream_t stream);
+/* _rl: also the run list of every field's sorted owned entries (rl->nseg == F, seg_cap >= cap/2 + 1; nullable) */
+int fmb_shard_sort_fields_rl(const int32_t* idsT_all_dev, int G, int me, int B, int F, const int32_t* field_off_dev, int cap,
+                             int32_t* skeys_dev, int32_t* perm_dev, int32_t* counts_dev, int32_t* overflow_dev,
+                             const fmb_runlist_t* rl, fmb_stream_t stream);
 /* The three exchanges without a collective call: with idsT_all, recv, ctx_all and a flag block in symmetric (peer
  * mapped) memory, producers store straight into the consumers' buffers over NVLink.  Every `peers` argument is a
  * HOST array of G (<= 8) device pointers, entry r = where THIS device maps rank r's copy of that buffer.

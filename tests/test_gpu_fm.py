@@ -1,6 +1,7 @@
 """GPU parity tests of the FM hot path (A1-A3, sort/segments, A6) through the C ABI.
 CUDA results are compared with the CPU oracle bit for bit (fp32 work mirrors ATen's op order)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -371,6 +372,36 @@ def test_full_size_properties_cfg4():
         m.bias.copy_(b0)
     l2 = m.update_embedding(e, None, None).item()
     assert l1 == l2 and torch.equal(m._table, t1)
+
+
+def test_full_size_cfg5_steps_bit_exact_vs_oracle():
+    """BASELINE cfg5 on one GPU, exactly as bench.py runs it: 39 fields, 33 M rows, k = 10, B = 8192, graph-replayed steps
+    with the next batch's sort riding along (dense fields: cluster radix sort + tail; the 26 sparse fields: hash pass; run
+    list; long runs first).  Losses and every touched row are bit-identical to the C oracle; untouched rows do not move."""
+    import fm_for_online_recommendation_b200 as pkg
+    from oracle.deep import OracleDeep
+    sizes = [63, 113, 126, 51, 224, 148, 100, 79, 104, 9, 32, 57, 82] + [1_269_185] * 26
+    k, B, lr = 10, 8192, 1e-4
+    os.environ["ORC_THREADS"] = str(os.cpu_count() or 1)
+    orc = OracleDeep("DeepFMAdam", sizes, k, 3, 400, lr=lr, seed=0)
+    orc.w1 *= np.float32(0.3); orc.V *= np.float32(0.3)         # unsaturated logits: gradients of every magnitude
+    m = pkg.DeepFMAdam(sizes, embedding_size=k, num_hidden_layers=3, neuron_per_hidden_layer=400, n=lr)
+    push(m, orc)
+    t0 = m._table.clone()
+    batches = [synth(sizes, B, 500 + i) for i in range(4)]
+    enc = [m.encode(Xi, None, Y) for Xi, _, Y in batches]
+    touched = torch.zeros(m._R, dtype=torch.bool, device="cuda")
+    for i in range(4):
+        got = float(m._fm_step(enc[i], 0, enc[i + 1] if i + 1 < 4 else None).cpu())
+        want = orc.update_embedding(batches[i][0], batches[i][1], batches[i][2])
+        assert np.float32(got) == np.float32(want), i
+        touched[enc[i].ids.reshape(-1).long()] = True
+    idx = torch.nonzero(touched).reshape(-1)
+    rows = m._table[idx].cpu().numpy()
+    ii = idx.cpu().numpy()
+    assert np.array_equal(rows[:, :k], orc.V[ii]) and np.array_equal(rows[:, k], orc.w1[ii])
+    assert np.float32(m.bias.item()) == np.float32(orc.bias.reshape(-1)[0])
+    assert torch.equal(m._table[~touched], t0[~touched])
 
 
 @pytest.mark.parametrize("op,fn", [(0, "orc_vec_sigmoid"), (1, "orc_vec_log_sigmoid"), (2, "orc_vec_sqrt_mkl"),
