@@ -194,6 +194,27 @@ __global__ void __launch_bounds__(256) fm_step_fused_kernel(const int32_t* __res
         const float4 v4 = *reinterpret_cast<const float4*>(rows_s + (size_t)ef * rp + q * 4);
         const float Sq[4] = {S4.x, S4.y, S4.z, S4.w};
         const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+        if (MODE != 2) {
+            // Saturated samples (the reference's N(0,1) initialisation puts |z| ~ 90 on Criteo-shaped rows) leave their
+            // rows exactly where they are; two exact item-level tests spare them the per-coordinate work.
+            // (i) delta == 0 (sigmoid rounded to y): every gradient is +0 after the `0 +`, and the Adam step of a zero
+            //     gradient returns p for every p (shortcut, or p + (-0) in the full pipeline); SGD: fma(+0, -lr, p) = p.
+            if (d == 0.0f) continue;
+            // (ii) |delta| < 1e-30 with |S_j| < 1e4 and 1e-9 < |p| < 1e4: |g| <= 2.0001e-26 is below the window test's
+            //     range, and the quarter-ulp bound |a|*0.1*|g|*1.0001e8 <= 2.001e-18 (|a| <= 10) is below
+            //     2^-26*|p| >= 1.49e-17: adam1_a returns p.
+            if (MODE == 0 && !XV && fabsf(d) < 1e-30f && fabsf(p.astep) <= 10.0f) {
+                bool same = true;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int j = q * 4 + t;
+                    const float av = fabsf(v[t]);
+                    if (j <= k) same = same && av > 1e-9f && av < 1e4f;
+                    if (j < k) same = same && fabsf(Sq[t]) < 1e4f;
+                }
+                if (same) continue;
+            }
+        }
         float o[4];
         bool moved = false;
         float zz[4] = {0.f, 0.f, 0.f, 0.f}, nn[4] = {0.f, 0.f, 0.f, 0.f};

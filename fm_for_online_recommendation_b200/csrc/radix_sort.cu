@@ -568,8 +568,10 @@ constexpr int CL = CL_SEGS;
 // STAGED: keys are first scattered into a LOCAL staging buffer in digit order, then copied to their destination
 // CTAs with lane-contiguous (coalesced) distributed-shared-memory stores; the direct version issued two
 // scattered 4-/2-byte remote stores per key, which is what bounded it (profiles/r1g).
-template <int THREADS, bool STAGED>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS)
+// MAXS: register slots per thread (keys of one CTA / THREADS, rounded up): 8 covers batches up to 8 192 with 256 threads and
+// keeps the kernel at <= 80 registers (3 CTAs per SM by registers instead of 2: its CTAs share the SMs with the fused kernel's tiles).
+template <int THREADS, bool STAGED, int MAXS>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, THREADS == 256 && MAXS == 8 ? 3 : 1)
 sort_fields_cluster_kernel(const int32_t* __restrict__ ids, int B, int F, const int32_t* __restrict__ field_off,
                            int32_t* __restrict__ skeys, int32_t* __restrict__ perm, int Bq, uint32_t* __restrict__ posflag,
                            int4* __restrict__ rl_entries, uint32_t* __restrict__ rl_segc, int rl_cap, int64_t max_rows) {
@@ -624,13 +626,13 @@ sort_fields_cluster_kernel(const int32_t* __restrict__ ids, int B, int F, const 
         const int shift = ps * RADIX_BITS;
         for (int i = threadIdx.x; i < WARPS * RADIX / 2; i += THREADS) reinterpret_cast<uint32_t*>(cnt)[i] = 0;
         __syncthreads();
-        uint32_t key[FS_MAX_SLOTS];
-        uint16_t rank[FS_MAX_SLOTS];
-        unsigned peers[FS_MAX_SLOTS];
+        uint32_t key[MAXS];
+        uint16_t rank[MAXS];
+        unsigned peers[MAXS];
         // peer masks of all slots first: the ballots of different slots are independent, so their latencies
         // overlap (issued slot after slot they were 560 cycles per slot: 9 dependent VOTEs each)
 #pragma unroll
-        for (int s = 0; s < FS_MAX_SLOTS; ++s) {
+        for (int s = 0; s < MAXS; ++s) {
             if (s < slots) {
                 const int idx = wbase + s * 32 + lane;
                 const bool valid = idx < n;
@@ -640,7 +642,7 @@ sort_fields_cluster_kernel(const int32_t* __restrict__ ids, int B, int F, const 
         }
         // then the (short) serial part: per-warp digit counters
 #pragma unroll
-        for (int s = 0; s < FS_MAX_SLOTS; ++s) {
+        for (int s = 0; s < MAXS; ++s) {
             if (s < slots) {
                 const int idx = wbase + s * 32 + lane;
                 const bool valid = idx < n;
@@ -678,7 +680,7 @@ sort_fields_cluster_kernel(const int32_t* __restrict__ ids, int B, int F, const 
             }
             __syncthreads();
 #pragma unroll
-            for (int s = 0; s < FS_MAX_SLOTS; ++s) {
+            for (int s = 0; s < MAXS; ++s) {
                 if (s < slots) {
                     const int idx = wbase + s * 32 + lane;
                     if (idx < n) {
@@ -733,7 +735,7 @@ sort_fields_cluster_kernel(const int32_t* __restrict__ ids, int B, int F, const 
         } else {
             // scatter (key, payload) straight into the destination CTA's next buffer
 #pragma unroll
-            for (int s = 0; s < FS_MAX_SLOTS; ++s) {
+            for (int s = 0; s < MAXS; ++s) {
                 if (s < slots) {
                     const int idx = wbase + s * 32 + lane;
                     if (idx < n) {
@@ -828,10 +830,11 @@ FMB_API int fmb_sort_segment(const int32_t* keys, int64_t N, int key_bits, void*
 // for graph-node identification in session.cu
 FMB_API int fmb_sort_fields_kernel_fns(const void** fns, int* nparams, int* skeys_arg) {
     fns[0] = (const void*)sort_fields_kernel; nparams[0] = 11; skeys_arg[0] = 4;
-    fns[1] = (const void*)sort_fields_cluster_kernel<256, true>; nparams[1] = 12; skeys_arg[1] = 4;
-    fns[2] = (const void*)sort_fields_cluster_kernel<1024, false>; nparams[2] = 12; skeys_arg[2] = 4;
+    fns[1] = (const void*)sort_fields_cluster_kernel<256, true, 16>; nparams[1] = 12; skeys_arg[1] = 4;
+    fns[2] = (const void*)sort_fields_cluster_kernel<1024, false, 16>; nparams[2] = 12; skeys_arg[2] = 4;
     fns[3] = (const void*)sparse_fields_kernel; nparams[3] = 11; skeys_arg[3] = 5;
-    return 4;
+    fns[4] = (const void*)sort_fields_cluster_kernel<256, true, 8>; nparams[4] = 12; skeys_arg[4] = 4;
+    return 5;
 }
 
 // Largest batch the per-field shared-memory sort accepts (cluster of 4 CTAs, 16-bit sample payload).
@@ -879,8 +882,9 @@ FMB_API int fmb_sort_fields_ex(const int32_t* ids, int B, int F, const int32_t* 
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(sort_fields_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(sort_fields_cluster_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(sort_fields_cluster_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(sort_fields_cluster_kernel<256, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(sort_fields_cluster_kernel<256, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(sort_fields_cluster_kernel<1024, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(sparse_fields_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         attr = true;
     }
@@ -894,11 +898,14 @@ FMB_API int fmb_sort_fields_ex(const int32_t* ids, int B, int F, const int32_t* 
                                                                                rle, rlc, rcap, split);
         FMB_CHECK_LAUNCH("sort_fields_kernel");
     } else {
-        if (Bq <= 256 * FS_MAX_SLOTS)
-            sort_fields_cluster_kernel<256, true><<<F * CL, 256, fmb::smem_sort_bytes(Bq) + (size_t)Bq * 6 + 16, stream>>>(
+        if (Bq <= 256 * 8)
+            sort_fields_cluster_kernel<256, true, 8><<<F * CL, 256, fmb::smem_sort_bytes(Bq) + (size_t)Bq * 6 + 16, stream>>>(
+                ids, B, F, field_off, sorted_keys, perm, Bq, posflag, rle, rlc, rcap, split);
+        else if (Bq <= 256 * FS_MAX_SLOTS)
+            sort_fields_cluster_kernel<256, true, 16><<<F * CL, 256, fmb::smem_sort_bytes(Bq) + (size_t)Bq * 6 + 16, stream>>>(
                 ids, B, F, field_off, sorted_keys, perm, Bq, posflag, rle, rlc, rcap, split);
         else
-            sort_fields_cluster_kernel<1024, false><<<F * CL, 1024, fmb::smem_sort_bytes(Bq), stream>>>(
+            sort_fields_cluster_kernel<1024, false, 16><<<F * CL, 1024, fmb::smem_sort_bytes(Bq), stream>>>(
                 ids, B, F, field_off, sorted_keys, perm, Bq, posflag, rle, rlc, rcap, split);
         FMB_CHECK_LAUNCH("sort_fields_cluster_kernel");
     }

@@ -57,6 +57,9 @@ struct StepVariant {
     cudaGraphNode_t n_fused, n_finish, n_sort_cur[2], n_sort_next[2];   // a per-field sort is up to two kernels (radix + sparse fields)
     int np_sort_cur[2], np_sort_next[2];
     int nlaunch;
+    // per-batch pointers the nodes currently hold: a node is only re-pointed when its pointers change (a host loop over
+    // two input slots, or one resident batch, replays the graph as it is)
+    const void *cur_ids, *cur_xv, *cur_y, *cur_sort_ids, *cur_next_ids, *cur_loss;
 };
 
 struct fmb_session {
@@ -481,35 +484,41 @@ FMB_API int fmb_session_fm_step_next(fmb_session* s, const int32_t* ids, const f
             s->gvar[slot] = key;
             v = &s->gvar[slot];
         }
-        {
+        if (v->cur_ids != ids || v->cur_xv != xv || v->cur_y != y) {
             const void* repl[16] = {nullptr};
             repl[0] = &ids; repl[1] = &xv; repl[2] = &y;
             rc = patch_node(v->exec, v->n_fused, 5, repl);
             if (rc) return rc;
+            v->cur_ids = ids; v->cur_xv = xv; v->cur_y = y;
         }
-        if (!pre) {
+        if (!pre && v->cur_sort_ids != ids) {
             const void* repl[16] = {nullptr};
             repl[0] = &ids;
             for (int j = 0; j < 2 && v->n_sort_cur[j]; ++j) {
                 rc = patch_node(v->exec, v->n_sort_cur[j], v->np_sort_cur[j], repl);
                 if (rc) return rc;
             }
+            v->cur_sort_ids = ids;
         }
-        if (next_ids) {
+        if (next_ids && v->cur_next_ids != next_ids) {
             const void* repl[16] = {nullptr};
             repl[0] = &next_ids;
             for (int j = 0; j < 2 && v->n_sort_next[j]; ++j) {
                 rc = patch_node(v->exec, v->n_sort_next[j], v->np_sort_next[j], repl);
                 if (rc) return rc;
             }
+            v->cur_next_ids = next_ids;
         }
         {   // the bias-step kernel writes the mean loss straight to the caller's scalar (a 4-byte copy behind every graph
             // launch was a stream operation of its own: ~4 us of bubble per step)
             float* lo = loss_dev ? loss_dev : s->d_loss;
-            const void* repl[16] = {nullptr};
-            repl[6] = &lo;
-            rc = patch_node(v->exec, v->n_finish, 9, repl);
-            if (rc) return rc;
+            if (v->cur_loss != lo) {
+                const void* repl[16] = {nullptr};
+                repl[6] = &lo;
+                rc = patch_node(v->exec, v->n_finish, 9, repl);
+                if (rc) return rc;
+                v->cur_loss = lo;
+            }
         }
         CU(cudaGraphLaunch(v->exec, stream));
         s->launches += v->nlaunch;
