@@ -318,6 +318,21 @@ def test_presorted_steps_bit_exact():
         assert_same_params(m, orc, exact=True)
 
 
+def test_large_batch_generic_sort_path_bit_exact():
+    """B > 65 536: the step sorts with the generic multi-pass radix sort, the position words and the run list (one segment,
+    short runs upwards / long runs downwards) come from pos_flags_kernel; the run kernel's long-run CTAs get 1 000-entry
+    chains.  Losses and parameters == oracle, with and without the next batch's sort riding along."""
+    sizes, k, B = [70, 9, 40000, 3000, 150000], 10, 70001
+    m, orc = _pair("FMAdam", sizes, k, lr=1e-3, scale=0.2)
+    batches = [synth(sizes, B, 80 + i, zipf=(i == 1)) for i in range(3)]
+    enc = [m.encode(*b) for b in batches]
+    for i in range(3):
+        loss = m._fm_step(enc[i], 0, enc[i + 1] if i == 0 else None)
+        want = orc.update_embedding(*batches[i])
+        assert np.float32(loss.item()) == np.float32(want), i
+    assert_same_params(m, orc, exact=True)
+
+
 def test_pipelined_host_entry_point_bit_exact():
     """fmb_session_fm_step_host_async (two slots, pinned and pageable sources) == oracle, step after step."""
     import fm_for_online_recommendation_b200 as pkg
