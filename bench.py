@@ -47,7 +47,8 @@ def synth_batches(sizes, B, nb, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region, every 200 ms like the profiling recipe's clocks
+    line (a 50 ms loop slowed the host entry point's submissions by a third: every poll takes the driver's lock)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -57,7 +58,7 @@ class ClockSampler:
         self.gpu = gpu_index
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "50"],
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
@@ -310,32 +311,45 @@ def run_ours(args):
     st = C.c_void_p(stream.cuda_stream)
     losses = []
 
+    NSLOT = lib.fmb_session_host_slots()      # 4 input slots: the host submits up to three steps ahead of the GPU
+
     def submit(i):
         j = i % NB
-        rc = lib.fmb_session_fm_step_host_async(sess, i & 1, C.c_void_p(pin_ids[j].data_ptr()), None,
+        rc = lib.fmb_session_fm_step_host_async(sess, i % NSLOT, C.c_void_p(pin_ids[j].data_ptr()), None,
                                                 C.c_void_p(pin_y[j].data_ptr()), B, tptr, bptr, model._key_bits, 0,
                                                 model._lr, 0, st)
         assert rc == 0, lib.fmb_last_error()
 
     def collect(i):
-        rc = lib.fmb_session_wait_loss(sess, i & 1, C.byref(loss))
+        rc = lib.fmb_session_wait_loss(sess, i % NSLOT, C.byref(loss))
         assert rc == 0, lib.fmb_last_error()
         losses.append(loss.value)
 
     def run_host(n, base):
+        # every step: H2D of ITS ids and labels, the step, its loss read back on the host -- collected NSLOT - 1 steps
+        # later, so that the copies and the sort of the following steps overlap the kernels of this one
         for i in range(n):
             submit(base + i)
-            if i > 0:
-                collect(base + i - 1)
-        collect(base + n - 1)
+            if i >= NSLOT - 1:
+                collect(base + i - (NSLOT - 1))
+        for i in range(max(0, n - (NSLOT - 1)), n):
+            collect(base + i)
 
-    run_host(max(W, 6), 0)
+    # warm-up of the host path: every slot's graphs (pre-sort, step) captured and replayed, and at least 50 ms of steps --
+    # the first milliseconds of host-to-device traffic after a device-resident phase run at a fraction of the link's rate
+    # (tools/e2e_trace.py: 103 M samples/s for the first 20 steps of a fresh process, 160-180 M after that)
+    n_warm_host = max(W, 3 * NSLOT)
+    run_host(n_warm_host, 0)
+    t_w = time.perf_counter()
+    while time.perf_counter() - t_w < 0.05 and n_warm_host < 4000:
+        run_host(4 * NSLOT, n_warm_host)
+        n_warm_host += 4 * NSLOT
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    run_host(K, 1000)
+    run_host(K, 8000)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    assert len(losses) == max(W, 6) + K and all(np.isfinite(losses))
+    assert len(losses) == n_warm_host + K and all(np.isfinite(losses))
     # the same through the blocking entry point (copy, step, wait), for reference
     def host_step(i):
         j = i % NB
@@ -452,7 +466,7 @@ def run_ours(args):
         "e2e": {"value": B * K / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": 4 * B * F + 4 * B,
                 "d2h_bytes_per_step": 4,
                 "api": "fmb_session_fm_step_host_async + fmb_session_wait_loss (pinned host ids/y in, loss out, "
-                       "two slots: copies of step t+1 overlap step t)",
+                       "four slots: the copies and the sort of the next steps overlap the kernels of step t)",
                 "blocking_value": B * K / e2e_blocking_s},
         "host_submit_ms_per_step": host_ms,
         "gpu_launches": int(launches), "step_graphs_cached": int(lib.fmb_session_graph_count(sess)),

@@ -129,6 +129,7 @@ _SIGS = {
                                     vp, C.c_size_t, vp]),
     "fmb_fm_backward_runs": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, C.c_size_t, vp]),
     "fmb_session_wait_loss": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float)]),
+    "fmb_session_host_slots": (C.c_int, []),
     "fmb_session_fm_step_host": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_float, C.c_int,
                                            C.POINTER(C.c_float), vp]),
 }

@@ -104,9 +104,12 @@ struct fmb_session {
     // second input slot + copy stream for the pipelined host entry point (slot 0 = the buffers above)
     int32_t* d_ids2; float* d_xv2; float* d_y2; float* d_loss2;
     int32_t* h_ids2; float* h_xv2; float* h_y2;
+    // slots 2 and 3 (allocated on first use): with four slots the host runs up to three steps ahead of the GPU
+    int32_t* d_idsx[2]; float* d_xvx[2]; float* d_yx[2];
+    int32_t* h_idsx[2]; float* h_xvx[2]; float* h_yx[2];
     cudaStream_t st_copy;
-    cudaEvent_t ev_h2d[2], ev_done[2];
-    int slot_used[2];
+    cudaEvent_t ev_h2d[4], ev_done[4];
+    int slot_used[4];
     int64_t launches;  // kernels launched through this session (bench.py's gpu_launches)
     // CUDA-graph cache of whole steps, keyed by every argument that is baked into the kernels
     cudaStream_t st0, st1, st2, st3, st4;   // st0/st1: graph capture (main / side branch); st2: pre-sorts; st3: sparse-field
@@ -115,6 +118,7 @@ struct fmb_session {
     int64_t steps_done;
     cudaEvent_t ev_fork, ev_fwd, ev_sort, ev_join;
     int use_graph, use_prio;
+    int host_path;         // set while fmb_session_fm_step_host_async runs its step (one graph per input slot)
     int use_pdl;           // FMB_PDL=0 switches the programmatic dependent launch of the run kernel off
     int sort_after;        // FMB_SORT_AFTER=1 (experiment; default 0): the next batch's sort waits for the fused kernel
     int sparse_ok;         // FMB_SORT_SPARSE_OK unless FMB_SPARSE=0: fields with >= 16*B rows skip the sort (radix_sort.cu)
@@ -153,7 +157,11 @@ FMB_API void fmb_session_destroy(fmb_session* s) {
     cudaFree(s->d_ids2); cudaFree(s->d_xv2); cudaFree(s->d_y2); cudaFree(s->d_loss2);
     cudaFreeHost(s->h_ids2); cudaFreeHost(s->h_xv2); cudaFreeHost(s->h_y2);
     if (s->st_copy) cudaStreamDestroy(s->st_copy);
-    for (int i = 0; i < 2; ++i) { if (s->ev_h2d[i]) cudaEventDestroy(s->ev_h2d[i]); if (s->ev_done[i]) cudaEventDestroy(s->ev_done[i]); }
+    for (int i = 0; i < 4; ++i) { if (s->ev_h2d[i]) cudaEventDestroy(s->ev_h2d[i]); if (s->ev_done[i]) cudaEventDestroy(s->ev_done[i]); }
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(s->d_idsx[i]); cudaFree(s->d_xvx[i]); cudaFree(s->d_yx[i]);
+        cudaFreeHost(s->h_idsx[i]); cudaFreeHost(s->h_xvx[i]); cudaFreeHost(s->h_yx[i]);
+    }
     for (int i = 0; i < s->ngraphs; ++i) { cudaGraphExecDestroy(s->gvar[i].exec); cudaGraphDestroy(s->gvar[i].graph); }
     if (s->st0) cudaStreamDestroy(s->st0);
     if (s->st1) cudaStreamDestroy(s->st1);
@@ -196,7 +204,7 @@ FMB_API int fmb_session_create(fmb_session** out, int F, int k, int64_t max_batc
     dm((void**)&s->d_loss2, 256);
     hm((void**)&s->h_ids2, N * 4); hm((void**)&s->h_xv2, N * 4); hm((void**)&s->h_y2, max_batch * 4);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st_copy, cudaStreamNonBlocking);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_h2d[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_done[i], cudaEventDisableTiming);
     }
@@ -470,8 +478,17 @@ FMB_API int fmb_session_fm_step_next(fmb_session* s, const int32_t* ids, const f
         key.pre = pre; key.has_next = next_ids != nullptr; key.cur = cur; key.table = table; key.bias = bias; key.lr = lr;
         StepVariant* v = nullptr;
         const size_t keylen = offsetof(StepVariant, graph);
+        // Several graphs may share a key: one per set of per-batch pointers, up to four (the host entry point's four
+        // input slots replay their graphs without re-pointing a node); beyond that the first one is re-pointed.
+        float* want_loss = loss_dev ? loss_dev : s->d_loss;
+        int same_key = 0;
         for (int i = 0; i < s->ngraphs; ++i)
-            if (memcmp(&s->gvar[i], &key, keylen) == 0) { v = &s->gvar[i]; break; }
+            if (memcmp(&s->gvar[i], &key, keylen) == 0) {
+                ++same_key;
+                if (!v) v = &s->gvar[i];
+                if (s->gvar[i].cur_ids == ids && s->gvar[i].cur_y == y && s->gvar[i].cur_loss == want_loss) { v = &s->gvar[i]; same_key = 99; break; }
+            }
+        if (v && same_key < 4 && s->host_path) v = nullptr;     // host path: capture one more instead of re-pointing
         if (!v) {
             rc = capture_variant(s, &key, ids, xv, y, table, bias, next_ids);
             if (rc) return rc;
@@ -609,8 +626,9 @@ static bool host_ptr_is_pinned(const void* p) {
     seen[nextw] = p; pinned[nextw] = r; nextw = (nextw + 1) % 16; if (nseen < 16) ++nseen;
     return r;
 }
-// Pipelined step with HOST inputs.  `slot` (0 or 1) selects one of two device input buffers: the copies of
-// step t+1 (on the session's copy stream) overlap the kernels of step t (on `stream`).  Pinned / registered
+// Pipelined step with HOST inputs.  `slot` (0..3) selects one of four device input buffers: the copies of
+// step t+1 (on the session's copy stream) overlap the kernels of step t (on `stream`); a caller that cycles through all four
+// slots and collects a step's loss three steps later never waits for the GPU while it submits (fmb_session_host_slots()).  Pinned / registered
 // host buffers are read in place, pageable ones go through the session's pinned staging area.  The loss
 // arrives in pinned memory; fmb_session_wait_loss(slot) waits for it.  Every step still moves its own
 // 4*B*F (+4*B*F) + 4*B bytes in and 4 bytes out.
@@ -618,16 +636,27 @@ FMB_API int fmb_session_fm_step_host_async(fmb_session* s, int slot, const int32
                                            const float* y_host, int B, float* table, float* bias, int key_bits,
                                            int loss_kind, float lr, int mode, cudaStream_t stream) {
     FMB_CHECK_ARG(s && ids_host && y_host && table && bias, "fmb_session_fm_step_host_async: null pointer");
-    FMB_CHECK_ARG(slot == 0 || slot == 1, "fmb_session_fm_step_host_async: slot must be 0 or 1");
+    FMB_CHECK_ARG(slot >= 0 && slot < 4, "fmb_session_fm_step_host_async: slot must be 0..3");
     FMB_CHECK_ARG(B > 0 && B <= s->maxB, "fmb_session_fm_step_host_async: B=%d exceeds session max_batch", B);
     const size_t N = (size_t)B * s->F;
-    int32_t* d_ids = slot ? s->d_ids2 : s->d_ids;
-    float* d_xv = slot ? s->d_xv2 : s->d_xv;
-    float* d_y = slot ? s->d_y2 : s->d_y;
+    if (slot >= 2 && !s->d_idsx[slot - 2]) {     // slots 2 and 3: buffers on first use
+        const size_t NN = (size_t)s->maxB * s->F;
+        const int j = slot - 2;
+        cudaError_t e = cudaMalloc((void**)&s->d_idsx[j], NN * 4);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_xvx[j], NN * 4);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_yx[j], (size_t)s->maxB * 4);
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_idsx[j], NN * 4);
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_xvx[j], NN * 4);
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_yx[j], (size_t)s->maxB * 4);
+        if (e != cudaSuccess) { fmb_set_error("fmb_session_fm_step_host_async: %s", cudaGetErrorString(e)); return FMB_ERR_CUDA; }
+    }
+    int32_t* d_ids = slot >= 2 ? s->d_idsx[slot - 2] : (slot ? s->d_ids2 : s->d_ids);
+    float* d_xv = slot >= 2 ? s->d_xvx[slot - 2] : (slot ? s->d_xv2 : s->d_xv);
+    float* d_y = slot >= 2 ? s->d_yx[slot - 2] : (slot ? s->d_y2 : s->d_y);
     float* d_loss = slot ? s->d_loss2 : s->d_loss;
-    int32_t* h_ids = slot ? s->h_ids2 : s->h_ids;
-    float* h_xv = slot ? s->h_xv2 : s->h_xv;
-    float* h_y = slot ? s->h_y2 : s->h_y;
+    int32_t* h_ids = slot >= 2 ? s->h_idsx[slot - 2] : (slot ? s->h_ids2 : s->h_ids);
+    float* h_xv = slot >= 2 ? s->h_xvx[slot - 2] : (slot ? s->h_xv2 : s->h_xv);
+    float* h_y = slot >= 2 ? s->h_yx[slot - 2] : (slot ? s->h_y2 : s->h_y);
     // the previous user of this slot (two steps ago) must be done with the device buffers and the staging area
     if (s->slot_used[slot]) CU(cudaEventSynchronize(s->ev_done[slot]));
     const void* src_ids = ids_host;
@@ -647,17 +676,22 @@ FMB_API int fmb_session_fm_step_host_async(fmb_session* s, int slot, const int32
     // the bias-step kernel writes the mean loss straight into the pinned result word (4 bytes over PCIe: the D2H of the
     // step, without a copy operation of its own)
     (void)d_loss;
+    s->host_path = 1;
     rc = fmb_session_fm_step(s, d_ids, xv_host ? d_xv : nullptr, d_y, B, table, bias, key_bits, loss_kind, lr,
                                  mode, s->h_loss + 8 * slot, stream);
+    s->host_path = 0;
     if (rc) return rc;
     CU(cudaEventRecord(s->ev_done[slot], stream));
     s->slot_used[slot] = 1;
     return FMB_OK;
 }
 
+// number of input slots of fmb_session_fm_step_host_async
+FMB_API int fmb_session_host_slots(void) { return 4; }
+
 // waits for the step last submitted on `slot` and returns its mean loss
 FMB_API int fmb_session_wait_loss(fmb_session* s, int slot, float* loss_host) {
-    FMB_CHECK_ARG(s && (slot == 0 || slot == 1) && s->slot_used[slot], "fmb_session_wait_loss: nothing submitted on slot %d", slot);
+    FMB_CHECK_ARG(s && slot >= 0 && slot < 4 && s->slot_used[slot], "fmb_session_wait_loss: nothing submitted on slot %d", slot);
     CU(cudaEventSynchronize(s->ev_done[slot]));
     if (loss_host) *loss_host = s->h_loss[8 * slot];
     return FMB_OK;

@@ -402,12 +402,14 @@ int fmb_session_fm_step_next(fmb_session* s, const int32_t* ids_dev, const float
                              float* table_dev, float* bias_dev, int key_bits, int loss_kind, float lr, int mode,
                              const int32_t* next_ids_dev, float* loss_dev, fmb_stream_t stream);
 
-/* pipelined host entry point: two input slots; the H2D copies of step t+1 run on the session's copy stream
- * while step t computes.  Pinned / registered host buffers are read in place.  fmb_session_wait_loss
+/* pipelined host entry point: fmb_session_host_slots() input slots (slot = 0..3); the H2D copies and the sort of the
+ * following steps run on the session's copy / side streams while step t computes.  Pinned / registered host buffers are read in place.  fmb_session_wait_loss
  * blocks until the step last submitted on `slot` has finished and returns its mean loss. */
 int fmb_session_fm_step_host_async(fmb_session* s, int slot, const int32_t* ids_host, const float* xv_host,
                                    const float* y_host, int B, float* table_dev, float* bias_dev, int key_bits,
                                    int loss_kind, float lr, int mode, fmb_stream_t stream);
+int fmb_session_host_slots(void);   /* input slots of fmb_session_fm_step_host_async (4): a caller cycling through all of
+                                      * them and collecting a loss three steps later never waits for the GPU to submit */
 int fmb_session_wait_loss(fmb_session* s, int slot, float* loss_host);
 
 #ifdef __cplusplus

@@ -333,30 +333,35 @@ def test_large_batch_generic_sort_path_bit_exact():
     assert_same_params(m, orc, exact=True)
 
 
-def test_pipelined_host_entry_point_bit_exact():
-    """fmb_session_fm_step_host_async (two slots, pinned and pageable sources) == oracle, step after step."""
+@pytest.mark.parametrize("nslot,nsteps,B", [(2, 5, 512), (4, 11, 512), (4, 9, 4100)])
+def test_pipelined_host_entry_point_bit_exact(nslot, nsteps, B):
+    """fmb_session_fm_step_host_async (nslot input slots, losses collected nslot - 1 steps later; pinned and pageable sources;
+    pre-sort graphs and one step graph per slot at B = 4100) == oracle, step after step."""
     import fm_for_online_recommendation_b200 as pkg
     lib = pkg.require_cuda()
-    sizes, k, B = [300, 40, 7, 2000, 3], 10, 512
+    assert lib.fmb_session_host_slots() >= nslot
+    sizes, k = [300, 40, 7, 2000, 3], 10
     m, orc = _pair("FMAdam", sizes, k, lr=1e-3, scale=0.2)
     s = m._get_session(B)
-    batches = [synth(sizes, B, 90 + i, zipf=(i % 2 == 0)) for i in range(5)]
+    batches = [synth(sizes, B, 90 + i, zipf=(i % 2 == 0)) for i in range(nsteps)]
     ids = [orc.global_ids(b[0]) for b in batches]
     ys = [np.ascontiguousarray(b[2], dtype=np.float32) for b in batches]
     pinned = [torch.from_numpy(a).pin_memory() for a in ids]      # even steps: pinned, read in place
     tp, bp = C.c_void_p(m._table.data_ptr()), C.c_void_p(m.bias.data_ptr())
     loss = C.c_float()
     got = []
-    for i in range(5):
+    lag = nslot - 1
+    for i in range(nsteps):
         src = C.c_void_p(pinned[i].data_ptr()) if i % 2 == 0 else ids[i].ctypes.data_as(C.c_void_p)
-        rc = lib.fmb_session_fm_step_host_async(s, i & 1, src, None, ys[i].ctypes.data_as(C.c_void_p), B, tp, bp,
+        rc = lib.fmb_session_fm_step_host_async(s, i % nslot, src, None, ys[i].ctypes.data_as(C.c_void_p), B, tp, bp,
                                                 m._key_bits, 0, m._lr, 0, None)
         assert rc == 0, lib.fmb_last_error()
-        if i > 0:
-            assert lib.fmb_session_wait_loss(s, (i - 1) & 1, C.byref(loss)) == 0
+        if i >= lag:
+            assert lib.fmb_session_wait_loss(s, (i - lag) % nslot, C.byref(loss)) == 0
             got.append(loss.value)
-    assert lib.fmb_session_wait_loss(s, 4 & 1, C.byref(loss)) == 0
-    got.append(loss.value)
+    for i in range(max(0, nsteps - lag), nsteps):
+        assert lib.fmb_session_wait_loss(s, i % nslot, C.byref(loss)) == 0
+        got.append(loss.value)
     want = [orc.update_embedding(b[0], b[1], b[2]) for b in batches]
     assert [np.float32(g) for g in got] == [np.float32(w) for w in want]
     assert_same_params(m, orc, exact=True)
