@@ -745,7 +745,7 @@ struct fmb_ftrl_t { float* zn; float* bias_zn; float beta, l1, l2; };   // inclu
 // rl (nullable): the runs of >= 2 entries found by the sort one step ahead (fmb_sort_fields_ex / fmb_pos_flags_ex); with it
 // one warp is started per RUN instead of per 32 sorted positions.
 
-static int g_runs_pdl = 0;
+static thread_local int g_runs_pdl = 0;   // per calling thread: set and consumed by consecutive calls of one host thread
 // internal (session.cu): the NEXT fmb_fm_backward_runs_list call is launched as a programmatic dependent of the kernel
 // in front of it on its stream (the fused kernel, which executes griddepcontrol.launch_dependents)
 FMB_API void fmb_runs_list_next_is_dependent(int on) { g_runs_pdl = on; }

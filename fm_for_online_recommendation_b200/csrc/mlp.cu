@@ -152,7 +152,7 @@ FMB_API int fmb_mlp_forward(const float* bi, int ldbi, const float* mlp, int B, 
         p.B = mlp + mlp_w_off(k, H, l); p.sbk = 1; p.sbn = nin;  // B(k,n) = W[n][k]
         p.C = act + (size_t)l * B * H; p.scm = H;
         p.M = B; p.N = H; p.K = nin; p.epi = EPI_BIAS_RELU; p.bias = mlp + mlp_w_off(k, H, l) + (size_t)H * nin;
-        launch_gemm(p, stream);
+        { const int rcg = launch_gemm(p, stream); if (rcg) return rcg; }
         if (head) head_sum_kernel<<<(B + 7) / 8, 256, 0, stream>>>(p.C, B, H, head + (size_t)l * B);
     }
     FMB_CHECK_LAUNCH("fmb_mlp_forward");
@@ -188,7 +188,7 @@ FMB_API int fmb_mlp_backward(const float* bi, int ldbi, const float* mlp, const 
         q.C = gmlp + mlp_w_off(k, H, l); q.scm = nin;
         q.M = H; q.N = nin; q.K = B; q.epi = EPI_NONE;
         q.colsum = gmlp + mlp_w_off(k, H, l) + (size_t)H * nin;
-        launch_gemm(q, stream);
+        { const int rcg = launch_gemm(q, stream); if (rcg) return rcg; }
         // gx[b][i] = sum_o gp[b][o] * W[o][i]  (masked by relu of the layer below)
         if (l > 0 || gbi) {
             GemmParams r = {};
@@ -197,7 +197,7 @@ FMB_API int fmb_mlp_backward(const float* bi, int ldbi, const float* mlp, const 
             r.M = B; r.N = nin; r.K = H;
             if (l > 0) { r.C = gnext; r.scm = H; r.epi = EPI_MASK; r.mask = act + (size_t)(l - 1) * B * H; r.smm = H; }
             else { r.C = gbi; r.scm = ldgbi; r.epi = EPI_NONE; }
-            launch_gemm(r, stream);
+            { const int rcg = launch_gemm(r, stream); if (rcg) return rcg; }
         }
         float* tmp = gp; gp = gnext; gnext = tmp;
     }

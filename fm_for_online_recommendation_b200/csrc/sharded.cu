@@ -471,6 +471,142 @@ __global__ void __launch_bounds__(256) shard_partial_forward_warp_kernel(Partial
     if (channel >= 0) publish_epoch_last_block(x, channel);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tile version of the partial forward (round 2): one CTA = PW_SB samples of one source rank.  The owned entries of the
+// tile (sample-major, field order -- the order of the per-sample sums) are compacted once with ballots and a block
+// prefix, their rows are gathered into shared memory with 16-byte cp.async copies, all in flight together (the fused
+// single-GPU kernel's gather), and 16 lanes per sample sum S, Q and the first-order weight in field order.  The
+// warp-per-sample kernel above issues 16.8 M warp instructions for the same 319 k row reads (unrolled 4 x 8 predicated
+// load slots per round whatever the sample owned): 35 us.  Bit-identical to it (tests/test_sharded.py with
+// FMB_SHARD_TILE_PARTIAL=1), but not yet faster: see sp_use_tile.
+// Rounds: the rows of at most `cap` entries are staged at a time (whole samples); with evenly spread ownership one
+// round covers the tile, skewed ownership takes more rounds.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sp_cp_async16(void* smem, const void* gmem) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(a), "l"(gmem));
+}
+__global__ void __launch_bounds__(256) shard_partial_forward_tile_kernel(PartialParams p, PeerPtrs dst, int to_peers,
+                                                                        ExchSync x, int channel, int cap) {
+    extern __shared__ __align__(16) unsigned char sp_sm[];
+    const int F = p.F, rp = p.cu * 4;
+    const int npairs = PW_SB * F, nblk = (npairs + 31) / 32;
+    int32_t* sid = reinterpret_cast<int32_t*>(sp_sm);                       // [F][PW_SB + 1]
+    int32_t* elist = sid + F * (PW_SB + 1);                                 // [PW_SB * F] local rows of the owned entries
+    uint32_t* bal = reinterpret_cast<uint32_t*>(elist + PW_SB * F);         // [nblk] ownership ballots of 32 pairs
+    uint32_t* boff = bal + nblk;                                            // [nblk + 1] exclusive prefix of their popcounts
+    uint32_t* start = boff + nblk + 1;                                      // [PW_SB + 1] first entry of every sample
+    float* rows_s = reinterpret_cast<float*>(start + PW_SB + 1 + ((nblk * 2 + PW_SB + 2) & 1 ? 1 : 0));
+    rows_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(rows_s) + 15) & ~(uintptr_t)15);   // [cap][rp]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t total = (int64_t)p.G * p.B;
+    const int64_t bg0 = (int64_t)blockIdx.x * PW_SB;     // B % 64 == 0: a block never straddles two ranks' slabs
+    const int r = (int)(bg0 / p.B), b0 = (int)(bg0 - (int64_t)r * p.B);
+    if (bg0 < total) {
+        const int32_t* slab = p.idsT_all + (size_t)r * F * p.B + b0;
+        for (int i = threadIdx.x; i < F * PW_SB; i += 256) {
+            const int f = i / PW_SB, sb = i - f * PW_SB;
+            sid[f * (PW_SB + 1) + sb] = __ldg(slab + (size_t)f * p.B + sb);
+        }
+        __syncthreads();
+        // ownership ballots of the pairs in sample-major order (pair i = sample i / F, field i % F)
+        for (int bi = warp; bi < nblk; bi += 8) {
+            const int i = bi * 32 + lane;
+            bool own = false;
+            if (i < npairs) { const int sb = i / F, f = i - sb * F; int32_t l; own = owned_by(sid[f * (PW_SB + 1) + sb], p.G, p.glog, p.me, l); }
+            const unsigned m = __ballot_sync(0xffffffffu, own);
+            if (lane == 0) bal[bi] = m;
+        }
+        __syncthreads();
+        if (warp == 0) {      // exclusive prefix over the blocks' popcounts
+            uint32_t carry = 0;
+            for (int c0 = 0; c0 < nblk; c0 += 32) {
+                const uint32_t v = c0 + lane < nblk ? __popc(bal[c0 + lane]) : 0u;
+                uint32_t inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                if (c0 + lane < nblk) boff[c0 + lane] = carry + inc - v;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) { boff[nblk] = carry; start[PW_SB] = carry; }
+        }
+        __syncthreads();
+        for (int bi = warp; bi < nblk; bi += 8) {
+            const int i = bi * 32 + lane;
+            if (i < npairs) {
+                const int sb = i / F, f = i - sb * F;
+                const unsigned m = bal[bi];
+                const uint32_t pos = boff[bi] + __popc(m & ((1u << lane) - 1u));
+                if (f == 0) start[sb] = pos;
+                if ((m >> lane) & 1u) { int32_t l; owned_by(sid[f * (PW_SB + 1) + sb], p.G, p.glog, p.me, l); elist[pos] = l; }
+            }
+        }
+        __syncthreads();
+        // rounds of whole samples whose entries fit the staging area
+        int s_lo = 0;
+        while (s_lo < PW_SB) {
+            const uint32_t e_lo = start[s_lo];
+            int s_hi = s_lo + 1;
+            while (s_hi < PW_SB && start[s_hi + 1] - e_lo <= (uint32_t)cap) ++s_hi;
+            const uint32_t e_hi = start[s_hi];
+            {   // gather: 16 B per cp.async, every row of the round in flight at once
+                const int q = threadIdx.x & ((1 << p.ql_log) - 1);
+                const int estep = 256 >> p.ql_log;
+                if (q < p.cu)
+                    for (uint32_t e = e_lo + (threadIdx.x >> p.ql_log); e < e_hi; e += estep)
+                        sp_cp_async16(rows_s + (size_t)(e - e_lo) * rp + q * 4, p.table + (size_t)elist[e] * p.rowp + q * 4);
+            }
+            asm volatile("cp.async.commit_group;\n" ::);
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            __syncthreads();
+            // 16 lanes per sample: lane j < k sums component j (and its square), lane k the first-order weight; field order
+            for (int sb = s_lo + (threadIdx.x >> 4); sb < s_hi; sb += 16) {
+                const int j = threadIdx.x & 15;
+                if (j <= p.k) {
+                    float S = 0.f, Q = 0.f;
+                    const float* rr = rows_s + (size_t)(start[sb] - e_lo) * rp + j;
+                    const int n = (int)(start[sb + 1] - start[sb]);
+                    for (int u = 0; u < n; ++u) { const float e = rr[(size_t)u * rp]; S = __fadd_rn(S, e); Q = __fadd_rn(Q, __fmul_rn(e, e)); }   // x == 1
+                    float* out = to_peers ? static_cast<float*>(dst.p[r]) + ((size_t)p.me * p.B + b0 + sb) * p.PW
+                                          : p.partial + (size_t)(bg0 + sb) * p.PW;
+                    if (j < p.k) { out[j] = S; out[p.kp4 + j] = Q; }
+                    else {
+                        out[2 * p.kp4] = S;
+                        if (j < p.kp4) { out[j] = 0.f; out[p.kp4 + j] = 0.f; }      // padding component
+                    }
+                } else if (j < p.kp4) {     // padding components
+                    float* out = to_peers ? static_cast<float*>(dst.p[r]) + ((size_t)p.me * p.B + b0 + sb) * p.PW
+                                          : p.partial + (size_t)(bg0 + sb) * p.PW;
+                    out[j] = 0.f; out[p.kp4 + j] = 0.f;
+                }
+            }
+            __syncthreads();
+            s_lo = s_hi;
+        }
+    }
+    if (channel >= 0) publish_epoch_last_block(x, channel);
+}
+static size_t sp_tile_smem(int F, int cu, int cap) {
+    const int npairs = PW_SB * F, nblk = (npairs + 31) / 32;
+    return (size_t)F * (PW_SB + 1) * 4 + (size_t)npairs * 4 + (size_t)(2 * nblk + 1 + PW_SB + 1 + 1) * 4 + 16 + (size_t)cap * cu * 16;
+}
+// staging capacity (entries): 1.5 x the tile's expected owned entries, at least one sample's worth, at most 1 024
+static int sp_tile_cap(int G, int F) {
+    int c = (PW_SB * F * 3 / 2 / G + 63) / 64 * 64;
+    if (c < 128) c = 128;
+    if (c > 1024) c = 1024;
+    return c;
+}
+static bool sp_use_tile(int k, int F) {
+    if (k > 15 || F > PW_MAXF) return false;
+    // Experiment, off by default (FMB_SHARD_TILE_PARTIAL=1): measured 51 us against the warp kernel's 38 at G = 8 and
+    // 31 against 33 at G = 2 (cold L2) -- 1 024 CTAs of 36 KB are 1.15 waves, and the tile's five barriers with two
+    // runtime divisions per pair and a serial search for the round's end cost more than the instructions saved.
+    static int forced = -2;
+    if (forced == -2) { const char* e = getenv("FMB_SHARD_TILE_PARTIAL"); forced = e ? (e[0] != '0') : 0; }
+    return forced != 0;
+}
+
 // mode bit 0: publish my next epoch of `channel` to every peer's flag word [channel][me];
 // mode bit 1: wait until every peer's epoch of `channel` has reached mine.
 __global__ void shard_signal_kernel(PeerPtrs peer_flags, uint32_t* flags_local, uint32_t* epoch_local, int channel, int G,
@@ -541,10 +677,17 @@ FMB_API int fmb_shard_partial_forward(const int32_t* idsT_all, const float* tabl
     p.ql_log = ilog2_ceil(p.cu); p.PW = fmb_shard_pw(k); p.partial = partial;
     const int spb = 256 >> p.ql_log;
     const int64_t n = (int64_t)G * B;
-    if (fmb_shard_use_warp_partial(G, B, F, k)) {   // warp-per-sample kernel
+    if (fmb_shard_use_warp_partial(G, B, F, k)) {   // one CTA per 64 samples of one source rank
         PeerPtrs none = {};
         ExchSync nox = {};
-        shard_partial_forward_warp_kernel<<<(unsigned)(n / PW_SB), 256, 0, stream>>>(p, none, 0, nox, -1);
+        if (sp_use_tile(k, F)) {
+            const int cap = sp_tile_cap(G, F);
+            static bool attr = false;
+            if (!attr) { cudaFuncSetAttribute(shard_partial_forward_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; }
+            shard_partial_forward_tile_kernel<<<(unsigned)(n / PW_SB), 256, sp_tile_smem(F, p.cu, cap), stream>>>(p, none, 0, nox, -1, cap);
+        } else {
+            shard_partial_forward_warp_kernel<<<(unsigned)(n / PW_SB), 256, 0, stream>>>(p, none, 0, nox, -1);
+        }
     } else {
         shard_partial_forward_kernel<<<(unsigned)((n + spb - 1) / spb), 256, 0, stream>>>(p);
     }
@@ -654,7 +797,12 @@ FMB_API int fmb_shard_partial_forward_peers(const int32_t* idsT_all, const float
     p.ql_log = ilog2_ceil(p.cu); p.PW = fmb_shard_pw(k); p.partial = nullptr;
     const int spb = 256 >> p.ql_log;
     const int64_t n = (int64_t)G * B;
-    if (fmb_shard_use_warp_partial(G, B, F, k))
+    if (fmb_shard_use_warp_partial(G, B, F, k) && sp_use_tile(k, F)) {
+        const int cap = sp_tile_cap(G, F);
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(shard_partial_forward_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; }
+        shard_partial_forward_tile_kernel<<<(unsigned)(n / PW_SB), 256, sp_tile_smem(F, p.cu, cap), stream>>>(p, pp, 1, x, publish_channel, cap);
+    } else if (fmb_shard_use_warp_partial(G, B, F, k))
         shard_partial_forward_warp_kernel<<<(unsigned)(n / PW_SB), 256, 0, stream>>>(p, pp, 1, x, publish_channel);
     else
         shard_partial_forward_peers_kernel<<<(unsigned)((n + spb - 1) / spb), 256, 0, stream>>>(p, pp, x, publish_channel);

@@ -358,6 +358,8 @@ class ShardedFM:
         self.launches += 1                        # the two wait kernels (phase_backward counts 9 for the rest)
         main.wait_stream(self._pre)
         self._slot = 1 - p
+        if not torch.cuda.is_current_stream_capturing():
+            self._poll()
         return loss
 
     def check_exchange(self):
@@ -447,8 +449,21 @@ class ShardedFM:
         self._slot = 0
         return self
 
+    _POLL_EVERY = 256      # steps between two reads of the device error words (a read synchronises the stream)
+
+    def _poll(self):
+        """A field that overflowed its per-field sort capacity loses gradient contributions, an exchange that timed out
+        leaves stale partials: neither may train on silently.  Both error words are read every _POLL_EVERY steps (and by
+        bench_main at the end) and raise."""
+        self._steps_since_poll = getattr(self, "_steps_since_poll", 0) + 1
+        if self._steps_since_poll >= self._POLL_EVERY:
+            self._steps_since_poll = 0
+            self.check_overflow()
+            self.check_exchange()
+
     def step_graphed_pipelined(self, y, ids_next):
         """update_embedding_pipelined(y, ids_next) through the captured graphs."""
+        self._poll()
         self._g_y.copy_(y, non_blocking=True)
         self._g_ids.copy_(ids_next, non_blocking=True)
         p = self._slot
