@@ -47,39 +47,39 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_hist_kernel(const int32_t*
     for (int i = threadIdx.x; i < RADIX; i += SORT_THREADS) hist[(size_t)i * ntiles + blockIdx.x] = h[i];
 }
 
-// in-place exclusive scan of `n` counters by one CTA of 1024 threads (n = 256 * ntiles)
-__global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t* __restrict__ hist, int64_t n) {
-    __shared__ uint32_t warp_tot[32];
+// Exclusive scan of the [RADIX][ntiles] histogram in two levels: CTA d scans row d in place (exclusive over the tiles)
+// and writes the row's total to rowtot[d]; the scatter kernel adds the exclusive prefix of the 256 row totals itself.
+// (One CTA scanning all 256 * ntiles counters serially was 470 us per pass at B = 262 144: the whole sort's time.)
+__global__ void __launch_bounds__(256) radix_scan_rows_kernel(uint32_t* __restrict__ hist, int ntiles, uint32_t* __restrict__ rowtot) {
+    __shared__ uint32_t warp_tot[8];
     __shared__ uint32_t carry_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* row = hist + (size_t)blockIdx.x * ntiles;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
     constexpr int IPT = 4;
-    for (int64_t base = 0; base < n; base += 1024 * IPT) {
-        const int64_t i0 = base + (int64_t)threadIdx.x * IPT;
+    for (int base = 0; base < ntiles; base += 256 * IPT) {
+        const int i0 = base + threadIdx.x * IPT;
         uint32_t v[IPT], sum = 0;
 #pragma unroll
-        for (int j = 0; j < IPT; ++j) { v[j] = (i0 + j < n) ? hist[i0 + j] : 0u; sum += v[j]; }
+        for (int j = 0; j < IPT; ++j) { v[j] = (i0 + j < ntiles) ? row[i0 + j] : 0u; sum += v[j]; }
         uint32_t inc = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
         if (lane == 31) warp_tot[warp] = inc;
         __syncthreads();
-        if (warp == 0) {
-            uint32_t w = warp_tot[lane], winc = w;
+        uint32_t before = 0, all = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
-            warp_tot[lane] = winc - w;  // exclusive over warps
-        }
-        __syncthreads();
+        for (int w = 0; w < 8; ++w) { const uint32_t t = warp_tot[w]; if (w < warp) before += t; all += t; }
         const uint32_t carry = carry_s;
-        uint32_t excl = carry + warp_tot[warp] + (inc - sum);
+        uint32_t excl = carry + before + (inc - sum);
 #pragma unroll
-        for (int j = 0; j < IPT; ++j) { if (i0 + j < n) hist[i0 + j] = excl; excl += v[j]; }
+        for (int j = 0; j < IPT; ++j) { if (i0 + j < ntiles) row[i0 + j] = excl; excl += v[j]; }
         __syncthreads();
-        if (threadIdx.x == 1023) carry_s = excl;  // total so far (last thread's running end)
+        if (threadIdx.x == 0) carry_s = carry + all;
         __syncthreads();
     }
+    if (threadIdx.x == 0) rowtot[blockIdx.x] = carry_s;
 }
 
 // stable scatter of one tile. vals_in == nullptr means "identity payload" (first pass).
@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(const int32
                                                                      const int32_t* __restrict__ vals_in, int64_t N,
                                                                      int shift, int ntiles,
                                                                      const uint32_t* __restrict__ scan,
+                                                                     const uint32_t* __restrict__ rowtot,
                                                                      int32_t* __restrict__ keys_out,
                                                                      int32_t* __restrict__ vals_out) {
     __shared__ uint32_t cnt[SORT_WARPS][RADIX];
@@ -94,6 +95,18 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(const int32
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&cnt[0][0])[i] = 0;
     for (int i = threadIdx.x; i < RADIX; i += SORT_THREADS) gbase[i] = scan[(size_t)i * ntiles + blockIdx.x];
+    __syncthreads();
+    if (warp == 0) {   // + exclusive prefix of the 256 digit totals (8 per lane)
+        uint32_t v[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[j] = rowtot[lane * 8 + j]; sum += v[j]; }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        uint32_t ex = inc - sum;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { gbase[lane * 8 + j] += ex; ex += v[j]; }
+    }
     __syncthreads();
     // warp-striped arrangement: warp w owns keys [w*32*KPT, (w+1)*32*KPT) of the tile, slot i is
     // 32 consecutive keys -> original order == (warp, slot, lane) order.
@@ -783,7 +796,7 @@ static int sort_ntiles(int64_t N) { return (int)((N + TILE - 1) / TILE); }
 // workspace: ping-pong key/val buffers + histogram
 FMB_API size_t fmb_sort_workspace_bytes(int64_t N) {
     const size_t n4 = ((size_t)N * 4 + 255) / 256 * 256;
-    const size_t h = ((size_t)RADIX * sort_ntiles(N) * 4 + 255) / 256 * 256;
+    const size_t h = ((size_t)RADIX * (sort_ntiles(N) + 1) * 4 + 255) / 256 * 256;   // histogram + the 256 row totals
     return 4 * n4 + h;
 }
 
@@ -812,8 +825,8 @@ FMB_API int fmb_sort_segment(const int32_t* keys, int64_t N, int key_bits, void*
         int32_t* vout = last ? perm : vbuf[p & 1];
         const int shift = p * RADIX_BITS;
         radix_hist_kernel<<<ntiles, SORT_THREADS, 0, stream>>>(kin, N, shift, ntiles, hist);
-        radix_scan_kernel<<<1, 1024, 0, stream>>>(hist, (int64_t)RADIX * ntiles);
-        radix_scatter_kernel<<<ntiles, SORT_THREADS, 0, stream>>>(kin, vin, N, shift, ntiles, hist, kout, vout);
+        radix_scan_rows_kernel<<<RADIX, 256, 0, stream>>>(hist, ntiles, hist + (size_t)RADIX * ntiles);
+        radix_scatter_kernel<<<ntiles, SORT_THREADS, 0, stream>>>(kin, vin, N, shift, ntiles, hist, hist + (size_t)RADIX * ntiles, kout, vout);
         kin = kout;
         vin = vout;
     }
