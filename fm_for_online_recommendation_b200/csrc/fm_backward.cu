@@ -23,6 +23,7 @@
 // (the entry-major layout cost one LDS.32 per entry: 64 instructions per 32 entries, 10.6 cycles per entry
 // measured with clock64; the add chain itself is 4).
 #include "fmb_common.cuh"
+#include <cstdlib>
 #include <cstring>
 #include <cuda.h>   // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link)
 
@@ -649,7 +650,9 @@ static int launch_runs(BwdParams& p, bool two, cudaStream_t stream) {
     if (per_sm < 1) per_sm = 1;
     if (per_sm * wpb > 32) per_sm = 32 / wpb;
     const unsigned nlong = (unsigned)sms;                                   // one long-run CTA per SM
-    unsigned nshort = (unsigned)(sms * (per_sm > 1 ? per_sm - 1 : 1));
+    static int short_per_sm = -1;      // experiment knob FMB_RUNS_SHORT_PER_SM (default: one slot less than fit)
+    if (short_per_sm < 0) { const char* e = getenv("FMB_RUNS_SHORT_PER_SM"); short_per_sm = e ? atoi(e) : 0; }
+    unsigned nshort = (unsigned)(sms * (short_per_sm > 0 ? short_per_sm : (per_sm > 1 ? per_sm - 1 : 1)));
     if (nshort > grid) nshort = grid;
     if (p.pdl) {
         cudaLaunchConfig_t cfg;

@@ -59,8 +59,9 @@ struct StepParams {
 // memory is then a constant and the field loop addresses with immediates), 0 = read it from the parameters;
 // XV = the batch carries real feature values (else all ones: no loads, no multiplications by x -- a product with 1.0f
 // is exact, so skipping it changes no bit); MODE = update rule (0 fresh-Adam sign step, 1 SGD, 2 FTRL-Proximal).
+// 32 registers (8 CTAs per SM): the 1 024 tiles of an 8 192-sample batch are then resident at once.
 template <int CU, bool XV, int MODE>
-__global__ void __launch_bounds__(256) fm_step_fused_kernel(const int32_t* __restrict__ ids, const float* __restrict__ xv,
+__global__ void __launch_bounds__(256, MODE == 2 ? 4 : 8) fm_step_fused_kernel(const int32_t* __restrict__ ids, const float* __restrict__ xv,
                                                             const float* __restrict__ y, const uint32_t* __restrict__ posflag,
                                                             StepParams p) {
     extern __shared__ __align__(16) float smem[];
@@ -225,27 +226,50 @@ __global__ void __launch_bounds__(256) fm_step_fused_kernel(const int32_t* __res
             zz[0] = z4.x; zz[1] = z4.y; zz[2] = z4.z; zz[3] = z4.w;
             nn[0] = n4.x; nn[1] = n4.y; nn[2] = n4.z; nn[3] = n4.w;
         }
+        float g[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
+        for (int t = 0; t < 4; ++t) {       // the entry's contribution = the row's gradient (0 + contribution)
             const int j = q * 4 + t;
-            o[t] = v[t];
-            if (j <= k) {
-                float a;
-                if (j < k) {
-                    const float ej = XV ? __fmul_rn(v[t], x) : v[t];
-                    a = __fsub_rn(__fmul_rn(d, Sq[t]), __fmul_rn(d, ej));
-                    if (XV) a = __fmul_rn(a, x);
-                } else {
-                    a = XV ? __fmul_rn(d, x) : d;
-                }
-                if (MODE == 2) {
-                    o[t] = fmb::ftrl_update(v[t], __fadd_rn(0.f, a), zz[t], nn[t], p.lr, p.ftrl.beta, p.ftrl.l1, p.ftrl.l2);
-                    moved = true;
-                } else {
-                    o[t] = fmb::apply_update_a(v[t], __fadd_rn(0.f, a), p.lr, p.astep, MODE);
-                    moved |= __float_as_int(o[t]) != __float_as_int(v[t]);
-                }
+            float a = 0.f;
+            if (j < k) {
+                const float ej = XV ? __fmul_rn(v[t], x) : v[t];
+                a = __fsub_rn(__fmul_rn(d, Sq[t]), __fmul_rn(d, ej));
+                if (XV) a = __fmul_rn(a, x);
+            } else if (j == k) {
+                a = XV ? __fmul_rn(d, x) : d;
             }
+            g[t] = __fadd_rn(0.f, a);
+            o[t] = v[t];
+        }
+        if (MODE == 2) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (q * 4 + t <= k) {
+                    o[t] = fmb::ftrl_update(v[t], g[t], zz[t], nn[t], p.lr, p.ftrl.beta, p.ftrl.l1, p.ftrl.l2);
+                    moved = true;
+                }
+        } else if (MODE == 1) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (q * 4 + t <= k) { o[t] = __fmaf_rn(g[t], -p.lr, v[t]); moved |= __float_as_int(o[t]) != __float_as_int(v[t]); }
+        } else {
+            // Adam: the window test on all four coordinates without a branch, then -- rarely -- the rest (the quarter-ulp
+            // shortcut and the full pipeline) for the coordinates it did not settle.  One divergent region per item
+            // instead of two per coordinate.
+            unsigned need = 0;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                float w;
+                const bool ok = fmb::adam1_window(v[t], g[t], p.astep, w);
+                if (q * 4 + t <= k) { if (ok) o[t] = w; else need |= 1u << t; }
+            }
+            if (need) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if ((need >> t) & 1u) o[t] = fmb::adam1_rest(v[t], g[t], p.astep, fmb::adam1_in_domain(g[t], p.astep));
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) moved |= __float_as_int(o[t]) != __float_as_int(v[t]);
         }
         if (moved) *reinterpret_cast<float4*>(p.table + (size_t)ids_s[ef] * p.rowp + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
         if (MODE == 2) {

@@ -111,9 +111,15 @@ __device__ __forceinline__ float powf_p(float b, float e) { return expf_p(__fmul
 // astep = -(lr / 0.1f), the (negated) bias-corrected step size: loop-invariant, so callers that update many
 // parameters compute it once (adam_astep) and call adam1_a.
 __device__ __forceinline__ float adam_astep(float lr) { return -__fdiv_rn(lr, 0.1f); }
-__device__ __forceinline__ float adam1_a(float p, float g, float a) {
-    const float bc2s = 0.03162277660168381f;
+// adam1_a in two parts, so that a caller with several coordinates per thread can run the cheap part on all of them
+// without branches and the rest only where it is needed (fm_step.cu):
+//   adam1_window: true + the result when the window test settles the coordinate; `in_domain` tells adam1_rest which way
+//   the test was skipped or failed.
+__device__ __forceinline__ bool adam1_in_domain(float g, float a) {
     const float ag = fabsf(g);
+    return ag >= 1e-25f && ag < 1e15f && fabsf(a) >= 1e-9f;
+}
+__device__ __forceinline__ bool adam1_window(float p, float g, float a, float& out) {
     // Exact window test (the common case: ~12 instructions, no sqrt, no division).  In real numbers the step is
     // Q = a*0.1f*g / (sqrt(0.001f)*|g|/c + 1e-8f) = A*g / (|g| + c0), A = a*0.1f/kappa, c0 = 1e-8f/kappa,
     // kappa = sqrt(0.001f)/c = 1.0000000775921325.  The roundings of the float pipeline below (m, v twice -- halved by
@@ -126,20 +132,26 @@ __device__ __forceinline__ float adam1_a(float p, float g, float a) {
     // (oracle/verify_math.c qbound: 6.3e8 cases, reciprocal perturbed by +-1 ulp), and 0 disagreements of the window
     // result with the full pipeline on 4e8 random (p, g, lr) triples (verify_math.c window).  The window is ambiguous
     // with probability ~ 2^-18 * lr / ulp(p); those fall through to the full pipeline.
-    if (ag >= 1e-25f && ag < 1e15f && fabsf(a) >= 1e-9f) {
-        float rc;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(__fadd_rn(ag, 9.99999905e-09f)));   // |g| + fl(1e-8f / kappa)
-        const float U = __fmul_rn(__fmul_rn(__fmul_rn(a, 0.099999994f), g), rc);              // a * fl(0.1f / kappa) * g
-        const float xa = __fmaf_rn(U, 1.9073486328125e-06f, U), xb = __fmaf_rn(-U, 1.9073486328125e-06f, U);
-        const float ra = __fadd_rn(p, xa), rb = __fadd_rn(p, xb);
-        if (ra == rb) return ra;
-    } else {
+    const float ag = fabsf(g);
+    float rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(__fadd_rn(ag, 9.99999905e-09f)));   // |g| + fl(1e-8f / kappa)
+    const float U = __fmul_rn(__fmul_rn(__fmul_rn(a, 0.099999994f), g), rc);              // a * fl(0.1f / kappa) * g
+    const float xa = __fmaf_rn(U, 1.9073486328125e-06f, U), xb = __fmaf_rn(-U, 1.9073486328125e-06f, U);
+    const float ra = __fadd_rn(p, xa), rb = __fadd_rn(p, xb);
+    out = ra;
+    return adam1_in_domain(g, a) && ra == rb;
+}
+// everything the window test did not settle: the quarter-ulp shortcut (only outside the window's domain, as in adam1_a's
+// original control flow), then the full pipeline
+__device__ __forceinline__ float adam1_rest(float p, float g, float a, bool in_domain) {
+    const float bc2s = 0.03162277660168381f;
+    if (!in_domain) {
         // Exact shortcut for the gradients of saturated logits (~1e-30).  The step is q = fl(fl(a*m)/d) with
         // d >= 1e-8f, so |q| <= |a|*0.1*|g|*1e8*(1+2^-22).  When that bound is below a quarter ulp of p the sum
         // fl(p+q) is p itself (and denormal operands would send div.rn/sqrt.rn down their ~100-instruction slow paths).
         const float ap = fabsf(p);
         if (ap > 1e-20f) {
-            const float bound = __fmul_rn(__fmul_rn(__fmul_rn(fabsf(a), 0.1f), ag), 1.0001e8f);
+            const float bound = __fmul_rn(__fmul_rn(__fmul_rn(fabsf(a), 0.1f), fabsf(g)), 1.0001e8f);
             if (bound < __fmul_rn(ap, 1.4901161e-8f)) return p;   // 2^-26 * |p|
         }
     }
@@ -161,6 +173,11 @@ __device__ __forceinline__ float adam1_a(float p, float g, float a) {
     }
     const float d = __fadd_rn(d1, 1e-8f);
     return __fadd_rn(p, __fdiv_rn(__fmul_rn(a, m), d));
+}
+__device__ __forceinline__ float adam1_a(float p, float g, float a) {
+    float out;
+    if (adam1_window(p, g, a, out)) return out;
+    return adam1_rest(p, g, a, adam1_in_domain(g, a));
 }
 __device__ __forceinline__ float adam1(float p, float g, float lr) { return adam1_a(p, g, adam_astep(lr)); }
 __device__ __forceinline__ float apply_update(float p, float g, float lr, int mode) {
