@@ -177,12 +177,12 @@ def cfg4_fit_record(lib, steps=30):
     m = pkg.DeepFMAdam(CRITEO_TINY, embedding_size=k, num_hidden_layers=L, neuron_per_hidden_layer=H, n=1e-4)
     enc = [m.encode(Xi, None, Y) for Xi, Y in synth_batches(CRITEO_TINY, B, 4, 7)]
     for i in range(4):
-        m._deep_fit(enc[i % 4])
+        m._deep_fit_graphed(enc[i % 4])
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
-        m._deep_fit(enc[i % 4])
+        m._deep_fit_graphed(enc[i % 4])
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps

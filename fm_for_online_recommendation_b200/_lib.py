@@ -53,6 +53,7 @@ _SIGS = {
     "fmb_mlp_backward": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
                                    C.c_int, vp, C.c_size_t, vp]),
     "fmb_set_tensor_cores": (None, [C.c_int]),
+    "fmb_tensor_cores_enabled": (C.c_int, []),
     "fmb_tensor_core_threshold_log2": (C.c_int, []),
     "fmb_gemm_tc_nt": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "fmb_gemm_tc_strided": (C.c_int, [vp, C.c_int64, C.c_int64, vp, C.c_int64, C.c_int64, vp, C.c_int64, C.c_int,

@@ -101,6 +101,10 @@ static int g_use_tc = -1;   // -1: read FMB_TC from the environment on first use
 // shape of the reference's own scripts (H = 10, B <= 2500, main_experiment.py:50-54) -- stay on the exact SIMT kernel.
 constexpr int TC_THRESHOLD_LOG2 = 24;
 FMB_API void fmb_set_tensor_cores(int on) { g_use_tc = on ? 1 : 0; }
+FMB_API int fmb_tensor_cores_enabled(void) {
+    if (g_use_tc < 0) { const char* e = getenv("FMB_TC"); g_use_tc = (e && e[0] == '0') ? 0 : 1; }
+    return g_use_tc;
+}
 FMB_API int fmb_tensor_core_threshold_log2(void) { return TC_THRESHOLD_LOG2; }
 
 namespace {

@@ -23,11 +23,12 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import FmbError, check, ptr
+from ._lib import FmbError, RunList, check, ptr
 
 UPDATE_ADAM1, UPDATE_SGD, UPDATE_FTRL = 0, 1, 2   # 2: per-coordinate FTRL-Proximal (enable_ftrl), FM-only steps
 LOSS_LOGITS, LOSS_LOGITS_OF_SIG = 0, 1
 _PRESORT_STANDALONE = __import__("os").environ.get("FMB_PRESORT_STANDALONE", "0") == "1"
+_DEEP_GRAPH = __import__("os").environ.get("FMB_DEEP_GRAPH", "1") != "0"   # tower `fit` replayed as one CUDA graph
 
 
 def _stream():
@@ -400,24 +401,42 @@ class _DeepBase(nn.Module):
         self.train()
         return self._fm_step(self.encode(Xi, Xv, Y), self._UE_LOSS, next_batch)
 
-    def _sort(self, e):
+    def _sort(self, e, with_runlist=False):
+        """Stable sort of the batch's row ids -> (sorted keys, permutation[, run list]).  with_runlist (per-field sort only):
+        also the run list the run kernel consumes (one warp per run, long runs first)."""
         N = e.B * self.field_size
         sk = self._buf("skeys", (N,), torch.int32)
         pm = self._buf("perm", (N,), torch.int32)
         if e.B <= self._lib.fmb_sort_fields_max_batch():
+            if with_runlist:
+                nseg, cap = C.c_int(), C.c_int()
+                self._lib.fmb_runlist_shape(e.B, self.field_size, C.byref(nseg), C.byref(cap))
+                ent = self._buf("rl_entries", (nseg.value * cap.value, 4), torch.int32)
+                cnt = self._buf("rl_counts", (2 * nseg.value,), torch.int32)
+                self._rl = RunList(ent.data_ptr(), cnt.data_ptr(), nseg.value, cap.value)
+                check(self._lib.fmb_sort_fields_ex(ptr(e.ids), e.B, self.field_size, ptr(self._field_off_dev), ptr(sk),
+                                                   ptr(pm), None, C.byref(self._rl), 0, _stream()), "fmb_sort_fields_ex")
+                return sk, pm, self._rl
             check(self._lib.fmb_sort_fields(ptr(e.ids), e.B, self.field_size, ptr(self._field_off_dev), ptr(sk),
                                             ptr(pm), _stream()), "fmb_sort_fields")
-            return sk, pm
+            return (sk, pm, None) if with_runlist else (sk, pm)
         wsb = self._lib.fmb_sort_workspace_bytes(N)
         ws = self._buf("sort_ws", (wsb,), torch.uint8)
         check(self._lib.fmb_sort_segment(ptr(e.ids), N, self._key_bits, ptr(ws), wsb, ptr(sk), ptr(pm), None, None,
                                          _stream()), "fmb_sort_segment")
-        return sk, pm
+        return (sk, pm, None) if with_runlist else (sk, pm)
 
     def _deep_fit(self, e):
         """DeepFMAdam.fit / NFMAdam.fit (deepfm_adam.py:106-117, nfm_adam.py:105-116)."""
         B, F, k, L, H = e.B, self.field_size, self.embedding_size, self._L, self._H
         lib, st = self._lib, _stream()
+        # the sort depends on the ids only: side stream, beside the forward pass and the tower's backward
+        main = torch.cuda.current_stream()
+        if getattr(self, "_sort_stream", None) is None:
+            self._sort_stream = torch.cuda.Stream(device=self.device)
+        self._sort_stream.wait_stream(main)
+        with torch.cuda.stream(self._sort_stream):
+            sk, pm, rl = self._sort(e, with_runlist=True)
         o = self._full_forward(e, need_S=True)
         delta = self._buf("delta", (B,))
         check(lib.fmb_loss_delta(self._FIT_LOSS, ptr(o["z"]), ptr(e.y), B, ptr(delta), None, st), "fmb_loss_delta")
@@ -427,17 +446,45 @@ class _DeepBase(nn.Module):
         ws = self._buf("mlp_ws", (wsb,), torch.uint8)
         check(lib.fmb_mlp_backward(ptr(o["bi"]), k, ptr(self._mlp), ptr(o["act"]), ptr(delta), L - 1, B, k, L, H,
                                    ptr(gmlp), ptr(gbi), self._kp4, ptr(ws), wsb, st), "fmb_mlp_backward")
-        sk, pm = self._sort(e)
+        main.wait_stream(self._sort_stream)
         N = B * F
         bwsb = lib.fmb_bwd_workspace_bytes(N, k)
         bws = self._buf("bwd_ws", (bwsb,), torch.uint8)
-        check(lib.fmb_fm_backward_update(ptr(sk), ptr(pm), N, ptr(e.xv), ptr(self._table), F, k, ptr(o["S"]),
-                                         ptr(delta), 0 if self._IS_NFM else 1, ptr(gbi), self._lr, self.update_mode,
-                                         ptr(bws), bwsb, st), "fmb_fm_backward_update")
+        check(lib.fmb_fm_backward_update_rl(ptr(sk), ptr(pm), N, N, ptr(e.xv), ptr(self._table), F, k, ptr(o["S"]), self._kp4,
+                                            ptr(delta), 1, 0 if self._IS_NFM else 1, ptr(gbi), 0x7FFFFFFF, self._lr,
+                                            self.update_mode, C.byref(rl) if rl is not None else None, ptr(bws), bwsb, st),
+              "fmb_fm_backward_update")
         check(lib.fmb_update_dense(ptr(self._mlp), ptr(gmlp), self._mlp.numel(), self._lr, self.update_mode, st),
               "fmb_update_dense")
         check(lib.fmb_finish_step(ptr(delta), None, B, ptr(self.bias), self._lr, self.update_mode, None, st),
               "fmb_finish_step")
+
+    def _deep_fit_graphed(self, e):
+        """_deep_fit as ONE CUDA graph per configuration: the step is ~25 kernel launches through ctypes, which the host
+        submits more slowly than the GPU runs them at cfg4's shapes.  First call of a configuration: eager (allocations,
+        function attributes); second: captured on static input buffers; afterwards: copy the batch in, replay."""
+        if not _DEEP_GRAPH or torch.cuda.is_current_stream_capturing():
+            return self._deep_fit(e)
+        key = (e.B, e.xv is not None, self._lr, self.update_mode, int(self._lib.fmb_tensor_cores_enabled()))
+        graphs = self.__dict__.setdefault("_fit_graphs", {})
+        ent = graphs.get(key)
+        if ent is None:
+            self._deep_fit(e)
+            graphs[key] = "warm"
+            return
+        if ent == "warm":
+            se = EncodedBatch(torch.empty_like(e.ids), None if e.xv is None else torch.empty_like(e.xv), torch.empty_like(e.y))
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                self._deep_fit(se)
+            ent = graphs[key] = (g, se)
+        g, se = ent
+        se.ids.copy_(e.ids, non_blocking=True)
+        if se.xv is not None:
+            se.xv.copy_(e.xv, non_blocking=True)
+        se.y.copy_(e.y, non_blocking=True)
+        g.replay()
 
     def _hedge_fit(self, e):
         """DeepFMOnn.fit / NFMOnn.fit (deepfm_onn.py:109-154): hedge backpropagation; only the tower and
@@ -475,7 +522,7 @@ class _DeepBase(nn.Module):
         elif self._IS_ONN:
             self._hedge_fit(e)
         else:
-            self._deep_fit(e)
+            self._deep_fit_graphed(e)
 
     # ------------------------------------------------------------------ predict / online loop (A8)
     def _predict_dev(self, e):

@@ -314,6 +314,7 @@ int fmb_mlp_backward(const float* bi_dev, int ldbi, const float* mlp_dev, const 
  * with fp32 accumulation in tensor memory (csrc/gemm_tc.cu, ~1e-6 relative); smaller ones -- every shape of the
  * reference's scripts -- on the exact SIMT kernel.  fmb_set_tensor_cores(0) (or FMB_TC=0) forces the exact path. */
 void fmb_set_tensor_cores(int on);
+int fmb_tensor_cores_enabled(void);
 int fmb_tensor_core_threshold_log2(void);
 int fmb_gemm_tc_nt(const float* A_dev /*[M,K]*/, const float* B_dev /*[N,K]*/, float* C_dev /*[M,N]*/, int M, int N,
                    int K, fmb_stream_t stream); /* C = A B^T on the tensor cores (tests) */
