@@ -189,7 +189,26 @@ def cfg4_fit_record(lib, steps=30):
     flop = 2 * B * (k * H + (L - 1) * H * H) * 3          # forward + dX + dW products of the tower
     peaks, _ = measured_peaks()
     tf32x3_peak = 1100.0 / 3                                # nominal dense TF32 (1.1 PFLOP/s) / 3 products per fp32-grade product
-    return {"workload": "cfg4: DeepFMAdam.fit, B=8192, k=10, tower 10-400-400-400, F=39, R=1006628", "steps": steps,
+    hedge = None
+    try:   # DeepFMOnn.fit at the same shape (hedge backpropagation, single backward pass with per-head injection)
+        torch.manual_seed(0)
+        mo = pkg.DeepFMOnn(CRITEO_TINY, embedding_size=k, num_hidden_layers=L, neuron_per_hidden_layer=H, n=1e-4, batch_size=B)
+        for i in range(4):
+            mo._hedge_fit_graphed(enc[i % 4])
+        torch.cuda.synchronize()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for i in range(steps):
+            mo._hedge_fit_graphed(enc[i % 4])
+        h1.record()
+        torch.cuda.synchronize()
+        hms = h0.elapsed_time(h1) / steps
+        hedge = {"workload": "cfg4: DeepFMOnn.fit (hedge backpropagation), same shape", "ms_per_step": hms,
+                 "value": B / (hms * 1e-3), "unit": "samples/s"}
+        del mo
+    except Exception as exc:  # noqa: BLE001
+        hedge = {"unavailable": f"{type(exc).__name__}: {exc}"}
+    return {"hedge_fit": hedge, "workload": "cfg4: DeepFMAdam.fit, B=8192, k=10, tower 10-400-400-400, F=39, R=1006628", "steps": steps,
             "ms_per_step": ms, "value": B / (ms * 1e-3), "unit": "samples/s",
             "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "peak": tf32x3_peak, "unit": "TFLOP/s",
                          "frac": flop / (ms * 1e-3) / 1e12 / tf32x3_peak,

@@ -34,6 +34,10 @@ _SIGS = {
     "fmb_afm_dense_update": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_float, C.c_int, vp, vp]),
     "fmb_fm_backward_runs_all": (C.c_int, [vp, C.c_int64, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, C.c_size_t, vp]),
     "fmb_rrf_run": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, vp, vp, vp, vp]),
+    "fmb_dataset_encode_ids": (C.c_int, [vp, C.c_int64, C.c_int, vp, vp, vp, vp]),
+    "fmb_dataset_take": (C.c_int, [vp, vp, vp, C.c_int, C.c_int64, vp, C.c_int64, vp, vp, vp, vp, vp, vp]),
+    "fmb_dict_encode_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
+    "fmb_dict_encode_first_seen": (C.c_int, [vp, C.c_int64, C.c_int, vp, vp, vp, vp, C.c_size_t, vp]),
     "fmb_metric_regression": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
     "fmb_metric_classification": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp]),
     "fmb_confusion": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
@@ -66,6 +70,8 @@ _SIGS = {
     "fmb_hedge_accumulate": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "fmb_hedge_apply": (C.c_int, [vp, vp, C.c_float, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                   C.c_float, vp]),
+    "fmb_mlp_backward_hedge": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_size_t,
+                                         vp]),
     "fmb_ftrl_fm_run": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, vp, vp, vp, vp, vp, vp, vp]),
     "fmb_sftrl_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "fmb_sftrl_run": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, vp, vp, vp, vp, vp,

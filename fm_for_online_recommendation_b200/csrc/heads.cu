@@ -52,10 +52,13 @@ __global__ void hedge_accumulate_kernel(float* acc, const float* g, const float*
     acc[t] = (t >= lo_i) ? term : __fadd_rn(acc[t], term);  // layer i itself is seen for the first time
 }
 
-// W -= n * acc (deepfm_onn.py:143-145), then the alpha update (:147-154). One CTA.
-__global__ void hedge_apply_kernel(float* mlp, const float* acc, int64_t n, float lr, float* alpha,
-                                   const float* loss_sum, int L, int B, float hb, float hs) {
-    for (int64_t t = threadIdx.x; t < n; t += blockDim.x) mlp[t] = __fsub_rn(mlp[t], __fmul_rn(lr, acc[t]));
+// W -= n * acc (deepfm_onn.py:143-145): elementwise over the whole tower (325 200 parameters at cfg4: a grid, not one CTA)
+__global__ void hedge_apply_w_kernel(float* mlp, const float* acc, int64_t n, float lr) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) mlp[t] = __fsub_rn(mlp[t], __fmul_rn(lr, acc[t]));
+}
+// the alpha update (deepfm_onn.py:147-154). One thread.
+__global__ void hedge_alpha_kernel(float* alpha, const float* loss_sum, int L, int B, float hb, float hs) {
     if (threadIdx.x == 0) {
         const float floorv = __fdiv_rn(hs, (float)L);
         for (int i = 0; i < L; ++i) {
@@ -118,7 +121,9 @@ FMB_API int fmb_hedge_accumulate(float* acc, const float* gmlp, const float* alp
 FMB_API int fmb_hedge_apply(float* mlp, const float* acc, float lr, float* alpha, const float* loss_sum, int B,
                             int k, int L, int H, float hb, float hs, cudaStream_t stream) {
     FMB_CHECK_ARG(mlp && acc && alpha && loss_sum && L > 0 && L < 512, "fmb_hedge_apply: bad arguments");
-    hedge_apply_kernel<<<1, 1024, 0, stream>>>(mlp, acc, (int64_t)w_off(k, H, L), lr, alpha, loss_sum, L, B, hb, hs);
+    const int64_t n = (int64_t)w_off(k, H, L);
+    hedge_apply_w_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(mlp, acc, n, lr);
+    hedge_alpha_kernel<<<1, 32, 0, stream>>>(alpha, loss_sum, L, B, hb, hs);
     FMB_CHECK_LAUNCH("hedge_apply_kernel");
     return FMB_OK;
 }

@@ -135,6 +135,15 @@ __global__ void top_grad_kernel(const float* __restrict__ act, const float* __re
     gp[i] = act[i] > 0.f ? gtop[i / H] : 0.f;
 }
 
+// hedge single pass: gp[b][o] = act[b][o] > 0 ? alpha[i] * gtop[b] : 0  (init != 0: overwrite; else add to gp)
+__global__ void hedge_inject_kernel(const float* __restrict__ act, const float* __restrict__ gtop,
+                                    const float* __restrict__ alpha, int i, int B, int H, int init, float* __restrict__ gp) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)B * H) return;
+    const float t = act[e] > 0.f ? __fmul_rn(alpha[i], gtop[e / H]) : 0.f;
+    gp[e] = init ? t : __fadd_rn(gp[e], t);
+}
+
 }  // namespace
 
 static size_t mlp_w_off(int k, int H, int l) {
@@ -206,5 +215,47 @@ FMB_API int fmb_mlp_backward(const float* bi, int ldbi, const float* mlp, const 
         float* tmp = gp; gp = gnext; gnext = tmp;
     }
     FMB_CHECK_LAUNCH("fmb_mlp_backward");
+    return FMB_OK;
+}
+
+// A7 in ONE backward pass (SURVEY.md A7 "equivalent single pass"): acc = sum_{i >= l} alpha_i dL_i/dW_l for every layer l,
+// obtained by injecting alpha_i * dL_i/d(head_i) at every head on the way down instead of running one backward pass per head
+// (deepfm_onn.py:127-141 runs L passes; hedge_accumulate adds them).  Same mathematics, different rounding (the L-pass form
+// rounds each alpha_i * grad_i separately): used for towers whose products run on the tensor cores, where the per-pass
+// results are themselves within tolerance, not bit-exact; the reference's own shapes (H = 10) keep the L-pass form.
+//   gtop_all [L,B]: d(BCELoss_i)/d(pre-sigmoid logit of head i) (fmb_hedge_head_grad), alpha [L] (device), acc: mlp layout.
+FMB_API int fmb_mlp_backward_hedge(const float* bi, int ldbi, const float* mlp, const float* act, const float* gtop_all,
+                                   const float* alpha, int B, int k, int L, int H, float* acc, void* ws, size_t ws_bytes,
+                                   cudaStream_t stream) {
+    FMB_CHECK_ARG(bi && mlp && act && gtop_all && alpha && acc && ws && L > 0, "fmb_mlp_backward_hedge: bad arguments");
+    if (ws_bytes < fmb_mlp_bwd_workspace_bytes(B, H)) { fmb_set_error("fmb_mlp_backward_hedge: workspace too small"); return FMB_ERR_WS; }
+    float* gp = (float*)ws;
+    float* gnext = gp + (size_t)B * H;
+    const int64_t n = (int64_t)B * H;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    hedge_inject_kernel<<<grid, 256, 0, stream>>>(act + (size_t)(L - 1) * B * H, gtop_all + (size_t)(L - 1) * B, alpha, L - 1, B, H, 1, gp);
+    for (int l = L - 1; l >= 0; --l) {
+        const int nin = l == 0 ? k : H;
+        const float* xin = l == 0 ? bi : act + (size_t)(l - 1) * B * H;
+        const int64_t ldx = l == 0 ? ldbi : H;
+        GemmParams q = {};
+        q.A = gp; q.sam = 1; q.sak = H;
+        q.B = xin; q.sbk = ldx; q.sbn = 1;
+        q.C = acc + mlp_w_off(k, H, l); q.scm = nin;
+        q.M = H; q.N = nin; q.K = B; q.epi = EPI_NONE;
+        q.colsum = acc + mlp_w_off(k, H, l) + (size_t)H * nin;
+        { const int rcg = launch_gemm(q, stream); if (rcg) return rcg; }
+        if (l > 0) {
+            GemmParams r = {};
+            r.A = gp; r.sam = H; r.sak = 1;
+            r.B = mlp + mlp_w_off(k, H, l); r.sbk = nin; r.sbn = 1;
+            r.M = B; r.N = nin; r.K = H;
+            r.C = gnext; r.scm = H; r.epi = EPI_MASK; r.mask = act + (size_t)(l - 1) * B * H; r.smm = H;
+            { const int rcg = launch_gemm(r, stream); if (rcg) return rcg; }
+            hedge_inject_kernel<<<grid, 256, 0, stream>>>(act + (size_t)(l - 1) * B * H, gtop_all + (size_t)(l - 1) * B, alpha, l - 1, B, H, 0, gnext);
+            float* tmp = gp; gp = gnext; gnext = tmp;
+        }
+    }
+    FMB_CHECK_LAUNCH("fmb_mlp_backward_hedge");
     return FMB_OK;
 }

@@ -39,10 +39,11 @@ class EncodedBatch:
     """Device-resident inputs: ids int32 [B,F] global row ids, xv fp32 [B,F] or None
     (all ones), y fp32 [B] or None."""
 
-    __slots__ = ("ids", "xv", "y", "B")
+    __slots__ = ("ids", "xv", "y", "B", "feature_sizes")
 
-    def __init__(self, ids, xv, y):
+    def __init__(self, ids, xv, y, feature_sizes=None):
         self.ids, self.xv, self.y, self.B = ids, xv, y, ids.shape[0]
+        self.feature_sizes = feature_sizes   # set by data.DeviceDataset: the table layout the global ids were built for
 
 
 class _ViewEmbedding(nn.Embedding):
@@ -102,6 +103,7 @@ class _DeepBase(nn.Module):
         self._rowp = self._lib.fmb_rowp(k)
         self._kp4 = self._lib.fmb_kp4(k)
         sizes = np.asarray(list(feature_sizes), dtype=np.int64)
+        self._feature_sizes_t = tuple(int(v) for v in sizes)
         self._offsets_np = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
         self._R = int(self._offsets_np[-1])
         if self._R >= 2 ** 31:
@@ -218,6 +220,8 @@ class _DeepBase(nn.Module):
     def encode(self, Xi, Xv=None, Y=None):
         """lists / ndarrays / tensors -> EncodedBatch on the device. Xi holds per-field local ids."""
         if isinstance(Xi, EncodedBatch):
+            if Xi.feature_sizes is not None and tuple(Xi.feature_sizes) != self._feature_sizes_t:
+                raise IndexError("index out of range in self: the batch was encoded for other feature_sizes")
             return Xi
         F = self.field_size
         if torch.is_tensor(Xi):
@@ -494,23 +498,69 @@ class _DeepBase(nn.Module):
             raise RuntimeError(f"shape '[{self._batch_size}]' is invalid for input of size {B}")  # out.view(batch_size)
         lib, st = self._lib, _stream()
         o = self._full_forward(e)
-        gtop = self._buf("delta", (B,))
         lossv = self._buf("lossv", (B,))
         loss_sum = self._buf("loss_sum", (L,))
-        gmlp = self._buf("gmlp", (self._mlp.numel(),))
         acc = self._buf("hedge_acc", (self._mlp.numel(),))
         wsb = lib.fmb_mlp_bwd_workspace_bytes(B, H)
         ws = self._buf("mlp_ws", (wsb,), torch.uint8)
-        for i in range(L):
-            check(lib.fmb_hedge_head_grad(ptr(o["players"][i]), ptr(e.y), B, ptr(gtop), ptr(lossv), st),
-                  "fmb_hedge_head_grad")
-            check(lib.fmb_sum_aten(ptr(lossv), B, ptr(loss_sum[i:]), st), "fmb_sum_aten")
-            check(lib.fmb_mlp_backward(ptr(o["bi"]), k, ptr(self._mlp), ptr(o["act"]), ptr(gtop), i, B, k, L, H,
-                                       ptr(gmlp), None, 0, ptr(ws), wsb, st), "fmb_mlp_backward")
-            check(lib.fmb_hedge_accumulate(ptr(acc), ptr(gmlp), ptr(self.alpha), i, k, L, H, st),
-                  "fmb_hedge_accumulate")
+        if self._hedge_single_pass(B):
+            # towers on the tensor cores (cfg4: B = 8 192, H = 400): ONE backward pass with alpha_i * dL_i/d(head_i) injected at
+            # every head instead of L passes of growing depth (half the products at L = 3)
+            gtop_all = self._buf("gtop_all", (L, B))
+            for i in range(L):
+                check(lib.fmb_hedge_head_grad(ptr(o["players"][i]), ptr(e.y), B, ptr(gtop_all[i]), ptr(lossv), st),
+                      "fmb_hedge_head_grad")
+                check(lib.fmb_sum_aten(ptr(lossv), B, ptr(loss_sum[i:]), st), "fmb_sum_aten")
+            check(lib.fmb_mlp_backward_hedge(ptr(o["bi"]), k, ptr(self._mlp), ptr(o["act"]), ptr(gtop_all), ptr(self.alpha),
+                                             B, k, L, H, ptr(acc), ptr(ws), wsb, st), "fmb_mlp_backward_hedge")
+        else:
+            gtop = self._buf("delta", (B,))
+            gmlp = self._buf("gmlp", (self._mlp.numel(),))
+            for i in range(L):
+                check(lib.fmb_hedge_head_grad(ptr(o["players"][i]), ptr(e.y), B, ptr(gtop), ptr(lossv), st),
+                      "fmb_hedge_head_grad")
+                check(lib.fmb_sum_aten(ptr(lossv), B, ptr(loss_sum[i:]), st), "fmb_sum_aten")
+                check(lib.fmb_mlp_backward(ptr(o["bi"]), k, ptr(self._mlp), ptr(o["act"]), ptr(gtop), i, B, k, L, H,
+                                           ptr(gmlp), None, 0, ptr(ws), wsb, st), "fmb_mlp_backward")
+                check(lib.fmb_hedge_accumulate(ptr(acc), ptr(gmlp), ptr(self.alpha), i, k, L, H, st),
+                      "fmb_hedge_accumulate")
         check(lib.fmb_hedge_apply(ptr(self._mlp), ptr(acc), self._lr, ptr(self.alpha), ptr(loss_sum), B, k, L, H,
                                   self._hb, self._hs, st), "fmb_hedge_apply")
+
+    def _hedge_single_pass(self, B):
+        """single-pass hedge backward only where the tower's H x H products are on the tensor cores (already within
+        tolerance rather than bit-exact); FMB_HEDGE_SINGLE=0/1 forces it off/on (tests)."""
+        env = __import__("os").environ.get("FMB_HEDGE_SINGLE")
+        if env is not None:
+            return env == "1"
+        return bool(self._lib.fmb_tensor_cores_enabled()) and self._L > 1 and \
+            B * self._H * self._H >= (1 << self._lib.fmb_tensor_core_threshold_log2())
+
+    def _hedge_fit_graphed(self, e):
+        """_hedge_fit as one CUDA graph per configuration when it takes the single-pass route (large towers: ~40 launches
+        through ctypes otherwise); same scheme as _deep_fit_graphed."""
+        if not _DEEP_GRAPH or torch.cuda.is_current_stream_capturing() or not self._hedge_single_pass(e.B):
+            return self._hedge_fit(e)
+        key = ("hedge", e.B, e.xv is not None, self._lr)
+        graphs = self.__dict__.setdefault("_fit_graphs", {})
+        ent = graphs.get(key)
+        if ent is None:
+            self._hedge_fit(e)
+            graphs[key] = "warm"
+            return
+        if ent == "warm":
+            se = EncodedBatch(torch.empty_like(e.ids), None if e.xv is None else torch.empty_like(e.xv), torch.empty_like(e.y))
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                self._hedge_fit(se)
+            ent = graphs[key] = (g, se)
+        g, se = ent
+        se.ids.copy_(e.ids, non_blocking=True)
+        if se.xv is not None:
+            se.xv.copy_(e.xv, non_blocking=True)
+        se.y.copy_(e.y, non_blocking=True)
+        g.replay()
 
     def fit(self, Xi, Xv, Y):
         self.train()
@@ -520,7 +570,7 @@ class _DeepBase(nn.Module):
         if not self._HAS_MLP:
             self._fm_step(e, self._FIT_LOSS)
         elif self._IS_ONN:
-            self._hedge_fit(e)
+            self._hedge_fit_graphed(e)
         else:
             self._deep_fit_graphed(e)
 

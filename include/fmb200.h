@@ -90,6 +90,24 @@ int fmb_rrf_run(const double* X_dev, const double* Y_dev, int N, int d, int D, i
                 double* gamma_dev, double* w_dev, const double* eps_dev, double* preds_dev, int* nvalid_dev,
                 fmb_stream_t stream);
 
+/* ---- device-resident input pipeline (csrc/dataset.cu) ------------------------------------------
+ * fmb_dataset_encode_ids: per-field local ids (the int64 LongTensor of deepfm_adam.py:47) -> global int32 row ids, with
+ *   nn.Embedding's range check (*err_dev = 1 on an id outside [0, feature_sizes[f])); field_off_dev int32 [F+1].
+ * fmb_dataset_take: dst row i = src row index_dev[i] -- the batch builders of utils/data_preprocess.py:154-264 and the
+ *   balance_* functions (:46-82, :120-151), which append one Python list per sample; xv / y may be NULL; pos_count_dev
+ *   (nullable, zeroed by the caller) counts labels == 1 (ratio_list); *err_dev = 1 on an index outside [0, n_src).
+ * fmb_dict_encode_first_seen: read_svm_file's vocabulary build (utils/data_preprocess.py:100-108, `list.index` per cell):
+ *   codes_dev [N,d] = index of X[i,c] among column c's distinct values in order of first appearance, sizes_dev [d] = their
+ *   number (feature_sizes); *err_dev = 2 when X holds a NaN. */
+int fmb_dataset_encode_ids(const int64_t* local_dev, int64_t n, int F, const int32_t* field_off_dev, int32_t* ids_dev,
+                           int* err_dev, fmb_stream_t stream);
+int fmb_dataset_take(const int32_t* ids_src_dev, const float* xv_src_dev, const float* y_src_dev, int F, int64_t n_src,
+                     const int64_t* index_dev, int64_t n, int32_t* ids_dst_dev, float* xv_dst_dev, float* y_dst_dev,
+                     int32_t* pos_count_dev, int* err_dev, fmb_stream_t stream);
+size_t fmb_dict_encode_workspace_bytes(int64_t N, int d);
+int fmb_dict_encode_first_seen(const double* X_dev, int64_t N, int d, int32_t* codes_dev, int32_t* sizes_dev, int* err_dev,
+                               void* ws_dev, size_t ws_bytes, fmb_stream_t stream);
+
 /* ---- metrics on the device (csrc/metrics.cu) -------------------------------------------------
  * running curves of utils/metric_manager.py:7-29 (fp64, sequential accumulation like the Python loops), confusion
  * counts of fm_adam.py:101-111 for a batch of predictions, exact ROC AUC ingredients (pair counts), torch.sigmoid of
@@ -343,6 +361,13 @@ int fmb_hedge_accumulate(float* acc_dev, const float* gmlp_dev, const float* alp
                          fmb_stream_t stream);
 int fmb_hedge_apply(float* mlp_dev, const float* acc_dev, float lr, float* alpha_dev, const float* loss_sum_dev,
                     int B, int k, int L, int H, float hb, float hs, fmb_stream_t stream);
+/* hedge backpropagation in ONE backward pass: acc = sum_{i>=l} alpha_i dL_i/dW_l for every layer l, by
+ * injecting alpha_i * gtop_all[i] at every head on the way down; replaces the L calls of fmb_mlp_backward +
+ * fmb_hedge_accumulate (deepfm_onn.py:127-141) when the tower's products run on the tensor cores (results within
+ * tolerance of the L-pass form, not bit-identical to it: each alpha_i * grad_i is no longer rounded separately). */
+int fmb_mlp_backward_hedge(const float* bi_dev, int ldbi, const float* mlp_dev, const float* act_dev,
+                           const float* gtop_all_dev /*[L,B]*/, const float* alpha_dev /*[L]*/, int B, int k, int L, int H,
+                           float* acc_dev, void* ws_dev, size_t ws_bytes, fmb_stream_t stream);
 
 /* ---- A8: per-example online mode as one persistent kernel ---------------------------------------
  * replaces run_experiment (fm_adam.py:90-119, same in all five classes): for each example in order,
