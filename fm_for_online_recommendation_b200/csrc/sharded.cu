@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(fmb::SS_THREADS) shard_sort_fields_kernel(
     const int32_t* __restrict__ idsT_all, int G, int glog, int me, int B, int F,
     const int32_t* __restrict__ field_off, int cap, int32_t* __restrict__ skeys, int32_t* __restrict__ perm,
     int32_t* __restrict__ counts, int32_t* __restrict__ overflow, int4* __restrict__ rl_entries,
-    uint32_t* __restrict__ rl_segc, int rl_cap) {
+    uint32_t* __restrict__ rl_segc, int rl_cap, uint32_t* __restrict__ posflag) {
     extern __shared__ __align__(16) unsigned char fs_smem[];
     uint32_t* kbuf0 = reinterpret_cast<uint32_t*>(fs_smem);
     uint32_t* kbuf1 = kbuf0 + cap;
@@ -203,6 +203,15 @@ __global__ void __launch_bounds__(fmb::SS_THREADS) shard_sort_fields_kernel(
     for (int i = threadIdx.x; i < cap; i += fmb::SS_THREADS) {
         skeys[(size_t)f * cap + i] = i < n ? (int32_t)kc[i] + base : 0x7fffffff;
         perm[(size_t)f * cap + i] = i < n ? (int32_t)pc[i] * F + f : 0;
+    }
+    // fused step (shard3.cu): per entry (field, global sample) its sorted position | multi-hit flag, field-major [F][G*B]
+    if (posflag) {
+        const size_t GB = (size_t)G * B;
+        for (int i = threadIdx.x; i < n; i += fmb::SS_THREADS) {
+            const uint32_t key = kc[i];
+            const bool multi = (i > 0 && kc[i - 1] == key) || (i + 1 < n && kc[i + 1] == key);
+            posflag[(size_t)f * GB + pc[i]] = (uint32_t)(f * cap + i) | (multi ? 0x80000000u : 0u);
+        }
     }
     // run list for the backward's run kernel (one segment per field; rl_segc = [F short counts | F long counts])
     if (rl_entries)
@@ -719,9 +728,11 @@ FMB_API int fmb_shard_unpack_ctx(const float* ctx_all, int64_t n, int k, float* 
 // _rl: also the run list of every field's sorted owned entries (rl: nseg == F, seg_cap >= cap / 2 + 1; nullable), for
 // fmb_fm_backward_update_rl
 struct fmb_runlist_t { int32_t* entries; uint32_t* seg_count; int nseg, seg_cap; };   // include/fmb200.h
-FMB_API int fmb_shard_sort_fields_rl(const int32_t* idsT_all, int G, int me, int B, int F, const int32_t* field_off,
+// _pf: also posflag [F][G*B] (nullable): sorted position | 0x80000000 when the row is hit more than once, for every entry
+// this rank owns (the other words are left untouched) -- what fmb_shard3_step reads
+FMB_API int fmb_shard_sort_fields_pf(const int32_t* idsT_all, int G, int me, int B, int F, const int32_t* field_off,
                                      int cap, int32_t* skeys, int32_t* perm, int32_t* counts, int32_t* overflow,
-                                     const fmb_runlist_t* rl, cudaStream_t stream) {
+                                     const fmb_runlist_t* rl, uint32_t* posflag, cudaStream_t stream) {
     FMB_CHECK_ARG(idsT_all && field_off && skeys && perm && counts && overflow, "fmb_shard_sort_fields: null pointer");
     FMB_CHECK_ARG(!rl || (rl->entries && rl->seg_count && rl->nseg == F && rl->seg_cap >= cap / 2 + 1 && F <= 2048),
                   "fmb_shard_sort_fields: run list must have F segments of at least cap/2 + 1 entries");
@@ -731,9 +742,15 @@ FMB_API int fmb_shard_sort_fields_rl(const int32_t* idsT_all, int G, int me, int
     if (!attr) { cudaFuncSetAttribute(shard_sort_fields_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr = true; }
     shard_sort_fields_kernel<<<F, fmb::SS_THREADS, fmb::smem_sort_bytes(cap), stream>>>(
         idsT_all, G, ilog2_exact(G), me, B, F, field_off, cap, skeys, perm, counts, overflow,
-        rl ? reinterpret_cast<int4*>(rl->entries) : nullptr, rl ? rl->seg_count : nullptr, rl ? rl->seg_cap : 0);
+        rl ? reinterpret_cast<int4*>(rl->entries) : nullptr, rl ? rl->seg_count : nullptr, rl ? rl->seg_cap : 0, posflag);
     FMB_CHECK_LAUNCH("shard_sort_fields_kernel");
     return FMB_OK;
+}
+
+FMB_API int fmb_shard_sort_fields_rl(const int32_t* idsT_all, int G, int me, int B, int F, const int32_t* field_off,
+                                     int cap, int32_t* skeys, int32_t* perm, int32_t* counts, int32_t* overflow,
+                                     const fmb_runlist_t* rl, cudaStream_t stream) {
+    return fmb_shard_sort_fields_pf(idsT_all, G, me, B, F, field_off, cap, skeys, perm, counts, overflow, rl, nullptr, stream);
 }
 
 FMB_API int fmb_shard_sort_fields(const int32_t* idsT_all, int G, int me, int B, int F, const int32_t* field_off,

@@ -146,8 +146,9 @@ class ShardedFM:
               "fmb_shard_partial_forward")
         return partial
 
-    def _sort_owned(self, idsT_all, slot):
-        """stable per-field sort of the entries this rank owns, on the CURRENT stream, into buffer set `slot`."""
+    def _sort_owned(self, idsT_all, slot, posflag=None):
+        """stable per-field sort of the entries this rank owns, on the CURRENT stream, into buffer set `slot`
+        (posflag: also every owned entry's sorted position | multi-hit flag, for the fused step)."""
         lib = self._lib
         G, F = self.G, self.F
         B = idsT_all.shape[2]
@@ -166,9 +167,9 @@ class ShardedFM:
             cnt = self._buf(f"rl_counts{slot}", (2 * F,), torch.int32)
             self._rl[slot] = RunList(ent.data_ptr(), cnt.data_ptr(), F, rcap)
             rl = C.byref(self._rl[slot])
-        check(lib.fmb_shard_sort_fields_rl(ptr(idsT_all), G, self.rank, B, F, ptr(self.field_off_dev), cap,
-                                           ptr(skeys), ptr(perm), ptr(counts), ptr(self.overflow), rl, _stream()),
-              "fmb_shard_sort_fields")
+        check(lib.fmb_shard_sort_fields_pf(ptr(idsT_all), G, self.rank, B, F, ptr(self.field_off_dev), cap,
+                                           ptr(skeys), ptr(perm), ptr(counts), ptr(self.overflow), rl, ptr(posflag),
+                                           _stream()), "fmb_shard_sort_fields")
 
     def phase_owner_forward(self, idsT_all):
         """idsT_all [G,F,B] -> partial [G,B,PW] (block r goes to rank r); also sorts the owned entries."""
@@ -283,31 +284,45 @@ class ShardedFM:
     # followed by epoch flags: csrc/sharded.cu "Peer-memory exchange".  Channels of the flag block:
     CH_IDS, CH_A2A, CH_CTX = 0, 1, 2
 
-    def _peer_setup(self, B):
-        """allocate idsT_all (two slots), recv, ctx_all and the flag block in symmetric memory and map the peers'
-        copies (collective: every rank calls it with the same B)."""
-        import torch.distributed._symmetric_memory as symm
+    def _peer_layout(self, B):
+        """sub-buffers of the exchange arena (int32 words, 256-byte aligned): name -> (offset, words)"""
         G, F = self.G, self.F
-        group = self.group if self.group is not None else dist.group.WORLD
-        words = {"ids0": G * F * B, "ids1": G * F * B, "recv": G * B * self.PW, "ctx": G * B * self.CW, "flags": 64}
+        T = self._lib.fmb_shard3_tiles(G, B, F, self.k)
+        words = {"ids0": G * F * B, "ids1": G * F * B, "recv": G * B * self.PW, "ctx": G * B * self.CW, "flags": 64,
+                 "tflags": max(2 * T, 64)}
         off, total = {}, 0
         for name, n in words.items():
-            off[name] = total
-            total += (n + 63) // 64 * 64          # 256-byte aligned sub-buffers
+            off[name] = (total, n)
+            total += (n + 63) // 64 * 64
+        return off, total, T
+
+    def _peer_bind(self, B, arena, base_ptrs, hdl=None):
+        """arena: MY zero-initialised exchange buffer; base_ptrs[r]: the address at which this device sees rank r's"""
+        G, F = self.G, self.F
+        off, total, T = self._peer_layout(B)
+        ptrs = {name: (C.c_void_p * G)(*[int(base_ptrs[r]) + 4 * o for r in range(G)]) for name, (o, _) in off.items()}
+        view = {name: arena[o:o + n] for name, (o, n) in off.items()}
+        self._peer = {"B": B, "arena": arena, "hdl": hdl, "ptrs": ptrs, "tiles": T,
+                      "ids": [view["ids0"].view(G, F, B), view["ids1"].view(G, F, B)],
+                      "recv": view["recv"].view(torch.float32).view(G, B, self.PW),
+                      "ctx": view["ctx"].view(torch.float32).view(G * B, self.CW),
+                      "flags": view["flags"], "tflags": view["tflags"],
+                      "posflag": [torch.zeros((F, G * B), dtype=torch.int32, device=self.device) for _ in range(2)] if T else None,
+                      "epoch": torch.zeros(16, dtype=torch.int32, device=self.device),   # epoch[8] | block counters[8]
+                      "error": torch.zeros(1, dtype=torch.int32, device=self.device)}
+
+    def _peer_setup(self, B):
+        """allocate idsT_all (two slots), recv, ctx_all and the flag blocks in symmetric memory and map the peers'
+        copies (collective: every rank calls it with the same B)."""
+        import torch.distributed._symmetric_memory as symm
+        group = self.group if self.group is not None else dist.group.WORLD
+        _, total, _ = self._peer_layout(B)
         arena = symm.empty(total, dtype=torch.int32, device=self.device)
         arena.zero_()
         hdl = symm.rendezvous(arena, group)
         torch.cuda.synchronize()
         dist.barrier(group=group)                  # every flag block is zero before anyone publishes
-        ptrs = {name: (C.c_void_p * G)(*[int(hdl.buffer_ptrs[r]) + 4 * o for r in range(G)]) for name, o in off.items()}
-        view = {name: arena[o:o + words[name]] for name, o in off.items()}
-        self._peer = {"B": B, "arena": arena, "hdl": hdl, "ptrs": ptrs,
-                      "ids": [view["ids0"].view(G, F, B), view["ids1"].view(G, F, B)],
-                      "recv": view["recv"].view(torch.float32).view(G, B, self.PW),
-                      "ctx": view["ctx"].view(torch.float32).view(G * B, self.CW),
-                      "flags": view["flags"],
-                      "epoch": torch.zeros(16, dtype=torch.int32, device=self.device),   # epoch[8] | block counters[8]
-                      "error": torch.zeros(1, dtype=torch.int32, device=self.device)}
+        self._peer_bind(B, arena, [int(hdl.buffer_ptrs[r]) for r in range(self.G)], hdl)
 
     def _sync_args(self):
         pr = self._peer
@@ -362,8 +377,116 @@ class ShardedFM:
             self._poll()
         return loss
 
+    # ---------------------------------------------------------------- the step as ONE kernel (csrc/shard3.cu)
+    CH_TILE = 3     # word of the sync block that counts the fused steps (the per-tile flags carry this epoch)
+
+    def fused_supported(self, B):
+        return self._lib.fmb_shard3_tiles(self.G, B, self.F, self.k) > 0
+
+    def _prepare_fused(self, ids, slot):
+        """ids of the NEXT batch: exchange, owner sort with the per-entry position words, on the _pre stream"""
+        pr, B = self._peer, ids.shape[0]
+        main = torch.cuda.current_stream()
+        self._pre.wait_stream(main)
+        with torch.cuda.stream(self._pre):
+            check(self._lib.fmb_shard_transpose_ids_peers(ptr(ids), B, self.F, self.G, self.rank,
+                                                          pr["ptrs"][f"ids{slot}"], *self._sync_args(), self.CH_IDS,
+                                                          _stream()), "fmb_shard_transpose_ids_peers")
+            self._signal(self.CH_IDS, 2)
+            self._sort_owned(pr["ids"][slot], slot, pr["posflag"][slot])
+
+    def prepare_fused(self, ids):
+        if getattr(self, "_peer", None) is None or self._peer["B"] != ids.shape[0]:
+            self._peer_setup(ids.shape[0])
+        if not self._peer["tiles"]:
+            raise RuntimeError("fused sharded step: shape not supported (G power of two, B % (8 G) == 0, k <= 15)")
+        self._slot = 0
+        self._prepare_fused(ids, 0)
+        torch.cuda.current_stream().wait_stream(self._pre)
+
+    def _fused_launch(self, y, p, loss_kind):
+        """the fused kernel + step-counter bump on the current stream (emulated ranks launch these on their own streams)"""
+        pr, lib, G, F, k = self._peer, self._lib, self.G, self.F, self.k
+        B, cap = pr["B"], self._cap
+        wsb = lib.fmb_bwd_workspace_bytes(F * cap, k)
+        ws = self._buf("bwd_ws", (wsb,), torch.uint8)
+        ep = C.c_void_p(pr["epoch"].data_ptr() + 4 * self.CH_TILE)
+        check(lib.fmb_shard3_step(ptr(pr["ids"][p]), ptr(self.table), ptr(self.bias), ptr(y), ptr(pr["posflag"][p]), G,
+                                  self.rank, B, F, k, cap, loss_kind, self.lr, self.update_mode, ptr(ws), wsb,
+                                  pr["ptrs"]["recv"], pr["ptrs"]["ctx"], pr["ptrs"]["tflags"], ptr(pr["recv"]), ptr(pr["ctx"]),
+                                  ptr(pr["tflags"]), ep, ptr(pr["error"]), _stream()), "fmb_shard3_step")
+        check(lib.fmb_shard3_bump(ep, _stream()), "fmb_shard3_bump")
+        return ws, wsb
+
+    def _fused_finish(self, ws, wsb, p):
+        """behind the fused kernel: run kernel over the staged multi-hit contributions (main) beside the bias step (side)"""
+        pr, lib, F, k, cap = self._peer, self._lib, self.F, self.k, self._cap
+        Btot = self.G * pr["B"]
+        main = torch.cuda.current_stream()
+        delta_all = self._buf("delta_all", (Btot,))
+        lossv_all = self._buf("lossv_all", (Btot,))
+        loss = torch.empty((), device=self.device)
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            check(lib.fmb_shard_unpack_ctx(ptr(pr["ctx"]), Btot, k, ptr(delta_all), ptr(lossv_all), _stream()),
+                  "fmb_shard_unpack_ctx")
+            check(lib.fmb_finish_step(ptr(delta_all), ptr(lossv_all), Btot, ptr(self.bias), self.lr,
+                                      self.update_mode, ptr(loss), _stream()), "fmb_finish_step")
+        rl = C.byref(self._rl[p]) if (_USE_RUNLIST and p in self._rl) else None
+        check(lib.fmb_fm_backward_runs_list(ptr(self._ws[f"skeys{p}"]), F * cap, ptr(self.table), F, k, self.lr,
+                                            self.update_mode, None, rl, ptr(ws), wsb, _stream()),
+              "fmb_fm_backward_runs_list")
+        self.launches += 6
+        main.wait_stream(self._side)
+        return loss
+
+    def update_embedding_fused(self, y, ids_next, loss_kind=0):
+        """update_embedding_peers with partial forward, both exchanges, combine and the row updates in ONE kernel whose
+        tiles keep their rows in shared memory (rows read once; per-tile flags instead of per-kernel epochs)."""
+        p = self._slot
+        main = torch.cuda.current_stream()
+        if ids_next is not None:
+            self._prepare_fused(ids_next, 1 - p)
+        ws, wsb = self._fused_launch(y, p, loss_kind)
+        loss = self._fused_finish(ws, wsb, p)
+        main.wait_stream(self._pre)
+        self._slot = 1 - p
+        if not torch.cuda.is_current_stream_capturing():
+            self._poll()
+        return loss
+
+    def capture_fused(self, ids, y, loss_kind=0):
+        """capture_peers for the fused step"""
+        self._g_ids = ids.clone()
+        self._g_y = y.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.prepare_fused(self._g_ids)
+            for _ in range(2):
+                self.update_embedding_fused(self._g_y, self._g_ids, loss_kind)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._pgraphs, self._pg_loss = [], []
+        for parity in (0, 1):
+            self._slot = parity
+            g = torch.cuda.CUDAGraph()
+            l0 = self.launches
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                loss = self.update_embedding_fused(self._g_y, self._g_ids, loss_kind)
+            self._graph_launches = self.launches - l0
+            self.launches = l0
+            self._pgraphs.append(g)
+            self._pg_loss.append(loss)
+        self._slot = 0
+        return self
+
     def check_exchange(self):
         v = int(self._peer["error"].item()) if getattr(self, "_peer", None) else 0
+        if v == 32:
+            raise RuntimeError("fused sharded step: a tile owned more entries than its shared-memory capacity (skewed ids)")
+        if v >= 16:
+            raise RuntimeError(f"fused sharded step: phase {v - 16} timed out waiting for a peer's tile flag")
         if v:
             raise RuntimeError(f"peer-memory exchange: channel {v - 1} timed out waiting for a peer's epoch flag")
 
@@ -495,6 +618,12 @@ def bench_main(args, sizes, config):
     pipelined = os.environ.get("FMB_SHARD_PIPELINE", "1") != "0"
     # exchanges: "peers" = stores into peer-mapped symmetric memory + epoch flags (default), "nccl" = collectives
     exchange = os.environ.get("FMB_SHARD_EXCHANGE", "peers") if pipelined else "nccl"
+    fused = exchange == "fused"          # csrc/shard3.cu: the step as one kernel with per-tile flags (needs the peer mapping)
+    if fused and not model.fused_supported(B):
+        print(f"[rank {rank}] fused sharded step does not support this shape; using the three-kernel peer path", file=sys.stderr, flush=True)
+        fused = False
+    if fused:
+        exchange = "peers"
     if exchange == "peers":
         # mapping the peers' buffers needs symmetric-memory support on this box; every rank must take the same path,
         # so the ranks agree (all-reduce of a success flag) and fall back to the NCCL exchange together, loudly
@@ -510,14 +639,16 @@ def bench_main(args, sizes, config):
         if int(flag.item()) == 0:
             exchange = "nccl"
             model._peer = None
-    prepare = model.prepare_peers if exchange == "peers" else model.prepare
+    fused = fused and exchange == "peers"
+    prepare = model.prepare_fused if fused else (model.prepare_peers if exchange == "peers" else model.prepare)
     if pipelined:
         # step i trains on batch i while batch i+1's ids are exchanged and sorted (update_embedding_pipelined)
         if use_graph:
-            (model.capture_peers if exchange == "peers" else model.capture_pipelined)(*enc[0])
+            (model.capture_fused if fused else model.capture_peers if exchange == "peers" else model.capture_pipelined)(*enc[0])
             run = model.step_graphed_pipelined
         else:
-            run = model.update_embedding_peers if exchange == "peers" else model.update_embedding_pipelined
+            run = (model.update_embedding_fused if fused else
+                   model.update_embedding_peers if exchange == "peers" else model.update_embedding_pipelined)
         prepare(enc[0][0])
 
         def step(i):
@@ -595,14 +726,18 @@ def bench_main(args, sizes, config):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(config, parallelism=f"row-sharded tables over {world} GPUs (r % G); ids / pooled partials / "
                                                "sample contexts exchanged by " +
-                                               ("stores into peer-mapped symmetric memory + epoch flags (no NCCL in the step)"
+                                               ("stores into peer-mapped symmetric memory inside ONE fused step kernel per rank (tiles "
+                                                "keep their rows in shared memory across both exchanges; per-tile flags; no NCCL "
+                                                "in the step)" if fused else
+                                                "stores into peer-mapped symmetric memory + epoch flags (no NCCL in the step)"
                                                 if exchange == "peers" else "NCCL all-gather + all-to-all + all-gather") +
                                                ("; next batch's id exchange + owner sort overlapped" if pipelined else ""),
                           global_batch=world * B),
             "clocks": clocks,
             "e2e": {"value": world * B * K / float(e2e.item()), "unit": "samples/s",
                     "h2d_bytes_per_step": 4 * B * F + 4 * B, "d2h_bytes_per_step": 4,
-                    "api": ("ShardedFM.update_embedding_peers" if exchange == "peers" else
+                    "api": ("ShardedFM.update_embedding_fused" if fused else
+                            "ShardedFM.update_embedding_peers" if exchange == "peers" else
                             "ShardedFM.update_embedding_pipelined" if pipelined else "ShardedFM.update_embedding") +
                            " (pinned host ids/y in, loss out, per rank)"},
             "gpu_launches": int(launches),

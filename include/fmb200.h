@@ -316,6 +316,28 @@ int fmb_shard_combine_peers(const float* recv_dev, const float* bias_dev, const 
 int fmb_shard_signal(void* const* flag_peers, uint32_t* flags_local_dev, uint32_t* sync_local_dev, int channel, int G,
                      int me, int mode, int* error_dev, fmb_stream_t stream);
 
+/* ---- the sharded step as ONE kernel per rank (csrc/shard3.cu): a CTA keeps the rows it owns for a tile of 8*G samples in
+ * shared memory across both exchanges (partials -> the samples' owner, context -> everyone) and updates from that copy;
+ * per-TILE epoch flags in peer-mapped memory instead of per-kernel ones.  Same arithmetic, same order, same results as the
+ * three-kernel path above (fm_adam.py:56-69 on the concatenated batch, owner-major fold).
+ *   fmb_shard3_tiles        tiles per step (0 = shape not supported: G in {1,2,4,8}, B % (8*G) == 0, G*B <= 65536, k <= 15);
+ *                           the tile-flag block holds 2 * tiles uint32 words, zero-initialised, mapped by every peer
+ *   fmb_shard_sort_fields_pf  fmb_shard_sort_fields_rl + posflag [F][G*B]: sorted position | 0x80000000 (row hit more than
+ *                           once) of every entry this rank owns
+ *   fmb_shard3_step         the step up to the staged multi-hit contributions; fmb_fm_backward_runs_list, fmb_shard_unpack_ctx
+ *                           and fmb_finish_step follow; epoch_dev: uint32 step counter (device), fmb_shard3_bump adds 1 behind
+ *                           the step; *error_dev: 16 + phase on a time-out, 32 when a tile's entry capacity overflowed */
+int fmb_shard3_tiles(int G, int B, int F, int k);
+int fmb_shard_sort_fields_pf(const int32_t* idsT_all_dev, int G, int me, int B, int F, const int32_t* field_off_dev, int cap,
+                             int32_t* skeys_dev, int32_t* perm_dev, int32_t* counts_dev, int32_t* overflow_dev,
+                             const fmb_runlist_t* rl, uint32_t* posflag_dev, fmb_stream_t stream);
+int fmb_shard3_step(const int32_t* idsT_all_dev, float* table_local_dev, const float* bias_dev, const float* y_dev,
+                    const uint32_t* posflag_dev, int G, int me, int B, int F, int k, int cap, int loss_kind, float lr, int mode,
+                    void* ws_dev, size_t ws_bytes, void* const* recv_peers, void* const* ctx_peers, void* const* tflag_peers,
+                    const float* recv_local_dev, const float* ctx_local_dev, const uint32_t* tflags_local_dev,
+                    const uint32_t* epoch_dev, int* error_dev, fmb_stream_t stream);
+int fmb_shard3_bump(uint32_t* epoch_dev, fmb_stream_t stream);
+
 /* ---- A4/A5: MLP tower on the Bi-Interaction vector (deepfm_adam.py:79-89, nfm_adam.py:78-88,
  * deepfm_onn.py:88-102).  mlp = W0[H,k] c0[H] W1[H,H] c1[H] ... (nn.Linear layouts, concatenated);
  * act [L,B,H] post-relu activations; head [L,B] = sum_j act[l][b][j]. fp32 SIMT, k-ascending FMA. */

@@ -181,7 +181,8 @@ def test_cuda_ranks_emulated_bit_exact(G, B):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("graph,peers", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("graph,peers", [(False, False), (True, False), (False, True), (True, True), (False, "fused"),
+                                         (True, "fused")])
 def test_pipelined_step_equals_unpipelined_world1_nccl(graph, peers):
     """ShardedFM.update_embedding_pipelined (ids of batch t+1 exchanged and sorted under step t) against
     update_embedding over a real NCCL group (world 1 here; tests/sharded_pipeline_check.py under torchrun for
@@ -192,6 +193,6 @@ def test_pipelined_step_equals_unpipelined_world1_nccl(graph, peers):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE="1", RANK="0", LOCAL_RANK="0")
     cmd = ([sys.executable, os.path.join(here, "sharded_pipeline_check.py")] + (["--graph"] if graph else []) +
-           (["--peers"] if peers else []))   # --peers: exchanges through peer-mapped symmetric memory + epoch flags
+           (["--fused"] if peers == "fused" else ["--peers"] if peers else []))   # --fused: one kernel per rank; --peers: exchanges through peer-mapped symmetric memory + epoch flags
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0 and "PIPELINE_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
