@@ -47,6 +47,7 @@ struct Step3Params {
     const uint32_t* tflags_local;
     const uint32_t* epoch;       // this step's epoch is *epoch + 1 (bumped by shard3_bump_kernel behind the step)
     int* error;                  // 16 + phase on a time-out, 32 on a tile's entry-capacity overflow
+    long long* tdbg;             // debug only: per-tile phase timestamps [T][8] (globaltimer ns), else NULL
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -87,6 +88,8 @@ __global__ void __launch_bounds__(256, 7) shard_step_fused_kernel(Step3Params p)
     const uint32_t e_now = *p.epoch + 1u;
     const int64_t GB = (int64_t)p.G * p.B;
     if (threadIdx.x == 0) { n_single = 0; n_multi = 0; }
+#define S3_TS(i) do { if (p.tdbg && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); p.tdbg[(size_t)blockIdx.x * 8 + (i)] = (long long)t_; } } while (0)
+    S3_TS(0);
 
     // ---- P0a: the tile's ids, coalesced rows of idsT_all[o]
     {
@@ -160,6 +163,7 @@ __global__ void __launch_bounds__(256, 7) shard_step_fused_kernel(Step3Params p)
         }
     }
     __syncthreads();
+    S3_TS(1);
     const int ne = n_ent;
     // ---- P1: gather the owned rows (the ids are dead: rows_s takes their place)
     {
@@ -171,28 +175,37 @@ __global__ void __launch_bounds__(256, 7) shard_step_fused_kernel(Step3Params p)
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     }
     __syncthreads();
+    S3_TS(2);
     // ---- P2 + P3: partial sums over the owned fields in field order, stored straight into recv of the samples' owner
     // (the lanes of a sample write 4*(k+1) contiguous bytes each for S and Q); then the tile's flag there
     const int jl = 1 << p.jl_log, j = threadIdx.x & (jl - 1);
     for (int s = threadIdx.x >> p.jl_log; s < SB; s += 256 >> p.jl_log) {
         float* out = static_cast<float*>(p.recv.p[o]) + ((size_t)p.me * p.B + b0 + s) * PW;
+        float S = 0.f, Q = 0.f;
         if (j <= k) {
-            float S = 0.f, Q = 0.f;
             const int u0 = start_s[s], u1 = start_s[s + 1];
             for (int u = u0; u < u1; ++u) {
                 const float e = rows_s[(size_t)u * rp + j];       // x == 1
                 S = __fadd_rn(S, e);
                 Q = __fadd_rn(Q, __fmul_rn(e, e));
             }
-            if (j < k) { out[j] = S; out[kp4 + j] = Q; }
-            else { out[2 * kp4] = S; if (j < kp4) { out[j] = 0.f; out[kp4 + j] = 0.f; } }
-        } else if (j < kp4) { out[j] = 0.f; out[kp4 + j] = 0.f; }
+        }
+        // 16-byte stores (4-byte stores over NVLink made this phase 11 us): lane 4q collects components 4q..4q+3 of S and
+        // of Q from its neighbours; padding components (k <= j < kp4) are zero; lane k holds the first-order sum
+        const float first = __shfl_sync(0xffffffffu, S, (lane & ~(jl - 1)) + k);
+        const float Sv = j < k ? S : 0.f, Qv = j < k ? Q : 0.f;
+        const float S1 = __shfl_down_sync(0xffffffffu, Sv, 1), S2 = __shfl_down_sync(0xffffffffu, Sv, 2), S3 = __shfl_down_sync(0xffffffffu, Sv, 3);
+        const float Q1 = __shfl_down_sync(0xffffffffu, Qv, 1), Q2 = __shfl_down_sync(0xffffffffu, Qv, 2), Q3 = __shfl_down_sync(0xffffffffu, Qv, 3);
+        if ((j & 3) == 0 && j < kp4) {
+            *reinterpret_cast<float4*>(out + j) = make_float4(Sv, S1, S2, S3);
+            *reinterpret_cast<float4*>(out + kp4 + j) = make_float4(Qv, Q1, Q2, Q3);
+        }
+        if (j == 1) *reinterpret_cast<float4*>(out + 2 * kp4) = make_float4(first, 0.f, 0.f, 0.f);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        st_release_sys(static_cast<uint32_t*>(p.tflags.p[o]) + (size_t)p.me * p.Tl + tl, e_now);
-    }
+    // release at system scope: the barrier orders the CTA's stores before thread 0's release (no separate fence.sc.sys)
+    if (threadIdx.x == 0) st_release_sys(static_cast<uint32_t*>(p.tflags.p[o]) + (size_t)p.me * p.Tl + tl, e_now);
+    S3_TS(3);
     // ---- P4: my own samples: fold the G partials in owner order, logit, loss, delta; context to every rank
     if (o == p.me) {
         if ((int)threadIdx.x < p.G)
@@ -235,11 +248,9 @@ __global__ void __launch_bounds__(256, 7) shard_step_fused_kernel(Step3Params p)
             for (int r = 0; r < p.G; ++r) static_cast<float4*>(p.ctx.p[r])[o4 + i] = v;
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence_system();
-            for (int r = 0; r < p.G; ++r) st_release_sys(static_cast<uint32_t*>(p.tflags.p[r]) + p.T + t, e_now);
-        }
+        if ((int)threadIdx.x < p.G) st_release_sys(static_cast<uint32_t*>(p.tflags.p[threadIdx.x]) + p.T + t, e_now);
     }
+    S3_TS(4);
     // ---- P5: the tile's context (S, delta) from the samples' owner
     if (threadIdx.x == 0)
         if (!wait_flag(p.tflags_local + p.T + t, e_now)) atomicExch(p.error, 16 + 5);
@@ -250,6 +261,7 @@ __global__ void __launch_bounds__(256, 7) shard_step_fused_kernel(Step3Params p)
         for (int i = threadIdx.x; i < n4; i += 256) reinterpret_cast<float4*>(ctx_s)[i] = __ldcg(src + i);
         __syncthreads();
     }
+    S3_TS(5);
     // ---- P6a: rows hit once in the global batch: gradient = 0 + contribution, update from the shared-memory copy
     const int ns = n_single, nm = n_multi;
     for (int it = threadIdx.x; it < ns * CU; it += 256) {
@@ -296,10 +308,12 @@ __global__ void __launch_bounds__(256, 7) shard_step_fused_kernel(Step3Params p)
             else if (jj == k) g[(size_t)u * p.Npad] = d;
         }
     }
+    S3_TS(6);
 }
 
 __global__ void shard3_bump_kernel(uint32_t* epoch) { *epoch += 1u; }
 
+static long long* g_s3_tdbg = nullptr;
 static int ilog2_exact3(int x) { int l = 0; while ((1 << l) < x) ++l; return (1 << l) == x ? l : -1; }
 static int ilog2_ceil3(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
 static int64_t npad3(int64_t N) { return (N + 3) / 4 * 4 + 64; }   // == bwd_npad (fm_backward.cu)
@@ -307,6 +321,8 @@ static int64_t npad3(int64_t N) { return (N + 3) / 4 * 4 + 64; }   // == bwd_npa
 }  // namespace
 
 extern "C" size_t fmb_bwd_workspace_bytes(int64_t, int);
+// debug hook (not in the public header): per-tile phase timestamps of the fused sharded step
+FMB_API void fmb_debug_set_shard3_timestamps(long long* dev) { g_s3_tdbg = dev; }
 
 // tile geometry of the fused sharded step: samples per tile (8 per rank: every rank's tile holds ~8*F owned entries whatever
 // G is), tiles per step, tile-flag words (2 * tiles, uint32, zero-initialised, in peer-mapped memory).  0 when the shape is
@@ -370,6 +386,7 @@ FMB_API int fmb_shard3_step(const int32_t* idsT_all, float* table_local, const f
         if (r < G && !(p.recv.p[r] && p.ctx.p[r] && p.tflags.p[r])) { fmb_set_error("fmb_shard3_step: peer pointer %d is null", r); return FMB_ERR_ARG; }
     }
     p.recv_local = recv_local; p.ctx_local = ctx_local; p.tflags_local = tflags_local; p.epoch = epoch_dev; p.error = error_dev;
+    p.tdbg = g_s3_tdbg;
     const size_t smem = smem_of(p.cap_e);
     FMB_CHECK_ARG(smem <= 200 * 1024, "fmb_shard3_step: tile too large for shared memory");
     void (*fn)(Step3Params) = nullptr;

@@ -199,10 +199,66 @@ __global__ void __launch_bounds__(fmb::SS_THREADS) shard_sort_fields_kernel(
     if (n > cap) { if (threadIdx.x == 0) atomicMax(overflow, n); n = cap; }
     if (threadIdx.x == 0) counts[f] = n;
     uint32_t* kc; uint16_t* pc;
-    fmb::smem_sort_passes(kbuf0, kbuf1, pbuf0, pbuf1, cnt, tot, n, passes, &kc, &pc);
-    for (int i = threadIdx.x; i < cap; i += fmb::SS_THREADS) {
-        skeys[(size_t)f * cap + i] = i < n ? (int32_t)kc[i] + base : 0x7fffffff;
-        perm[(size_t)f * cap + i] = i < n ? (int32_t)pc[i] * F + f : 0;
+    // Sparse field under the fused step's contract (posflag given: only the entries of rows hit MORE THAN ONCE need a
+    // position, a sorted key and a run; the caller cleared posflag, so rows hit once read 0 = "single"): no sort of the n
+    // owned entries -- a shared-memory hash table marks the entries whose row occurs twice, those (a few hundred of 8 192
+    // at 1.27 M rows per field) are compacted in sample order and sorted alone.  Same idea as radix_sort.cu's
+    // sparse_fields_kernel; the three radix passes over every entry were most of the owner sort's 60-100 us.
+    int hslots = 1;
+    while (hslots * 2 <= cap) hslots *= 2;
+    const bool hashed = posflag != nullptr && n >= 64 && (unsigned long long)nloc >= 8ull * (unsigned)n && 4 * n <= 3 * hslots &&
+                        cap <= fmb::SS_WARPS * fmb::SS_RADIX * 2;
+    if (hashed) {
+        uint32_t* tab = kbuf1;                                   // [hslots] entry index + 1, 0 = empty
+        uint8_t* flag = reinterpret_cast<uint8_t*>(cnt);         // [cap] (the radix counters' 16 KB)
+        for (int i = threadIdx.x; i < hslots; i += fmb::SS_THREADS) tab[i] = 0u;
+        for (int i = threadIdx.x; i < n; i += fmb::SS_THREADS) flag[i] = 0;
+        __syncthreads();
+        const uint32_t hmask = (uint32_t)hslots - 1u;
+        const int hshift = 32 - (31 - __clz(hslots));
+        for (int i = threadIdx.x; i < n; i += fmb::SS_THREADS) {
+            const uint32_t key = kbuf0[i];
+            uint32_t sl = (key * 2654435761u) >> hshift;
+            for (;;) {
+                const uint32_t old = atomicCAS(&tab[sl], 0u, (uint32_t)i + 1u);
+                if (old == 0u) break;
+                if (kbuf0[old - 1] == key) { flag[old - 1] = 1; flag[i] = 1; break; }
+                sl = (sl + 1u) & hmask;
+            }
+        }
+        __syncthreads();
+        // compaction of the marked entries in (global) sample order: thread t owns entries [t*per, (t+1)*per)
+        const int per = (n + fmb::SS_THREADS - 1) / fmb::SS_THREADS;
+        const int i0 = threadIdx.x * per;
+        int mine = 0;
+        for (int u = 0; u < per; ++u) if (i0 + u < n) mine += flag[i0 + u];
+        int inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) wtot[warp] = inc;
+        __syncthreads();
+        int wpre = 0, nm = 0;
+        for (int w = 0; w < fmb::SS_WARPS; ++w) { const int c = wtot[w]; if (w < warp) wpre += c; nm += c; }
+        {
+            int o = wpre + inc - mine;
+            for (int u = 0; u < per; ++u)
+                if (i0 + u < n && flag[i0 + u]) { kbuf1[o] = kbuf0[i0 + u]; pbuf1[o] = pbuf0[i0 + u]; ++o; }   // the table is dead: all marks are set
+        }
+        __syncthreads();
+        fmb::smem_sort_passes(kbuf1, kbuf0, pbuf1, pbuf0, cnt, tot, nm, passes, &kc, &pc);
+        n = nm;
+        if (threadIdx.x == 0) counts[f] = n;
+        const int nw = min(cap, n + 192);                        // the run kernel probes keys behind a run's end
+        for (int i = threadIdx.x; i < nw; i += fmb::SS_THREADS) {
+            skeys[(size_t)f * cap + i] = i < n ? (int32_t)kc[i] + base : 0x7fffffff;
+            perm[(size_t)f * cap + i] = i < n ? (int32_t)pc[i] * F + f : 0;
+        }
+    } else {
+        fmb::smem_sort_passes(kbuf0, kbuf1, pbuf0, pbuf1, cnt, tot, n, passes, &kc, &pc);
+        for (int i = threadIdx.x; i < cap; i += fmb::SS_THREADS) {
+            skeys[(size_t)f * cap + i] = i < n ? (int32_t)kc[i] + base : 0x7fffffff;
+            perm[(size_t)f * cap + i] = i < n ? (int32_t)pc[i] * F + f : 0;
+        }
     }
     // fused step (shard3.cu): per entry (field, global sample) its sorted position | multi-hit flag, field-major [F][G*B]
     if (posflag) {
@@ -237,12 +293,14 @@ struct ExchSync {
 __device__ __forceinline__ void publish_epoch_last_block(const ExchSync& x, int channel) {
     __syncthreads();                 // the block's stores are ordered before thread 0's fence (barrier + cumulativity:
     if (threadIdx.x == 0) {          // the grid-barrier idiom of cooperative groups); one fence.sys per block, not per thread
-        __threadfence_system();
+        // acq_rel is what the pattern needs (this block's stores before the counter; the last block's read of the counter
+        // before its flag stores); __threadfence_system() is fence.sc.sys, measurably slower with 256+ blocks of peer stores
+        asm volatile("fence.acq_rel.sys;\n" ::: "memory");
         const unsigned nb = gridDim.x * gridDim.y * gridDim.z;
         const unsigned prev = atomicAdd(x.sync_local + 8 + channel, 1u);
         if (prev == nb - 1) {
             x.sync_local[8 + channel] = 0;
-            __threadfence_system();
+            asm volatile("fence.acq_rel.sys;\n" ::: "memory");
             const uint32_t e = x.sync_local[channel] + 1;
             x.sync_local[channel] = e;
             for (int r = 0; r < x.G; ++r) {   // one fence (above), then G relaxed system-scope stores
@@ -270,15 +328,30 @@ __device__ __forceinline__ void wait_epoch(const ExchSync& x, int channel) {
     __syncthreads();
 }
 
-// ids [B,F] -> slab `me` of every rank's idsT_all [G][F][B]
-__global__ void transpose_ids_peers_kernel(const int32_t* __restrict__ ids, int B, int F, int G, int me, PeerPtrs dst,
-                                           ExchSync x, int channel) {
-    const int64_t n = (int64_t)B * F;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int f = (int)(i / B), b = (int)(i - (int64_t)f * B);
-        const int32_t v = ids[(size_t)b * F + f];
-        const size_t o = (size_t)me * F * B + i;
-        for (int r = 0; r < G; ++r) static_cast<int32_t*>(dst.p[r])[o] = v;
+// ids [B,F] -> slab `me` of every rank's idsT_all [G][F][B].  A block stages 32 samples x F ids (one contiguous run of the
+// sample-major input: coalesced reads) in shared memory and writes, per field, 32 consecutive ids (128 B) to each of the G
+// destinations; the strided-read version took 56 us beside the step's kernels at B = 8 192, F = 39.
+constexpr int TR_SB = 32;
+__global__ void __launch_bounds__(256) transpose_ids_peers_kernel(const int32_t* __restrict__ ids, int B, int F, int G, int me, PeerPtrs dst,
+                                                                  ExchSync x, int channel) {
+    extern __shared__ int32_t tr_s[];                  // [TR_SB][F + 1]
+    const int nb = (B + TR_SB - 1) / TR_SB;
+    for (int blk = blockIdx.x; blk < nb; blk += gridDim.x) {
+        const int b0 = blk * TR_SB, n = min(TR_SB, B - b0);
+        for (int i = threadIdx.x; i < n * F; i += blockDim.x) {
+            const int s = i / F, f = i - s * F;
+            tr_s[s * (F + 1) + f] = __ldg(ids + (size_t)b0 * F + i);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < F * TR_SB; i += blockDim.x) {
+            const int f = i / TR_SB, s = i - f * TR_SB;
+            if (s < n) {
+                const int32_t v = tr_s[s * (F + 1) + f];
+                const size_t o = (size_t)me * F * B + (size_t)f * B + b0 + s;
+                for (int r = 0; r < G; ++r) static_cast<int32_t*>(dst.p[r])[o] = v;
+            }
+        }
+        __syncthreads();
     }
     if (channel >= 0) publish_epoch_last_block(x, channel);
 }
@@ -728,8 +801,9 @@ FMB_API int fmb_shard_unpack_ctx(const float* ctx_all, int64_t n, int k, float* 
 // _rl: also the run list of every field's sorted owned entries (rl: nseg == F, seg_cap >= cap / 2 + 1; nullable), for
 // fmb_fm_backward_update_rl
 struct fmb_runlist_t { int32_t* entries; uint32_t* seg_count; int nseg, seg_cap; };   // include/fmb200.h
-// _pf: also posflag [F][G*B] (nullable): sorted position | 0x80000000 when the row is hit more than once, for every entry
-// this rank owns (the other words are left untouched) -- what fmb_shard3_step reads
+// _pf: also posflag [F][G*B] (nullable): sorted position | 0x80000000 when the row is hit more than once -- what
+// fmb_shard3_step reads.  The buffer is cleared here first (memset on `stream`); fields with many more rows than owned entries
+// then write only the words of their multi-hit entries and list only those in skeys / perm (hash pass instead of the sort)
 FMB_API int fmb_shard_sort_fields_pf(const int32_t* idsT_all, int G, int me, int B, int F, const int32_t* field_off,
                                      int cap, int32_t* skeys, int32_t* perm, int32_t* counts, int32_t* overflow,
                                      const fmb_runlist_t* rl, uint32_t* posflag, cudaStream_t stream) {
@@ -740,6 +814,10 @@ FMB_API int fmb_shard_sort_fields_pf(const int32_t* idsT_all, int G, int me, int
     FMB_CHECK_ARG((int64_t)G * B <= 65536, "fmb_shard_sort_fields: G*B must be <= 65536 (16-bit sample payload)");
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(shard_sort_fields_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr = true; }
+    if (posflag) {
+        const cudaError_t me_ = cudaMemsetAsync(posflag, 0, (size_t)F * G * B * sizeof(uint32_t), stream);
+        if (me_ != cudaSuccess) { fmb_set_error("fmb_shard_sort_fields: %s", cudaGetErrorString(me_)); return FMB_ERR_CUDA; }
+    }
     shard_sort_fields_kernel<<<F, fmb::SS_THREADS, fmb::smem_sort_bytes(cap), stream>>>(
         idsT_all, G, ilog2_exact(G), me, B, F, field_off, cap, skeys, perm, counts, overflow,
         rl ? reinterpret_cast<int4*>(rl->entries) : nullptr, rl ? rl->seg_count : nullptr, rl ? rl->seg_cap : 0, posflag);
@@ -790,8 +868,9 @@ FMB_API int fmb_shard_transpose_ids_peers(const int32_t* ids, int B, int F, int 
     ExchSync x;
     if (int rc = fill_sync(x, flag_peers, flags_local, sync_local, error_dev, G, me, publish_channel >= 0, "fmb_shard_transpose_ids_peers")) return rc;
     const int64_t n = (int64_t)B * F;
-    const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, 296);   // grid-stride: few blocks, few fences
-    transpose_ids_peers_kernel<<<blocks, 256, 0, stream>>>(ids, B, F, G, me, pp, x, publish_channel);
+    const unsigned blocks = (unsigned)std::min<int64_t>((B + TR_SB - 1) / TR_SB, 296);   // grid-stride: few blocks, few fences
+    (void)n;
+    transpose_ids_peers_kernel<<<blocks, 256, (size_t)TR_SB * (F + 1) * 4, stream>>>(ids, B, F, G, me, pp, x, publish_channel);
     FMB_CHECK_LAUNCH("transpose_ids_peers_kernel");
     return FMB_OK;
 }

@@ -63,6 +63,61 @@ def test_fused_step_emulated_ranks_bit_exact(G, B, zipf_cap):
         assert np.float32(m.bias.item()) == np.float32(orc.bias[0])
 
 
+@pytest.mark.parametrize("G,B", [(2, 256), (8, 128)])
+def test_fused_step_hash_pass_of_sparse_fields_bit_exact(G, B):
+    """fields with many more rows than owned entries take the owner sort's hash pass (only multi-hit entries are listed):
+    two such fields (300 007 and 50 021 rows) whose ids are drawn from a few hundred distinct rows spread over the range, so
+    that rows hit once, twice and many times all occur; still bit-identical to the oracle in sharded order"""
+    from oracle.deep import OracleDeep
+    sizes = [9, 300007, 5, 50021, 64, 3]
+    k, steps = 6, 3
+    orc = OracleDeep("FMAdam", sizes, k, lr=0.01, seed=1)
+    orc.V *= np.float32(0.3)
+    V0, w0, b0 = orc.V.copy(), orc.w1.copy(), orc.bias.copy()
+    orc.set_shard_order(G)
+    rs = np.random.RandomState(5)
+    batches, want_losses = [], []
+    for s in range(steps):
+        n = G * B
+        Xi = np.stack([rs.randint(0, 9, n), (rs.randint(0, 700, n) * 428) % 300007, rs.randint(0, 5, n),
+                       (rs.randint(0, 2000, n) * 25) % 50021, rs.randint(0, 64, n), rs.randint(0, 3, n)], 1)
+        Y = (rs.uniform(size=n) < 0.4).astype(np.float32)
+        batches.append((Xi, Y))
+        want_losses.append(orc.update_embedding(Xi, np.ones(Xi.shape, np.float32), Y))
+    ranks = [sh.ShardedFM(sizes, k, n=0.01, init="zeros", world=G, rank=r) for r in range(G)]
+    for m in ranks:
+        m.load_full(V0, w0, b0)
+    _attach(ranks, B)
+    streams = [torch.cuda.Stream() for _ in range(G)]
+    for (Xi, Y), want in zip(batches, want_losses):
+        enc = [m.encode(Xi[r * B:(r + 1) * B], Y[r * B:(r + 1) * B]) for r, m in enumerate(ranks)]
+        for m, e in zip(ranks, enc):
+            pr = m._peer
+            sh.check(m._lib.fmb_shard_transpose_ids_peers(sh.ptr(e[0]), B, m.F, G, m.rank, pr["ptrs"]["ids0"], *m._sync_args(), -1,
+                                                          sh._stream()), "transpose")
+        torch.cuda.synchronize()
+        for m in ranks:
+            m._sort_owned(m._peer["ids"][0], 0, m._peer["posflag"][0])
+        torch.cuda.synchronize()
+        # the hash pass lists only multi-hit entries: fewer than the owned entries of the big fields
+        cnts = ranks[0]._ws["counts0"].cpu().numpy()
+        assert cnts[1] < B and cnts[3] < B, cnts
+        held = []
+        for m, e, st in zip(ranks, enc, streams):
+            with torch.cuda.stream(st):
+                held.append(m._fused_launch(e[1], 0, 0))
+        torch.cuda.synchronize()
+        for m in ranks:
+            m.check_exchange()
+            m.check_overflow()
+        losses = [float(m._fused_finish(ws, wsb, 0).item()) for m, (ws, wsb) in zip(ranks, held)]
+        assert all(np.float32(l) == np.float32(want) for l in losses), (losses, want)
+    for r, m in enumerate(ranks):
+        V, w1 = m.local_params()
+        assert np.array_equal(V, sh.shard_from_full(orc.V, G, r))
+        assert np.array_equal(w1, sh.shard_from_full(orc.w1, G, r))
+
+
 def test_fused_step_reports_tile_overflow_and_unsupported_shapes():
     m = sh.ShardedFM(SIZES, K, n=0.01, init="zeros", world=2, rank=0)
     assert m.fused_supported(64) and not m.fused_supported(40)          # B % (8 G)
