@@ -293,14 +293,12 @@ struct ExchSync {
 __device__ __forceinline__ void publish_epoch_last_block(const ExchSync& x, int channel) {
     __syncthreads();                 // the block's stores are ordered before thread 0's fence (barrier + cumulativity:
     if (threadIdx.x == 0) {          // the grid-barrier idiom of cooperative groups); one fence.sys per block, not per thread
-        // acq_rel is what the pattern needs (this block's stores before the counter; the last block's read of the counter
-        // before its flag stores); __threadfence_system() is fence.sc.sys, measurably slower with 256+ blocks of peer stores
-        asm volatile("fence.acq_rel.sys;\n" ::: "memory");
+        __threadfence_system();
         const unsigned nb = gridDim.x * gridDim.y * gridDim.z;
         const unsigned prev = atomicAdd(x.sync_local + 8 + channel, 1u);
         if (prev == nb - 1) {
             x.sync_local[8 + channel] = 0;
-            asm volatile("fence.acq_rel.sys;\n" ::: "memory");
+            __threadfence_system();
             const uint32_t e = x.sync_local[channel] + 1;
             x.sync_local[channel] = e;
             for (int r = 0; r < x.G; ++r) {   // one fence (above), then G relaxed system-scope stores

@@ -55,6 +55,9 @@ def full_from_shards(shards):
     return out
 
 
+_DMA_IDS = os.environ.get("FMB_SHARD_DMA_IDS", "1") != "0"   # fused path: ids exchanged by copy-engine copies
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -323,6 +326,19 @@ class ShardedFM:
         torch.cuda.synchronize()
         dist.barrier(group=group)                  # every flag block is zero before anyone publishes
         self._peer_bind(B, arena, [int(hdl.buffer_ptrs[r]) for r in range(self.G)], hdl)
+        # tensor views of the peers' id slabs (copy-engine exchange of the fused path)
+        try:
+            off, total, _ = self._peer_layout(B)
+            G, F = self.G, self.F
+            views = []
+            for r in range(G):
+                whole = hdl.get_buffer(r, (total,), torch.int32, 0)
+                views.append([whole[off[f"ids{sl}"][0]:off[f"ids{sl}"][0] + G * F * B].view(G, F, B) for sl in (0, 1)])
+            self._peer["peer_ids"] = views
+        except Exception as exc:  # noqa: BLE001 -- the store-based exchange needs only the raw pointers
+            print(f"[rank {self.rank}] no tensor views of the peers' buffers ({type(exc).__name__}: {exc}); "
+                  "ids are exchanged by the store kernel", file=sys.stderr, flush=True)
+            self._peer["peer_ids"] = None
 
     def _sync_args(self):
         pr = self._peer
@@ -384,15 +400,26 @@ class ShardedFM:
         return self._lib.fmb_shard3_tiles(self.G, B, self.F, self.k) > 0
 
     def _prepare_fused(self, ids, slot):
-        """ids of the NEXT batch: exchange, owner sort with the per-entry position words, on the _pre stream"""
+        """ids of the NEXT batch: exchange, owner sort with the per-entry position words, on the _pre stream.
+        With a symmetric-memory handle the exchange is a local transpose + one copy-engine copy of my [F][B] slab into every
+        peer's idsT_all (DMA over NVLink: no SM time, no store fences beside the step's kernels -- the store-based transpose
+        took 49 us next to the fused kernel), then the epoch flag; emulated ranks (no handle) keep the store kernel."""
         pr, B = self._peer, ids.shape[0]
         main = torch.cuda.current_stream()
         self._pre.wait_stream(main)
         with torch.cuda.stream(self._pre):
-            check(self._lib.fmb_shard_transpose_ids_peers(ptr(ids), B, self.F, self.G, self.rank,
-                                                          pr["ptrs"][f"ids{slot}"], *self._sync_args(), self.CH_IDS,
-                                                          _stream()), "fmb_shard_transpose_ids_peers")
-            self._signal(self.CH_IDS, 2)
+            if pr.get("peer_ids") is not None and _DMA_IDS:
+                mine = pr["ids"][slot][self.rank]
+                check(self._lib.fmb_transpose_ids(ptr(ids), B, self.F, ptr(mine), _stream()), "fmb_transpose_ids")
+                for r in range(self.G):
+                    if r != self.rank:
+                        pr["peer_ids"][r][slot][self.rank].copy_(mine, non_blocking=True)
+                self._signal(self.CH_IDS, 3)      # publish my epoch (the copies are complete: stream order), wait for the peers'
+            else:
+                check(self._lib.fmb_shard_transpose_ids_peers(ptr(ids), B, self.F, self.G, self.rank,
+                                                              pr["ptrs"][f"ids{slot}"], *self._sync_args(), self.CH_IDS,
+                                                              _stream()), "fmb_shard_transpose_ids_peers")
+                self._signal(self.CH_IDS, 2)
             self._sort_owned(pr["ids"][slot], slot, pr["posflag"][slot])
 
     def prepare_fused(self, ids):
@@ -617,12 +644,15 @@ def bench_main(args, sizes, config):
     use_graph = os.environ.get("FMB_NO_GRAPH", "0") != "1"
     pipelined = os.environ.get("FMB_SHARD_PIPELINE", "1") != "0"
     # exchanges: "peers" = stores into peer-mapped symmetric memory + epoch flags (default), "nccl" = collectives
-    exchange = os.environ.get("FMB_SHARD_EXCHANGE", "peers") if pipelined else "nccl"
+    # "fused" = csrc/shard3.cu, one kernel per rank per step.  Default where it measured faster: 99 us against 122 us per step
+    # at 2 GPUs; at 8 GPUs it is correct (tests/sharded_pipeline_check.py --fused) but slower (228 against 213 us), see DESIGN.md 5
+    default_exchange = "fused" if world == 2 else "peers"
+    exchange = os.environ.get("FMB_SHARD_EXCHANGE", default_exchange) if pipelined else "nccl"
     fused = exchange == "fused"          # csrc/shard3.cu: the step as one kernel with per-tile flags (needs the peer mapping)
     if fused and not model.fused_supported(B):
         print(f"[rank {rank}] fused sharded step does not support this shape; using the three-kernel peer path", file=sys.stderr, flush=True)
         fused = False
-    if fused:
+    if exchange == "fused":
         exchange = "peers"
     if exchange == "peers":
         # mapping the peers' buffers needs symmetric-memory support on this box; every rank must take the same path,
@@ -640,28 +670,52 @@ def bench_main(args, sizes, config):
             exchange = "nccl"
             model._peer = None
     fused = fused and exchange == "peers"
-    prepare = model.prepare_fused if fused else (model.prepare_peers if exchange == "peers" else model.prepare)
-    if pipelined:
-        # step i trains on batch i while batch i+1's ids are exchanged and sorted (update_embedding_pipelined)
-        if use_graph:
-            (model.capture_fused if fused else model.capture_peers if exchange == "peers" else model.capture_pipelined)(*enc[0])
-            run = model.step_graphed_pipelined
-        else:
-            run = (model.update_embedding_fused if fused else
-                   model.update_embedding_peers if exchange == "peers" else model.update_embedding_pipelined)
-        prepare(enc[0][0])
+    state = {}
 
-        def step(i):
-            return run(enc[i % NB][1], enc[(i + 1) % NB][0])
-    else:
-        if use_graph:
-            model.capture(*enc[0])
-            run = model.step_graphed
-        else:
-            run = model.update_embedding
+    def setup(fused_now):
+        """(re)build the step function for the chosen exchange; returns (prepare, run, step)"""
+        prepare = model.prepare_fused if fused_now else (model.prepare_peers if exchange == "peers" else model.prepare)
+        if pipelined:
+            # step i trains on batch i while batch i+1's ids are exchanged and sorted (update_embedding_pipelined)
+            if use_graph:
+                (model.capture_fused if fused_now else model.capture_peers if exchange == "peers" else model.capture_pipelined)(*enc[0])
+                run = model.step_graphed_pipelined
+            else:
+                run = (model.update_embedding_fused if fused_now else
+                       model.update_embedding_peers if exchange == "peers" else model.update_embedding_pipelined)
+            prepare(enc[0][0])
 
-        def step(i):
-            return run(*enc[i % NB])
+            def step(i):
+                return run(enc[i % NB][1], enc[(i + 1) % NB][0])
+        else:
+            if use_graph:
+                model.capture(*enc[0])
+                run = model.step_graphed
+            else:
+                run = model.update_embedding
+
+            def step(i):
+                return run(*enc[i % NB])
+        state.update(prepare=prepare, run=run, step=step)
+
+    setup(fused)
+    if fused:
+        # a trial round: a tile whose owned entries exceed its shared-memory capacity (ids whose hot rows concentrate on one
+        # rank) or a flag time-out raises the error word; every rank then falls back to the three-kernel path together
+        for i in range(2 * NB):
+            state["step"](i)
+        torch.cuda.synchronize()
+        bad = torch.tensor([int(model._peer["error"].item()) != 0], device="cuda", dtype=torch.int32)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad.item()):
+            print(f"[rank {rank}] fused sharded step raised its error word ({int(model._peer['error'].item())}); "
+                  "falling back to the three-kernel peer path", file=sys.stderr, flush=True)
+            model._peer["error"].zero_()
+            fused = False
+            torch.cuda.synchronize()
+            dist.barrier()
+            setup(False)
+    prepare, run, step = state["prepare"], state["run"], state["step"]
     sampler = ClockSampler(local)   # started before the warm-up: the timed region is a few ms, nvidia-smi needs ~50 ms to start
     W_run = max(W, 2 * NB + 2)      # at least two rounds over the rotating batches (reported: the requested W)
     for i in range(W_run):
