@@ -441,7 +441,10 @@ FMB_API int fmb_fm_step_fused_ex(const int32_t* ids, const float* xv, const floa
     // at least ~6 tiles per SM when the batch allows it: the tiles of an SM are then in different phases (gather, reduce,
     // update) at any time and the 148 SMs finish together (8 192 samples: 1 024 tiles of 8 instead of 512 of 16, measured
     // 64 instead of 75 us per step, profiles/r2_sweep_tile.txt)
-    while (SB > 8 && (B + SB - 1) / SB < 6 * 148) SB >>= 1;
+    // ... and 8-sample tiles at ANY batch size: 20.7 KB per CTA keeps 8 CTAs (64 warps) per SM resident instead of 5 with
+    // 16-sample tiles; the kernel is latency-bound (55 % "no eligible warp" at B = 65 536 with 16-sample tiles,
+    // profiles/r2_final3_fused_ncu_summary.txt): measured 158.0 vs 164.1 us per launch and 363 vs 391 us per step there
+    while (SB > 8) SB >>= 1;
     {   // experiment knob: FMB_STEP_SB caps the samples per tile
         static int cap = -1;
         if (cap < 0) { const char* e = getenv("FMB_STEP_SB"); cap = e ? atoi(e) : 0; }
