@@ -36,6 +36,37 @@ def test_oracle_matches_reference(name):
             np.testing.assert_allclose(mine @ mine.T, ref @ ref.T, rtol=1e-9, atol=1e-12)
 
 
+def test_oracle_matches_reference_at_full_size_cfg2():
+    """BASELINE.json configs[1] at its full size (59 535 cod-rna-shaped samples x 8 features, m = 40, 'cls'): fixture from the
+    live reference (tests/golden/make_golden_classical_full.py: every 8th online prediction, final state, stream metrics)."""
+    from golden.make_golden_classical import codrna
+    g = dict(np.load(GOLDEN + "/classical_full.npz"))
+    N, seed, eta, m, _, stride = (float(v) for v in g["meta"])
+    N, m, stride = int(N), int(m), int(stride)
+    assert N == 59535 and m == 40
+    X, y = codrna(N, int(seed))
+
+    def stream(pred):
+        pred = np.asarray(pred, np.float64)
+        return [auc(pred, y), float(np.mean(np.sign(pred) == np.sign(y))), rmse(pred, y)]
+
+    p, st = oc.fm_ftrl(X, y, "cls", eta, m, g["ftrl_w1_init"], g["ftrl_W2_init"])
+    assert np.array_equal(p[::stride], g["ftrl_pred"])                   # 'cls' predictions are signs
+    assert [round(v, 4) for v in stream(p)] == [round(float(v), 4) for v in g["ftrl_metrics"]]
+    np.testing.assert_allclose(st["w1"], g["ftrl_w1"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(st["W2"], g["ftrl_W2"], rtol=1e-12, atol=1e-14)
+    for tag, van in (("ccfm", False), ("vanila", True)):
+        p, st = oc.sftrl(X, y, "cls", eta, m, vanila=van)
+        assert np.array_equal(p[::stride], g[tag + "_pred"])
+        assert [round(v, 4) for v in stream(p)] == [round(float(v), 4) for v in g[tag + "_metrics"]]
+        assert [st["row_count_p"], st["row_count_n"]] == g[tag + "_rc"].tolist()
+        for key, mine in (("BTP", st["BT_P"]), ("BTN", st["BT_N"])):
+            ref = g[f"{tag}_{key}"]
+            np.testing.assert_allclose(mine @ mine.T, ref @ ref.T, rtol=1e-9, atol=1e-11)
+        if van:
+            np.testing.assert_allclose(st["w"].reshape(-1), g["vanila_w"].reshape(-1), rtol=1e-9, atol=1e-13)
+
+
 def metrics_match(pred, ref, y, task):
     """north_star: AUC and RMSE identical to 4 decimal places (online prediction streams)."""
     if task == "reg":
