@@ -67,6 +67,58 @@ def test_oracle_matches_reference_at_full_size_cfg2():
             np.testing.assert_allclose(st["w"].reshape(-1), g["vanila_w"].reshape(-1), rtol=1e-9, atol=1e-13)
 
 
+def ml100k_case():
+    """first 20 000 time-ordered ratings of the reference's bundled ml-100k `ua.base` as the one-hot user | item | bias matrix
+    of utils/data_manager.py:18-48 (d = 2626), from the committed triples"""
+    g = dict(np.load(GOLDEN + "/ml100k_kat.npz"))
+    N, NU, NI, eta, m, stride = (float(v) for v in g["meta"])
+    N, NU, NI, m, stride = int(N), int(NU), int(NI), int(m), int(stride)
+    u, it = g["user"].astype(np.int64), g["item"].astype(np.int64)
+    X = np.zeros((N, NU + NI + 1))
+    X[np.arange(N), u] = 1
+    X[np.arange(N), NU + it] = 1
+    X[:, -1] = 1
+    Z = np.random.RandomState(2626).standard_normal((X.shape[1], 4))
+    return g, X, g["rating"].astype(np.float64), eta, m, stride, Z
+
+
+# SURVEY.md section 4: known answers on the bundled data (reg, eta = 0.005, m = 5), "expect agreement to ~1e-8"
+SURVEY_KAT = {
+    "ccfm": (1.0218898321, [0, 0.16, 0.31228865, 3.64095492, 2.95804486, 3.83643576]),
+    "vanila": (1.0447981956, [0, 0.12, 0.34185643, 3.49008605, 3.08330353, 3.95040156]),
+    "ftrl": (1.0822492538, [18.44102295, -0.2867719, 0.20292217, 3.17376672, 3.11692213, 3.99502804]),
+}
+
+
+def test_oracle_reproduces_the_ml100k_known_answers():
+    """the survey's known-answer table AND the fixture generated from the live reference on the same rows
+    (tests/golden/make_golden_ml100k.py): cumulative MSE, tabulated predictions, every 5th prediction, final state"""
+    g, X, y, eta, m, stride, Z = ml100k_case()
+    kat = g["kat_idx"]
+
+    def check_stream(tag, p):
+        mse, preds = SURVEY_KAT[tag]
+        assert abs(np.mean((p - y) ** 2) - mse) < 1e-8 and abs(np.mean((p - y) ** 2) - g[tag + "_mse"][0]) < 1e-11
+        np.testing.assert_allclose(p[kat], preds, rtol=0, atol=1e-8)
+        np.testing.assert_allclose(p[kat], g[tag + "_kat"], rtol=1e-10, atol=1e-11)
+        np.testing.assert_allclose(p[::stride], g[tag + "_pred"], rtol=1e-10, atol=1e-10)
+        assert round(rmse(p, y), 4) == round(float(np.sqrt(g[tag + "_mse"][0])), 4)
+
+    for tag, van in (("ccfm", False), ("vanila", True)):
+        p, st = oc.sftrl(X, y, "reg", eta, m, vanila=van)
+        check_stream(tag, p)
+        assert [st["row_count_p"], st["row_count_n"]] == g[tag + "_rc"].tolist()
+        for key, BT in (("BTP", st["BT_P"]), ("BTN", st["BT_N"])):
+            np.testing.assert_allclose(np.linalg.svd(BT, compute_uv=False), g[f"{tag}_{key}_sv"], rtol=1e-10, atol=1e-12)
+            np.testing.assert_allclose(BT @ (BT.T @ Z[:BT.shape[0]]), g[f"{tag}_{key}_probe"], rtol=1e-9, atol=1e-10)
+        if van:
+            np.testing.assert_allclose(st["w"].reshape(-1), g["vanila_w"].reshape(-1), rtol=1e-10, atol=1e-13)
+    p, st = oc.fm_ftrl(X, y, "reg", eta, m, g["ftrl_w1_init"].astype(np.float64), g["ftrl_W2_init"].astype(np.float64))
+    check_stream("ftrl", p)
+    np.testing.assert_allclose(st["w1"], g["ftrl_w1"], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(st["W2"] @ Z[:-1], g["ftrl_W2_probe"], rtol=1e-11, atol=1e-14)
+
+
 def metrics_match(pred, ref, y, task):
     """north_star: AUC and RMSE identical to 4 decimal places (online prediction streams)."""
     if task == "reg":

@@ -1,8 +1,11 @@
-"""BASELINE.json configs[1] at its FULL size on the GPU (59 535 x 8, m = 40, 'cls'): the three CUDA learners against the
-live-reference fixture tests/golden/classical_full.npz (CPU twin: test_oracle_matches_reference_at_full_size_cfg2).
+"""The three CUDA classical learners at full size against live-reference fixtures:
+  * BASELINE.json configs[1] (59 535 x 8, m = 40, 'cls'): tests/golden/classical_full.npz
+    (CPU twin: test_oracle_matches_reference_at_full_size_cfg2);
+  * SURVEY.md section 4's known answers on the bundled ml-100k rows (20 000 x 2626 one-hot, 'reg', m = 5):
+    tests/golden/ml100k_kat.npz (CPU twin: test_oracle_reproduces_the_ml100k_known_answers).
 
-NOT part of `pytest -m gpu` yet: written after the round's GPU budget was spent, so it has not run on a B200.  Promote it to a
-test once `gpurun -- python tools/check_cfg2_full.py` has printed CFG2_FULL_OK.
+NOT part of `pytest -m gpu` yet: written after the round's GPU budget was spent, so it has not run on a B200.  Promote both to
+tests once `gpurun -- python tools/check_classical_full.py` has printed CFG2_FULL_OK and ML100K_KAT_OK.
 """
 import contextlib
 import io
@@ -56,5 +59,33 @@ def main():
     print("CFG2_FULL_OK")
 
 
+def ml100k():
+    import torch
+    import fm_for_online_recommendation_b200 as pkg
+    from test_classical import SURVEY_KAT, ml100k_case
+    g, X, y, eta, m, stride, Z = ml100k_case()
+    kat = g["kat_idx"]
+    T = torch.DoubleTensor
+    for tag, cls in (("ccfm", pkg.SFTRL_CCFM), ("vanila", pkg.SFTRL_Vanila), ("ftrl", pkg.FM_FTRL)):
+        with contextlib.redirect_stdout(io.StringIO()):
+            torch.manual_seed(0)
+            mdl = cls(T(X), T(y), "reg", eta, m)
+            p, _, secs = mdl.online_learning()
+        p = np.asarray(p, np.float64).reshape(-1)
+        mse, preds = SURVEY_KAT[tag]
+        print("%-6s %.3f s  mse %.10f (survey %.10f)  max |pred - reference| %.2e" %
+              (tag, secs, np.mean((p - y) ** 2), mse, np.abs(p[::stride] - g[tag + "_pred"]).max()))
+        assert abs(np.mean((p - y) ** 2) - mse) < 1e-8
+        np.testing.assert_allclose(p[kat], preds, rtol=0, atol=1e-8)
+        np.testing.assert_allclose(p[::stride], g[tag + "_pred"], rtol=1e-9, atol=1e-9)
+        if tag != "ftrl":
+            assert [mdl.row_count_p, mdl.row_count_n] == g[tag + "_rc"].tolist()
+            for key, BT in (("BTP", mdl.BT_P), ("BTN", mdl.BT_N)):
+                BT = BT.cpu().numpy()
+                np.testing.assert_allclose(BT @ (BT.T @ Z[:BT.shape[0]]), g[f"{tag}_{key}_probe"], rtol=1e-8, atol=1e-9)
+    print("ML100K_KAT_OK")
+
+
 if __name__ == "__main__":
     main()
+    ml100k()
