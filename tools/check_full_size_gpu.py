@@ -1,11 +1,16 @@
-"""The three CUDA classical learners at full size against live-reference fixtures:
+"""Full-size GPU checks against live-reference fixtures that were written AFTER the round's GPU budget was spent.
+
+The three CUDA classical learners:
   * BASELINE.json configs[1] (59 535 x 8, m = 40, 'cls'): tests/golden/classical_full.npz
     (CPU twin: test_oracle_matches_reference_at_full_size_cfg2);
   * SURVEY.md section 4's known answers on the bundled ml-100k rows (20 000 x 2626 one-hot, 'reg', m = 5):
     tests/golden/ml100k_kat.npz (CPU twin: test_oracle_reproduces_the_ml100k_known_answers).
 
-NOT part of `pytest -m gpu` yet: written after the round's GPU budget was spent, so it has not run on a B200.  Promote both to
-tests once `gpurun -- python tools/check_classical_full.py` has printed CFG2_FULL_OK and ML100K_KAT_OK.
+The five CUDA deep classes through the experiment scripts' flow at its real length (100 pre-training steps on a 2 500-sample
+batch, run_experiment over a 2 500-sample stream): tests/golden/online_full.npz (CPU twin: tests/test_online_full.py).
+
+NOT part of `pytest -m gpu` yet: none of this has run on a B200.  Promote each part to a test once
+`gpurun -- python tools/check_full_size_gpu.py` has printed CFG2_FULL_OK, ML100K_KAT_OK and ONLINE_FULL_OK.
 """
 import contextlib
 import io
@@ -86,6 +91,45 @@ def ml100k():
     print("ML100K_KAT_OK")
 
 
+def online_full():
+    import torch
+    import fm_for_online_recommendation_b200 as pkg
+    from test_online_full import CFG, G
+    from traj_common import batch, init_tables
+    pre, lr, L, H = G["meta"]
+    w1, V = init_tables(CFG)
+    pXi, pXv, pY = batch(CFG, 0)
+    oXi, oXv, oY = batch(CFG, 1)
+    for kind in ("FMAdam", "DeepFMAdam", "NFMAdam", "DeepFMOnn", "NFMOnn"):
+        kw = dict(embedding_size=10, n=float(lr))
+        if kind != "FMAdam":
+            kw.update(num_hidden_layers=int(L), neuron_per_hidden_layer=int(H))
+        m = getattr(pkg, kind)(CFG["sizes"], **kw)
+        with torch.no_grad():
+            t = torch.zeros_like(m._table)
+            t[:, :10] = torch.from_numpy(V)
+            t[:, 10] = torch.from_numpy(w1)
+            m._table.copy_(t)
+            m.bias.copy_(torch.from_numpy(G[kind + "_init_bias"]).reshape(m.bias.shape))
+            if kind != "FMAdam":
+                m._mlp.copy_(torch.from_numpy(G[kind + "_init_mlp"]))
+            if kind + "_init_alpha" in G:
+                m.alpha.copy_(torch.from_numpy(G[kind + "_init_alpha"]))
+        losses = np.asarray([float(m.update_embedding(pXi, pXv, pY).cpu()) for _ in range(int(pre))], np.float32)
+        secs, acc, roc, conf = m.run_experiment(oXi, oXv, [int(v) for v in oY])
+        want = dict(zip(("tp", "fp", "tn", "fn"), G[kind + "_conf"].tolist()))
+        print("%-10s losses bit-equal: %s   confusion %s (reference %s)   %.3f s" %
+              (kind, np.array_equal(losses, G[kind + "_pre_loss"]), conf, want, secs))
+        assert np.array_equal(losses, G[kind + "_pre_loss"]) and conf == want
+        assert [acc, roc["tpr"], roc["fpr"]] == G[kind + "_acc_roc"].tolist()
+        rows = G["rows"]
+        tab = m._table.cpu().numpy()
+        dv = np.abs(tab[rows, :10] - G[kind + "_V"]) / np.maximum(np.abs(G[kind + "_V"]), 1e-3)
+        assert dv.max() <= 1e-5, dv.max()
+    print("ONLINE_FULL_OK")
+
+
 if __name__ == "__main__":
     main()
     ml100k()
+    online_full()
