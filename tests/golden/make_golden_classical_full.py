@@ -67,7 +67,21 @@ def main():
             if tag == "vanila":
                 out[f"{tag}_w"] = mdl.w.numpy().copy()
             out[f"{tag}_seconds"] = np.array([time.time() - t0])
-    for k in ("ftrl", "ccfm", "vanila"):
+        # RRF_Online on the same stream; the constructor draws gamma / w / eps from the CPU RNGs
+        from models.models_online.RRF_Online import RRF_Online
+        t0 = time.time()
+        np.random.seed(5)
+        torch.manual_seed(5)
+        mdl = RRF_Online(T(X), T(y), TASK, num_sampled_spectral=10)
+        out["rrf_gamma0"], out["rrf_w0"], out["rrf_eps"] = mdl.gamma.numpy().copy(), mdl.w.numpy().copy(), mdl.eps.numpy().copy()
+        pred, _, _ = mdl.online_learning()
+        pred = np.asarray([float(p) for p in pred])
+        out["rrf_n"] = np.array([len(pred)])
+        out["rrf_pred"] = pred[::STRIDE].copy()
+        out["rrf_metrics"] = stream_metrics(pred, y[:len(pred)])
+        out["rrf_w"], out["rrf_gamma"] = mdl.w.numpy().copy(), mdl.gamma.numpy().copy()
+        out["rrf_seconds"] = np.array([time.time() - t0])
+    for k in ("ftrl", "ccfm", "vanila", "rrf"):
         print(k, "reference seconds on this host:", float(out[k + "_seconds"][0]), "metrics", out[k + "_metrics"])
     np.savez_compressed(os.path.join(HERE, "classical_full.npz"), **out)
 

@@ -65,6 +65,12 @@ def test_oracle_matches_reference_at_full_size_cfg2():
             np.testing.assert_allclose(mine @ mine.T, ref @ ref.T, rtol=1e-9, atol=1e-11)
         if van:
             np.testing.assert_allclose(st["w"].reshape(-1), g["vanila_w"].reshape(-1), rtol=1e-9, atol=1e-13)
+    # RRF_Online over the same 59 535-sample stream
+    p, st = oc.rrf_online(X, y, "cls", g["rrf_gamma0"], g["rrf_w0"], g["rrf_eps"])
+    assert len(p) == int(g["rrf_n"][0])
+    assert np.array_equal(p[::stride], g["rrf_pred"])
+    np.testing.assert_allclose(st["w"], g["rrf_w"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(st["gamma"], g["rrf_gamma"], rtol=1e-9, atol=1e-12)
 
 
 def ml100k_case():

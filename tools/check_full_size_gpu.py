@@ -61,6 +61,17 @@ def main():
             ref = g[f"{tag}_{key}"]
             mine = mine.cpu().numpy()
             np.testing.assert_allclose(mine @ mine.T, ref @ ref.T, rtol=1e-8, atol=1e-10)
+    np.random.seed(5)
+    torch.manual_seed(5)
+    with contextlib.redirect_stdout(io.StringIO()):
+        mdl = pkg.RRF_Online(T(X), T(y), "cls", num_sampled_spectral=10)
+        assert np.array_equal(mdl.gamma.cpu().numpy(), g["rrf_gamma0"]) and np.array_equal(mdl.eps.cpu().numpy(), g["rrf_eps"])
+        p, _, secs = mdl.online_learning()
+    p = np.asarray(p, np.float64).reshape(-1)
+    print("RRF_Online  %.3f s  sign mismatches: %d" % (secs, int((p[::stride] != g["rrf_pred"]).sum())))
+    assert len(p) == int(g["rrf_n"][0]) and np.array_equal(p[::stride], g["rrf_pred"])
+    np.testing.assert_allclose(mdl.w.cpu().numpy(), g["rrf_w"], rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(mdl.gamma.cpu().numpy(), g["rrf_gamma"], rtol=1e-8, atol=1e-11)
     print("CFG2_FULL_OK")
 
 
