@@ -105,3 +105,46 @@ def test_cuda_reproduces_reference_trajectory_bit_for_bit(name):
     if losses:
         got = torch.stack([l.reshape(()) for l in losses]).cpu().numpy()
         assert np.array_equal(got, g["losses"])
+
+
+# ------------------------------------------------------------------------------------------------ tower models, `fit`
+# MKL's sgemm summation order is not mirrored, so the tower's products differ from the reference's in the last bit now and
+# then and the sign step amplifies that: these trajectories are held to stated tolerances, not to bit equality.  Measured
+# against the live reference over 3 000 steps (tools/tower_fit_drift.py, profiles/r2_tower_fit_drift.json): at most 1.2 % of
+# the table coordinates and 0.7 % of the tower weights beyond 1e-5 (worst 1.1e-3 relative to max(|w|, 1e-3)), held-out scores
+# within 1.4e-5, AUC and RMSE equal to 6 decimals at every checkpoint.
+TOWER_FRAC_TABLE, TOWER_FRAC_MLP, TOWER_WORST, TOWER_SCORE = 0.03, 0.02, 5e-3, 1e-4
+
+
+@pytest.mark.parametrize("kind", ["DeepFMAdam", "NFMAdam", "DeepFMOnn"])
+def test_oracle_follows_the_reference_through_1000_fit_steps_of_the_tower_models(kind):
+    from oracle.deep import OracleDeep
+    g = dict(np.load(os.path.join(GOLDEN, "traj_tower_fit.npz")))
+    cfg = dict(sizes=[957, 4082, 7, 7, 2, 3, 2, 9, 80, 233], B=256, seed=41, scale=0.2, kw=dict(embedding_size=10))
+    L, H, lr, steps = g["meta"]
+    L, H, steps = int(L), int(H), int(steps)
+    orc = OracleDeep(kind, cfg["sizes"], 10, L, H, lr=float(lr), **(dict(batch_size=cfg["B"]) if "Onn" in kind else {}))
+    orc.w1[:], orc.V[:] = init_tables(cfg)
+    orc.bias[:], orc.mlp[:] = g[kind + "_init_bias"], g[kind + "_init_mlp"]
+    if kind + "_init_alpha" in g:
+        orc.alpha[:] = g[kind + "_init_alpha"]
+    eXi, eXv, eY = batch(cfg, EVAL_STEP)
+    rows = g["rows"]
+    rel = lambda a, b: np.abs(a.astype(np.float64) - b) / np.maximum(np.abs(b.astype(np.float64)), 1e-3)
+    for s in range(steps):
+        Xi, Xv, Y = batch(cfg, s)
+        orc.fit(Xi, Xv, Y)
+        if (s + 1) in g["ckpt"]:
+            tag = "%s_s%d_" % (kind, s + 1)
+            rV, rM = rel(orc.V[rows], g[tag + "V"]), rel(orc.mlp, g[tag + "mlp"])
+            assert (rV > TOL).mean() <= TOWER_FRAC_TABLE and rV.max() <= TOWER_WORST, (s + 1, (rV > TOL).mean(), rV.max())
+            assert (rM > TOL).mean() <= TOWER_FRAC_MLP and rM.max() <= TOWER_WORST, (s + 1, (rM > TOL).mean(), rM.max())
+            assert rel(orc.w1[rows], g[tag + "w1"]).max() <= TOWER_WORST and rel(orc.bias, g[tag + "bias"]).max() <= TOL * 10
+            if tag + "alpha" in g:
+                assert rel(orc.alpha, g[tag + "alpha"]).max() <= TOL
+            f = orc.forward(eXi, eXv)
+            z, ref = (f[0] if isinstance(f, tuple) else f), g[tag + "eval_z"]
+            assert np.abs(z.astype(np.float64) - ref).max() <= TOWER_SCORE
+            assert round(auc(z, eY), 4) == round(auc(ref, eY), 4)
+            sg = lambda v: 1.0 / (1.0 + np.exp(-np.asarray(v, np.float64)))
+            assert round(rmse(sg(z), eY), 4) == round(rmse(sg(ref), eY), 4)
