@@ -156,9 +156,25 @@ def reference_classes_rate(B=8192, steps=5, threads=None):
         for i in range(steps):
             m.update_embedding(batches[i % 2][0], ones, batches[i % 2][1])
         dt = time.perf_counter() - t0
-        return {"value": steps * B / dt, "unit": "samples/s", "cores": threads, "kind": "reference",
-                "sample": f"{steps} DeepFMAdam(use_cuda=False).update_embedding steps of B={B} at configs[3]'s shape "
-                          f"(F=39, R=1006628, k=10) in {dt:.1f}s, torch {torch.__version__} CPU, {threads} threads"}
+        rec = {"value": steps * B / dt, "unit": "samples/s", "cores": threads, "kind": "reference",
+               "sample": f"{steps} DeepFMAdam(use_cuda=False).update_embedding steps of B={B} at configs[3]'s shape "
+                         f"(F=39, R=1006628, k=10) in {dt:.1f}s, torch {torch.__version__} CPU, {threads} threads"}
+        # the same step with the scripts' real inputs (Python lists of lists, converted by the reference on
+        # every call: deepfm_adam.py:47-48,57-58) and on ONE host thread
+        lists = [(b[0].tolist(), ones.tolist(), b[1].tolist()) for b in batches]
+        t0 = time.perf_counter()
+        for i in range(2):
+            m.update_embedding(*lists[i % 2])
+        rec["list_inputs"] = {"value": 2 * B / (time.perf_counter() - t0), "unit": "samples/s", "cores": threads,
+                              "sample": "2 steps, Xi / Xv / Y as Python lists (the scripts' interface)"}
+        torch.set_num_threads(1)
+        t0 = time.perf_counter()
+        for i in range(2):
+            m.update_embedding(batches[i % 2][0], ones, batches[i % 2][1])
+        rec["one_thread"] = {"value": 2 * B / (time.perf_counter() - t0), "unit": "samples/s", "cores": 1,
+                             "sample": "2 steps, ndarray inputs, torch.set_num_threads(1)"}
+        torch.set_num_threads(threads)
+        return rec
     except Exception as exc:  # noqa: BLE001
         return {"unavailable": f"{type(exc).__name__}: {exc}"}
     finally:
