@@ -148,3 +148,31 @@ def test_oracle_follows_the_reference_through_1000_fit_steps_of_the_tower_models
             assert round(auc(z, eY), 4) == round(auc(ref, eY), 4)
             sg = lambda v: 1.0 / (1.0 + np.exp(-np.asarray(v, np.float64)))
             assert round(rmse(sg(z), eY), 4) == round(rmse(sg(ref), eY), 4)
+
+
+# ------------------------------------------------------------------------------------------------ plain SGD (update mode 1)
+@pytest.mark.parametrize("name", ["cfg1", "frappe_zipf", "deepfm_fm_part"])
+def test_oracle_reproduces_sgd_trajectories_bit_for_bit(name):
+    """BASELINE.json configs[0] ("FM k = 10 offline SGD"): the live reference's forward pass + torch autograd +
+    torch.optim.SGD over 1 000 steps (tests/golden/make_trajectory_sgd.py).  Under SGD the gradient's VALUE reaches the
+    weights (the reference's own fresh-Adam step only keeps its sign), so bit equality here pins the BCE backward and the
+    duplicate-row summation order of embedding_dense_backward, Zipf ids included."""
+    from golden.make_trajectory_sgd import CASES, CKPT, cfg_of
+    from oracle.deep import OracleDeep
+    from _util import synth
+    g = dict(np.load(os.path.join(GOLDEN, "traj_sgd.npz")))
+    kind, sizes, B, zipf, (L, H), lr, steps = CASES[name]
+    orc = OracleDeep(kind, sizes, 10, L, H, lr=lr, update_mode=1)
+    orc.w1[:], orc.V[:] = init_tables(cfg_of(name))
+    orc.bias[:] = g[name + "_init_bias"]
+    if L:
+        orc.mlp[:] = g[name + "_init_mlp"]
+    losses = []
+    for s in range(steps):
+        Xi, Xv, Y = synth(sizes, B, 7000 + s, zipf=zipf)
+        losses.append(orc.update_embedding(Xi, Xv, Y))
+        if (s + 1) in CKPT:
+            assert digest(orc.V, orc.w1, orc.bias.reshape(1)) == str(g["%s_s%d_digest" % (name, s + 1)]), s + 1
+    assert np.array_equal(np.asarray(losses, np.float32), g[name + "_losses"])
+    rows = g[name + "_rows"]
+    assert np.array_equal(orc.V[rows], g[name + "_V"]) and np.array_equal(orc.w1[rows], g[name + "_w1"])

@@ -10,7 +10,8 @@ The five CUDA deep classes through the experiment scripts' flow at its real leng
 batch, run_experiment over a 2 500-sample stream): tests/golden/online_full.npz (CPU twin: tests/test_online_full.py).
 
 NOT part of `pytest -m gpu` yet: none of this has run on a B200.  Promote each part to a test once
-`gpurun -- python tools/check_full_size_gpu.py` has printed CFG2_FULL_OK, ML100K_KAT_OK and ONLINE_FULL_OK.
+`gpurun -- python tools/check_full_size_gpu.py` has printed CFG2_FULL_OK, ML100K_KAT_OK, ONLINE_FULL_OK and SGD_TRAJ_OK
+(the last one: 1 000-step plain-SGD trajectories, tests/golden/traj_sgd.npz).
 """
 import contextlib
 import io
@@ -140,7 +141,43 @@ def online_full():
     print("ONLINE_FULL_OK")
 
 
+def sgd_trajectories():
+    """tests/golden/traj_sgd.npz (CPU twin: test_oracle_reproduces_sgd_trajectories_bit_for_bit)"""
+    import torch
+    import fm_for_online_recommendation_b200 as pkg
+    from _util import synth
+    from golden.make_trajectory_sgd import CASES, CKPT, cfg_of
+    from traj_common import digest, init_tables
+    g = dict(np.load(GOLDEN + "/traj_sgd.npz"))
+    for name, (kind, sizes, B, zipf, (L, H), lr, steps) in CASES.items():
+        kw = dict(embedding_size=10, n=lr, update_mode=1)
+        if L:
+            kw.update(num_hidden_layers=L, neuron_per_hidden_layer=H)
+        m = getattr(pkg, kind)(sizes, **kw)
+        w1, V = init_tables(cfg_of(name))
+        with torch.no_grad():
+            t = torch.zeros_like(m._table)
+            t[:, :10] = torch.from_numpy(V)
+            t[:, 10] = torch.from_numpy(w1)
+            m._table.copy_(t)
+            m.bias.copy_(torch.from_numpy(g[name + "_init_bias"]).reshape(m.bias.shape))
+            if L:
+                m._mlp.copy_(torch.from_numpy(g[name + "_init_mlp"]))
+        losses = []
+        for s in range(steps):
+            Xi, Xv, Y = synth(sizes, B, 7000 + s, zipf=zipf)
+            losses.append(float(m.update_embedding(Xi, Xv, Y).cpu()))
+            if (s + 1) in CKPT:
+                tab = m._table.cpu().numpy()
+                d = digest(np.ascontiguousarray(tab[:, :10]), np.ascontiguousarray(tab[:, 10]), m.bias.detach().cpu().numpy().reshape(1))
+                assert d == str(g["%s_s%d_digest" % (name, s + 1)]), (name, s + 1)
+        assert np.array_equal(np.asarray(losses, np.float32), g[name + "_losses"]), name
+        print("%-15s %d SGD steps bit-identical with the live reference + torch.optim.SGD" % (name, steps))
+    print("SGD_TRAJ_OK")
+
+
 if __name__ == "__main__":
     main()
     ml100k()
     online_full()
+    sgd_trajectories()
