@@ -29,6 +29,8 @@ CASES = {
     "cfg1": ("FMAdam", [943, 1682], 256, False, (0, 0), 0.01, 1000),
     "frappe_zipf": ("FMAdam", FRAPPE, 256, True, (0, 0), 0.01, 1000),       # many duplicate rows per batch
     "deepfm_fm_part": ("DeepFMAdam", FRAPPE, 250, True, (2, 8), 0.01, 1000),  # forward_fm of a tower class; B % 32 != 0
+    # NFM's update_embedding puts the loss on sigmoid(z) (nfm_adam.py:99): the second loss variant, backward through sigmoid
+    "nfm_loss_of_sigmoid": ("NFMAdam", FRAPPE, 250, True, (1, 16), 0.05, 1000),
 }
 CKPT = (1, 100, 1000)
 
@@ -42,6 +44,7 @@ def main():
     _import_reference()
     from models.models_online_deep.deepfm_adam import DeepFMAdam
     from models.models_online_deep.fm_adam import FMAdam
+    from models.models_online_deep.nfm_adam import NFMAdam
     torch.set_num_threads(1)
     out = {}
     for name, (kind, sizes, B, zipf, (L, H), lr, steps) in CASES.items():
@@ -49,7 +52,7 @@ def main():
         if L:
             kw.update(num_hidden_layers=L, neuron_per_hidden_layer=H)
         torch.manual_seed(5)
-        m = {"FMAdam": FMAdam, "DeepFMAdam": DeepFMAdam}[kind](sizes, use_cuda=False, **kw)
+        m = {"FMAdam": FMAdam, "DeepFMAdam": DeepFMAdam, "NFMAdam": NFMAdam}[kind](sizes, use_cuda=False, **kw)
         set_tables(m, *init_tables(cfg_of(name)))
         p = flat_params(m)
         out[name + "_init_bias"], out[name + "_init_mlp"] = p["bias"], p["mlp"]
@@ -59,7 +62,7 @@ def main():
             Xi, Xv, Y = synth(sizes, B, 7000 + s, zipf=zipf)
             opt.zero_grad()
             z = m.forward_fm(Xi.tolist(), Xv.tolist()) if hasattr(m, "forward_fm") else m.forward(Xi.tolist(), Xv.tolist())
-            loss = F.binary_cross_entropy_with_logits(z, torch.from_numpy(Y))
+            loss = F.binary_cross_entropy_with_logits(torch.sigmoid(z) if kind == "NFMAdam" else z, torch.from_numpy(Y))
             loss.backward()
             opt.step()
             losses.append(float(loss.detach()))

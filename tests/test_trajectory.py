@@ -151,7 +151,7 @@ def test_oracle_follows_the_reference_through_1000_fit_steps_of_the_tower_models
 
 
 # ------------------------------------------------------------------------------------------------ plain SGD (update mode 1)
-@pytest.mark.parametrize("name", ["cfg1", "frappe_zipf", "deepfm_fm_part"])
+@pytest.mark.parametrize("name", ["cfg1", "frappe_zipf", "deepfm_fm_part", "nfm_loss_of_sigmoid"])
 def test_oracle_reproduces_sgd_trajectories_bit_for_bit(name):
     """BASELINE.json configs[0] ("FM k = 10 offline SGD"): the live reference's forward pass + torch autograd +
     torch.optim.SGD over 1 000 steps (tests/golden/make_trajectory_sgd.py).  Under SGD the gradient's VALUE reaches the
