@@ -31,6 +31,8 @@ CASES = {
     "deepfm_fm_part": ("DeepFMAdam", FRAPPE, 250, True, (2, 8), 0.01, 1000),  # forward_fm of a tower class; B % 32 != 0
     # NFM's update_embedding puts the loss on sigmoid(z) (nfm_adam.py:99): the second loss variant, backward through sigmoid
     "nfm_loss_of_sigmoid": ("NFMAdam", FRAPPE, 250, True, (1, 16), 0.05, 1000),
+    # real-valued Xv (data_preprocess.py:113: the svm reader's values): a name ending in _xv draws Xv from U(0.25, 2)
+    "frappe_zipf_xv": ("FMAdam", FRAPPE, 256, True, (0, 0), 0.01, 1000),
 }
 CKPT = (1, 100, 1000)
 
@@ -59,7 +61,7 @@ def main():
         opt = torch.optim.SGD(m.parameters(), lr=lr)
         losses = []
         for s in range(steps):
-            Xi, Xv, Y = synth(sizes, B, 7000 + s, zipf=zipf)
+            Xi, Xv, Y = synth(sizes, B, 7000 + s, real_xv=name.endswith("_xv"), zipf=zipf)
             opt.zero_grad()
             z = m.forward_fm(Xi.tolist(), Xv.tolist()) if hasattr(m, "forward_fm") else m.forward(Xi.tolist(), Xv.tolist())
             loss = F.binary_cross_entropy_with_logits(torch.sigmoid(z) if kind == "NFMAdam" else z, torch.from_numpy(Y))

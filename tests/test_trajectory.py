@@ -151,7 +151,7 @@ def test_oracle_follows_the_reference_through_1000_fit_steps_of_the_tower_models
 
 
 # ------------------------------------------------------------------------------------------------ plain SGD (update mode 1)
-@pytest.mark.parametrize("name", ["cfg1", "frappe_zipf", "deepfm_fm_part", "nfm_loss_of_sigmoid"])
+@pytest.mark.parametrize("name", ["cfg1", "frappe_zipf", "deepfm_fm_part", "nfm_loss_of_sigmoid", "frappe_zipf_xv"])
 def test_oracle_reproduces_sgd_trajectories_bit_for_bit(name):
     """BASELINE.json configs[0] ("FM k = 10 offline SGD"): the live reference's forward pass + torch autograd +
     torch.optim.SGD over 1 000 steps (tests/golden/make_trajectory_sgd.py).  Under SGD the gradient's VALUE reaches the
@@ -169,7 +169,7 @@ def test_oracle_reproduces_sgd_trajectories_bit_for_bit(name):
         orc.mlp[:] = g[name + "_init_mlp"]
     losses = []
     for s in range(steps):
-        Xi, Xv, Y = synth(sizes, B, 7000 + s, zipf=zipf)
+        Xi, Xv, Y = synth(sizes, B, 7000 + s, real_xv=name.endswith("_xv"), zipf=zipf)
         losses.append(orc.update_embedding(Xi, Xv, Y))
         if (s + 1) in CKPT:
             assert digest(orc.V, orc.w1, orc.bias.reshape(1)) == str(g["%s_s%d_digest" % (name, s + 1)]), s + 1

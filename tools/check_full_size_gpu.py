@@ -165,7 +165,7 @@ def sgd_trajectories():
                 m._mlp.copy_(torch.from_numpy(g[name + "_init_mlp"]))
         losses = []
         for s in range(steps):
-            Xi, Xv, Y = synth(sizes, B, 7000 + s, zipf=zipf)
+            Xi, Xv, Y = synth(sizes, B, 7000 + s, real_xv=name.endswith("_xv"), zipf=zipf)
             losses.append(float(m.update_embedding(Xi, Xv, Y).cpu()))
             if (s + 1) in CKPT:
                 tab = m._table.cpu().numpy()
